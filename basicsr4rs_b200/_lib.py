@@ -1,0 +1,80 @@
+"""ctypes binding of the srb200 C-ABI (include/srb200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (plain ``nvcc -shared``) and
+loaded from ``basicsr4rs_b200/csrc/libsrb200.so``.  There is **no fallback**: if the library is
+missing, or a call returns a non-zero status, a ``RuntimeError`` is raised -- the product path
+never routes through PyTorch ops or the CPU oracle.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libsrb200.so')
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU = 0, 1, 2, 3
+OUT_NHWC, OUT_SHUFFLE, OUT_NCHW_F32 = 0, 1, 2
+MASK_NONE, MASK_SIGN, MASK_DGELU = 0, 1, 2
+
+
+class TapGemmDesc(ctypes.Structure):
+    """Mirror of ``srb200_tapgemm_desc`` (include/srb200.h)."""
+    _fields_ = [
+        ('B', c_int32), ('H', c_int32), ('W', c_int32), ('Cin', c_int32), ('src_r', c_int32),
+        ('Cout', c_int32), ('ksize', c_int32), ('flip', c_int32), ('act', c_int32),
+        ('act_slope', c_float), ('alpha', c_float), ('mask_mode', c_int32), ('mask_slope', c_float),
+        ('out_mode', c_int32), ('out_r', c_int32), ('out_c', c_int32), ('out_scale', c_float),
+    ]
+
+
+# every symbol include/srb200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    'srb200_version': (c_char_p, []),
+    'srb200_strerror': (c_char_p, [c_int]),
+    'srb200_check_device': (c_int, [c_int]),
+    'srb200_pixel_shuffle_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p]),
+    'srb200_pixel_shuffle_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p]),
+    'srb200_window_remap': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
+    'srb200_roll_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'srb200_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float,
+                                    c_void_p]),
+    'srb200_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float,
+                                    c_void_p]),
+    'srb200_pack_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                   c_void_p]),
+    'srb200_unpack_wgrad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                    c_float, c_void_p]),
+    'srb200_tapgemm': (c_int, [POINTER(TapGemmDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
+    'srb200_wgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p]),
+    'srb200_colsum': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsrb200.so once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f'{LIB_PATH} is missing: build it with `python __graft_entry__.py build` '
+                           '(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU/PyTorch fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library diverge
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().srb200_strerror(status).decode()
+        raise RuntimeError(f'{what} failed: {msg} (status {status})')

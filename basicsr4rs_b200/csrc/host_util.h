@@ -1,0 +1,86 @@
+// Host-side helpers shared by the C-ABI entry points: TMA tensor-map encoding through the
+// driver entry point (no link-time libcuda dependency) and launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/srb200.h"
+
+namespace srb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+            cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides[i] is the
+// byte stride of dim i+1 (dim 0 is contiguous).
+inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return SRB200_EDRIVER;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr,
+                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SRB200_OK : SRB200_EDRIVER;
+}
+
+inline int num_sms() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+inline int launch_status() {
+  return cudaPeekAtLastError() == cudaSuccess ? SRB200_OK : SRB200_ELAUNCH;
+}
+
+// spatial tile (tw x th pixels, tw*th == npix) minimising padded area for an H x W image
+inline void pick_tile(int H, int W, int npix, int* tw, int* th) {
+  long best = -1;
+  int btw = 16, bth = npix / 16;
+  for (int w = 4; w <= 64 && w <= npix; w *= 2) {
+    int h = npix / w;
+    if (h < 1 || w * h != npix) continue;
+    long tx = (W + w - 1) / w, ty = (H + h - 1) / h;
+    long area = tx * ty;
+    // prefer fewer tiles; tie-break towards wider tiles (longer contiguous runs)
+    if (best < 0 || area < best || (area == best && w > btw && w <= 16)) {
+      best = area;
+      btw = w;
+      bth = h;
+    }
+  }
+  *tw = btw;
+  *th = bth;
+}
+
+}  // namespace srb

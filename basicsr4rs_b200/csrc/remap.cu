@@ -1,0 +1,562 @@
+// Bit-exact index remaps and layout conversions (HBM-bound; 128-bit accesses on both sides):
+// pixel_shuffle / unshuffle (NCHW and NHWC), window partition / reverse fused with the cyclic
+// shift, roll, NCHW fp32 <-> NHWC bf16 entry/exit, weight pack / unpack, column sums.
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace srb {
+
+static inline int grid_for(size_t work, int block) {
+  size_t g = (work + block - 1) / block;
+  return static_cast<int>(g > 0x7FFFFFFF ? 0x7FFFFFFF : (g == 0 ? 1 : g));
+}
+
+// ------------------------------------------------------------------ pixel shuffle, NCHW
+// thread: VEC consecutive x of one (b, c, y); moves r*r*VEC elements with 16-byte accesses.
+template <typename T, int R, bool INVERSE>
+__global__ void pixel_shuffle_nchw_vec(const T* __restrict__ in, T* __restrict__ out, int B, int C,
+                                       int H, int W) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int Wv = W / VEC;
+  const size_t total = static_cast<size_t>(B) * C * H * Wv;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xv = static_cast<int>(idx % Wv);
+    const int y = static_cast<int>((idx / Wv) % H);
+    const int c = static_cast<int>((idx / (static_cast<size_t>(Wv) * H)) % C);
+    const int b = static_cast<int>(idx / (static_cast<size_t>(Wv) * H * C));
+    const int x = xv * VEC;
+    const size_t plane = static_cast<size_t>(H) * W;
+    // "small" side: [B, C*R*R, H, W]; "big" side: [B, C, H*R, W*R]
+    const T* sm_base = (INVERSE ? out : in) +
+                       (static_cast<size_t>(b) * C * R * R + static_cast<size_t>(c) * R * R) * plane +
+                       static_cast<size_t>(y) * W + x;
+    const T* bg_base = (INVERSE ? in : out) +
+                       ((static_cast<size_t>(b) * C + c) * H * R + static_cast<size_t>(y) * R) *
+                           (static_cast<size_t>(W) * R) +
+                       static_cast<size_t>(x) * R;
+    T big[R][VEC * R];
+    if (!INVERSE) {
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          T v[VEC];
+          *reinterpret_cast<uint4*>(v) =
+              __ldg(reinterpret_cast<const uint4*>(sm_base + (i * R + j) * plane));
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) big[i][e * R + j] = v[e];
+        }
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+          *reinterpret_cast<uint4*>(const_cast<T*>(bg_base) + static_cast<size_t>(i) * W * R +
+                                    q * VEC) = *reinterpret_cast<uint4*>(&big[i][q * VEC]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int q = 0; q < R; ++q)
+          *reinterpret_cast<uint4*>(&big[i][q * VEC]) = __ldg(reinterpret_cast<const uint4*>(
+              bg_base + static_cast<size_t>(i) * W * R + q * VEC));
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          T v[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) v[e] = big[i][e * R + j];
+          *reinterpret_cast<uint4*>(const_cast<T*>(sm_base) + (i * R + j) * plane) =
+              *reinterpret_cast<uint4*>(v);
+        }
+    }
+  }
+}
+
+template <typename T, bool INVERSE>
+__global__ void pixel_shuffle_nchw_scalar(const T* __restrict__ in, T* __restrict__ out, int B,
+                                          int C, int H, int W, int R) {
+  const size_t total = static_cast<size_t>(B) * C * H * R * W * R;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(idx % (W * R));
+    const int Y = static_cast<int>((idx / (W * R)) % (H * R));
+    const int c = static_cast<int>((idx / (static_cast<size_t>(W) * R * H * R)) % C);
+    const int b = static_cast<int>(idx / (static_cast<size_t>(W) * R * H * R * C));
+    const int y = Y / R, i = Y % R, x = X / R, j = X % R;
+    const size_t small =
+        ((static_cast<size_t>(b) * C * R * R + static_cast<size_t>(c) * R * R + i * R + j) * H + y) *
+            W +
+        x;
+    if (!INVERSE)
+      out[idx] = in[small];
+    else
+      out[small] = in[idx];
+  }
+}
+
+// ------------------------------------------------------------------ pixel shuffle, NHWC
+// small: [B,H,W,C*R*R] (channel = c*R*R + i*R + j); big: [B,H*R,W*R,C].
+// thread: VEC consecutive c of one pixel -> R*R 16-byte loads, R*R 16-byte stores.
+template <typename T, int R, bool INVERSE>
+__global__ void pixel_shuffle_nhwc_vec(const T* __restrict__ in, T* __restrict__ out, int B, int C,
+                                       int H, int W) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int R2 = R * R;
+  const int Cv = C / VEC;
+  const size_t total = static_cast<size_t>(B) * H * W * Cv;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % Cv);
+    const size_t pix = idx / Cv;
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    const T* sm = (INVERSE ? out : in) + pix * (static_cast<size_t>(C) * R2) +
+                  static_cast<size_t>(cv) * VEC * R2;
+    const T* bg = (INVERSE ? in : out) +
+                  ((static_cast<size_t>(b) * H * R + static_cast<size_t>(y) * R) *
+                       (static_cast<size_t>(W) * R) +
+                   static_cast<size_t>(x) * R) *
+                      C +
+                  static_cast<size_t>(cv) * VEC;
+    T s[VEC * R2];
+    if (!INVERSE) {
+#pragma unroll
+      for (int q = 0; q < R2; ++q)
+        *reinterpret_cast<uint4*>(&s[q * VEC]) = __ldg(reinterpret_cast<const uint4*>(sm) + q);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          T v[VEC];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) v[e] = s[e * R2 + i * R + j];
+          *reinterpret_cast<uint4*>(const_cast<T*>(bg) +
+                                    (static_cast<size_t>(i) * W * R + j) * C) =
+              *reinterpret_cast<uint4*>(v);
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          T v[VEC];
+          *reinterpret_cast<uint4*>(v) = __ldg(
+              reinterpret_cast<const uint4*>(bg + (static_cast<size_t>(i) * W * R + j) * C));
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) s[e * R2 + i * R + j] = v[e];
+        }
+#pragma unroll
+      for (int q = 0; q < R2; ++q)
+        *(reinterpret_cast<uint4*>(const_cast<T*>(sm)) + q) = *reinterpret_cast<uint4*>(&s[q * VEC]);
+    }
+  }
+}
+
+template <typename T, bool INVERSE>
+__global__ void pixel_shuffle_nhwc_scalar(const T* __restrict__ in, T* __restrict__ out, int B,
+                                          int C, int H, int W, int R) {
+  const size_t total = static_cast<size_t>(B) * H * R * W * R * C;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    const int X = static_cast<int>((idx / C) % (W * R));
+    const int Y = static_cast<int>((idx / (static_cast<size_t>(C) * W * R)) % (H * R));
+    const int b = static_cast<int>(idx / (static_cast<size_t>(C) * W * R * H * R));
+    const int y = Y / R, i = Y % R, x = X / R, j = X % R;
+    const size_t small = ((static_cast<size_t>(b) * H + y) * W + x) * (static_cast<size_t>(C) * R * R) +
+                         static_cast<size_t>(c) * R * R + i * R + j;
+    if (!INVERSE)
+      out[idx] = in[small];
+    else
+      out[small] = in[idx];
+  }
+}
+
+// ------------------------------------------------------------------ token-row remaps
+// Both window partition(+shift) and roll move whole C-element token rows; VT is the access type.
+// map_mode 0: window remap, 1: roll.
+template <typename VT>
+__global__ void token_remap(const VT* __restrict__ in, VT* __restrict__ out, int B, int H, int W,
+                            int Cv /* row length in VT units */, int ws, int s0, int s1,
+                            int map_mode, int inverse) {
+  const size_t total = static_cast<size_t>(B) * H * W * Cv;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % Cv);
+    const size_t tok = idx / Cv;  // index on the "destination-ordered" side (see below)
+    size_t img_tok, other_tok;
+    if (map_mode == 0) {
+      // tok enumerates window order: ((b*nWh + wy)*nWw + wx)*ws*ws + iy*ws + ix
+      const int nWw = W / ws, nWh = H / ws;
+      const int ix = static_cast<int>(tok % ws);
+      const int iy = static_cast<int>((tok / ws) % ws);
+      const int wx = static_cast<int>((tok / (ws * ws)) % nWw);
+      const int wy = static_cast<int>((tok / (static_cast<size_t>(ws) * ws * nWw)) % nWh);
+      const int b = static_cast<int>(tok / (static_cast<size_t>(ws) * ws * nWw * nWh));
+      int yy = wy * ws + iy + s0;
+      int xx = wx * ws + ix + s0;
+      if (yy >= H) yy -= H;
+      if (xx >= W) xx -= W;
+      img_tok = (static_cast<size_t>(b) * H + yy) * W + xx;
+      other_tok = tok;
+      // forward: win[tok] = img[img_tok]; inverse: img[img_tok] = win[tok]
+      if (!inverse)
+        out[other_tok * Cv + cv] = __ldg(in + img_tok * Cv + cv);
+      else
+        out[img_tok * Cv + cv] = __ldg(in + other_tok * Cv + cv);
+    } else {
+      // roll: out[b, (y+s0)%H, (x+s1)%W] = in[b, y, x]; tok enumerates the output
+      const int x = static_cast<int>(tok % W);
+      const int y = static_cast<int>((tok / W) % H);
+      const int b = static_cast<int>(tok / (static_cast<size_t>(W) * H));
+      int ys = y - s0, xs = x - s1;
+      ys %= H;
+      if (ys < 0) ys += H;
+      xs %= W;
+      if (xs < 0) xs += W;
+      img_tok = (static_cast<size_t>(b) * H + ys) * W + xs;
+      out[tok * Cv + cv] = __ldg(in + img_tok * Cv + cv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ NCHW fp32 <-> NHWC bf16
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                    int B, int C, int H, int W, int Cp,
+                                    const float* __restrict__ shift, float scale) {
+  const int groups = Cp / 8;
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const size_t total = npix * groups;
+  const size_t plane = static_cast<size_t>(H) * W;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx % npix;  // pixel fastest: coalesced plane reads
+    const int g = static_cast<int>(idx / npix);
+    const size_t b = pix / plane, yx = pix % plane;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      v[e] = 0.0f;
+      if (c < C) {
+        const float sh = shift != nullptr ? __ldg(shift + c) : 0.0f;
+        v[e] = (__ldg(in + (b * C + c) * plane + yx) - sh) * scale;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + pix * Cp + g * 8) = o;
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                    int B, int C, int H, int W, int Cp,
+                                    const float* __restrict__ shift, float scale) {
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = npix * C;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = idx % npix;
+    const int c = static_cast<int>(idx / npix);
+    const size_t b = pix / plane, yx = pix % plane;
+    const float sh = shift != nullptr ? __ldg(shift + c) : 0.0f;
+    out[(b * C + c) * plane + yx] = __bfloat162float(in[pix * Cp + c]) * scale + sh;
+  }
+}
+
+// ------------------------------------------------------------------ weight pack / unpack
+__global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int taps,
+                                   const int32_t* __restrict__ perm_out, int Np,
+                                   const int32_t* __restrict__ perm_in, int Kp, int transpose,
+                                   __nv_bfloat16* __restrict__ out) {
+  const size_t total = static_cast<size_t>(taps) * Np * Kp;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int n, k;
+    const int t = static_cast<int>(idx / (static_cast<size_t>(Np) * Kp));
+    const size_t rem = idx % (static_cast<size_t>(Np) * Kp);
+    if (!transpose) {
+      n = static_cast<int>(rem / Kp);
+      k = static_cast<int>(rem % Kp);
+    } else {
+      k = static_cast<int>(rem / Np);
+      n = static_cast<int>(rem % Np);
+    }
+    const int o = perm_out != nullptr ? perm_out[n] : (n < Co ? n : -1);
+    const int i = perm_in != nullptr ? perm_in[k] : (k < Ci ? k : -1);
+    float v = 0.0f;
+    if (o >= 0 && i >= 0) v = __ldg(w + (static_cast<size_t>(o) * Ci + i) * taps + t);
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ gw, int Co,
+                                    int Ci, int taps, const int32_t* __restrict__ perm_out, int Np,
+                                    const int32_t* __restrict__ perm_in, int Kp, float alpha) {
+  const size_t total = static_cast<size_t>(taps) * Np * Kp;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(idx / (static_cast<size_t>(Np) * Kp));
+    const size_t rem = idx % (static_cast<size_t>(Np) * Kp);
+    const int n = static_cast<int>(rem / Kp);
+    const int k = static_cast<int>(rem % Kp);
+    const int o = perm_out != nullptr ? perm_out[n] : (n < Co ? n : -1);
+    const int i = perm_in != nullptr ? perm_in[k] : (k < Ci ? k : -1);
+    if (o >= 0 && i >= 0) gw[(static_cast<size_t>(o) * Ci + i) * taps + t] = alpha * acc[idx];
+  }
+}
+
+// ------------------------------------------------------------------ column sums (bias gradient)
+// dy [rows, C] bf16 -> out[view*C + c] += sum; view = pixel-unshuffle phase of the row (r > 1).
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ out,
+                              long long rows, int C, int r, int Wf, int rows_per_block) {
+  extern __shared__ float s_sum[];  // [r*r*C]
+  const int nsum = r * r * C;
+  for (int i = threadIdx.x; i < nsum; i += blockDim.x) s_sum[i] = 0.0f;
+  __syncthreads();
+  const int groups = C / 8;
+  const int g = threadIdx.x % groups;
+  const int rl = threadIdx.x / groups;
+  const int lanes = blockDim.x / groups;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  if (rl < lanes) {
+    if (r == 1) {
+      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (long long row = r0 + rl; row < r1; row += lanes) {
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(dy + row * C + g * 8));
+        a[0] += bf16_lo(m.x);
+        a[1] += bf16_hi(m.x);
+        a[2] += bf16_lo(m.y);
+        a[3] += bf16_hi(m.y);
+        a[4] += bf16_lo(m.z);
+        a[5] += bf16_hi(m.z);
+        a[6] += bf16_lo(m.w);
+        a[7] += bf16_hi(m.w);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&s_sum[g * 8 + e], a[e]);
+    } else {
+      for (long long row = r0 + rl; row < r1; row += lanes) {
+        const int X = static_cast<int>(row % Wf);
+        const int Y = static_cast<int>(row / Wf);
+        const int view = (Y % r) * r + (X % r);
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(dy + row * C + g * 8));
+        float* s = &s_sum[view * C + g * 8];
+        atomicAdd(s + 0, bf16_lo(m.x));
+        atomicAdd(s + 1, bf16_hi(m.x));
+        atomicAdd(s + 2, bf16_lo(m.y));
+        atomicAdd(s + 3, bf16_hi(m.y));
+        atomicAdd(s + 4, bf16_lo(m.z));
+        atomicAdd(s + 5, bf16_hi(m.z));
+        atomicAdd(s + 6, bf16_lo(m.w));
+        atomicAdd(s + 7, bf16_hi(m.w));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nsum; i += blockDim.x) atomicAdd(out + i, s_sum[i]);
+}
+
+template <typename T>
+static int dispatch_ps_nchw(const void* in, void* out, int B, int C, int H, int W, int r,
+                            int inverse, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = (r == 2 || r == 3) && (W % VEC == 0) &&
+                      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  const T* i = static_cast<const T*>(in);
+  T* o = static_cast<T*>(out);
+  if (vec_ok) {
+    const size_t work = static_cast<size_t>(B) * C * H * (W / VEC);
+    const int g = grid_for(work, 256);
+    if (r == 2) {
+      if (!inverse) pixel_shuffle_nchw_vec<T, 2, false><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+      else pixel_shuffle_nchw_vec<T, 2, true><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+    } else {
+      if (!inverse) pixel_shuffle_nchw_vec<T, 3, false><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+      else pixel_shuffle_nchw_vec<T, 3, true><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+    }
+  } else {
+    const size_t work = static_cast<size_t>(B) * C * H * r * W * r;
+    const int g = grid_for(work, 256);
+    if (!inverse) pixel_shuffle_nchw_scalar<T, false><<<g, 256, 0, st>>>(i, o, B, C, H, W, r);
+    else pixel_shuffle_nchw_scalar<T, true><<<g, 256, 0, st>>>(i, o, B, C, H, W, r);
+  }
+  return launch_status();
+}
+
+template <typename T>
+static int dispatch_ps_nhwc(const void* in, void* out, int B, int C, int H, int W, int r,
+                            int inverse, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = (r == 2 || r == 3) && (C % VEC == 0) &&
+                      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  const T* i = static_cast<const T*>(in);
+  T* o = static_cast<T*>(out);
+  if (vec_ok) {
+    const size_t work = static_cast<size_t>(B) * H * W * (C / VEC);
+    const int g = grid_for(work, 256);
+    if (r == 2) {
+      if (!inverse) pixel_shuffle_nhwc_vec<T, 2, false><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+      else pixel_shuffle_nhwc_vec<T, 2, true><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+    } else {
+      if (!inverse) pixel_shuffle_nhwc_vec<T, 3, false><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+      else pixel_shuffle_nhwc_vec<T, 3, true><<<g, 256, 0, st>>>(i, o, B, C, H, W);
+    }
+  } else {
+    const size_t work = static_cast<size_t>(B) * C * H * r * W * r;
+    const int g = grid_for(work, 256);
+    if (!inverse) pixel_shuffle_nhwc_scalar<T, false><<<g, 256, 0, st>>>(i, o, B, C, H, W, r);
+    else pixel_shuffle_nhwc_scalar<T, true><<<g, 256, 0, st>>>(i, o, B, C, H, W, r);
+  }
+  return launch_status();
+}
+
+static int dispatch_token_remap(const void* in, void* out, int B, int H, int W, int C,
+                                int elem_bytes, int ws, int s0, int s1, int mode, int inverse,
+                                cudaStream_t st) {
+  const size_t row_bytes = static_cast<size_t>(C) * elem_bytes;
+  const bool a16 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (row_bytes % 16 == 0 && a16) {
+    const int Cv = static_cast<int>(row_bytes / 16);
+    const int g = grid_for(static_cast<size_t>(B) * H * W * Cv, 256);
+    token_remap<uint4><<<g, 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), B,
+                                          H, W, Cv, ws, s0, s1, mode, inverse);
+  } else if (row_bytes % 4 == 0) {
+    const int Cv = static_cast<int>(row_bytes / 4);
+    const int g = grid_for(static_cast<size_t>(B) * H * W * Cv, 256);
+    token_remap<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(in),
+                                             static_cast<uint32_t*>(out), B, H, W, Cv, ws, s0, s1,
+                                             mode, inverse);
+  } else {
+    const int Cv = static_cast<int>(row_bytes / 2);
+    const int g = grid_for(static_cast<size_t>(B) * H * W * Cv, 256);
+    token_remap<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(in),
+                                             static_cast<uint16_t*>(out), B, H, W, Cv, ws, s0, s1,
+                                             mode, inverse);
+  }
+  return launch_status();
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" int srb200_pixel_shuffle_nchw(const void* in, void* out, int B, int C_out, int H, int W,
+                                         int r, int elem_bytes, int inverse,
+                                         srb200_stream_t stream) {
+  if (!in || !out || B <= 0 || C_out <= 0 || H <= 0 || W <= 0 || r < 1) return SRB200_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (elem_bytes == 2) return dispatch_ps_nchw<uint16_t>(in, out, B, C_out, H, W, r, inverse, st);
+  if (elem_bytes == 4) return dispatch_ps_nchw<uint32_t>(in, out, B, C_out, H, W, r, inverse, st);
+  return SRB200_EINVAL;
+}
+
+extern "C" int srb200_pixel_shuffle_nhwc(const void* in, void* out, int B, int C_out, int H, int W,
+                                         int r, int elem_bytes, int inverse,
+                                         srb200_stream_t stream) {
+  if (!in || !out || B <= 0 || C_out <= 0 || H <= 0 || W <= 0 || r < 1) return SRB200_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (elem_bytes == 2) return dispatch_ps_nhwc<uint16_t>(in, out, B, C_out, H, W, r, inverse, st);
+  if (elem_bytes == 4) return dispatch_ps_nhwc<uint32_t>(in, out, B, C_out, H, W, r, inverse, st);
+  return SRB200_EINVAL;
+}
+
+extern "C" int srb200_window_remap(const void* in, void* out, int B, int H, int W, int C, int ws,
+                                   int shift, int elem_bytes, int inverse, srb200_stream_t stream) {
+  if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || ws <= 0) return SRB200_EINVAL;
+  if (H % ws != 0 || W % ws != 0 || shift < 0 || shift >= ws) return SRB200_EINVAL;
+  if (elem_bytes != 2 && elem_bytes != 4) return SRB200_EINVAL;
+  return dispatch_token_remap(in, out, B, H, W, C, elem_bytes, ws, shift, shift, 0, inverse,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int srb200_roll_nhwc(const void* in, void* out, int B, int H, int W, int C, int sy,
+                                int sx, int elem_bytes, srb200_stream_t stream) {
+  if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0) return SRB200_EINVAL;
+  if (elem_bytes != 2 && elem_bytes != 4) return SRB200_EINVAL;
+  return dispatch_token_remap(in, out, B, H, W, C, elem_bytes, 1, sy, sx, 1, 0,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int srb200_nchw_to_nhwc(const float* in, void* out_bf16, int B, int C, int H, int W,
+                                   int C_pad, const float* shift, float scale,
+                                   srb200_stream_t stream) {
+  if (!in || !out_bf16 || B <= 0 || C <= 0 || H <= 0 || W <= 0) return SRB200_EINVAL;
+  if (C_pad < C || C_pad % 8 != 0 || (reinterpret_cast<uintptr_t>(out_bf16) & 15u)) return SRB200_EINVAL;
+  const size_t work = static_cast<size_t>(B) * H * W * (C_pad / 8);
+  nchw_to_nhwc_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, static_cast<__nv_bfloat16*>(out_bf16), B, C, H, W, C_pad, shift, scale);
+  return launch_status();
+}
+
+extern "C" int srb200_nhwc_to_nchw(const void* in_bf16, float* out, int B, int C, int H, int W,
+                                   int C_pad, const float* shift, float scale,
+                                   srb200_stream_t stream) {
+  if (!in_bf16 || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0 || C_pad < C) return SRB200_EINVAL;
+  const size_t work = static_cast<size_t>(B) * H * W * C;
+  nhwc_to_nchw_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in_bf16), out, B, C, H, W, C_pad, shift, scale);
+  return launch_status();
+}
+
+extern "C" int srb200_pack_weight(const float* w, int Co, int Ci, int taps,
+                                  const int32_t* perm_out, int Np, const int32_t* perm_in, int Kp,
+                                  int transpose, void* out_bf16, srb200_stream_t stream) {
+  if (!w || !out_bf16 || Co <= 0 || Ci <= 0 || taps <= 0 || Np <= 0 || Kp <= 0) return SRB200_EINVAL;
+  const size_t work = static_cast<size_t>(taps) * Np * Kp;
+  pack_weight_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, Co, Ci, taps, perm_out, Np, perm_in, Kp, transpose, static_cast<__nv_bfloat16*>(out_bf16));
+  return launch_status();
+}
+
+extern "C" int srb200_unpack_wgrad(const float* acc, float* gw, int Co, int Ci, int taps,
+                                   const int32_t* perm_out, int Np, const int32_t* perm_in, int Kp,
+                                   float alpha, srb200_stream_t stream) {
+  if (!acc || !gw || Co <= 0 || Ci <= 0 || taps <= 0 || Np <= 0 || Kp <= 0) return SRB200_EINVAL;
+  const size_t work = static_cast<size_t>(taps) * Np * Kp;
+  unpack_wgrad_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, gw, Co, Ci, taps, perm_out, Np, perm_in, Kp, alpha);
+  return launch_status();
+}
+
+extern "C" int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int C, int r, int Wf,
+                             srb200_stream_t stream) {
+  if (!dy_bf16 || !out || rows <= 0 || C <= 0 || C % 8 != 0 || r < 1 || r > 3) return SRB200_EINVAL;
+  if (C / 8 > 256 || (r > 1 && Wf <= 0)) return SRB200_EINVAL;
+  const int rows_per_block = 512;
+  const int grid = static_cast<int>((rows + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<grid, 256, r * r * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy_bf16), out, rows, C, r, Wf, rows_per_block);
+  return launch_status();
+}
+
+extern "C" const char* srb200_version(void) { return "srb200 0.1 (sm_100a)"; }
+
+extern "C" const char* srb200_strerror(int code) {
+  switch (code) {
+    case SRB200_OK: return "ok";
+    case SRB200_EINVAL: return "invalid argument (shape / alignment / flags)";
+    case SRB200_EARCH: return "device is not sm_100 (B200)";
+    case SRB200_EDRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+    case SRB200_ELAUNCH: return "kernel launch failed";
+  }
+  return "unknown error";
+}
+
+extern "C" int srb200_check_device(int dev) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return SRB200_EARCH;
+  return major == 10 ? SRB200_OK : SRB200_EARCH;
+}

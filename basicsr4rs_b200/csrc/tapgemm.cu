@@ -1,0 +1,472 @@
+// tap-GEMM: conv3x3 / conv1x1 / Linear as a TMA-fed tcgen05 implicit GEMM (sm_100a).
+//
+//   out[b,y,x,n] = epi( sum_{tap,k} A[b, y+dy(tap), x+dx(tap), k] * Wp[tap][n][k] )
+//
+// * A is an NHWC bf16 tensor read through a 4-D TMA tensor map (C, W, H, B): one box is a
+//   (64 ch) x (tw x th = 128 pixel) spatial patch; the 3x3 halo is a coordinate offset and the
+//   zero padding of nn.Conv2d(padding=1) is TMA's out-of-bounds zero fill -- no im2col buffer,
+//   no padded copy, no index arithmetic per element.
+// * Wp is [taps][N][K] bf16 (K-major), one 2-D box (64 x BLOCK_N) per k-block.
+// * both land in 128B-swizzled smem rows, are consumed by tcgen05.mma (M=128, N=BLOCK_N,
+//   K=16) issued by one thread, accumulate in TMEM (fp32, double-buffered across tiles) and
+//   are drained by 4 epilogue warps with tcgen05.ld while the next tile's MMAs run.
+// * persistent CTAs (one per SM), static round-robin tile schedule.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace srb {
+
+struct TapGemmParams {
+  CUtensorMap tmap_a[9];  // one per source view (src_r^2 <= 9)
+  CUtensorMap tmap_w;
+  int B, H, W;
+  int tile_w, tile_h, tiles_x, tiles_y;
+  int m_tiles, n_tiles;
+  int kchunks_per_src;  // Cin / 64
+  int num_src;          // src_r^2
+  int Cout;             // packed N
+  int taps, ksize, flip;
+  // epilogue
+  const float* bias;
+  const __nv_bfloat16* mask_src;
+  const __nv_bfloat16* residual;
+  const float* out_shift;
+  void* out;
+  __nv_bfloat16* aux_out;
+  int act;
+  float act_slope, alpha;
+  int mask_mode;
+  float mask_slope;
+  int out_mode, out_r, out_c;
+  float out_scale;
+};
+
+template <int BLOCK_N>
+struct TapCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
+                                   : (2 * BLOCK_N <= 64)  ? 64
+                                   : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256
+                                                          : 512;
+  static constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;  // epilogue columns per tcgen05.ld
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+  using Cfg = TapCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int CHUNK = Cfg::CHUNK;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
+    tma_prefetch_desc(&p.tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int kchunks = p.kchunks_per_src * p.num_src;
+  const int num_kb = p.taps * kchunks;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_t = t % p.n_tiles;
+        const int m_t = t / p.n_tiles;
+        const int tx = m_t % p.tiles_x;
+        const int ty = (m_t / p.tiles_x) % p.tiles_y;
+        const int b = m_t / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h, n0 = n_t * BLOCK_N;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          int dy = 0, dx = 0;
+          if (p.ksize == 3) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+            if (p.flip) {
+              dy = -dy;
+              dx = -dx;
+            }
+          }
+          for (int kc = 0; kc < kchunks; ++kc) {
+            const int src = kc / p.kchunks_per_src;
+            const int c0 = (kc - src * p.kchunks_per_src) * 64;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            tma_load_4d(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
+            tma_load_2d(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64, tap * p.Cout + n0);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a0 + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b0 + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // tile row == TMEM lane
+    const int ly = row / p.tile_w, lx = row - ly * p.tile_w;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int n_t = t % p.n_tiles;
+      const int m_t = t / p.n_tiles;
+      const int tx = m_t % p.tiles_x;
+      const int ty = (m_t / p.tiles_x) % p.tiles_y;
+      const int b = m_t / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.tile_w + lx, y = ty * p.tile_h + ly;
+      const int n0 = n_t * BLOCK_N;
+      const bool valid = (x < p.W) && (y < p.H);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+      const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / CHUNK; ++c) {
+        uint32_t r[CHUNK];
+        if constexpr (CHUNK == 32) {
+          tmem_ld32(taddr + c * CHUNK, r);
+        } else {
+          tmem_ld16(taddr + c * CHUNK, r);
+        }
+        tmem_ld_wait();
+        float v[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(r[j]);
+        const int nc = n0 + c * CHUNK;
+        if (p.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + nc);
+#pragma unroll
+          for (int j = 0; j < CHUNK / 4; ++j) {
+            const float4 bv = __ldg(bp + j);
+            v[4 * j + 0] += bv.x;
+            v[4 * j + 1] += bv.y;
+            v[4 * j + 2] += bv.z;
+            v[4 * j + 3] += bv.w;
+          }
+        }
+        if (valid) {
+          // element offset of (pixel, channel nc) in an NHWC tensor shaped like `out`
+          size_t off;
+          if (p.out_mode == SRB200_OUT_SHUFFLE) {
+            const int r2 = p.out_r * p.out_r;
+            const int C = p.Cout / r2;
+            const int ij = nc / C, cc = nc - ij * C;
+            const int i = ij / p.out_r, j = ij - i * p.out_r;
+            off = ((static_cast<size_t>(b) * p.H * p.out_r + static_cast<size_t>(y) * p.out_r + i) *
+                       (static_cast<size_t>(p.W) * p.out_r) +
+                   static_cast<size_t>(x) * p.out_r + j) *
+                      C +
+                  cc;
+          } else {
+            off = pix * p.Cout + nc;
+          }
+          if (p.aux_out != nullptr) {
+            uint4* ap = reinterpret_cast<uint4*>(p.aux_out + off);
+#pragma unroll
+            for (int j = 0; j < CHUNK / 8; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              ap[j] = o;
+            }
+          }
+          if (p.act == SRB200_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (p.act == SRB200_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * p.act_slope;
+          } else if (p.act == SRB200_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) v[j] = gelu_erf(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) v[j] *= p.alpha;
+          if (p.mask_mode != SRB200_MASK_NONE) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
+#pragma unroll
+            for (int j = 0; j < CHUNK / 8; ++j) {
+              const uint4 m = __ldg(mp + j);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float m0 = bf16_lo(mw[q]), m1 = bf16_hi(mw[q]);
+                if (p.mask_mode == SRB200_MASK_SIGN) {
+                  v[8 * j + 2 * q + 0] *= (m0 > 0.0f) ? 1.0f : p.mask_slope;
+                  v[8 * j + 2 * q + 1] *= (m1 > 0.0f) ? 1.0f : p.mask_slope;
+                } else {
+                  v[8 * j + 2 * q + 0] *= dgelu_erf(m0);
+                  v[8 * j + 2 * q + 1] *= dgelu_erf(m1);
+                }
+              }
+            }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+            for (int j = 0; j < CHUNK / 8; ++j) {
+              const uint4 m = __ldg(rp + j);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[8 * j + 2 * q + 0] += bf16_lo(mw[q]);
+                v[8 * j + 2 * q + 1] += bf16_hi(mw[q]);
+              }
+            }
+          }
+          if (p.out_mode == SRB200_OUT_NCHW_F32) {
+            float* op = reinterpret_cast<float*>(p.out);
+            const size_t plane = static_cast<size_t>(p.H) * p.W;
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+              const int ch = nc + j;
+              if (ch < p.out_c) {
+                const float sh = p.out_shift != nullptr ? __ldg(p.out_shift + ch) : 0.0f;
+                op[(static_cast<size_t>(b) * p.out_c + ch) * plane + static_cast<size_t>(y) * p.W +
+                   x] = v[j] * p.out_scale + sh;
+              }
+            }
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
+#pragma unroll
+            for (int j = 0; j < CHUNK / 8; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              op[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BLOCK_N>
+static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
+  using Cfg = TapCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return SRB200_ELAUNCH;
+    configured = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  tapgemm_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+  return launch_status();
+}
+
+static int pick_block_n(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 192 == 0) return 192;
+  if (Cout % 128 == 0) return 128;
+  if (Cout % 64 == 0) return 64;
+  if (Cout == 16 || Cout == 32 || Cout == 48) return 16;
+  return 0;
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
+                              const void* w_packed, const float* bias, const void* mask_src,
+                              const void* residual, const float* out_shift, void* out,
+                              void* aux_out, srb200_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d || !in_bf16 || !w_packed || !out) return SRB200_EINVAL;
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0) return SRB200_EINVAL;
+  if (d->Cin <= 0 || d->Cin % 64 != 0) return SRB200_EINVAL;
+  if (d->ksize != 1 && d->ksize != 3) return SRB200_EINVAL;
+  if (d->src_r < 1 || d->src_r > 3) return SRB200_EINVAL;
+  const int bn = pick_block_n(d->Cout);
+  if (bn == 0) return SRB200_EINVAL;
+  if (d->mask_mode != SRB200_MASK_NONE && !mask_src) return SRB200_EINVAL;
+  if (d->out_mode == SRB200_OUT_SHUFFLE) {
+    const int r2 = d->out_r * d->out_r;
+    if (d->out_r < 2 || d->out_r > 3 || d->Cout % r2 != 0 || (d->Cout / r2) % 32 != 0)
+      return SRB200_EINVAL;
+  } else if (d->out_mode == SRB200_OUT_NCHW_F32) {
+    if (d->out_c <= 0 || d->out_c > d->Cout || mask_src || residual || aux_out)
+      return SRB200_EINVAL;
+  } else if (d->out_mode != SRB200_OUT_NHWC) {
+    return SRB200_EINVAL;
+  }
+  if ((reinterpret_cast<uintptr_t>(in_bf16) | reinterpret_cast<uintptr_t>(w_packed) |
+       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask_src) |
+       reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(aux_out) |
+       reinterpret_cast<uintptr_t>(bias)) &
+      15u)
+    return SRB200_EINVAL;
+
+  TapGemmParams p;
+  p.B = d->B;
+  p.H = d->H;
+  p.W = d->W;
+  pick_tile(d->H, d->W, 128, &p.tile_w, &p.tile_h);
+  p.tiles_x = (d->W + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (d->H + p.tile_h - 1) / p.tile_h;
+  p.m_tiles = d->B * p.tiles_x * p.tiles_y;
+  p.n_tiles = d->Cout / bn;
+  p.kchunks_per_src = d->Cin / 64;
+  p.num_src = d->src_r * d->src_r;
+  p.Cout = d->Cout;
+  p.ksize = d->ksize;
+  p.taps = d->ksize * d->ksize;
+  p.flip = d->flip;
+  p.bias = bias;
+  p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out_shift = out_shift;
+  p.out = out;
+  p.aux_out = static_cast<__nv_bfloat16*>(aux_out);
+  p.act = d->act;
+  p.act_slope = d->act_slope;
+  p.alpha = d->alpha;
+  p.mask_mode = d->mask_mode;
+  p.mask_slope = d->mask_slope;
+  p.out_mode = d->out_mode;
+  p.out_r = d->out_r;
+  p.out_c = d->out_c;
+  p.out_scale = d->out_scale;
+
+  // A views: in[B, H*r, W*r, Cin], view (i,j): element (b,y,x,c) at ((b*H*r + y*r+i)*W*r + x*r+j)*Cin + c
+  const int r = d->src_r;
+  const uint64_t C = static_cast<uint64_t>(d->Cin);
+  const uint64_t Wf = static_cast<uint64_t>(d->W) * r, Hf = static_cast<uint64_t>(d->H) * r;
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < r; ++j) {
+      const __nv_bfloat16* base =
+          static_cast<const __nv_bfloat16*>(in_bf16) + (static_cast<uint64_t>(i) * Wf + j) * C;
+      const uint64_t dims[4] = {C, static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                                static_cast<uint64_t>(d->B)};
+      const uint64_t strides[3] = {r * C * 2, r * Wf * C * 2, Hf * Wf * C * 2};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h),
+                               1};
+      const int rc = make_tmap_bf16(&p.tmap_a[i * r + j], base, 4, dims, strides, box);
+      if (rc != SRB200_OK) return rc;
+    }
+  {
+    const uint64_t K = static_cast<uint64_t>(p.num_src) * C;
+    const uint64_t dims[2] = {K, static_cast<uint64_t>(p.taps) * d->Cout};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    const int rc = make_tmap_bf16(&p.tmap_w, w_packed, 2, dims, strides, box);
+    if (rc != SRB200_OK) return rc;
+  }
+  switch (bn) {
+    case 256: return launch_tapgemm<256>(p, stream);
+    case 192: return launch_tapgemm<192>(p, stream);
+    case 128: return launch_tapgemm<128>(p, stream);
+    case 64: return launch_tapgemm<64>(p, stream);
+    case 16: return launch_tapgemm<16>(p, stream);
+  }
+  return SRB200_EINVAL;
+}

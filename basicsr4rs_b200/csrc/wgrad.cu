@@ -1,0 +1,276 @@
+// Weight gradient of conv3x3 / conv1x1 / Linear as a tcgen05 GEMM whose reduction runs over
+// pixels (sm_100a):
+//
+//   acc[tap][n][k] += sum_{b,y,x} dY[b,y,x,n] * X[b, y+dy(tap), x+dx(tap), k]
+//
+// Both operands are read straight from the NHWC activations with the same 4-D TMA tensor maps
+// the forward uses: a box is (64 ch) x (64-pixel spatial patch), i.e. 64 smem rows of 128 B with
+// the GEMM-K (pixel) index selecting the row -- the "MN-major" UMMA operand layout
+// (LBO = distance between 64-channel blocks, SBO = distance between 8-pixel groups).
+// A = dY (M = 128 output channels), B = shifted X (N = BLOCK_N input channels), D in TMEM.
+// Work unit = (tap, m-tile, n-tile, pixel split); partial sums are merged with vector fp32
+// atomics into `acc` (zeroed by the caller), so any split count is legal.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace srb {
+
+struct WgradParams {
+  CUtensorMap tmap_dy[9];
+  CUtensorMap tmap_x;
+  float* acc;
+  int B, H, W;
+  int tile_w, tile_h, tiles_x, tiles_y;
+  int total_kb;  // B * tiles_x * tiles_y
+  int splits;
+  int N, K;      // dY channels (rows of acc), X channels (cols of acc)
+  int m_tiles, n_tiles;
+  int taps, ksize;
+  int dy_c;      // channels per dY view (N / dy_r^2)
+};
+
+template <int BLOCK_N>
+struct WgCfg {
+  static constexpr int A_BYTES = 128 * 128;          // 2 boxes of [64 px][64 ch]
+  static constexpr int B_BYTES = BLOCK_N * 128;      // BLOCK_N/64 boxes
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 1);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work unit
+  int u = blockIdx.x;
+  const int split = u % p.splits;
+  u /= p.splits;
+  const int n_t = u % p.n_tiles;
+  u /= p.n_tiles;
+  const int m_t = u % p.m_tiles;
+  const int tap = u / p.m_tiles;
+  const int kb_begin = static_cast<int>((static_cast<long long>(p.total_kb) * split) / p.splits);
+  const int kb_end = static_cast<int>((static_cast<long long>(p.total_kb) * (split + 1)) / p.splits);
+  const int m0 = m_t * 128, n0 = n_t * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_x);
+    tma_prefetch_desc(&p.tmap_dy[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int dy = 0, dx = 0;
+      if (p.ksize == 3) {
+        dy = tap / 3 - 1;
+        dx = tap % 3 - 1;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int tx = kb % p.tiles_x;
+        const int ty = (kb / p.tiles_x) % p.tiles_y;
+        const int b = kb / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const int n = m0 + mb * 64;        // packed dY channel
+          const int view = n / p.dy_c;       // pixel-unshuffle view (0 when dy_r == 1)
+          const int c = n - view * p.dy_c;
+          // channels beyond N fall outside the tensor map and are zero-filled
+          tma_load_4d(smem_a(stage) + mb * 8192, &p.tmap_dy[n < p.N ? view : 0], full_bar(stage),
+                      n < p.N ? c : p.dy_c, x0, y0, b);
+        }
+#pragma unroll
+        for (int nb = 0; nb < BLOCK_N / 64; ++nb)
+          tma_load_4d(smem_b(stage) + nb * 8192, &p.tmap_x, full_bar(stage), n0 + nb * 64, x0 + dx,
+                      y0 + dy, b);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, 8192, 1024);
+          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    if (kb_end > kb_begin) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int n = m0 + row;
+      float* dst = p.acc + (static_cast<size_t>(tap) * p.N + n) * p.K + n0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + 4 * j), v);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BLOCK_N>
+static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return SRB200_ELAUNCH;
+    configured = true;
+  }
+  const int grid = p.taps * p.m_tiles * p.n_tiles * p.splits;
+  wgrad_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+  return launch_status();
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc, int B, int H,
+                            int W, int N, int K, int ksize, int dy_r, srb200_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dy_bf16 || !x_bf16 || !acc) return SRB200_EINVAL;
+  if (B <= 0 || H <= 0 || W <= 0 || N <= 0 || K <= 0) return SRB200_EINVAL;
+  if (N % 64 != 0 || K % 64 != 0) return SRB200_EINVAL;
+  if (ksize != 1 && ksize != 3) return SRB200_EINVAL;
+  if (dy_r < 1 || dy_r > 3 || N % (dy_r * dy_r) != 0 || (N / (dy_r * dy_r)) % 64 != 0)
+    return SRB200_EINVAL;
+  int bn;
+  if (K % 256 == 0) bn = 256;
+  else if (K % 192 == 0) bn = 192;
+  else if (K % 128 == 0) bn = 128;
+  else bn = 64;
+
+  WgradParams p;
+  p.acc = acc;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  pick_tile(H, W, 64, &p.tile_w, &p.tile_h);
+  p.tiles_x = (W + p.tile_w - 1) / p.tile_w;
+  p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
+  p.total_kb = B * p.tiles_x * p.tiles_y;
+  p.N = N;
+  p.K = K;
+  p.m_tiles = (N + 127) / 128;
+  p.n_tiles = K / bn;
+  p.ksize = ksize;
+  p.taps = ksize * ksize;
+  p.dy_c = N / (dy_r * dy_r);
+  const int units = p.taps * p.m_tiles * p.n_tiles;
+  int splits = num_sms() / units;
+  if (splits < 1) splits = 1;
+  if (splits > p.total_kb) splits = p.total_kb;
+  // keep each split long enough to amortise the pipeline fill / atomic epilogue
+  while (splits > 1 && p.total_kb / splits < 8) --splits;
+  p.splits = splits;
+
+  const uint32_t box[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
+  {
+    const uint64_t C = static_cast<uint64_t>(K);
+    const uint64_t dims[4] = {C, static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {C * 2, static_cast<uint64_t>(W) * C * 2,
+                                 static_cast<uint64_t>(H) * W * C * 2};
+    const int rc = make_tmap_bf16(&p.tmap_x, x_bf16, 4, dims, strides, box);
+    if (rc != SRB200_OK) return rc;
+  }
+  {
+    const int r = dy_r;
+    const uint64_t C = static_cast<uint64_t>(p.dy_c);
+    const uint64_t Wf = static_cast<uint64_t>(W) * r, Hf = static_cast<uint64_t>(H) * r;
+    for (int i = 0; i < r; ++i)
+      for (int j = 0; j < r; ++j) {
+        const __nv_bfloat16* base =
+            static_cast<const __nv_bfloat16*>(dy_bf16) + (static_cast<uint64_t>(i) * Wf + j) * C;
+        const uint64_t dims[4] = {C, static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                                  static_cast<uint64_t>(B)};
+        const uint64_t strides[3] = {r * C * 2, r * Wf * C * 2, Hf * Wf * C * 2};
+        const int rc = make_tmap_bf16(&p.tmap_dy[i * r + j], base, 4, dims, strides, box);
+        if (rc != SRB200_OK) return rc;
+      }
+  }
+  switch (bn) {
+    case 256: return launch_wgrad<256>(p, stream);
+    case 192: return launch_wgrad<192>(p, stream);
+    case 128: return launch_wgrad<128>(p, stream);
+    case 64: return launch_wgrad<64>(p, stream);
+  }
+  return SRB200_EINVAL;
+}

@@ -1,0 +1,200 @@
+"""Thin tensor-level wrappers over the srb200 C-ABI (no autograd).
+
+Each function validates tensors (CUDA, contiguous, dtype), allocates the outputs with PyTorch's
+caching allocator, forwards raw ``data_ptr()``s on the *current* stream and turns a non-zero
+status into ``RuntimeError`` -- the same contract as the reference's pybind shims
+(basicsr/ops/fused_act/src/fused_bias_act.cpp:10-26, CHECK_CUDA / CHECK_CONTIGUOUS).
+"""
+import ctypes
+
+import torch
+
+from ... import _lib as L
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _chk(t, name, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor')
+    if not t.is_contiguous():
+        raise RuntimeError(f'{name} must be contiguous')
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f'{name} must be {dtype}, got {t.dtype}')
+
+
+def _esize(t):
+    es = t.element_size()
+    if es not in (2, 4):
+        raise RuntimeError('index remaps support 2- and 4-byte element types')
+    return es
+
+
+# ------------------------------------------------------------------ index remaps (bit-exact)
+def pixel_shuffle_nchw(x, r, inverse=False):
+    """nn.PixelShuffle(r) (arch_util.py:135,138) / its inverse on NCHW tensors."""
+    _chk(x, 'x')
+    lib = L.load()
+    if not inverse:
+        b, c, h, w = x.shape
+        assert c % (r * r) == 0
+        co = c // (r * r)
+        out = torch.empty((b, co, h * r, w * r), dtype=x.dtype, device=x.device)
+    else:
+        b, co, hh, ww = x.shape
+        assert hh % r == 0 and ww % r == 0
+        h, w = hh // r, ww // r
+        out = torch.empty((b, co * r * r, h, w), dtype=x.dtype, device=x.device)
+    L.check(lib.srb200_pixel_shuffle_nchw(_ptr(x), _ptr(out), b, co, h, w, r, _esize(x), int(inverse), _stream()),
+            'pixel_shuffle_nchw')
+    return out
+
+
+def pixel_shuffle_nhwc(x, r, inverse=False):
+    _chk(x, 'x')
+    lib = L.load()
+    if not inverse:
+        b, h, w, c = x.shape
+        co = c // (r * r)
+        out = torch.empty((b, h * r, w * r, co), dtype=x.dtype, device=x.device)
+    else:
+        b, hh, ww, co = x.shape
+        h, w = hh // r, ww // r
+        out = torch.empty((b, h, w, co * r * r), dtype=x.dtype, device=x.device)
+    L.check(lib.srb200_pixel_shuffle_nhwc(_ptr(x), _ptr(out), b, co, h, w, r, _esize(x), int(inverse), _stream()),
+            'pixel_shuffle_nhwc')
+    return out
+
+
+def window_partition(x, ws, shift=0):
+    """roll(-shift) + window_partition (swinir_arch.py:293-300): [B,H,W,C] -> [B*nW, ws, ws, C]."""
+    _chk(x, 'x')
+    b, h, w, c = x.shape
+    out = torch.empty((b * (h // ws) * (w // ws), ws, ws, c), dtype=x.dtype, device=x.device)
+    L.check(L.load().srb200_window_remap(_ptr(x), _ptr(out), b, h, w, c, ws, shift, _esize(x), 0, _stream()),
+            'window_partition')
+    return out
+
+
+def window_reverse(win, ws, h, w, shift=0):
+    """window_reverse + roll(+shift) (swinir_arch.py:309-316): [B*nW, ws, ws, C] -> [B,H,W,C]."""
+    _chk(win, 'win')
+    c = win.shape[-1]
+    b = win.shape[0] // ((h // ws) * (w // ws))
+    out = torch.empty((b, h, w, c), dtype=win.dtype, device=win.device)
+    L.check(L.load().srb200_window_remap(_ptr(win), _ptr(out), b, h, w, c, ws, shift, _esize(win), 1, _stream()),
+            'window_reverse')
+    return out
+
+
+def roll_nhwc(x, sy, sx):
+    _chk(x, 'x')
+    b, h, w, c = x.shape
+    out = torch.empty_like(x)
+    L.check(L.load().srb200_roll_nhwc(_ptr(x), _ptr(out), b, h, w, c, sy, sx, _esize(x), _stream()), 'roll_nhwc')
+    return out
+
+
+# ------------------------------------------------------------------ layout entry / exit
+def nchw_to_nhwc(x, c_pad, shift=None, scale=1.0):
+    _chk(x, 'x', torch.float32)
+    b, c, h, w = x.shape
+    out = torch.empty((b, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().srb200_nchw_to_nhwc(_ptr(x), _ptr(out), b, c, h, w, c_pad, _ptr(shift), float(scale), _stream()),
+            'nchw_to_nhwc')
+    return out
+
+
+def nhwc_to_nchw(x, c, shift=None, scale=1.0):
+    _chk(x, 'x', torch.bfloat16)
+    b, h, w, c_pad = x.shape
+    out = torch.empty((b, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(L.load().srb200_nhwc_to_nchw(_ptr(x), _ptr(out), b, c, h, w, c_pad, _ptr(shift), float(scale), _stream()),
+            'nhwc_to_nchw')
+    return out
+
+
+# ------------------------------------------------------------------ weights
+def pack_weight(w, n_pad, k_pad, perm_out=None, perm_in=None, transpose=False):
+    """fp32 [Co, Ci, kh, kw] (or [Co, Ci]) -> bf16 [taps, n_pad, k_pad] (or [taps, k_pad, n_pad])."""
+    _chk(w, 'w', torch.float32)
+    co, ci = w.shape[0], w.shape[1]
+    taps = w.numel() // (co * ci)
+    shape = (taps, k_pad, n_pad) if transpose else (taps, n_pad, k_pad)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    L.check(L.load().srb200_pack_weight(_ptr(w), co, ci, taps, _ptr(perm_out), n_pad, _ptr(perm_in), k_pad,
+                                        int(transpose), _ptr(out), _stream()), 'pack_weight')
+    return out
+
+
+def unpack_wgrad(acc, w_shape, perm_out=None, perm_in=None, alpha=1.0):
+    """fp32 [taps, n_pad, k_pad] accumulator -> fp32 gradient shaped like the nn.Parameter."""
+    _chk(acc, 'acc', torch.float32)
+    taps, n_pad, k_pad = acc.shape
+    co, ci = w_shape[0], w_shape[1]
+    alloc = torch.zeros if (perm_out is not None or perm_in is not None) else torch.empty
+    gw = alloc(tuple(w_shape), dtype=torch.float32, device=acc.device)
+    L.check(L.load().srb200_unpack_wgrad(_ptr(acc), _ptr(gw), co, ci, taps, _ptr(perm_out), n_pad, _ptr(perm_in),
+                                         k_pad, float(alpha), _stream()), 'unpack_wgrad')
+    return gw
+
+
+# ------------------------------------------------------------------ tap-GEMM
+def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alpha=1.0, mask_src=None,
+            mask_mode=L.MASK_NONE, mask_slope=0.0, residual=None, flip=False, src_r=1, out_mode=L.OUT_NHWC,
+            out_r=1, out_c=0, out_scale=1.0, out_shift=None, want_aux=False):
+    """conv3x3 / conv1x1 / Linear on NHWC bf16 (see include/srb200.h: srb200_tapgemm)."""
+    _chk(x, 'x', torch.bfloat16)
+    _chk(wp, 'wp', torch.bfloat16)
+    b, hf, wf, cin = x.shape
+    h, w = hf // src_r, wf // src_r
+    d = L.TapGemmDesc(B=b, H=h, W=w, Cin=cin, src_r=src_r, Cout=cout, ksize=ksize, flip=int(flip), act=act,
+                      act_slope=act_slope, alpha=alpha, mask_mode=mask_mode, mask_slope=mask_slope,
+                      out_mode=out_mode, out_r=out_r, out_c=out_c, out_scale=out_scale)
+    if out_mode == L.OUT_NHWC:
+        out = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
+    elif out_mode == L.OUT_SHUFFLE:
+        out = torch.empty((b, h * out_r, w * out_r, cout // (out_r * out_r)), dtype=torch.bfloat16, device=x.device)
+    else:
+        out = torch.empty((b, out_c, h, w), dtype=torch.float32, device=x.device)
+    aux = torch.empty_like(out) if want_aux else None
+    for t, name in ((mask_src, 'mask_src'), (residual, 'residual')):
+        if t is not None:
+            _chk(t, name, torch.bfloat16)
+            if t.shape != out.shape:
+                raise RuntimeError(f'{name} shape {tuple(t.shape)} != out shape {tuple(out.shape)}')
+    if bias is not None:
+        _chk(bias, 'bias', torch.float32)
+        assert bias.numel() == cout
+    L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),
+                                    _ptr(out_shift), _ptr(out), _ptr(aux), _stream()), 'tapgemm')
+    return (out, aux) if want_aux else out
+
+
+def wgrad(dy, x, *, ksize, dy_r=1):
+    """fp32 [taps, N, K] = sum_pixels dY^T X_shifted (see srb200_wgrad)."""
+    _chk(dy, 'dy', torch.bfloat16)
+    _chk(x, 'x', torch.bfloat16)
+    b, h, w, k = x.shape
+    n = dy.shape[-1] * dy_r * dy_r
+    assert dy.shape[0] == b and dy.shape[1] == h * dy_r and dy.shape[2] == w * dy_r
+    acc = torch.zeros((ksize * ksize, n, k), dtype=torch.float32, device=x.device)
+    L.check(L.load().srb200_wgrad(_ptr(dy), _ptr(x), _ptr(acc), b, h, w, n, k, ksize, dy_r, _stream()), 'wgrad')
+    return acc
+
+
+def colsum(dy, r=1):
+    """bias gradient: fp32 [r*r*C] column sums of an NHWC bf16 tensor (phase-separated when r > 1)."""
+    _chk(dy, 'dy', torch.bfloat16)
+    c = dy.shape[-1]
+    rows = dy.numel() // c
+    out = torch.zeros((r * r * c,), dtype=torch.float32, device=dy.device)
+    L.check(L.load().srb200_colsum(_ptr(dy), _ptr(out), rows, c, r, dy.shape[2] if dy.dim() == 4 else 0, _stream()),
+            'colsum')
+    return out

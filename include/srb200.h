@@ -1,0 +1,143 @@
+/*
+ * srb200 -- C ABI of the B200-native (sm_100a) super-resolution hot path.
+ *
+ * This is the drop-in boundary for watercore2001/BasicSR4RS' EDSR / RCAN / SwinIR
+ * forward+backward.  Every entry point replaces a group of aten:: library calls the
+ * reference issues from basicsr/archs/{arch_util,edsr_arch,rcan_arch,swinir_arch}.py
+ * (file:line given per function).  Conventions:
+ *   - plain device pointers + sizes; no torch types
+ *   - the caller owns every buffer (workspaces included); the library never
+ *     allocates, never synchronises, never changes the current device
+ *   - work is enqueued on `stream` and is asynchronous w.r.t. the host
+ *   - return 0 on success, a negative SRB200_E* code otherwise
+ *
+ * Activation layout inside a network: NHWC, bf16, channel count padded to a multiple
+ * of 64 with zeros ("NHWC64").  Weights are fp32 nn.Parameters on the host side and are
+ * repacked to bf16 tap-major GEMM operands by srb200_pack_weight (derived cache).
+ */
+#ifndef SRB200_H_
+#define SRB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* srb200_stream_t; /* cudaStream_t */
+
+enum {
+  SRB200_OK = 0,
+  SRB200_EINVAL = -1,   /* bad shape / alignment / flag combination */
+  SRB200_EARCH = -2,    /* device is not sm_100 */
+  SRB200_EDRIVER = -3,  /* cuTensorMapEncodeTiled unavailable or failed */
+  SRB200_ELAUNCH = -4   /* kernel launch failed */
+};
+
+enum { SRB200_ACT_NONE = 0, SRB200_ACT_RELU = 1, SRB200_ACT_LRELU = 2, SRB200_ACT_GELU = 3 };
+enum {
+  SRB200_OUT_NHWC = 0,     /* bf16 [B,H,W,ldo]                                         */
+  SRB200_OUT_SHUFFLE = 1,  /* bf16 [B,H*r,W*r,Cout/r^2]: nn.PixelShuffle fused in store */
+  SRB200_OUT_NCHW_F32 = 2  /* fp32 [B,out_c,H,W], v*out_scale + out_shift[c]            */
+};
+enum { SRB200_MASK_NONE = 0, SRB200_MASK_SIGN = 1, SRB200_MASK_DGELU = 2 };
+
+const char* srb200_version(void);
+const char* srb200_strerror(int code);
+/* 0 when device `dev` can run the kernels (compute capability 10.x). */
+int srb200_check_device(int dev);
+
+/* ------------------------------------------------------------------ index remaps
+ * Bit-exact; any 2-byte or 4-byte element type (elem_bytes = 2 | 4).
+ * pixel_shuffle: nn.PixelShuffle(r) of arch_util.py:131-139 on NCHW:
+ *   out[b, c, y*r+i, x*r+j] = in[b, c*r*r + i*r + j, y, x];  bwd = its inverse.        */
+int srb200_pixel_shuffle_nchw(const void* in, void* out, int B, int C_out, int H, int W, int r,
+                              int elem_bytes, int inverse, srb200_stream_t stream);
+/* Same map on NHWC tensors: in [B,H,W,C*r*r] (channel = c*r*r+i*r+j) -> out [B,H*r,W*r,C]. */
+int srb200_pixel_shuffle_nhwc(const void* in, void* out, int B, int C_out, int H, int W, int r,
+                              int elem_bytes, int inverse, srb200_stream_t stream);
+/* window_partition (swinir_arch.py:63-75) fused with the cyclic shift torch.roll(x,(-s,-s),(1,2))
+ * (swinir_arch.py:293-296):  win[(b*nWh+wy)*nWw+wx, iy, ix, :] = x[b, (wy*ws+iy+s)%H, (wx*ws+ix+s)%W, :]
+ * inverse=1 is window_reverse (:78-92) followed by roll(+s,+s) (:313-316).               */
+int srb200_window_remap(const void* in, void* out, int B, int H, int W, int C, int ws, int shift,
+                        int elem_bytes, int inverse, srb200_stream_t stream);
+/* torch.roll(x, (sy,sx), dims=(1,2)) on [B,H,W,C]. */
+int srb200_roll_nhwc(const void* in, void* out, int B, int H, int W, int C, int sy, int sx,
+                     int elem_bytes, srb200_stream_t stream);
+
+/* ------------------------------------------------------------------ layout entry/exit
+ * NCHW fp32 -> NHWC bf16 with C_pad channels (zeros beyond C):
+ *   out[b,y,x,c] = bf16((in[b,c,y,x] - shift[c]) * scale)     (edsr_arch.py:53, mean/range)
+ * shift may be NULL (=0).                                                                */
+int srb200_nchw_to_nhwc(const float* in, void* out_bf16, int B, int C, int H, int W, int C_pad,
+                        const float* shift, float scale, srb200_stream_t stream);
+/* NHWC bf16 (C_pad channels) -> NCHW fp32, out = in*scale + shift[c] (edsr_arch.py:59).   */
+int srb200_nhwc_to_nchw(const void* in_bf16, float* out, int B, int C, int H, int W, int C_pad,
+                        const float* shift, float scale, srb200_stream_t stream);
+
+/* ------------------------------------------------------------------ weight packing
+ * conv / linear weight fp32 [Co, Ci, taps] (OIHW flattened; taps = 1 or 9) -> bf16
+ *   transpose=0: out[t][n][k] = w[perm_out[n]][perm_in[k]][t]   (fprop operand, [taps][Np][Kp])
+ *   transpose=1: out[t][k][n] = w[perm_out[n]][perm_in[k]][t]   (dgrad operand, [taps][Kp][Np])
+ * perm_* are device int32 arrays mapping packed index -> original index, -1 = zero pad.   */
+int srb200_pack_weight(const float* w, int Co, int Ci, int taps, const int32_t* perm_out, int Np,
+                       const int32_t* perm_in, int Kp, int transpose, void* out_bf16,
+                       srb200_stream_t stream);
+/* inverse of pack for the weight gradient: gw[perm_out[n]][perm_in[k]][t] = alpha*acc[t][n][k]. */
+int srb200_unpack_wgrad(const float* acc, float* gw, int Co, int Ci, int taps,
+                        const int32_t* perm_out, int Np, const int32_t* perm_in, int Kp,
+                        float alpha, srb200_stream_t stream);
+
+/* ------------------------------------------------------------------ tap-GEMM (conv3x3 / conv1x1 / Linear)
+ * out[b,y,x,n] = epi( sum_{t,k} A[b, y+dy(t), x+dx(t), k] * Wp[t][n][k] )
+ * TMA-fed tcgen05 implicit GEMM, fp32 accumulation in TMEM.  Replaces nn.Conv2d(…,3,1,1)
+ * (arch_util.py:79-80,134,137; edsr_arch.py:44-48; rcan_arch.py:39-41,65,109-121;
+ * swinir_arch.py:532,818,834-837) and nn.Linear (swinir_arch.py:51-53,135-137), forward
+ * and the data gradient (flip=1 with the transposed pack).
+ * epi(v): v += bias[n]; act; v *= alpha; mask (v *= act'(mask_src)); v += residual.       */
+typedef struct {
+  int32_t B, H, W;      /* GEMM rows = B*H*W output pixels                                 */
+  int32_t Cin;          /* channels of A per source view, multiple of 64                   */
+  int32_t src_r;        /* 1, or r: A is read through a pixel-unshuffle view of
+                           in[B,H*r,W*r,Cin]; K per tap = r*r*Cin ordered (i*r+j, c)       */
+  int32_t Cout;         /* packed N, multiple of 16                                        */
+  int32_t ksize;        /* 1 or 3                                                          */
+  int32_t flip;         /* 0: taps as correlation (fprop); 1: negated offsets (dgrad)      */
+  int32_t act;          /* SRB200_ACT_*                                                    */
+  float act_slope;      /* LeakyReLU negative slope                                        */
+  float alpha;          /* scale after activation (res_scale)                              */
+  int32_t mask_mode;    /* SRB200_MASK_*                                                   */
+  float mask_slope;
+  int32_t out_mode;     /* SRB200_OUT_*                                                    */
+  int32_t out_r;        /* pixel-shuffle factor for SRB200_OUT_SHUFFLE                     */
+  int32_t out_c;        /* SRB200_OUT_NCHW_F32: real channel count (<= Cout)               */
+  float out_scale;      /* SRB200_OUT_NCHW_F32                                             */
+} srb200_tapgemm_desc;
+
+int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16, const void* w_packed,
+                   const float* bias,          /* [Cout] or NULL                           */
+                   const void* mask_src,       /* bf16, layout of out, or NULL             */
+                   const void* residual,       /* bf16, layout of out, or NULL             */
+                   const float* out_shift,     /* [out_c] for NCHW_F32 or NULL             */
+                   void* out,                  /* see out_mode                             */
+                   void* aux_out,              /* optional bf16 copy of the pre-activation */
+                   srb200_stream_t stream);
+
+/* ------------------------------------------------------------------ weight gradient
+ * acc[t][n][k] += sum_{b,y,x} dY[b,y,x,n] * X[b, y+dy(t), x+dx(t), k]      (fp32 atomics)
+ * tcgen05 GEMM with both operands MN-major, split over pixels.  acc must be zeroed by the
+ * caller; finish with srb200_unpack_wgrad.  dy_r > 1 reads dY through the pixel-unshuffle
+ * view (gradient of the fused PixelShuffle store).                                        */
+int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc, int B, int H, int W,
+                 int N /* dY channels (packed) */, int K /* X channels */, int ksize, int dy_r,
+                 srb200_stream_t stream);
+/* bias gradient: out[c] += sum over rows of dY[rows, C] (fp32 atomics; zero `out` first).
+ * r > 1: dY is [B, H*r, Wf = W*r, C] and out[((Y%r)*r + X%r)*C + c] collects the r*r
+ * pixel-unshuffle phases separately (bias gradient of a conv whose store fused PixelShuffle). */
+int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int C, int r, int Wf,
+                  srb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB200_H_ */

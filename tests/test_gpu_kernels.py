@@ -1,0 +1,275 @@
+"""Kernel-level parity on the B200 (``-m gpu``): every C-ABI entry point against a plain PyTorch
+fp32 reference of the same op on identical (bf16-rounded) inputs.
+
+Bars: bit-exact for the index remaps; for the tensor-core kernels the only rounding that differs
+from the fp32 reference is the bf16 store (rel 2^-9) plus fp32 accumulation order, so
+``|err| <= 1e-2 * max|ref| `` is asserted (observed ~3e-3).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _raw():
+    from basicsr4rs_b200.ops.sr_b200 import raw
+    return raw
+
+
+def _L():
+    from basicsr4rs_b200 import _lib
+    return _lib
+
+
+# ------------------------------------------------------------------ remaps
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('r,shape', [(2, (2, 8, 6, 8)), (2, (1, 4, 5, 7)), (3, (2, 18, 4, 8)), (3, (1, 9, 3, 5)),
+                                     (4, (1, 16, 3, 4))])
+def test_pixel_shuffle_nchw_bit_exact(cuda, dtype, r, shape):
+    raw = _raw()
+    x = torch.randn(shape, device=cuda).to(dtype)
+    ref = F.pixel_shuffle(x, r)
+    out = raw.pixel_shuffle_nchw(x, r)
+    assert out.shape == ref.shape and torch.equal(out.view(torch.uint8), ref.view(torch.uint8))
+    back = raw.pixel_shuffle_nchw(out, r, inverse=True)
+    assert torch.equal(back.view(torch.uint8), x.view(torch.uint8))
+    assert torch.equal(back, F.pixel_unshuffle(ref, r))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('r,b,c,h,w', [(2, 2, 64, 6, 8), (2, 1, 3, 5, 7), (3, 1, 8, 4, 4), (2, 1, 256, 12, 12)])
+def test_pixel_shuffle_nhwc_bit_exact(cuda, dtype, r, b, c, h, w):
+    raw = _raw()
+    x_nchw = torch.randn((b, c * r * r, h, w), device=cuda).to(dtype)
+    ref = F.pixel_shuffle(x_nchw, r).permute(0, 2, 3, 1).contiguous()
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()
+    out = raw.pixel_shuffle_nhwc(x, r)
+    assert torch.equal(out.view(torch.uint8), ref.view(torch.uint8))
+    back = raw.pixel_shuffle_nhwc(out, r, inverse=True)
+    assert torch.equal(back.view(torch.uint8), x.view(torch.uint8))
+
+
+def _ref_window_partition(x, ws):
+    b, h, w, c = x.shape
+    x = x.view(b, h // ws, ws, w // ws, ws, c)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, ws, ws, c)
+
+
+def _ref_window_reverse(win, ws, h, w):
+    b = int(win.shape[0] / (h * w / ws / ws))
+    x = win.view(b, h // ws, w // ws, ws, ws, -1)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(b, h, w, -1)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('b,h,w,c,ws,shift', [(2, 16, 24, 180, 8, 0), (2, 16, 24, 180, 8, 4), (1, 64, 64, 192, 8, 4),
+                                              (1, 12, 18, 60, 6, 3), (1, 14, 14, 7, 7, 3)])
+def test_window_remap_bit_exact(cuda, dtype, b, h, w, c, ws, shift):
+    raw = _raw()
+    x = torch.randn((b, h, w, c), device=cuda).to(dtype)
+    shifted = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2)) if shift else x
+    ref = _ref_window_partition(shifted, ws)
+    out = raw.window_partition(x, ws, shift)
+    assert torch.equal(out.view(torch.uint8), ref.view(torch.uint8))
+    rev_ref = _ref_window_reverse(ref, ws, h, w)
+    if shift:
+        rev_ref = torch.roll(rev_ref, shifts=(shift, shift), dims=(1, 2))
+    rev = raw.window_reverse(out, ws, h, w, shift)
+    assert torch.equal(rev.view(torch.uint8), rev_ref.view(torch.uint8))
+    assert torch.equal(rev.view(torch.uint8), x.view(torch.uint8))  # round trip
+
+
+@pytest.mark.parametrize('sy,sx', [(-4, -4), (4, 4), (3, -5), (0, 1)])
+def test_roll_bit_exact(cuda, sy, sx):
+    raw = _raw()
+    x = torch.randn((2, 16, 24, 180), device=cuda).to(torch.bfloat16)
+    assert torch.equal(raw.roll_nhwc(x, sy, sx), torch.roll(x, shifts=(sy, sx), dims=(1, 2)))
+
+
+def test_layout_entry_exit(cuda):
+    raw = _raw()
+    x = torch.rand((2, 3, 10, 12), device=cuda)
+    mean = torch.tensor([0.4488, 0.4371, 0.4040], device=cuda)
+    y = raw.nchw_to_nhwc(x, 64, shift=mean, scale=255.0)
+    ref = ((x - mean.view(1, 3, 1, 1)) * 255.0).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(y[..., :3], ref) and torch.count_nonzero(y[..., 3:]) == 0
+    z = raw.nhwc_to_nchw(y, 3, shift=mean, scale=1 / 255.0)
+    ref_z = ref.float().permute(0, 3, 1, 2) * (1 / 255.0) + mean.view(1, 3, 1, 1)
+    assert torch.allclose(z, ref_z, atol=1e-6)
+
+
+# ------------------------------------------------------------------ tap-GEMM
+def _mk_conv(cuda, b, h, w, cin, cout, ks, seed=0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    x = torch.randn((b, cin, h, w), generator=g).to(cuda)
+    wt = (torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks)**0.5).to(cuda)
+    bias = torch.randn((cout,), generator=g).to(cuda)
+    return x, wt, bias
+
+
+def _nhwc_bf16(x, cpad):
+    b, c, h, w = x.shape
+    out = torch.zeros((b, h, w, cpad), dtype=torch.bfloat16, device=x.device)
+    out[..., :c] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out
+
+
+def _pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def _assert_close(out, ref, tol=1e-2):
+    err = (out.float() - ref.float()).abs().max().item()
+    scale = ref.float().abs().max().item()
+    assert err <= tol * scale + 1e-6, f'max err {err:.4g} vs scale {scale:.4g}'
+
+
+@pytest.mark.parametrize('b,h,w,cin,cout,ks', [
+    (1, 8, 16, 64, 64, 3),
+    (2, 16, 16, 64, 256, 3),
+    (2, 48, 48, 256, 256, 3),
+    (1, 20, 13, 128, 192, 3),
+    (2, 9, 31, 192, 128, 3),
+    (2, 16, 16, 192, 384, 1),
+    (1, 24, 24, 64, 3, 3),
+    (1, 7, 5, 3, 64, 3),
+])
+def test_tapgemm_conv_fwd(cuda, b, h, w, cin, cout, ks):
+    raw, L = _raw(), _L()
+    x, wt, bias = _mk_conv(cuda, b, h, w, cin, cout, ks)
+    kp = _pad_to(cin, 64)
+    np_ = 16 if cout <= 16 else _pad_to(cout, 64)
+    xb = _nhwc_bf16(x, kp)
+    wp = raw.pack_weight(wt, np_, kp)
+    bp = torch.zeros(np_, device=cuda)
+    bp[:cout] = bias
+    ref = F.conv2d(xb[..., :cin].float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, padding=ks // 2)
+    if np_ == 16:
+        out = raw.tapgemm(xb, wp, ksize=ks, cout=np_, bias=bp, out_mode=L.OUT_NCHW_F32, out_c=cout, out_scale=0.5,
+                          out_shift=bias)
+        _assert_close(out, ref * 0.5 + bias.view(1, -1, 1, 1), 2e-3)
+        return
+    out = raw.tapgemm(xb, wp, ksize=ks, cout=np_, bias=bp)
+    _assert_close(out[..., :cout].permute(0, 3, 1, 2), ref)
+    assert torch.count_nonzero(out[..., cout:]) == 0
+
+
+def test_tapgemm_epilogues(cuda):
+    raw, L = _raw(), _L()
+    b, h, w, c = 2, 16, 24, 64
+    x, wt, bias = _mk_conv(cuda, b, h, w, c, c, 3, seed=1)
+    xb = _nhwc_bf16(x, c)
+    wp = raw.pack_weight(wt, c, c)
+    conv = F.conv2d(xb.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, padding=1)
+    nhwc = lambda t: t.permute(0, 2, 3, 1)
+    # bias + relu
+    out = raw.tapgemm(xb, wp, ksize=3, cout=c, bias=bias, act=L.ACT_RELU)
+    _assert_close(out, nhwc(F.relu(conv)))
+    # leaky relu 0.01 + aux (pre-activation)
+    out, aux = raw.tapgemm(xb, wp, ksize=3, cout=c, bias=bias, act=L.ACT_LRELU, act_slope=0.01, want_aux=True)
+    _assert_close(out, nhwc(F.leaky_relu(conv, 0.01)))
+    _assert_close(aux, nhwc(conv))
+    # gelu
+    out = raw.tapgemm(xb, wp, ksize=3, cout=c, bias=bias, act=L.ACT_GELU)
+    _assert_close(out, nhwc(F.gelu(conv)))
+    # res_scale + identity  (ResidualBlockNoBN tail, arch_util.py:85-88)
+    out = raw.tapgemm(xb, wp, ksize=3, cout=c, bias=bias, alpha=0.1, residual=xb)
+    _assert_close(out, nhwc(conv * 0.1) + xb.float())
+    # sign mask (ReLU backward) + residual
+    m = torch.randn((b, h, w, c), device=cuda).to(torch.bfloat16)
+    out = raw.tapgemm(xb, wp, ksize=3, cout=c, mask_src=m, mask_mode=L.MASK_SIGN, mask_slope=0.0, residual=xb)
+    conv_nb = conv - bias.view(1, -1, 1, 1)
+    _assert_close(out, nhwc(conv_nb) * (m.float() > 0) + xb.float())
+    # dgelu mask
+    out = raw.tapgemm(xb, wp, ksize=3, cout=c, mask_src=m, mask_mode=L.MASK_DGELU)
+    mm = m.float().requires_grad_(True)
+    F.gelu(mm).sum().backward()
+    _assert_close(out, nhwc(conv_nb) * mm.grad)
+
+
+@pytest.mark.parametrize('r,cin,cfeat', [(2, 64, 64), (2, 128, 256), (3, 64, 64)])
+def test_tapgemm_pixel_shuffle_store(cuda, r, cin, cfeat):
+    """Upsample conv + nn.PixelShuffle (arch_util.py:134-138) with the shuffle fused in the store."""
+    raw, L = _raw(), _L()
+    b, h, w = 2, 12, 16
+    cout = cfeat * r * r
+    x, wt, bias = _mk_conv(cuda, b, h, w, cin, cout, 3, seed=2)
+    xb = _nhwc_bf16(x, cin)
+    # packed channel p = ij*cfeat + c  <-  original o = c*r*r + ij
+    p = torch.arange(cout, device=cuda)
+    perm = ((p % cfeat) * (r * r) + p // cfeat).to(torch.int32)
+    wp = raw.pack_weight(wt, cout, cin, perm_out=perm)
+    out = raw.tapgemm(xb, wp, ksize=3, cout=cout, bias=bias[perm.long()].contiguous(), out_mode=L.OUT_SHUFFLE, out_r=r)
+    ref = F.pixel_shuffle(F.conv2d(xb.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, padding=1), r)
+    assert out.shape == (b, h * r, w * r, cfeat)
+    _assert_close(out, ref.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize('b,h,w,cin,cout,ks', [(2, 16, 16, 64, 64, 3), (1, 20, 13, 128, 192, 3), (2, 16, 16, 192, 384, 1),
+                                               (2, 48, 48, 256, 256, 3)])
+def test_tapgemm_dgrad(cuda, b, h, w, cin, cout, ks):
+    raw = _raw()
+    x, wt, _ = _mk_conv(cuda, b, h, w, cin, cout, ks, seed=3)
+    dy = torch.randn((b, h, w, cout), device=cuda).to(torch.bfloat16)
+    wpt = raw.pack_weight(wt, cout, cin, transpose=True)  # [taps][cin][cout]
+    dx = raw.tapgemm(dy, wpt, ksize=ks, cout=cin, flip=True)
+    xr = x.clone().requires_grad_(True)
+    y = F.conv2d(xr, wt.to(torch.bfloat16).float(), None, padding=ks // 2)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    _assert_close(dx, xr.grad.permute(0, 2, 3, 1))
+
+
+def test_tapgemm_dgrad_unshuffle_view(cuda):
+    """dgrad of the upsample conv reads dY through the pixel-unshuffle TMA views (src_r=2)."""
+    raw = _raw()
+    b, h, w, cin, cfeat, r = 2, 12, 16, 64, 64, 2
+    cout = cfeat * r * r
+    x, wt, _ = _mk_conv(cuda, b, h, w, cin, cout, 3, seed=4)
+    dy_hr = torch.randn((b, h * r, w * r, cfeat), device=cuda).to(torch.bfloat16)
+    p = torch.arange(cout, device=cuda)
+    perm = ((p % cfeat) * (r * r) + p // cfeat).to(torch.int32)
+    wpt = raw.pack_weight(wt, cout, cin, perm_out=perm, transpose=True)  # [taps][cin][packed cout]
+    dx = raw.tapgemm(dy_hr, wpt, ksize=3, cout=cin, flip=True, src_r=r)
+    xr = x.clone().requires_grad_(True)
+    y = F.pixel_shuffle(F.conv2d(xr, wt.to(torch.bfloat16).float(), None, padding=1), r)
+    y.backward(dy_hr.float().permute(0, 3, 1, 2))
+    _assert_close(dx, xr.grad.permute(0, 2, 3, 1))
+
+
+# ------------------------------------------------------------------ wgrad / colsum
+@pytest.mark.parametrize('b,h,w,cin,cout,ks', [(2, 16, 16, 64, 64, 3), (2, 48, 48, 256, 256, 3), (1, 20, 13, 128, 192, 3),
+                                               (2, 16, 16, 192, 384, 1), (4, 24, 24, 64, 256, 3)])
+def test_wgrad(cuda, b, h, w, cin, cout, ks):
+    raw = _raw()
+    x, wt, _ = _mk_conv(cuda, b, h, w, cin, cout, ks, seed=5)
+    xb = _nhwc_bf16(x, cin)
+    dy = torch.randn((b, h, w, cout), device=cuda).to(torch.bfloat16)
+    acc = raw.wgrad(dy, xb, ksize=ks)
+    gw = raw.unpack_wgrad(acc, wt.shape, alpha=0.5)
+    wr = wt.clone().requires_grad_(True)
+    y = F.conv2d(xb.float().permute(0, 3, 1, 2), wr, None, padding=ks // 2)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    _assert_close(gw, wr.grad * 0.5, 2e-3)
+    gb = raw.colsum(dy)
+    _assert_close(gb, dy.float().sum((0, 1, 2)), 1e-3)
+
+
+def test_wgrad_unshuffle_view(cuda):
+    raw = _raw()
+    b, h, w, cin, cfeat, r = 2, 12, 16, 64, 64, 2
+    cout = cfeat * r * r
+    x, wt, _ = _mk_conv(cuda, b, h, w, cin, cout, 3, seed=6)
+    xb = _nhwc_bf16(x, cin)
+    dy_hr = torch.randn((b, h * r, w * r, cfeat), device=cuda).to(torch.bfloat16)
+    p = torch.arange(cout, device=cuda)
+    perm = ((p % cfeat) * (r * r) + p // cfeat).to(torch.int32)
+    acc = raw.wgrad(dy_hr, xb, ksize=3, dy_r=r)
+    gw = raw.unpack_wgrad(acc, wt.shape, perm_out=perm)
+    wr = wt.clone().requires_grad_(True)
+    br = torch.zeros(cout, device=cuda, requires_grad=True)
+    y = F.pixel_shuffle(F.conv2d(xb.float().permute(0, 3, 1, 2), wr, br, padding=1), r)
+    y.backward(dy_hr.float().permute(0, 3, 1, 2))
+    _assert_close(gw, wr.grad, 2e-3)
+    gb = raw.colsum(dy_hr, r=r)  # packed order (ij, c)
+    _assert_close(gb, br.grad[perm.long()], 1e-3)
