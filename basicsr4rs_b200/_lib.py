@@ -52,6 +52,7 @@ SIGNATURES = {
     'srb200_wgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_void_p]),
     'srb200_colsum': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    'srb200_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
 }
 
 _lib = None
@@ -74,7 +75,12 @@ def load():
     return lib
 
 
+launch_count = 0  # every successful C-ABI compute call enqueues exactly one CUDA kernel
+
+
 def check(status, what):
+    global launch_count
+    launch_count += 1
     if status != 0:
         msg = load().srb200_strerror(status).decode()
         raise RuntimeError(f'{what} failed: {msg} (status {status})')

@@ -278,40 +278,41 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, 
                                    const int32_t* __restrict__ perm_out, int Np,
                                    const int32_t* __restrict__ perm_in, int Kp, int transpose,
                                    __nv_bfloat16* __restrict__ out) {
-  const size_t total = static_cast<size_t>(taps) * Np * Kp;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+  // thread = one (n, k) pair, all taps: the `taps` source floats are contiguous (OIHW), and for a fixed
+  // tap consecutive threads write consecutive bf16 (k fastest, or n fastest when transposing).
+  const size_t pairs = static_cast<size_t>(Np) * Kp;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < pairs;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     int n, k;
-    const int t = static_cast<int>(idx / (static_cast<size_t>(Np) * Kp));
-    const size_t rem = idx % (static_cast<size_t>(Np) * Kp);
     if (!transpose) {
-      n = static_cast<int>(rem / Kp);
-      k = static_cast<int>(rem % Kp);
+      n = static_cast<int>(idx / Kp);
+      k = static_cast<int>(idx % Kp);
     } else {
-      k = static_cast<int>(rem / Np);
-      n = static_cast<int>(rem % Np);
+      k = static_cast<int>(idx / Np);
+      n = static_cast<int>(idx % Np);
     }
     const int o = perm_out != nullptr ? perm_out[n] : (n < Co ? n : -1);
     const int i = perm_in != nullptr ? perm_in[k] : (k < Ci ? k : -1);
-    float v = 0.0f;
-    if (o >= 0 && i >= 0) v = __ldg(w + (static_cast<size_t>(o) * Ci + i) * taps + t);
-    out[idx] = __float2bfloat16_rn(v);
+    const bool live = (o >= 0 && i >= 0);
+    const float* src = w + (static_cast<size_t>(live ? o : 0) * Ci + (live ? i : 0)) * taps;
+    for (int t = 0; t < taps; ++t)
+      out[static_cast<size_t>(t) * pairs + idx] = __float2bfloat16_rn(live ? __ldg(src + t) : 0.0f);
   }
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ gw, int Co,
                                     int Ci, int taps, const int32_t* __restrict__ perm_out, int Np,
                                     const int32_t* __restrict__ perm_in, int Kp, float alpha) {
-  const size_t total = static_cast<size_t>(taps) * Np * Kp;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+  const size_t pairs = static_cast<size_t>(Np) * Kp;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < pairs;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int t = static_cast<int>(idx / (static_cast<size_t>(Np) * Kp));
-    const size_t rem = idx % (static_cast<size_t>(Np) * Kp);
-    const int n = static_cast<int>(rem / Kp);
-    const int k = static_cast<int>(rem % Kp);
+    const int n = static_cast<int>(idx / Kp);
+    const int k = static_cast<int>(idx % Kp);
     const int o = perm_out != nullptr ? perm_out[n] : (n < Co ? n : -1);
     const int i = perm_in != nullptr ? perm_in[k] : (k < Ci ? k : -1);
-    if (o >= 0 && i >= 0) gw[(static_cast<size_t>(o) * Ci + i) * taps + t] = alpha * acc[idx];
+    if (o < 0 || i < 0) continue;
+    float* dst = gw + (static_cast<size_t>(o) * Ci + i) * taps;
+    for (int t = 0; t < taps; ++t) dst[t] = alpha * __ldg(acc + static_cast<size_t>(t) * pairs + idx);
   }
 }
 
@@ -333,8 +334,28 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __res
   if (rl < lanes) {
     if (r == 1) {
       float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (long long row = r0 + rl; row < r1; row += lanes) {
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(dy + row * C + g * 8));
+      const __nv_bfloat16* base = dy + g * 8;
+      long long row = r0 + rl;
+      // 4 independent 16-byte loads in flight per thread
+      for (; row + 3LL * lanes < r1; row += 4LL * lanes) {
+        uint4 m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          m[u] = __ldg(reinterpret_cast<const uint4*>(base + (row + static_cast<long long>(u) * lanes) * C));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[0] += bf16_lo(m[u].x);
+          a[1] += bf16_hi(m[u].x);
+          a[2] += bf16_lo(m[u].y);
+          a[3] += bf16_hi(m[u].y);
+          a[4] += bf16_lo(m[u].z);
+          a[5] += bf16_hi(m[u].z);
+          a[6] += bf16_lo(m[u].w);
+          a[7] += bf16_hi(m[u].w);
+        }
+      }
+      for (; row < r1; row += lanes) {
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(base + row * C));
         a[0] += bf16_lo(m.x);
         a[1] += bf16_hi(m.x);
         a[2] += bf16_lo(m.y);
@@ -366,6 +387,26 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __res
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nsum; i += blockDim.x) atomicAdd(out + i, s_sum[i]);
+}
+
+// ------------------------------------------------------------------ activation backward
+// out = g * act'(y): y is the (post-activation) forward output, so sign(y) == sign(pre-activation)
+// for ReLU / LeakyReLU (arch_util.py:81, swinir_arch.py:836).
+__global__ void act_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                               uint4* __restrict__ out, size_t nvec, float slope) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < nvec;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 gv = __ldg(g + idx), yv = __ldg(y + idx);
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a = bf16_lo(gw[q]) * (bf16_lo(yw[q]) > 0.0f ? 1.0f : slope);
+      const float b = bf16_hi(gw[q]) * (bf16_hi(yw[q]) > 0.0f ? 1.0f : slope);
+      ow[q] = pack_bf16x2(a, b);
+    }
+    out[idx] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
 }
 
 template <typename T>
@@ -514,7 +555,7 @@ extern "C" int srb200_pack_weight(const float* w, int Co, int Ci, int taps,
                                   const int32_t* perm_out, int Np, const int32_t* perm_in, int Kp,
                                   int transpose, void* out_bf16, srb200_stream_t stream) {
   if (!w || !out_bf16 || Co <= 0 || Ci <= 0 || taps <= 0 || Np <= 0 || Kp <= 0) return SRB200_EINVAL;
-  const size_t work = static_cast<size_t>(taps) * Np * Kp;
+  const size_t work = static_cast<size_t>(Np) * Kp;
   pack_weight_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, Co, Ci, taps, perm_out, Np, perm_in, Kp, transpose, static_cast<__nv_bfloat16*>(out_bf16));
   return launch_status();
@@ -524,7 +565,7 @@ extern "C" int srb200_unpack_wgrad(const float* acc, float* gw, int Co, int Ci, 
                                    const int32_t* perm_out, int Np, const int32_t* perm_in, int Kp,
                                    float alpha, srb200_stream_t stream) {
   if (!acc || !gw || Co <= 0 || Ci <= 0 || taps <= 0 || Np <= 0 || Kp <= 0) return SRB200_EINVAL;
-  const size_t work = static_cast<size_t>(taps) * Np * Kp;
+  const size_t work = static_cast<size_t>(Np) * Kp;
   unpack_wgrad_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       acc, gw, Co, Ci, taps, perm_out, Np, perm_in, Kp, alpha);
   return launch_status();
@@ -534,10 +575,27 @@ extern "C" int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int 
                              srb200_stream_t stream) {
   if (!dy_bf16 || !out || rows <= 0 || C <= 0 || C % 8 != 0 || r < 1 || r > 3) return SRB200_EINVAL;
   if (C / 8 > 256 || (r > 1 && Wf <= 0)) return SRB200_EINVAL;
-  const int rows_per_block = 512;
+  // >= 4 blocks per SM when the tensor allows it; each block covers a contiguous slab of rows
+  long long rpb = rows / (static_cast<long long>(num_sms()) * 4);
+  if (rpb < 32) rpb = 32;
+  if (rpb > 256) rpb = 256;
+  const int rows_per_block = static_cast<int>(rpb);
   const int grid = static_cast<int>((rows + rows_per_block - 1) / rows_per_block);
   colsum_kernel<<<grid, 256, r * r * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy_bf16), out, rows, C, r, Wf, rows_per_block);
+  return launch_status();
+}
+
+extern "C" int srb200_act_bwd(const void* g_bf16, const void* y_bf16, void* out_bf16, int64_t n,
+                              float slope, srb200_stream_t stream) {
+  if (!g_bf16 || !y_bf16 || !out_bf16 || n <= 0 || n % 8 != 0) return SRB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(g_bf16) | reinterpret_cast<uintptr_t>(y_bf16) |
+       reinterpret_cast<uintptr_t>(out_bf16)) & 15u)
+    return SRB200_EINVAL;
+  const size_t nvec = static_cast<size_t>(n) / 8;
+  act_bwd_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g_bf16), static_cast<const uint4*>(y_bf16),
+      static_cast<uint4*>(out_bf16), nvec, slope);
   return launch_status();
 }
 

@@ -16,6 +16,33 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class EventProbe:
+    """Times selected kernel launches with CUDA events on the launching stream (bench.py's roofline
+    leg): ``probe = EventProbe(lambda kind, info: ...)``; ``raw.PROBE = probe``; read ``probe.ms()``."""
+
+    def __init__(self, predicate, limit=4096):
+        self.predicate, self.limit, self.pairs = predicate, limit, []
+
+    def begin(self, kind, info):
+        if len(self.pairs) >= self.limit or not self.predicate(kind, info):
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        return ev
+
+    def end(self, ev):
+        if ev is not None:
+            ev[1].record()
+            self.pairs.append(ev)
+
+    def ms(self):
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in self.pairs]
+
+
+PROBE = None
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -172,8 +199,11 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
     if bias is not None:
         _chk(bias, 'bias', torch.float32)
         assert bias.numel() == cout
+    ev = PROBE.begin('tapgemm', (b, h, w, cin * src_r * src_r, cout, ksize)) if PROBE is not None else None
     L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),
                                     _ptr(out_shift), _ptr(out), _ptr(aux), _stream()), 'tapgemm')
+    if ev is not None:
+        PROBE.end(ev)
     return (out, aux) if want_aux else out
 
 
@@ -197,4 +227,13 @@ def colsum(dy, r=1):
     out = torch.zeros((r * r * c,), dtype=torch.float32, device=dy.device)
     L.check(L.load().srb200_colsum(_ptr(dy), _ptr(out), rows, c, r, dy.shape[2] if dy.dim() == 4 else 0, _stream()),
             'colsum')
+    return out
+
+
+def act_bwd(g, y, slope=0.0):
+    """g * act'(y) for ReLU / LeakyReLU given the forward output y."""
+    _chk(g, 'g', torch.bfloat16)
+    _chk(y, 'y', torch.bfloat16)
+    out = torch.empty_like(g)
+    L.check(L.load().srb200_act_bwd(_ptr(g), _ptr(y), _ptr(out), g.numel(), float(slope), _stream()), 'act_bwd')
     return out

@@ -1,0 +1,264 @@
+"""autograd.Function wrappers around the srb200 C-ABI -- the counterpart of the reference's
+``basicsr/ops/<op>/<op>.py`` modules (e.g. ops/fused_act/fused_act.py:30-78): ``ctx.save_for_backward``
+in forward, explicit kernels in backward, gradients returned through normal autograd so DDP's
+bucket hooks fire during backward (basicsr/models/base_model.py:98-99).
+
+Inside a network every activation is an NHWC bf16 tensor whose channel count is padded to a multiple
+of 64 ("NHWC64"); nn.Parameters stay fp32 in the reference's OIHW / [out,in] layout and are repacked
+to bf16 GEMM operands on the fly (cached per parameter version, never stored in the state dict).
+"""
+import torch
+from torch.autograd import Function
+
+from ... import _lib as L
+from . import raw
+
+ACT_CODES = {None: L.ACT_NONE, 'relu': L.ACT_RELU, 'lrelu': L.ACT_LRELU, 'gelu': L.ACT_GELU}
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+# ------------------------------------------------------------------ derived caches
+_perm_cache = {}
+
+
+def shuffle_perm(c_feat, r, device):
+    """packed out-channel p = ij*c_feat + c  ->  original nn.Conv2d out-channel c*r*r + ij, so that one
+    GEMM N-tile holds a single PixelShuffle phase (arch_util.py:134-138)."""
+    key = ('shuffle', c_feat, r, str(device))
+    if key not in _perm_cache:
+        p = torch.arange(c_feat * r * r, device=device)
+        _perm_cache[key] = ((p % c_feat) * (r * r) + p // c_feat).to(torch.int32)
+    return _perm_cache[key]
+
+
+def _packed(weight, kind, n_pad, k_pad, perm_out=None, perm_in=None):
+    """bf16 GEMM operand of an fp32 parameter, cached on the parameter until it is modified in place
+    (optimizer step bumps ``_version``) or re-allocated (``.to(device)`` / deepcopy change ``data_ptr``)."""
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture the repack kernel must be part of the graph (it re-reads the live
+        # parameter storage on every replay), so the host-side cache is bypassed
+        return raw.pack_weight(weight.detach(), n_pad, k_pad, perm_out=perm_out, perm_in=perm_in,
+                               transpose=(kind == 'dgrad'))
+    cache = weight.__dict__.setdefault('_srb200_pack', {})
+    tag = (weight.data_ptr(), weight._version)
+    if cache.get('tag') != tag:
+        cache.clear()
+        cache['tag'] = tag
+    if kind not in cache:
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        cache[kind] = raw.pack_weight(w, n_pad, k_pad, perm_out=perm_out, perm_in=perm_in,
+                                      transpose=(kind == 'dgrad'))
+    return cache[kind]
+
+
+def _padded_bias(bias, n_pad, perm_out=None):
+    if bias is None:
+        return None
+    capturing = torch.cuda.is_current_stream_capturing()  # see _packed: no host-side cache inside a capture
+    cache = bias.__dict__.setdefault('_srb200_pack', {})
+    tag = (bias.data_ptr(), bias._version)
+    if cache.get('tag') != tag:
+        cache.clear()
+        cache['tag'] = tag
+    if capturing or 'b' not in cache:
+        b = bias.detach().float()
+        if perm_out is not None:
+            key = ('safe', id(perm_out))
+            if key not in _perm_cache:
+                _perm_cache[key] = (perm_out.clamp(min=0).long(), perm_out >= 0)
+            safe, valid = _perm_cache[key]
+            bp = torch.where(valid, b[safe], torch.zeros((), device=b.device))
+        elif b.numel() == n_pad:
+            bp = b
+        else:
+            bp = torch.zeros(n_pad, device=b.device)
+            bp[:b.numel()] = b
+        bp = bp.contiguous()
+        if capturing:
+            return bp
+        cache['b'] = bp
+    return cache['b']
+
+
+def _unpad_bias_grad(gb_packed, bias, perm_out=None):
+    if perm_out is None:
+        return gb_packed[:bias.numel()].clone()
+    key = ('scatter', id(perm_out))
+    if key not in _perm_cache:  # static index tensors (boolean masking would sync and cannot be graph-captured)
+        src = torch.nonzero(perm_out >= 0).flatten()
+        _perm_cache[key] = (src, perm_out[src].long())
+    src, dst = _perm_cache[key]
+    gb = torch.zeros_like(bias, dtype=torch.float32)
+    gb[dst] = gb_packed[src]
+    return gb
+
+
+# ------------------------------------------------------------------ NCHW fp32 image -> NHWC64 bf16
+class _ImageToNHWC(Function):
+    """(x - mean) * img_range (edsr_arch.py:53) fused with the NCHW fp32 -> NHWC bf16 conversion."""
+
+    @staticmethod
+    def forward(ctx, x, shift, scale, c_pad):
+        ctx.c = x.shape[1]
+        ctx.scale = scale
+        return raw.nchw_to_nhwc(x.contiguous().float(), c_pad, shift=shift, scale=scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = raw.nhwc_to_nchw(g.contiguous(), ctx.c, shift=None, scale=ctx.scale)
+        return gx, None, None, None
+
+
+def image_to_nhwc(x, shift, scale, c_pad=64):
+    return _ImageToNHWC.apply(x, shift, scale, c_pad)
+
+
+# ------------------------------------------------------------------ generic conv / linear
+class _ConvNHWC(Function):
+    """y = act(conv(x) + b) * alpha (+ residual), optional fused PixelShuffle store.
+
+    Replaces nn.Conv2d(cin, cout, k, 1, k//2) [+ ReLU / LeakyReLU] [+ skip add] [+ nn.PixelShuffle(r)]
+    (arch_util.py:79-88,134-138; edsr_arch.py:44-56; swinir_arch.py:532,818,834-837).
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, ksize, act, slope, alpha, shuffle_r):
+        cout, cin = weight.shape[0], weight.shape[1]
+        k_pad = x.shape[-1]
+        assert k_pad == pad64(cin), f'input has {k_pad} channels, expected {pad64(cin)}'
+        if shuffle_r > 1:
+            c_feat = cout // (shuffle_r * shuffle_r)
+            assert c_feat % 64 == 0, 'fused PixelShuffle needs num_feat % 64 == 0'
+            perm = shuffle_perm(c_feat, shuffle_r, x.device)
+            n_pad = cout
+        else:
+            perm = None
+            n_pad = pad64(cout)
+        wp = _packed(weight, 'fprop', n_pad, k_pad, perm_out=perm)
+        bp = _padded_bias(bias, n_pad, perm)
+        y = raw.tapgemm(x, wp, ksize=ksize, cout=n_pad, bias=bp, act=ACT_CODES[act], act_slope=slope, alpha=alpha,
+                        residual=residual, out_mode=L.OUT_SHUFFLE if shuffle_r > 1 else L.OUT_NHWC, out_r=shuffle_r)
+        ctx.save_for_backward(x, weight, bias, y if act is not None else None)
+        ctx.cfg = (ksize, act, slope, alpha, shuffle_r, n_pad, k_pad)
+        ctx.perm = perm
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, bias, y = ctx.saved_tensors
+        ksize, act, slope, alpha, shuffle_r, n_pad, k_pad = ctx.cfg
+        perm = ctx.perm
+        g = g.contiguous()
+        g_res = g if ctx.has_res else None
+        if act is not None:
+            assert act in ('relu', 'lrelu'), 'gelu backward goes through the fused MLP function'
+            g = raw.act_bwd(g, y, slope if act == 'lrelu' else 0.0)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[1]:
+            acc = raw.wgrad(g, x, ksize=ksize, dy_r=shuffle_r)
+            gw = raw.unpack_wgrad(acc, weight.shape, perm_out=perm, alpha=alpha)
+        if bias is not None and ctx.needs_input_grad[2]:
+            gb = _unpad_bias_grad(raw.colsum(g, r=shuffle_r), bias, perm) * alpha
+        if ctx.needs_input_grad[0]:
+            wpt = _packed(weight, 'dgrad', n_pad, k_pad, perm_out=perm)
+            gx = raw.tapgemm(g, wpt, ksize=ksize, cout=k_pad, alpha=alpha, flip=True, src_r=shuffle_r)
+        return gx, gw, gb, g_res, None, None, None, None, None
+
+
+def conv_nhwc(x, weight, bias=None, residual=None, act=None, slope=0.0, alpha=1.0, shuffle_r=1):
+    """conv3x3 (weight [Co,Ci,3,3]), conv1x1 or Linear (weight [Co,Ci,1,1] / [Co,Ci]) on NHWC64 bf16."""
+    ksize = weight.shape[-1] if weight.dim() == 4 else 1
+    return _ConvNHWC.apply(x, weight, bias, residual, ksize, act, slope, float(alpha), shuffle_r)
+
+
+# ------------------------------------------------------------------ fused ResidualBlockNoBN
+class _ResBlockNoBN(Function):
+    """x + conv2(relu(conv1(x))) * res_scale  (arch_util.py:85-88) as two tap-GEMMs whose epilogues
+    carry bias+ReLU and bias*res_scale+identity; backward fuses the ReLU mask and the skip-gradient
+    add into the two dgrad epilogues (no standalone elementwise pass in either direction)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, res_scale):
+        c = w1.shape[0]
+        cp = pad64(c)
+        assert x.shape[-1] == cp
+        h = raw.tapgemm(x, _packed(w1, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b1, cp), act=L.ACT_RELU)
+        y = raw.tapgemm(h, _packed(w2, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b2, cp), alpha=res_scale,
+                        residual=x)
+        ctx.save_for_backward(x, h, w1, b1, w2, b2)
+        ctx.res_scale = res_scale
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, h, w1, b1, w2, b2 = ctx.saved_tensors
+        s = ctx.res_scale
+        cp = x.shape[-1]
+        g = g.contiguous()
+        gw1 = gb1 = gw2 = gb2 = gx = None
+        if ctx.needs_input_grad[3]:
+            gw2 = raw.unpack_wgrad(raw.wgrad(g, h, ksize=3), w2.shape, alpha=s)
+        if b2 is not None and ctx.needs_input_grad[4]:
+            gb2 = raw.colsum(g)[:b2.numel()] * s
+        # d(pre-activation of conv1) = dgrad_conv2(s*g) masked by relu'(h)
+        gh = raw.tapgemm(g, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, alpha=s, flip=True, mask_src=h,
+                         mask_mode=L.MASK_SIGN, mask_slope=0.0)
+        if ctx.needs_input_grad[1]:
+            gw1 = raw.unpack_wgrad(raw.wgrad(gh, x, ksize=3), w1.shape)
+        if b1 is not None and ctx.needs_input_grad[2]:
+            gb1 = raw.colsum(gh)[:b1.numel()].clone()
+        if ctx.needs_input_grad[0]:
+            gx = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g)
+        return gx, gw1, gb1, gw2, gb2, None
+
+
+def res_block_nobn(x, w1, b1, w2, b2, res_scale):
+    return _ResBlockNoBN.apply(x, w1, b1, w2, b2, float(res_scale))
+
+
+# ------------------------------------------------------------------ conv_last + exit
+class _ConvToImage(Function):
+    """conv_last (F -> num_out_ch) fused with ``x / img_range + mean`` and the NHWC bf16 -> NCHW fp32
+    exit (edsr_arch.py:58-59; rcan_arch.py:132-133; swinir_arch.py:900,920)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_scale, out_shift):
+        cout, cin = weight.shape[0], weight.shape[1]
+        assert cout <= 16, 'fused image exit supports up to 16 output channels'
+        k_pad = x.shape[-1]
+        assert k_pad == pad64(cin)
+        wp = _packed(weight, 'fprop', 16, k_pad)
+        bp = _padded_bias(bias, 16)
+        y = raw.tapgemm(x, wp, ksize=weight.shape[-1], cout=16, bias=bp, out_mode=L.OUT_NCHW_F32, out_c=cout,
+                        out_scale=out_scale, out_shift=out_shift)
+        ctx.save_for_backward(x, weight, bias)
+        ctx.out_scale = out_scale
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, bias = ctx.saved_tensors
+        cout = weight.shape[0]
+        k_pad = x.shape[-1]
+        ks = weight.shape[-1]
+        # dL/d(conv out) = g * out_scale, as NHWC bf16 padded to 64 channels (GEMM K/N granularity)
+        gn = raw.nchw_to_nhwc(g.contiguous().float(), 64, shift=None, scale=ctx.out_scale)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[1]:
+            gw = raw.unpack_wgrad(raw.wgrad(gn, x, ksize=ks), weight.shape)
+        if bias is not None and ctx.needs_input_grad[2]:
+            gb = raw.colsum(gn)[:cout].clone()
+        if ctx.needs_input_grad[0]:
+            wpt = _packed(weight, 'dgrad', 64, k_pad)
+            gx = raw.tapgemm(gn, wpt, ksize=ks, cout=k_pad, flip=True)
+        return gx, gw, gb, None, None
+
+
+def conv_to_image(x, weight, bias, out_scale, out_shift):
+    return _ConvToImage.apply(x, weight, bias, float(out_scale), out_shift)

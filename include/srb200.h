@@ -137,6 +137,10 @@ int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc, int B, int
 int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int C, int r, int Wf,
                   srb200_stream_t stream);
 
+/* out = g * act'(y) for ReLU (slope 0) / LeakyReLU, y = forward output (bf16, n % 8 == 0). */
+int srb200_act_bwd(const void* g_bf16, const void* y_bf16, void* out_bf16, int64_t n, float slope,
+                   srb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

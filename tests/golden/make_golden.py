@@ -4,7 +4,7 @@
 
 For each case the reference nn.Module is built, its state dict is overwritten by the by-name seeded
 filler (oracle.sr_oracle.fill_state_dict_, so no weights need to be shipped), and
-input / output / selected gradients of ``L1(out, gt)`` are saved to ``tests/golden/<case>.pt`` (fp32, CPU).
+input / output / L1 loss value / selected gradients of the smooth loss ``mean((out-gt)^2)`` are saved to ``tests/golden/<case>.pt`` (fp32, CPU).
 The GPU box has no /root/reference: tests read only these fixtures.
 """
 import os
@@ -74,13 +74,15 @@ def run_case(ref, name):
     x = torch.rand(in_shape, generator=g)
     out = net(x)
     gt = torch.rand(out.shape, generator=g)
-    loss = (out - gt).abs().mean()
-    loss.backward()
+    loss = (out - gt).abs().mean()  # L1Loss value (losses/basic_loss.py:28)
+    # gradients are taken of a SMOOTH loss: d L1 / d out = sign(out - gt) / N flips wherever a bf16-path output
+    # crosses gt, which would make gradient parity measure the loss' discontinuity instead of the kernels
+    ((out - gt)**2).mean().backward()
     params = dict(net.named_parameters())
     keys = [k for k in GRAD_KEYS[arch] if k in params]
     fixture = {
         'arch': arch, 'kwargs': kwargs, 'x': x, 'gt': gt, 'out': out.detach(), 'loss': loss.detach(),
-        'grads': {k: compress(params[k].grad) for k in keys},
+        'grads': {k: compress(params[k].grad) for k in keys}, 'grad_loss': 'mse',
         'state_keys': list(sd.keys()),
         'state_shapes': {k: tuple(v.shape) for k, v in sd.items()},
         'n_params': sum(p.numel() for p in net.parameters()),
