@@ -27,6 +27,11 @@ class TapGemmDesc(ctypes.Structure):
     ]
 
 
+class TapGemmExt(ctypes.Structure):
+    """Mirror of ``srb200_tapgemm_ext``."""
+    _fields_ = [('residual_f32', c_void_p), ('out_f32', c_void_p), ('alpha_per_sample', c_void_p)]
+
+
 # every symbol include/srb200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     'srb200_version': (c_char_p, []),
@@ -48,11 +53,22 @@ SIGNATURES = {
     'srb200_unpack_wgrad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                     c_float, c_void_p]),
     'srb200_tapgemm': (c_int, [POINTER(TapGemmDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_void_p]),
+                               c_void_p, c_void_p, POINTER(TapGemmExt), c_void_p]),
     'srb200_wgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_void_p]),
     'srb200_colsum': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     'srb200_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+    'srb200_layernorm_fwd': (c_int, [c_void_p] * 6 + [c_int64, c_int, c_int, c_float, c_void_p]),
+    'srb200_layernorm_bwd': (c_int, [c_void_p] * 9 + [c_int64, c_int, c_int, c_void_p]),
+    'srb200_scale_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    'srb200_window_attention_fwd': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_float, c_void_p]),
+    'srb200_window_attention_bwd': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
+    'srb200_channel_pool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'srb200_channel_dot': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    'srb200_ca_fc': (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]),
+    'srb200_ca_apply': (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_void_p]),
+    'srb200_ca_fc_bwd': (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_void_p]),
+    'srb200_ca_apply_bwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
 }
 
 _lib = None

@@ -3,7 +3,7 @@ the remaining YAML keys, exactly like the reference's ``basicsr/archs/__init__.p
 from copy import deepcopy
 
 from ..utils.registry import ARCH_REGISTRY
-from . import arch_util, edsr_arch  # noqa: F401  (importing registers the archs)
+from . import arch_util, edsr_arch, rcan_arch, swinir_arch  # noqa: F401  (importing registers the archs)
 
 __all__ = ['build_network', 'ARCH_REGISTRY']
 

@@ -1,0 +1,122 @@
+"""RCAN on the srb200 kernels -- drop-in for the reference's ``basicsr/archs/rcan_arch.py`` (:8-135):
+same class names, constructor / YAML keys, parameter names, shapes and init order."""
+import torch
+from torch import nn as nn
+
+from ..ops import sr_b200 as ops
+from ..utils.registry import ARCH_REGISTRY
+from .arch_util import Upsample, make_layer, nchw_roundtrip, require_cuda
+from .edsr_arch import _MeanShiftMixin
+
+
+class ChannelAttention(nn.Module):
+    """x * sigmoid(conv1x1(relu(conv1x1(avgpool(x)))))  (reference rcan_arch.py:8-24)."""
+
+    def __init__(self, num_feat, squeeze_factor=16):
+        super(ChannelAttention, self).__init__()
+        self.attention = nn.Sequential(
+            nn.AdaptiveAvgPool2d(1), nn.Conv2d(num_feat, num_feat // squeeze_factor, 1, padding=0),
+            nn.ReLU(inplace=True), nn.Conv2d(num_feat // squeeze_factor, num_feat, 1, padding=0), nn.Sigmoid())
+
+    def fc_params(self):
+        a, b = self.attention[1], self.attention[3]
+        return a.weight, a.bias, b.weight, b.bias
+
+
+class RCAB(nn.Module):
+    """Residual channel attention block (reference rcan_arch.py:27-46), one fused autograd function."""
+
+    def __init__(self, num_feat, squeeze_factor=16, res_scale=1):
+        super(RCAB, self).__init__()
+        self.res_scale = res_scale
+
+        self.rcab = nn.Sequential(
+            nn.Conv2d(num_feat, num_feat, 3, 1, 1), nn.ReLU(True), nn.Conv2d(num_feat, num_feat, 3, 1, 1),
+            ChannelAttention(num_feat, squeeze_factor))
+
+    def forward_nhwc(self, t, t32=None):
+        """``t32``: optional fp32 twin of the bf16 stream ``t``; returns (y, y32) when given."""
+        c1, c2, ca = self.rcab[0], self.rcab[2], self.rcab[3]
+        return ops.rcab(t, c1.weight, c1.bias, c2.weight, c2.bias, *ca.fc_params(), self.res_scale, x32=t32)
+
+    def forward(self, x):
+        return nchw_roundtrip(self.forward_nhwc, x, 'RCAB')
+
+
+class ResidualGroup(nn.Module):
+    """num_block x RCAB, conv, + skip (reference rcan_arch.py:49-68); the skip add rides the conv epilogue."""
+
+    def __init__(self, num_feat, num_block, squeeze_factor=16, res_scale=1):
+        super(ResidualGroup, self).__init__()
+
+        self.residual_group = make_layer(
+            RCAB, num_block, num_feat=num_feat, squeeze_factor=squeeze_factor, res_scale=res_scale)
+        self.conv = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+
+    def forward_nhwc(self, t, t32=None):
+        if t32 is None:
+            r = t
+            for block in self.residual_group:
+                r = block.forward_nhwc(r)
+            return ops.conv_nhwc(r, self.conv.weight, self.conv.bias, residual=t)
+        r, r32 = t, t32
+        for block in self.residual_group:
+            r, r32 = block.forward_nhwc(r, r32)
+        return ops.conv_nhwc(r, self.conv.weight, self.conv.bias, residual=t, residual32=t32, want_f32=True)
+
+    def forward(self, x):
+        return nchw_roundtrip(self.forward_nhwc, x, 'ResidualGroup')
+
+
+@ARCH_REGISTRY.register()
+class RCAN(nn.Module, _MeanShiftMixin):
+    """Residual Channel Attention Network (reference rcan_arch.py:71-135).
+
+    Args (identical to the reference): num_in_ch, num_out_ch, num_feat=64, num_group=10, num_block=16,
+    squeeze_factor=16, upscale=4, res_scale=1, img_range=255., rgb_mean=(0.4488, 0.4371, 0.4040).
+    """
+
+    def __init__(self,
+                 num_in_ch,
+                 num_out_ch,
+                 num_feat=64,
+                 num_group=10,
+                 num_block=16,
+                 squeeze_factor=16,
+                 upscale=4,
+                 res_scale=1,
+                 img_range=255.,
+                 rgb_mean=(0.4488, 0.4371, 0.4040)):
+        super(RCAN, self).__init__()
+
+        self.img_range = img_range
+        self.mean = torch.Tensor(rgb_mean).view(1, 3, 1, 1)
+
+        self.conv_first = nn.Conv2d(num_in_ch, num_feat, 3, 1, 1)
+        self.body = make_layer(
+            ResidualGroup,
+            num_group,
+            num_feat=num_feat,
+            num_block=num_block,
+            squeeze_factor=squeeze_factor,
+            res_scale=res_scale)
+        self.conv_after_body = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.upsample = Upsample(upscale, num_feat)
+        self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
+
+    def forward(self, x):
+        require_cuda(x, 'RCAN')
+        mean = self._device_mean(x)
+        t = ops.image_to_nhwc(x, mean, self.img_range, ops.pad64(x.shape[1]))
+        # The skip stream is carried twice: bf16 (differentiable, feeds the tensor cores) and fp32 (what the
+        # skip adds read and write).  200 stacked res_scale=1 additions in bf16 alone drift past the 1e-2
+        # output bar (1.16e-2 for bf16 autocast of the reference itself).
+        first, first32 = ops.conv_nhwc(t, self.conv_first.weight, self.conv_first.bias, want_f32=True)
+        res, res32 = first, first32
+        for group in self.body:
+            res, res32 = group.forward_nhwc(res, res32)
+        res = ops.conv_nhwc(res, self.conv_after_body.weight, self.conv_after_body.bias, residual=first,
+                            residual32=first32)
+        up = self.upsample.forward_nhwc(res)
+        out = ops.conv_to_image(up, self.conv_last.weight, self.conv_last.bias, 1.0 / self.img_range, mean)
+        return out if out.dtype == x.dtype else out.to(x.dtype)

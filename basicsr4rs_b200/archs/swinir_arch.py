@@ -1,0 +1,417 @@
+"""SwinIR on the srb200 kernels -- drop-in for the reference's ``basicsr/archs/swinir_arch.py``.
+
+Module tree, constructor / YAML keys, parameter and buffer names, shapes and init order follow the
+reference (WindowAttention :95-191, SwinTransformerBlock :194-341, BasicLayer :393-477, RSTB :480-568,
+PatchEmbed / PatchUnEmbed :571-644, Upsample(OneStep) :647-690, SwinIR :693-933) so that state dicts
+(550 entries for the classical x4 model, incl. the ``relative_position_index`` / ``attn_mask`` buffers) and
+seeded random inits are interchangeable.  What differs is how ``forward`` computes:
+
+* tokens [B, H*W, C] *are* NHWC pixels, so PatchEmbed / PatchUnEmbed / window_partition / window_reverse /
+  torch.roll never materialise -- they are address arithmetic inside the fused window-attention kernel;
+* one autograd function per SwinTransformerBlock (ops/sr_b200/swin_ops.py): LayerNorm kernels, tcgen05
+  tap-GEMMs for qkv / proj / fc1 / fc2 with bias, GELU, DropPath scale and skip add in their epilogues;
+* the shifted-window mask is analytic (any H, W multiple of the window), the stored ``attn_mask`` buffer
+  is kept only for state-dict compatibility -- nothing is rebuilt on the CPU per call (cf. :305-306);
+* 3x3 convs, pixel-shuffle upsampler and image entry / exit as in EDSR.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from ..ops import sr_b200 as ops
+from ..ops.sr_b200 import swin_ops
+from ..utils.registry import ARCH_REGISTRY
+from .arch_util import Upsample, require_cuda, to_2tuple, trunc_normal_
+from .edsr_arch import _MeanShiftMixin
+
+KERNEL_WINDOW = 8  # the fused attention kernel is specialised for 8x8 windows (64 tokens)
+
+
+def drop_path_scale(batch, drop_prob, training, device):
+    """Per-sample stochastic-depth factor floor(keep + U[0,1)) / keep as fp32 [B] (reference :14-26), or None."""
+    if drop_prob == 0. or not training:
+        return None
+    keep = 1 - drop_prob
+    return ((keep + torch.rand((batch,), dtype=torch.float32, device=device)).floor_() / keep).contiguous()
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample; in the fused block it becomes a per-sample epilogue scale."""
+
+    def __init__(self, drop_prob=None):
+        super(DropPath, self).__init__()
+        self.drop_prob = drop_prob
+
+    def scale(self, batch, device):
+        return drop_path_scale(batch, self.drop_prob or 0., self.training, device)
+
+
+class Mlp(nn.Module):
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+
+def window_partition(x, window_size):
+    """(b, h, w, c) -> (num_windows*b, ws, ws, c); bit-exact remap kernel (reference :63-75)."""
+    return ops.raw.window_partition(x.contiguous(), window_size, 0)
+
+
+def window_reverse(windows, window_size, h, w):
+    """(num_windows*b, ws, ws, c) -> (b, h, w, c) (reference :78-92)."""
+    return ops.raw.window_reverse(windows.contiguous(), window_size, h, w, 0)
+
+
+def _relative_position_index(ws):
+    ch, cw = torch.arange(ws[0]), torch.arange(ws[1])
+    coords = torch.stack(torch.meshgrid([ch, cw], indexing='ij')).flatten(1)
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws[0] - 1
+    rel[:, :, 1] += ws[1] - 1
+    rel[:, :, 0] *= 2 * ws[1] - 1
+    return rel.sum(-1)
+
+
+class WindowAttention(nn.Module):
+    """Parameter holder of W-MSA / SW-MSA (relative_position_bias_table, qkv, proj)."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.dim = dim
+        self.window_size = window_size
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim**-0.5
+
+        self.relative_position_bias_table = nn.Parameter(
+            torch.zeros((2 * window_size[0] - 1) * (2 * window_size[1] - 1), num_heads))
+        self.register_buffer('relative_position_index', _relative_position_index(window_size))
+
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+        trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.softmax = nn.Softmax(dim=-1)
+        self._qk_scale_override = qk_scale
+
+    def extra_repr(self) -> str:
+        return f'dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}'
+
+
+class SwinTransformerBlock(nn.Module):
+
+    def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        if min(self.input_resolution) <= self.window_size:
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.window_size, 'shift_size must in 0-window_size'
+
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, window_size=to_2tuple(self.window_size), num_heads=num_heads,
+                                    qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+        self.register_buffer('attn_mask', self.calculate_mask(self.input_resolution) if self.shift_size > 0 else None)
+        if drop > 0. or attn_drop > 0.:
+            raise NotImplementedError('srb200 SwinIR: drop / attn_drop > 0 are not supported (all shipped YAMLs use 0)')
+        if qk_scale is not None:
+            raise NotImplementedError('srb200 SwinIR: qk_scale override is not supported')
+
+    def calculate_mask(self, x_size):
+        """0 / -100 SW-MSA mask; state-dict compatibility only (the kernel derives it analytically)."""
+        h, w = x_size
+        ws, s = self.window_size, self.shift_size
+        img = torch.zeros((1, h, w, 1))
+        cnt = 0
+        for hs in (slice(0, -ws), slice(-ws, -s), slice(-s, None)):
+            for wsl in (slice(0, -ws), slice(-ws, -s), slice(-s, None)):
+                img[:, hs, wsl, :] = cnt
+                cnt += 1
+        mw = img.view(1, h // ws, ws, w // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws)
+        m = mw.unsqueeze(1) - mw.unsqueeze(2)
+        return m.masked_fill(m != 0, float(-100.0)).masked_fill(m == 0, float(0.0))
+
+    def forward_nhwc(self, t):
+        """t: [B, H, W, pad64(C)] bf16."""
+        if self.window_size != KERNEL_WINDOW:
+            raise NotImplementedError(f'srb200 fused window attention supports window_size {KERNEL_WINDOW} '
+                                      f'(got {self.window_size}); other sizes are a documented next step')
+        b = t.shape[0]
+        dp = self.drop_path
+        a1 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None
+        a2 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None
+        at, m = self.attn, self.mlp
+        return swin_ops.swin_block(t, self.norm1.weight, self.norm1.bias, at.qkv.weight, at.qkv.bias,
+                                   at.relative_position_bias_table, at.proj.weight, at.proj.bias, self.norm2.weight,
+                                   self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias,
+                                   self.num_heads, self.window_size, self.shift_size, a1, a2)
+
+    def extra_repr(self) -> str:
+        return (f'dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, '
+                f'window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}')
+
+
+class BasicLayer(nn.Module):
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, downsample=None,
+                 use_checkpoint=False):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList([
+            SwinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads,
+                                 window_size=window_size, shift_size=0 if (i % 2 == 0) else window_size // 2,
+                                 mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop,
+                                 attn_drop=attn_drop,
+                                 drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                                 norm_layer=norm_layer) for i in range(depth)
+        ])
+        self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample is not None else None
+
+    def forward_nhwc(self, t):
+        for blk in self.blocks:
+            if self.use_checkpoint and torch.is_grad_enabled():
+                t = torch.utils.checkpoint.checkpoint(blk.forward_nhwc, t, use_reentrant=False)
+            else:
+                t = blk.forward_nhwc(t)
+        return t
+
+    def extra_repr(self) -> str:
+        return f'dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}'
+
+
+class PatchEmbed(nn.Module):
+    """[B,C,H,W] -> [B,H*W,C] (+ LayerNorm).  In NHWC the reshape is the identity; only the norm computes."""
+
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        img_size = to_2tuple(img_size)
+        patch_size = to_2tuple(patch_size)
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.patches_resolution = [img_size[0] // patch_size[0], img_size[1] // patch_size[1]]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.in_chans = in_chans
+        self.embed_dim = embed_dim
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def forward_nhwc(self, t):
+        return swin_ops.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps) if self.norm is not None else t
+
+
+class PatchUnEmbed(nn.Module):
+    """[B,H*W,C] -> [B,C,H,W]; the identity in NHWC."""
+
+    def __init__(self, img_size=224, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        img_size = to_2tuple(img_size)
+        patch_size = to_2tuple(patch_size)
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.patches_resolution = [img_size[0] // patch_size[0], img_size[1] // patch_size[1]]
+        self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
+        self.in_chans = in_chans
+        self.embed_dim = embed_dim
+
+
+class RSTB(nn.Module):
+    """Residual Swin Transformer Block: BasicLayer -> conv3x3 -> + x; the skip add rides the conv epilogue."""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, downsample=None,
+                 use_checkpoint=False, img_size=224, patch_size=4, resi_connection='1conv'):
+        super(RSTB, self).__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.residual_group = BasicLayer(dim=dim, input_resolution=input_resolution, depth=depth,
+                                         num_heads=num_heads, window_size=window_size, mlp_ratio=mlp_ratio,
+                                         qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                         drop_path=drop_path, norm_layer=norm_layer, downsample=downsample,
+                                         use_checkpoint=use_checkpoint)
+        if resi_connection == '1conv':
+            self.conv = nn.Conv2d(dim, dim, 3, 1, 1)
+        elif resi_connection == '3conv':
+            self.conv = nn.Sequential(
+                nn.Conv2d(dim, dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(dim // 4, dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(dim // 4, dim, 3, 1, 1))
+        self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=0, embed_dim=dim,
+                                      norm_layer=None)
+        self.patch_unembed = PatchUnEmbed(img_size=img_size, patch_size=patch_size, in_chans=0, embed_dim=dim,
+                                          norm_layer=None)
+
+    def forward_nhwc(self, t):
+        return _resi_conv(self.conv, self.residual_group.forward_nhwc(t), t)
+
+
+def _resi_conv(conv, r, skip):
+    """'1conv' / '3conv' residual connection (reference :532-539, :818-824) + skip, on NHWC bf16."""
+    if isinstance(conv, nn.Conv2d):
+        return ops.conv_nhwc(r, conv.weight, conv.bias, residual=skip)
+    c0, c2, c4 = conv[0], conv[2], conv[4]
+    r = ops.conv_nhwc(r, c0.weight, c0.bias, act='lrelu', slope=0.2)
+    r = ops.conv_nhwc(r, c2.weight, c2.bias, act='lrelu', slope=0.2)
+    return ops.conv_nhwc(r, c4.weight, c4.bias, residual=skip)
+
+
+class UpsampleOneStep(nn.Sequential):
+    """conv(num_feat -> scale^2 * num_out_ch) + PixelShuffle for lightweight SR (reference :669-690)."""
+
+    def __init__(self, scale, num_feat, num_out_ch, input_resolution=None):
+        self.num_feat = num_feat
+        self.input_resolution = input_resolution
+        m = [nn.Conv2d(num_feat, (scale**2) * num_out_ch, 3, 1, 1), nn.PixelShuffle(scale)]
+        super(UpsampleOneStep, self).__init__(*m)
+
+
+@ARCH_REGISTRY.register()
+class SwinIR(nn.Module, _MeanShiftMixin):
+    """SwinIR (classical / lightweight / real-world SR, denoising) -- same constructor as the reference."""
+
+    def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=96, depths=(6, 6, 6, 6),
+                 num_heads=(6, 6, 6, 6), window_size=7, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
+                 use_checkpoint=False, upscale=2, img_range=1., upsampler='', resi_connection='1conv', **kwargs):
+        super(SwinIR, self).__init__()
+        num_in_ch = in_chans
+        num_out_ch = in_chans
+        num_feat = 64
+        self.img_range = img_range
+        if in_chans == 3:
+            self.mean = torch.Tensor((0.4488, 0.4371, 0.4040)).view(1, 3, 1, 1)
+        else:
+            self.mean = torch.zeros(1, 1, 1, 1)
+        self.upscale = upscale
+        self.upsampler = upsampler
+
+        self.conv_first = nn.Conv2d(num_in_ch, embed_dim, 3, 1, 1)
+
+        self.num_layers = len(depths)
+        self.embed_dim = embed_dim
+        self.ape = ape
+        self.patch_norm = patch_norm
+        self.num_features = embed_dim
+        self.mlp_ratio = mlp_ratio
+
+        self.patch_embed = PatchEmbed(img_size=img_size, patch_size=patch_size, in_chans=embed_dim,
+                                      embed_dim=embed_dim, norm_layer=norm_layer if self.patch_norm else None)
+        num_patches = self.patch_embed.num_patches
+        patches_resolution = self.patch_embed.patches_resolution
+        self.patches_resolution = patches_resolution
+        self.patch_unembed = PatchUnEmbed(img_size=img_size, patch_size=patch_size, in_chans=embed_dim,
+                                          embed_dim=embed_dim, norm_layer=norm_layer if self.patch_norm else None)
+
+        if self.ape:
+            self.absolute_pos_embed = nn.Parameter(torch.zeros(1, num_patches, embed_dim))
+            trunc_normal_(self.absolute_pos_embed, std=.02)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.layers = nn.ModuleList()
+        for i_layer in range(self.num_layers):
+            self.layers.append(
+                RSTB(dim=embed_dim, input_resolution=(patches_resolution[0], patches_resolution[1]),
+                     depth=depths[i_layer], num_heads=num_heads[i_layer], window_size=window_size,
+                     mlp_ratio=self.mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
+                     attn_drop=attn_drop_rate, drop_path=dpr[sum(depths[:i_layer]):sum(depths[:i_layer + 1])],
+                     norm_layer=norm_layer, downsample=None, use_checkpoint=use_checkpoint, img_size=img_size,
+                     patch_size=patch_size, resi_connection=resi_connection))
+        self.norm = norm_layer(self.num_features)
+
+        if resi_connection == '1conv':
+            self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        elif resi_connection == '3conv':
+            self.conv_after_body = nn.Sequential(
+                nn.Conv2d(embed_dim, embed_dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(embed_dim // 4, embed_dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                nn.Conv2d(embed_dim // 4, embed_dim, 3, 1, 1))
+
+        if self.upsampler == 'pixelshuffle':
+            self.conv_before_upsample = nn.Sequential(
+                nn.Conv2d(embed_dim, num_feat, 3, 1, 1), nn.LeakyReLU(inplace=True))
+            self.upsample = Upsample(upscale, num_feat)
+            self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
+        elif self.upsampler == 'pixelshuffledirect':
+            self.upsample = UpsampleOneStep(upscale, embed_dim, num_out_ch,
+                                            (patches_resolution[0], patches_resolution[1]))
+        elif self.upsampler == 'nearest+conv':
+            assert self.upscale == 4, 'only support x4 now.'
+            self.conv_before_upsample = nn.Sequential(
+                nn.Conv2d(embed_dim, num_feat, 3, 1, 1), nn.LeakyReLU(inplace=True))
+            self.conv_up1 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_up2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+            self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
+            self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        else:
+            self.conv_last = nn.Conv2d(embed_dim, num_out_ch, 3, 1, 1)
+
+        self.apply(self._init_weights)
+        if ape:
+            raise NotImplementedError('srb200 SwinIR: ape=True is not supported (no shipped YAML uses it)')
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            trunc_normal_(m.weight, std=.02)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'absolute_pos_embed'}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {'relative_position_bias_table'}
+
+    def forward_features_nhwc(self, t):
+        """patch_embed(+norm) -> RSTBs -> norm -> patch_unembed, all on [B,H,W,pad64(C)] bf16 (reference :876-889)."""
+        t = self.patch_embed.forward_nhwc(t)
+        for layer in self.layers:
+            t = layer.forward_nhwc(t)
+        return swin_ops.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps)
+
+    def forward(self, x):
+        require_cuda(x, 'SwinIR')
+        mean = self._device_mean(x) if self.mean.numel() == x.shape[1] else None
+        t = ops.image_to_nhwc(x, mean, self.img_range, ops.pad64(x.shape[1]))
+        first = ops.conv_nhwc(t, self.conv_first.weight, self.conv_first.bias)
+        feat = _resi_conv(self.conv_after_body, self.forward_features_nhwc(first), first)
+        inv = 1.0 / self.img_range
+        if self.upsampler == 'pixelshuffle':
+            c = self.conv_before_upsample[0]
+            u = ops.conv_nhwc(feat, c.weight, c.bias, act='lrelu', slope=self.conv_before_upsample[1].negative_slope)
+            u = self.upsample.forward_nhwc(u)
+            out = ops.conv_to_image(u, self.conv_last.weight, self.conv_last.bias, inv, mean)
+        elif self.upsampler == '':
+            # denoising / JPEG-CAR: x + conv_last(res) in normalised space == x + conv_last(res) / img_range
+            out = x.float() + ops.conv_to_image(feat, self.conv_last.weight, self.conv_last.bias, inv, None)
+        else:
+            raise NotImplementedError(f"srb200 SwinIR: upsampler '{self.upsampler}' is not on the B200 path yet "
+                                      "(classical 'pixelshuffle' and '' are); there is no PyTorch fallback")
+        return out if out.dtype == x.dtype else out.to(x.dtype)

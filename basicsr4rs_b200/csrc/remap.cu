@@ -317,11 +317,15 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __rest
 }
 
 // ------------------------------------------------------------------ column sums (bias gradient)
-// dy [rows, C] bf16 -> out[view*C + c] += sum; view = pixel-unshuffle phase of the row (r > 1).
+// dy [rows, C] bf16 -> out[view*C + c] += sum; view = pixel-unshuffle phase of the row (R > 1).
+// thread = one 8-channel group x one row lane; R*R register accumulator sets, one smem reduction and
+// one global atomic per (block, column).
+template <int R>
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ out,
-                              long long rows, int C, int r, int Wf, int rows_per_block) {
-  extern __shared__ float s_sum[];  // [r*r*C]
-  const int nsum = r * r * C;
+                              long long rows, int C, int Wf, int rows_per_block) {
+  extern __shared__ float s_sum[];  // [R*R*C]
+  constexpr int V = R * R;
+  const int nsum = V * C;
   for (int i = threadIdx.x; i < nsum; i += blockDim.x) s_sum[i] = 0.0f;
   __syncthreads();
   const int groups = C / 8;
@@ -332,58 +336,46 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __res
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
   if (rl < lanes) {
-    if (r == 1) {
-      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const __nv_bfloat16* base = dy + g * 8;
-      long long row = r0 + rl;
-      // 4 independent 16-byte loads in flight per thread
-      for (; row + 3LL * lanes < r1; row += 4LL * lanes) {
-        uint4 m[4];
+    float a[V][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          m[u] = __ldg(reinterpret_cast<const uint4*>(base + (row + static_cast<long long>(u) * lanes) * C));
+    for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          a[0] += bf16_lo(m[u].x);
-          a[1] += bf16_hi(m[u].x);
-          a[2] += bf16_lo(m[u].y);
-          a[3] += bf16_hi(m[u].y);
-          a[4] += bf16_lo(m[u].z);
-          a[5] += bf16_hi(m[u].z);
-          a[6] += bf16_lo(m[u].w);
-          a[7] += bf16_hi(m[u].w);
-        }
-      }
-      for (; row < r1; row += lanes) {
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(base + row * C));
-        a[0] += bf16_lo(m.x);
-        a[1] += bf16_hi(m.x);
-        a[2] += bf16_lo(m.y);
-        a[3] += bf16_hi(m.y);
-        a[4] += bf16_lo(m.z);
-        a[5] += bf16_hi(m.z);
-        a[6] += bf16_lo(m.w);
-        a[7] += bf16_hi(m.w);
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&s_sum[g * 8 + e], a[e]);
-    } else {
-      for (long long row = r0 + rl; row < r1; row += lanes) {
+      for (int e = 0; e < 8; ++e) a[v][e] = 0.0f;
+    const __nv_bfloat16* base = dy + g * 8;
+    auto add = [&](const uint4& m, long long row) {
+      int view = 0;
+      if (R > 1) {
         const int X = static_cast<int>(row % Wf);
         const int Y = static_cast<int>(row / Wf);
-        const int view = (Y % r) * r + (X % r);
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(dy + row * C + g * 8));
-        float* s = &s_sum[view * C + g * 8];
-        atomicAdd(s + 0, bf16_lo(m.x));
-        atomicAdd(s + 1, bf16_hi(m.x));
-        atomicAdd(s + 2, bf16_lo(m.y));
-        atomicAdd(s + 3, bf16_hi(m.y));
-        atomicAdd(s + 4, bf16_lo(m.z));
-        atomicAdd(s + 5, bf16_hi(m.z));
-        atomicAdd(s + 6, bf16_lo(m.w));
-        atomicAdd(s + 7, bf16_hi(m.w));
+        view = (Y % R) * R + (X % R);
       }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float w = (v == view) ? 1.0f : 0.0f;  // predicated adds keep a[][] in registers
+        a[v][0] += w * bf16_lo(m.x);
+        a[v][1] += w * bf16_hi(m.x);
+        a[v][2] += w * bf16_lo(m.y);
+        a[v][3] += w * bf16_hi(m.y);
+        a[v][4] += w * bf16_lo(m.z);
+        a[v][5] += w * bf16_hi(m.z);
+        a[v][6] += w * bf16_lo(m.w);
+        a[v][7] += w * bf16_hi(m.w);
+      }
+    };
+    long long row = r0 + rl;
+    for (; row + 3LL * lanes < r1; row += 4LL * lanes) {  // 4 independent 16-byte loads in flight
+      uint4 m[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        m[u] = __ldg(reinterpret_cast<const uint4*>(base + (row + static_cast<long long>(u) * lanes) * C));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) add(m[u], row + static_cast<long long>(u) * lanes);
     }
+    for (; row < r1; row += lanes) add(__ldg(reinterpret_cast<const uint4*>(base + row * C)), row);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&s_sum[v * C + g * 8 + e], a[v][e]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nsum; i += blockDim.x) atomicAdd(out + i, s_sum[i]);
@@ -578,11 +570,15 @@ extern "C" int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int 
   // >= 4 blocks per SM when the tensor allows it; each block covers a contiguous slab of rows
   long long rpb = rows / (static_cast<long long>(num_sms()) * 4);
   if (rpb < 32) rpb = 32;
-  if (rpb > 256) rpb = 256;
+  if (rpb > 512) rpb = 512;
   const int rows_per_block = static_cast<int>(rpb);
   const int grid = static_cast<int>((rows + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<<<grid, 256, r * r * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy_bf16), out, rows, C, r, Wf, rows_per_block);
+  const size_t smem = static_cast<size_t>(r) * r * C * sizeof(float);
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (r == 1) colsum_kernel<1><<<grid, 256, smem, st>>>(dy, out, rows, C, Wf, rows_per_block);
+  else if (r == 2) colsum_kernel<2><<<grid, 256, smem, st>>>(dy, out, rows, C, Wf, rows_per_block);
+  else colsum_kernel<3><<<grid, 256, smem, st>>>(dy, out, rows, C, Wf, rows_per_block);
   return launch_status();
 }
 

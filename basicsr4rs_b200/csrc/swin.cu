@@ -1,0 +1,257 @@
+// SwinIR token-wise kernels on NHWC bf16 (tokens == pixels, C padded to a multiple of 64 with zeros):
+//   LayerNorm forward / backward over the C real channels (swinir_arch.py:240,251,288,321,602,886),
+//   warp-per-token, fp32 statistics, 128-bit accesses, gamma/beta gradients reduced warp -> CTA -> atomics;
+//   per-sample row scaling (DropPath backward, swinir_arch.py:14-26).
+// HBM-bound: fwd moves 2*T*C*2 B, bwd 3*T*C*2 B (+ residual-gradient add fused).
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace srb {
+
+constexpr int LN_MAX_VEC = 4;  // up to 4 x (32 lanes x 8 ch) = 1024 padded channels
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void ln_unpack(const uint4& m, float* v) {
+  v[0] = bf16_lo(m.x);
+  v[1] = bf16_hi(m.x);
+  v[2] = bf16_lo(m.y);
+  v[3] = bf16_hi(m.y);
+  v[4] = bf16_lo(m.z);
+  v[5] = bf16_hi(m.z);
+  v[6] = bf16_lo(m.w);
+  v[7] = bf16_hi(m.w);
+}
+__device__ __forceinline__ uint4 ln_pack(const float* v) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                    pack_bf16x2(v[6], v[7]));
+}
+
+template <int NVEC>
+__global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, long long T, int C, int Cp,
+                                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = Cp / 8;
+  for (long long t = warp_global; t < T; t += nwarps) {
+    float v[NVEC][8];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int vec = lane + 32 * i;
+      if (vec < nv) {
+        ln_unpack(__ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec), v[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += (vec * 8 + e < C) ? v[i][e] : 0.0f;
+      }
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(C);
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int vec = lane + 32 * i;
+      if (vec < nv) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[i][e] - mean;
+          sq += (vec * 8 + e < C) ? d * d : 0.0f;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int vec = lane + 32 * i;
+      if (vec < nv) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = vec * 8 + e;
+          o[e] = (c < C) ? (v[i][e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.0f;
+        }
+        *(reinterpret_cast<uint4*>(y + t * Cp) + vec) = ln_pack(o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[t] = mean;
+      if (rstd_out) rstd_out[t] = rstd;
+    }
+  }
+}
+
+// gx = LN'(gy) (+ gres);  ggamma[c] += sum_t gy*xhat;  gbeta[c] += sum_t gy
+template <int NVEC>
+__global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
+                                     const __nv_bfloat16* __restrict__ x,
+                                     const float* __restrict__ mean_in,
+                                     const float* __restrict__ rstd_in,
+                                     const float* __restrict__ gamma,
+                                     const __nv_bfloat16* __restrict__ gres,
+                                     __nv_bfloat16* __restrict__ gx, float* __restrict__ ggamma,
+                                     float* __restrict__ gbeta, long long T, int C, int Cp) {
+  extern __shared__ float s_red[];  // [2][Cp]
+  for (int i = threadIdx.x; i < 2 * Cp; i += blockDim.x) s_red[i] = 0.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = Cp / 8;
+  float ag[NVEC][8], ab[NVEC][8], gm[NVEC][8];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ag[i][e] = 0.0f;
+      ab[i][e] = 0.0f;
+      const int c = (lane + 32 * i) * 8 + e;
+      gm[i][e] = (c < C) ? __ldg(gamma + c) : 0.0f;
+    }
+  for (long long t = warp_global; t < T; t += nwarps) {
+    const float mean = __ldg(mean_in + t), rstd = __ldg(rstd_in + t);
+    float g[NVEC][8], xh[NVEC][8];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int vec = lane + 32 * i;
+      if (vec < nv) {
+        float xv[8];
+        ln_unpack(__ldg(reinterpret_cast<const uint4*>(gy + t * Cp) + vec), g[i]);
+        ln_unpack(__ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec), xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool live = vec * 8 + e < C;
+          xh[i][e] = live ? (xv[e] - mean) * rstd : 0.0f;
+          const float gv = live ? g[i][e] : 0.0f;
+          ag[i][e] += gv * xh[i][e];
+          ab[i][e] += gv;
+          g[i][e] = gv * gm[i][e];  // d xhat
+          s1 += g[i][e];
+          s2 += g[i][e] * xh[i][e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / static_cast<float>(C);
+    s2 = warp_sum(s2) / static_cast<float>(C);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int vec = lane + 32 * i;
+      if (vec < nv) {
+        float o[8], r[8];
+        if (gres != nullptr) ln_unpack(__ldg(reinterpret_cast<const uint4*>(gres + t * Cp) + vec), r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool live = vec * 8 + e < C;
+          float d = live ? rstd * (g[i][e] - s1 - xh[i][e] * s2) : 0.0f;
+          if (gres != nullptr) d += r[e];
+          o[e] = d;
+        }
+        *(reinterpret_cast<uint4*>(gx + t * Cp) + vec) = ln_pack(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int vec = lane + 32 * i;
+    if (vec < nv) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_red[vec * 8 + e], ag[i][e]);
+        atomicAdd(&s_red[Cp + vec * 8 + e], ab[i][e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(ggamma + c, s_red[c]);
+    atomicAdd(gbeta + c, s_red[Cp + c]);
+  }
+}
+
+__global__ void scale_rows_kernel(const uint4* __restrict__ g, const float* __restrict__ alpha,
+                                  uint4* __restrict__ out, size_t nvec, size_t vec_per_sample) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < nvec;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float a = __ldg(alpha + idx / vec_per_sample);
+    float v[8];
+    ln_unpack(__ldg(g + idx), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= a;
+    out[idx] = ln_pack(v);
+  }
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" int srb200_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta,
+                                    void* y_bf16, float* mean, float* rstd, int64_t T, int C, int Cp,
+                                    float eps, srb200_stream_t stream) {
+  if (!x_bf16 || !gamma || !beta || !y_bf16 || T <= 0 || C <= 0 || Cp < C || Cp % 8 != 0)
+    return SRB200_EINVAL;
+  if (Cp > 256 * LN_MAX_VEC) return SRB200_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int block = 256;
+  long long blocks = (T + 7) / 8;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
+  __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+  const int g = static_cast<int>(blocks);
+  if (Cp <= 256) layernorm_fwd_kernel<1><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps);
+  else if (Cp <= 512) layernorm_fwd_kernel<2><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps);
+  else layernorm_fwd_kernel<4><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps);
+  return launch_status();
+}
+
+extern "C" int srb200_layernorm_bwd(const void* gy_bf16, const void* x_bf16, const float* mean,
+                                    const float* rstd, const float* gamma, const void* gres_bf16,
+                                    void* gx_bf16, float* ggamma, float* gbeta, int64_t T, int C,
+                                    int Cp, srb200_stream_t stream) {
+  if (!gy_bf16 || !x_bf16 || !mean || !rstd || !gamma || !gx_bf16 || !ggamma || !gbeta)
+    return SRB200_EINVAL;
+  if (T <= 0 || C <= 0 || Cp < C || Cp % 8 != 0 || Cp > 256 * LN_MAX_VEC) return SRB200_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int block = 256;
+  long long blocks = (T + 63) / 64;  // >= 8 tokens per warp so the column atomics amortise
+  const long long cap = static_cast<long long>(num_sms()) * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = 2 * static_cast<size_t>(Cp) * sizeof(float);
+  const __nv_bfloat16* gy = static_cast<const __nv_bfloat16*>(gy_bf16);
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
+  const __nv_bfloat16* gr = static_cast<const __nv_bfloat16*>(gres_bf16);
+  __nv_bfloat16* gx = static_cast<__nv_bfloat16*>(gx_bf16);
+  const int g = static_cast<int>(blocks);
+  if (Cp <= 256)
+    layernorm_bwd_kernel<1><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+  else if (Cp <= 512)
+    layernorm_bwd_kernel<2><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+  else
+    layernorm_bwd_kernel<4><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+  return launch_status();
+}
+
+extern "C" int srb200_scale_rows(const void* g_bf16, const float* alpha, void* out_bf16, int B,
+                                 int64_t elems_per_sample, srb200_stream_t stream) {
+  if (!g_bf16 || !alpha || !out_bf16 || B <= 0 || elems_per_sample <= 0 || elems_per_sample % 8 != 0)
+    return SRB200_EINVAL;
+  const size_t vps = static_cast<size_t>(elems_per_sample) / 8;
+  const size_t nvec = vps * B;
+  size_t blocks = (nvec + 255) / 256;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  scale_rows_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g_bf16), alpha, static_cast<uint4*>(out_bf16), nvec, vps);
+  return launch_status();
+}

@@ -39,6 +39,9 @@ struct TapGemmParams {
   const float* out_shift;
   void* out;
   __nv_bfloat16* aux_out;
+  const float* residual_f32;  // optional fp32 residual (layout of out)
+  float* out_f32;             // optional fp32 copy of the result (layout of out)
+  const float* alpha_b;       // optional per-sample scale [B] (stochastic depth)
   int act;
   float act_slope, alpha;
   int mask_mode;
@@ -276,8 +279,11 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < CHUNK; ++j) v[j] = gelu_erf(v[j]);
           }
+          {
+            const float al = p.alpha_b != nullptr ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) v[j] *= p.alpha;
+            for (int j = 0; j < CHUNK; ++j) v[j] *= al;
+          }
           if (p.mask_mode != SRB200_MASK_NONE) {
             const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
 #pragma unroll
@@ -309,6 +315,23 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
                 v[8 * j + 2 * q + 1] += bf16_hi(mw[q]);
               }
             }
+          }
+          if (p.residual_f32 != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + off);
+#pragma unroll
+            for (int j = 0; j < CHUNK / 4; ++j) {
+              const float4 m = __ldg(rp + j);
+              v[4 * j + 0] += m.x;
+              v[4 * j + 1] += m.y;
+              v[4 * j + 2] += m.z;
+              v[4 * j + 3] += m.w;
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float4* fp = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+            for (int j = 0; j < CHUNK / 4; ++j)
+              fp[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
           if (p.out_mode == SRB200_OUT_NCHW_F32) {
             float* op = reinterpret_cast<float*>(p.out);
@@ -379,7 +402,8 @@ using namespace srb;
 extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
                               const void* w_packed, const float* bias, const void* mask_src,
                               const void* residual, const float* out_shift, void* out,
-                              void* aux_out, srb200_stream_t stream_) {
+                              void* aux_out, const srb200_tapgemm_ext* ext,
+                              srb200_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!d || !in_bf16 || !w_packed || !out) return SRB200_EINVAL;
   if (d->B <= 0 || d->H <= 0 || d->W <= 0) return SRB200_EINVAL;
@@ -427,6 +451,12 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.out_shift = out_shift;
   p.out = out;
   p.aux_out = static_cast<__nv_bfloat16*>(aux_out);
+  p.residual_f32 = ext ? ext->residual_f32 : nullptr;
+  p.out_f32 = ext ? ext->out_f32 : nullptr;
+  p.alpha_b = ext ? ext->alpha_per_sample : nullptr;
+  if ((p.residual_f32 || p.out_f32) && d->out_mode == SRB200_OUT_NCHW_F32) return SRB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(p.residual_f32) | reinterpret_cast<uintptr_t>(p.out_f32)) & 15u)
+    return SRB200_EINVAL;
   p.act = d->act;
   p.act_slope = d->act_slope;
   p.alpha = d->alpha;

@@ -175,7 +175,8 @@ def unpack_wgrad(acc, w_shape, perm_out=None, perm_in=None, alpha=1.0):
 # ------------------------------------------------------------------ tap-GEMM
 def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alpha=1.0, mask_src=None,
             mask_mode=L.MASK_NONE, mask_slope=0.0, residual=None, flip=False, src_r=1, out_mode=L.OUT_NHWC,
-            out_r=1, out_c=0, out_scale=1.0, out_shift=None, want_aux=False):
+            out_r=1, out_c=0, out_scale=1.0, out_shift=None, want_aux=False, residual_f32=None, want_f32=False,
+            alpha_per_sample=None):
     """conv3x3 / conv1x1 / Linear on NHWC bf16 (see include/srb200.h: srb200_tapgemm)."""
     _chk(x, 'x', torch.bfloat16)
     _chk(wp, 'wp', torch.bfloat16)
@@ -199,12 +200,22 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
     if bias is not None:
         _chk(bias, 'bias', torch.float32)
         assert bias.numel() == cout
+    out32 = torch.empty(out.shape, dtype=torch.float32, device=x.device) if want_f32 else None
+    ext = None
+    if residual_f32 is not None or want_f32 or alpha_per_sample is not None:
+        for t, name in ((residual_f32, 'residual_f32'), (alpha_per_sample, 'alpha_per_sample')):
+            if t is not None:
+                _chk(t, name, torch.float32)
+        ext = ctypes.byref(L.TapGemmExt(residual_f32.data_ptr() if residual_f32 is not None else None,
+                                        out32.data_ptr() if out32 is not None else None,
+                                        alpha_per_sample.data_ptr() if alpha_per_sample is not None else None))
     ev = PROBE.begin('tapgemm', (b, h, w, cin * src_r * src_r, cout, ksize)) if PROBE is not None else None
     L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),
-                                    _ptr(out_shift), _ptr(out), _ptr(aux), _stream()), 'tapgemm')
+                                    _ptr(out_shift), _ptr(out), _ptr(aux), ext, _stream()), 'tapgemm')
     if ev is not None:
         PROBE.end(ev)
-    return (out, aux) if want_aux else out
+    res = (out,) + ((aux,) if want_aux else ()) + ((out32,) if want_f32 else ())
+    return res if len(res) > 1 else out
 
 
 def wgrad(dy, x, *, ksize, dy_r=1):
@@ -237,3 +248,76 @@ def act_bwd(g, y, slope=0.0):
     out = torch.empty_like(g)
     L.check(L.load().srb200_act_bwd(_ptr(g), _ptr(y), _ptr(out), g.numel(), float(slope), _stream()), 'act_bwd')
     return out
+
+
+# ------------------------------------------------------------------ RCAN channel attention
+def channel_pool(t):
+    """AdaptiveAvgPool2d(1) (rcan_arch.py:19) of NHWC bf16 -> fp32 [B, C]."""
+    _chk(t, 't', torch.bfloat16)
+    b, h, w, c = t.shape
+    out = torch.zeros((b, c), dtype=torch.float32, device=t.device)
+    L.check(L.load().srb200_channel_pool(_ptr(t), _ptr(out), b, h * w, c, _stream()), 'channel_pool')
+    return out
+
+
+def channel_dot(a, m, scale=1.0):
+    """fp32 [B, C] = scale * sum_hw a * m."""
+    _chk(a, 'a', torch.bfloat16)
+    _chk(m, 'm', torch.bfloat16)
+    b, h, w, c = a.shape
+    out = torch.zeros((b, c), dtype=torch.float32, device=a.device)
+    L.check(L.load().srb200_channel_dot(_ptr(a), _ptr(m), _ptr(out), b, h * w, c, float(scale), _stream()),
+            'channel_dot')
+    return out
+
+
+def ca_fc(p, w1, b1, w2, b2):
+    """z = relu(W1 p + b1), s = sigmoid(W2 z + b2) (rcan_arch.py:19-20); weights as stored ([Cr,C,1,1], [C,Cr,1,1])."""
+    for t, n in ((p, 'p'), (w1, 'w1'), (b1, 'b1'), (w2, 'w2'), (b2, 'b2')):
+        _chk(t, n, torch.float32)
+    b, c = p.shape
+    cr = w1.shape[0]
+    z = torch.empty((b, cr), dtype=torch.float32, device=p.device)
+    s = torch.empty((b, c), dtype=torch.float32, device=p.device)
+    L.check(L.load().srb200_ca_fc(_ptr(p), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(z), _ptr(s), b, c, cr,
+                                  _stream()), 'ca_fc')
+    return z, s
+
+
+def ca_apply(t, x, s, res_scale, x32=None, want_f32=False):
+    """y = x + res_scale * t * s[b, c] (rcan_arch.py:24,45-46); optional fp32 skip stream in / out."""
+    _chk(t, 't', torch.bfloat16)
+    if x32 is not None:
+        _chk(x32, 'x32', torch.float32)
+    else:
+        _chk(x, 'x', torch.bfloat16)
+    b, h, w, c = t.shape
+    y = torch.empty_like(t)
+    y32 = torch.empty(t.shape, dtype=torch.float32, device=t.device) if want_f32 else None
+    L.check(L.load().srb200_ca_apply(_ptr(t), _ptr(x) if x32 is None else None, _ptr(x32), _ptr(s), _ptr(y),
+                                     _ptr(y32), b, h * w, c, float(res_scale), _stream()), 'ca_apply')
+    return (y, y32) if want_f32 else y
+
+
+def ca_fc_bwd(gs, s, z, p, w1, w2):
+    b, c = s.shape
+    cr = z.shape[1]
+    dev = s.device
+    gw1 = torch.empty((cr, c, 1, 1), dtype=torch.float32, device=dev)
+    gb1 = torch.empty((cr,), dtype=torch.float32, device=dev)
+    gw2 = torch.empty((c, cr, 1, 1), dtype=torch.float32, device=dev)
+    gb2 = torch.empty((c,), dtype=torch.float32, device=dev)
+    gp = torch.empty((b, c), dtype=torch.float32, device=dev)
+    L.check(L.load().srb200_ca_fc_bwd(_ptr(gs), _ptr(s), _ptr(z), _ptr(p), _ptr(w1), _ptr(w2), _ptr(gw1), _ptr(gb1),
+                                      _ptr(gw2), _ptr(gb2), _ptr(gp), b, c, cr, _stream()), 'ca_fc_bwd')
+    return gw1, gb1, gw2, gb2, gp
+
+
+def ca_apply_bwd(g, s, gp, res_scale):
+    """gt = res_scale * g * s[b, c] + gp[b, c] / HW."""
+    _chk(g, 'g', torch.bfloat16)
+    b, h, w, c = g.shape
+    gt = torch.empty_like(g)
+    L.check(L.load().srb200_ca_apply_bwd(_ptr(g), _ptr(s), _ptr(gp), _ptr(gt), b, h * w, c, float(res_scale),
+                                         _stream()), 'ca_apply_bwd')
+    return gt

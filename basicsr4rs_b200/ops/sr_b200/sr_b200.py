@@ -127,7 +127,8 @@ class _ConvNHWC(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, ksize, act, slope, alpha, shuffle_r):
+    def forward(ctx, x, weight, bias, residual, ksize, act, slope, alpha, shuffle_r, residual32=None,
+                want_f32=False):
         cout, cin = weight.shape[0], weight.shape[1]
         k_pad = x.shape[-1]
         assert k_pad == pad64(cin), f'input has {k_pad} channels, expected {pad64(cin)}'
@@ -142,15 +143,23 @@ class _ConvNHWC(Function):
         wp = _packed(weight, 'fprop', n_pad, k_pad, perm_out=perm)
         bp = _padded_bias(bias, n_pad, perm)
         y = raw.tapgemm(x, wp, ksize=ksize, cout=n_pad, bias=bp, act=ACT_CODES[act], act_slope=slope, alpha=alpha,
-                        residual=residual, out_mode=L.OUT_SHUFFLE if shuffle_r > 1 else L.OUT_NHWC, out_r=shuffle_r)
+                        residual=residual if residual32 is None else None, residual_f32=residual32,
+                        want_f32=want_f32, out_mode=L.OUT_SHUFFLE if shuffle_r > 1 else L.OUT_NHWC,
+                        out_r=shuffle_r)
+        y32 = None
+        if want_f32:
+            y, y32 = y
         ctx.save_for_backward(x, weight, bias, y if act is not None else None)
         ctx.cfg = (ksize, act, slope, alpha, shuffle_r, n_pad, k_pad)
         ctx.perm = perm
         ctx.has_res = residual is not None
+        if want_f32:
+            ctx.mark_non_differentiable(y32)
+            return y, y32
         return y
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, *unused):
         x, weight, bias, y = ctx.saved_tensors
         ksize, act, slope, alpha, shuffle_r, n_pad, k_pad = ctx.cfg
         perm = ctx.perm
@@ -168,13 +177,18 @@ class _ConvNHWC(Function):
         if ctx.needs_input_grad[0]:
             wpt = _packed(weight, 'dgrad', n_pad, k_pad, perm_out=perm)
             gx = raw.tapgemm(g, wpt, ksize=ksize, cout=k_pad, alpha=alpha, flip=True, src_r=shuffle_r)
-        return gx, gw, gb, g_res, None, None, None, None, None
+        return gx, gw, gb, g_res, None, None, None, None, None, None, None
 
 
-def conv_nhwc(x, weight, bias=None, residual=None, act=None, slope=0.0, alpha=1.0, shuffle_r=1):
-    """conv3x3 (weight [Co,Ci,3,3]), conv1x1 or Linear (weight [Co,Ci,1,1] / [Co,Ci]) on NHWC64 bf16."""
+def conv_nhwc(x, weight, bias=None, residual=None, act=None, slope=0.0, alpha=1.0, shuffle_r=1, residual32=None,
+              want_f32=False):
+    """conv3x3 (weight [Co,Ci,3,3]), conv1x1 or Linear (weight [Co,Ci,1,1] / [Co,Ci]) on NHWC64 bf16.
+
+    ``residual`` is the differentiable bf16 skip input; ``residual32`` (optional, same values in fp32, never
+    differentiated) is what the epilogue actually adds when given.  ``want_f32`` also returns the fp32 result."""
     ksize = weight.shape[-1] if weight.dim() == 4 else 1
-    return _ConvNHWC.apply(x, weight, bias, residual, ksize, act, slope, float(alpha), shuffle_r)
+    return _ConvNHWC.apply(x, weight, bias, residual, ksize, act, slope, float(alpha), shuffle_r, residual32,
+                           want_f32)
 
 
 # ------------------------------------------------------------------ fused ResidualBlockNoBN
@@ -262,3 +276,57 @@ class _ConvToImage(Function):
 
 def conv_to_image(x, weight, bias, out_scale, out_shift):
     return _ConvToImage.apply(x, weight, bias, float(out_scale), out_shift)
+
+
+# ------------------------------------------------------------------ fused RCAB (RCAN)
+class _RCAB(Function):
+    """x + res_scale * CA(conv2(relu(conv1(x))))  (rcan_arch.py:36-46, ChannelAttention :16-24).
+
+    forward : tap-GEMM(+bias+ReLU) ; tap-GEMM(+bias) ; pool ; FC+sigmoid ; fused scale+residual pass
+    backward: channel_dot (d s) ; FC backward ; fused d t pass ; wgrad/colsum/dgrad(+ReLU mask) for conv2 ;
+              wgrad/colsum/dgrad(+skip gradient) for conv1
+    """
+
+    @staticmethod
+    def forward(ctx, x, x32, w1, b1, w2, b2, wa1, ba1, wa2, ba2, res_scale):
+        # x is the differentiable bf16 stream; x32 (optional, never differentiated) is the same stream in
+        # fp32 -- when given, the skip add reads / writes it and (y, y32) is returned
+        c = w1.shape[0]
+        cp = pad64(c)
+        assert x.shape[-1] == cp == c, 'RCAB kernels need num_feat % 64 == 0'
+        h = raw.tapgemm(x, _packed(w1, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b1, cp), act=L.ACT_RELU)
+        t = raw.tapgemm(h, _packed(w2, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b2, cp))
+        p = raw.channel_pool(t)
+        z, s = raw.ca_fc(p, wa1.detach().contiguous(), ba1.detach(), wa2.detach().contiguous(), ba2.detach())
+        ctx.save_for_backward(x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2)
+        ctx.res_scale = res_scale
+        if x32 is None:
+            return raw.ca_apply(t, x, s, res_scale)
+        y, y32 = raw.ca_apply(t, None, s, res_scale, x32=x32, want_f32=True)
+        ctx.mark_non_differentiable(y32)
+        return y, y32
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2 = ctx.saved_tensors
+        rs = ctx.res_scale
+        cp = x.shape[-1]
+        g = g.contiguous()
+        gs = raw.channel_dot(g, t, scale=rs)                       # d s[b,c] = res_scale * sum_hw g * t
+        gwa1, gba1, gwa2, gba2, gp = raw.ca_fc_bwd(gs, s, z, p, wa1.detach().contiguous(), wa2.detach().contiguous())
+        gt = raw.ca_apply_bwd(g, s, gp, rs)                        # d t
+        gw2 = raw.unpack_wgrad(raw.wgrad(gt, h, ksize=3), w2.shape)
+        gb2 = raw.colsum(gt)[:b2.numel()].clone()
+        gh = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
+                         mask_mode=L.MASK_SIGN, mask_slope=0.0)
+        gw1 = raw.unpack_wgrad(raw.wgrad(gh, x, ksize=3), w1.shape)
+        gb1 = raw.colsum(gh)[:b1.numel()].clone()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g)
+        return gx, None, gw1, gb1, gw2, gb2, gwa1, gba1, gwa2, gba2, None
+
+
+def rcab(x, w1, b1, w2, b2, wa1, ba1, wa2, ba2, res_scale, x32=None):
+    """Returns y, or (y, y32) when the fp32 skip stream ``x32`` is carried along."""
+    return _RCAB.apply(x, x32, w1, b1, w2, b2, wa1, ba1, wa2, ba2, float(res_scale))

@@ -1,0 +1,195 @@
+"""SwinIR ops on the srb200 C-ABI: LayerNorm, fused window attention and the fused
+SwinTransformerBlock autograd function (reference swinir_arch.py:283-323).
+
+Layouts (all NHWC bf16, tokens == pixels):
+  stream  [B,H,W,Cs]      Cs = pad64(C)              channels >= C are zero
+  qkv     [B,H,W,3*Ca]    Ca = num_heads*32          channel = which*Ca + head*32 + d, d >= head_dim zero
+  attn o  [B,H,W,Ca]
+  mlp     [B,H,W,Ch]      Ch = pad64(hidden)
+The padding lives only in the packed bf16 weight copies (index maps below); parameters keep the
+reference's shapes, so state dicts are interchangeable.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from ... import _lib as L
+from . import raw
+from .raw import _chk, _ptr, _stream
+from .sr_b200 import _packed, _padded_bias, _perm_cache, _unpad_bias_grad, pad64
+
+HD_PAD = 32
+LN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------ raw wrappers
+def layernorm_fwd(x, gamma, beta, c, eps=LN_EPS):
+    _chk(x, 'x', torch.bfloat16)
+    cp = x.shape[-1]
+    t = x.numel() // cp
+    y = torch.empty_like(x)
+    mean = torch.empty((t,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((t,), dtype=torch.float32, device=x.device)
+    L.check(L.load().srb200_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), t, c, cp,
+                                          float(eps), _stream()), 'layernorm_fwd')
+    return y, mean, rstd
+
+
+def layernorm_bwd(gy, x, mean, rstd, gamma, c, gres=None):
+    _chk(gy, 'gy', torch.bfloat16)
+    cp = x.shape[-1]
+    t = x.numel() // cp
+    gx = torch.empty_like(x)
+    gg = torch.zeros((c,), dtype=torch.float32, device=x.device)
+    gb = torch.zeros((c,), dtype=torch.float32, device=x.device)
+    L.check(L.load().srb200_layernorm_bwd(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(gres), _ptr(gx),
+                                          _ptr(gg), _ptr(gb), t, c, cp, _stream()), 'layernorm_bwd')
+    return gx, gg, gb
+
+
+def scale_rows(g, alpha):
+    _chk(g, 'g', torch.bfloat16)
+    out = torch.empty_like(g)
+    b = g.shape[0]
+    L.check(L.load().srb200_scale_rows(_ptr(g), _ptr(alpha), _ptr(out), b, g.numel() // b, _stream()), 'scale_rows')
+    return out
+
+
+def window_attention_fwd(qkv, table, num_heads, ws, shift, scale):
+    _chk(qkv, 'qkv', torch.bfloat16)
+    _chk(table, 'rpb_table', torch.float32)
+    b, h, w, c3 = qkv.shape
+    ca = c3 // 3
+    out = torch.empty((b, h, w, ca), dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.load().srb200_window_attention_fwd(_ptr(qkv), _ptr(table), _ptr(out), b, h, w, num_heads, ca, ws, shift,
+                                                 float(scale), _stream()), 'window_attention_fwd')
+    return out
+
+
+def window_attention_bwd(qkv, gout, table, num_heads, ws, shift, scale):
+    _chk(gout, 'gout', torch.bfloat16)
+    b, h, w, c3 = qkv.shape
+    ca = c3 // 3
+    gqkv = torch.empty_like(qkv)
+    gtable = torch.zeros_like(table)
+    L.check(L.load().srb200_window_attention_bwd(_ptr(qkv), _ptr(gout), _ptr(table), _ptr(gqkv), _ptr(gtable), b, h, w,
+                                                 num_heads, ca, ws, shift, float(scale), _stream()),
+            'window_attention_bwd')
+    return gqkv, gtable
+
+
+# ------------------------------------------------------------------ index maps (packed -> original, -1 = zero)
+def head_perm(num_heads, head_dim, parts, device):
+    """packed p = part*Ca + head*32 + d  ->  original part*C + head*head_dim + d (or -1 when d >= head_dim)."""
+    key = ('head', num_heads, head_dim, parts, str(device))
+    if key not in _perm_cache:
+        ca = num_heads * HD_PAD
+        p = torch.arange(parts * ca, device=device)
+        part, rem = p // ca, p % ca
+        head, d = rem // HD_PAD, rem % HD_PAD
+        orig = part * (num_heads * head_dim) + head * head_dim + d
+        _perm_cache[key] = torch.where(d < head_dim, orig, torch.full_like(orig, -1)).to(torch.int32)
+    return _perm_cache[key]
+
+
+# ------------------------------------------------------------------ LayerNorm
+class _LayerNorm(Function):
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        c = gamma.numel()
+        y, mean, rstd = layernorm_fwd(x, gamma.detach(), beta.detach(), c, eps)
+        ctx.save_for_backward(x, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, gamma = ctx.saved_tensors
+        gx, gg, gb = layernorm_bwd(gy.contiguous(), x, mean, rstd, gamma.detach(), gamma.numel())
+        return gx, gg, gb, None
+
+
+def layer_norm(x, gamma, beta, eps=LN_EPS):
+    return _LayerNorm.apply(x, gamma, beta, eps)
+
+
+# ------------------------------------------------------------------ fused SwinTransformerBlock
+class _SwinBlock(Function):
+    """x + DropPath(proj(WindowAttn(LN1(x)))) then + DropPath(fc2(GELU(fc1(LN2(.)))))  (swinir_arch.py:283-323).
+
+    forward : LN ; tap-GEMM qkv(+bias) ; fused window attention ; tap-GEMM proj(+bias, x alpha[b], + x) ; LN ;
+              tap-GEMM fc1(+bias, GELU, pre-activation kept) ; tap-GEMM fc2(+bias, x alpha[b], + x1)
+    backward: the mirror image, with d GELU fused into fc2's dgrad epilogue and both skip-gradient adds fused
+              into the LayerNorm backward kernels.
+    """
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                num_heads, ws, shift, alpha1, alpha2):
+        c = n1w.numel()
+        cs = x.shape[-1]
+        assert cs == pad64(c)
+        hd = c // num_heads
+        assert hd <= HD_PAD and (num_heads * HD_PAD) % 64 == 0, 'window attention kernel: head_dim <= 32, even heads'
+        ca = num_heads * HD_PAD
+        hidden = fc1_w.shape[0]
+        ch = pad64(hidden)
+        dev = x.device
+        p_qkv = head_perm(num_heads, hd, 3, dev)
+        p_o = head_perm(num_heads, hd, 1, dev)
+        scale = hd**-0.5
+
+        xn, mean1, rstd1 = layernorm_fwd(x, n1w.detach(), n1b.detach(), c)
+        qkv = raw.tapgemm(xn, _packed(qkv_w, 'fprop', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=3 * ca,
+                          bias=_padded_bias(qkv_b, 3 * ca, p_qkv))
+        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale)
+        x1 = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
+                         bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1)
+        xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c)
+        h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=_padded_bias(fc1_b, ch),
+                           act=L.ACT_GELU, want_aux=True)
+        x2 = raw.tapgemm(h, _packed(fc2_w, 'fprop', cs, ch), ksize=1, cout=cs, bias=_padded_bias(fc2_b, cs),
+                         residual=x1, alpha_per_sample=alpha2)
+        ctx.save_for_backward(x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table,
+                              proj_w, proj_b, n2w, fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2)
+        ctx.cfg = (c, cs, ca, ch, hd, num_heads, ws, shift, scale)
+        return x2
+
+    @staticmethod
+    def backward(ctx, g2):
+        (x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table, proj_w, proj_b, n2w,
+         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = ctx.saved_tensors
+        c, cs, ca, ch, hd, num_heads, ws, shift, scale = ctx.cfg
+        dev = x.device
+        p_qkv = head_perm(num_heads, hd, 3, dev)
+        p_o = head_perm(num_heads, hd, 1, dev)
+        g2 = g2.contiguous()
+        # ---- MLP branch
+        g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
+        g_fc2_w = raw.unpack_wgrad(raw.wgrad(g2s, h, ksize=1), fc2_w.shape)
+        g_fc2_b = raw.colsum(g2s)[:fc2_b.numel()].clone()
+        ga = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
+                         mask_mode=L.MASK_DGELU)
+        g_fc1_w = raw.unpack_wgrad(raw.wgrad(ga, xn2, ksize=1), fc1_w.shape)
+        g_fc1_b = raw.colsum(ga)[:fc1_b.numel()].clone()
+        gxn2 = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True)
+        gx1, g_n2w, g_n2b = layernorm_bwd(gxn2, x1, mean2, rstd2, n2w.detach(), c, gres=g2)
+        # ---- attention branch
+        g1s = scale_rows(gx1, alpha1) if alpha1 is not None else gx1
+        g_proj_w = raw.unpack_wgrad(raw.wgrad(g1s, o, ksize=1), proj_w.shape, perm_in=p_o)
+        g_proj_b = raw.colsum(g1s)[:proj_b.numel()].clone()
+        go = raw.tapgemm(g1s, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
+        gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale)
+        g_qkv_w = raw.unpack_wgrad(raw.wgrad(gqkv, xn, ksize=1), qkv_w.shape, perm_out=p_qkv)
+        g_qkv_b = _unpad_bias_grad(raw.colsum(gqkv), qkv_b, p_qkv) if qkv_b is not None else None
+        gxn = raw.tapgemm(gqkv, _packed(qkv_w, 'dgrad', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=cs, flip=True)
+        gx, g_n1w, g_n1b = layernorm_bwd(gxn, x, mean1, rstd1, n1w.detach(), c, gres=gx1)
+        return (gx, g_n1w, g_n1b, g_qkv_w, g_qkv_b, g_table, g_proj_w, g_proj_b, g_n2w, g_n2b, g_fc1_w, g_fc1_b,
+                g_fc2_w, g_fc2_b, None, None, None, None, None)
+
+
+def swin_block(x, n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, num_heads, ws,
+               shift, alpha1=None, alpha2=None):
+    return _SwinBlock.apply(x, n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                            num_heads, ws, shift, alpha1, alpha2)

@@ -114,6 +114,13 @@ typedef struct {
   float out_scale;      /* SRB200_OUT_NCHW_F32                                             */
 } srb200_tapgemm_desc;
 
+/* optional extras of the epilogue (pass NULL when unused) */
+typedef struct {
+  const float* residual_f32;     /* fp32 residual, layout of out: v += residual_f32 (fp32 skip stream)  */
+  float* out_f32;                /* additionally store the fp32 result (layout of out)                  */
+  const float* alpha_per_sample; /* [B] extra scale per batch sample (DropPath, swinir_arch.py:14-26)   */
+} srb200_tapgemm_ext;
+
 int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16, const void* w_packed,
                    const float* bias,          /* [Cout] or NULL                           */
                    const void* mask_src,       /* bf16, layout of out, or NULL             */
@@ -121,6 +128,7 @@ int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16, const void
                    const float* out_shift,     /* [out_c] for NCHW_F32 or NULL             */
                    void* out,                  /* see out_mode                             */
                    void* aux_out,              /* optional bf16 copy of the pre-activation */
+                   const srb200_tapgemm_ext* ext, /* optional, may be NULL                 */
                    srb200_stream_t stream);
 
 /* ------------------------------------------------------------------ weight gradient
@@ -136,6 +144,60 @@ int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc, int B, int
  * pixel-unshuffle phases separately (bias gradient of a conv whose store fused PixelShuffle). */
 int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int C, int r, int Wf,
                   srb200_stream_t stream);
+
+/* ------------------------------------------------------------------ RCAN channel attention
+ * ChannelAttention (rcan_arch.py:8-24) + RCAB tail (rcan_arch.py:44-46) on NHWC bf16 [B,HW,C]:
+ *   channel_pool : out[b,c] += mean_hw t[b,hw,c]                     (AdaptiveAvgPool2d(1); zero out first)
+ *   channel_dot  : out[b,c] += scale * sum_hw a[b,hw,c]*b[b,hw,c]    (backward: d s)
+ *   ca_fc        : z = relu(W1 p + b1), s = sigmoid(W2 z + b2)       (the two 1x1 convs, fp32 params as stored)
+ *   ca_apply     : y = x + res_scale * t * s[b,c]                    (x * y and res * res_scale + x fused)
+ *   ca_fc_bwd    : parameter grads of the two 1x1 convs (summed over the batch) and gp = dL/dp
+ *   ca_apply_bwd : gt = res_scale * g * s[b,c] + gp[b,c] / HW        (dL/dt incl. the pool branch)        */
+int srb200_channel_pool(const void* t_bf16, float* out, int B, int HW, int C, srb200_stream_t stream);
+int srb200_channel_dot(const void* a_bf16, const void* b_bf16, float* out, int B, int HW, int C,
+                       float scale, srb200_stream_t stream);
+int srb200_ca_fc(const float* p, const float* w1, const float* b1, const float* w2, const float* b2,
+                 float* z, float* s, int B, int C, int Cr, srb200_stream_t stream);
+/* x_f32 / y_f32 (optional): carry the skip stream in fp32 next to its bf16 copy -- RCAN stacks 200
+ * res_scale=1 additions and needs it to stay inside the 1e-2 output bar.   */
+int srb200_ca_apply(const void* t_bf16, const void* x_bf16, const float* x_f32, const float* s,
+                    void* y_bf16, float* y_f32, int B, int HW, int C, float res_scale,
+                    srb200_stream_t stream);
+int srb200_ca_fc_bwd(const float* gs, const float* s, const float* z, const float* p, const float* w1,
+                     const float* w2, float* gw1, float* gb1, float* gw2, float* gb2, float* gp,
+                     int B, int C, int Cr, srb200_stream_t stream);
+int srb200_ca_apply_bwd(const void* g_bf16, const float* s, const float* gp, void* gt_bf16, int B,
+                        int HW, int C, float res_scale, srb200_stream_t stream);
+
+/* ------------------------------------------------------------------ SwinIR token kernels
+ * nn.LayerNorm(C, eps) over the C real channels of NHWC bf16 rows padded to Cp (pads stay 0)
+ * (swinir_arch.py:240,251,288,321,602,886).  mean/rstd [T] fp32 are saved for the backward.
+ * bwd: gx = LN'(gy) + gres (gres optional: fused add of the skip-path gradient);
+ *      ggamma[c] += sum_t gy*xhat, gbeta[c] += sum_t gy (zero them first).                               */
+int srb200_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16,
+                         float* mean, float* rstd, int64_t T, int C, int Cp, float eps,
+                         srb200_stream_t stream);
+int srb200_layernorm_bwd(const void* gy_bf16, const void* x_bf16, const float* mean, const float* rstd,
+                         const float* gamma, const void* gres_bf16, void* gx_bf16, float* ggamma,
+                         float* gbeta, int64_t T, int C, int Cp, srb200_stream_t stream);
+/* out[b, :] = g[b, :] * alpha[b]  (DropPath backward, swinir_arch.py:14-26)                              */
+int srb200_scale_rows(const void* g_bf16, const float* alpha, void* out_bf16, int B,
+                      int64_t elems_per_sample, srb200_stream_t stream);
+/* Fused (shifted-)window attention, WindowAttention.forward minus the two Linear layers
+ * (swinir_arch.py:151-172) together with roll / window_partition / window_reverse / roll
+ * (:293-316) and the analytic 0/-100 mask (:262-281):
+ *   qkv [B,H,W,3*Cp] bf16, channel = which*Cp + head*32 + d  (head_dim <= 32, zero padded)
+ *   out [B,H,W,Cp]   bf16, channel = head*32 + d
+ *   rpb_table fp32 [(2*ws-1)^2, num_heads] exactly as stored in the state dict
+ * window_size must be 8; H, W multiples of 8; shift in [0, 8).
+ * bwd also accumulates the bias-table gradient into g_rpb_table (zero it first).                         */
+int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table, void* out_bf16, int B,
+                                int H, int W, int num_heads, int Cp, int window_size, int shift,
+                                float scale, srb200_stream_t stream);
+int srb200_window_attention_bwd(const void* qkv_bf16, const void* gout_bf16, const float* rpb_table,
+                                void* gqkv_bf16, float* g_rpb_table, int B, int H, int W,
+                                int num_heads, int Cp, int window_size, int shift, float scale,
+                                srb200_stream_t stream);
 
 /* out = g * act'(y) for ReLU (slope 0) / LeakyReLU, y = forward output (bf16, n % 8 == 0). */
 int srb200_act_bwd(const void* g_bf16, const void* y_bf16, void* out_bf16, int64_t n, float slope,

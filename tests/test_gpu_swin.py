@@ -1,0 +1,183 @@
+"""SwinIR parity on the B200 (``-m gpu``): LayerNorm and fused window-attention kernels against plain
+PyTorch fp32 compositions of the reference's own steps (roll -> window_partition -> softmax(qk^T*s + bias +
+mask) v -> window_reverse -> roll), the fused block against the oracle block, and the SwinIR arch against
+the reference golden vectors / the CPU oracle (bars: see tests/test_gpu_nets.py)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import sr_oracle
+from tests.test_gpu_nets import GOLDEN, MAX_ABS, PSNR_TOL, _build, _check_grad
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from basicsr4rs_b200.ops.sr_b200 import swin_ops
+    return swin_ops
+
+
+@pytest.mark.parametrize('c,cp,tokens', [(180, 192, 1000), (60, 64, 333), (360, 384, 77)])
+def test_layernorm_fwd_bwd(cuda, c, cp, tokens):
+    so = _ops()
+    g = torch.Generator().manual_seed(0)
+    x = torch.zeros((1, tokens, 1, cp))
+    x[..., :c] = torch.randn((1, tokens, 1, c), generator=g) * 3 + 1
+    x = x.to(cuda).to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(c, generator=g)).to(cuda)
+    y, mean, rstd = so.layernorm_fwd(x, gamma, beta, c)
+    xr = x[..., :c].float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (c,), gr, br, 1e-5)
+    assert torch.allclose(y[..., :c].float(), ref, atol=3e-2, rtol=1e-2)
+    assert torch.count_nonzero(y[..., c:]) == 0
+    assert torch.allclose(mean, xr.detach().mean(-1).flatten(), atol=1e-4)
+    gy = torch.zeros_like(x)
+    gy[..., :c] = torch.randn((1, tokens, 1, c), generator=g).to(cuda).to(torch.bfloat16)
+    gres = torch.zeros_like(x)
+    gres[..., :c] = torch.randn((1, tokens, 1, c), generator=g).to(cuda).to(torch.bfloat16)
+    ref.backward(gy[..., :c].float())
+    gx, gg, gb = so.layernorm_bwd(gy, x, mean, rstd, gamma, c, gres=gres)
+    want = xr.grad + gres[..., :c].float()
+    assert torch.allclose(gx[..., :c].float(), want, atol=2e-2 * want.abs().max().item())
+    assert torch.allclose(gg, gr.grad, rtol=1e-3, atol=1e-3 * gr.grad.abs().max().item())
+    assert torch.allclose(gb, br.grad, rtol=1e-3, atol=1e-3 * br.grad.abs().max().item())
+
+
+def _ref_window_attention(qkv_pad, table, nh, hd, ws, shift, h, w):
+    """fp32 PyTorch restatement of swinir_arch.py:293-316 + :151-172 given the (padded) qkv tensor."""
+    b = qkv_pad.shape[0]
+    ca = nh * 32
+    q, k, v = [qkv_pad[..., i * ca:(i + 1) * ca].reshape(b, h, w, nh, 32)[..., :hd] for i in range(3)]
+
+    def part(t):  # [b,h,w,nh,hd] -> [b*nW, nh, ws*ws, hd]
+        if shift:
+            t = torch.roll(t, shifts=(-shift, -shift), dims=(1, 2))
+        t = sr_oracle.window_partition(t.reshape(b, h, w, nh * hd), ws).reshape(-1, ws * ws, nh, hd)
+        return t.permute(0, 2, 1, 3)
+
+    q, k, v = part(q), part(k), part(v)
+    attn = (q * hd**-0.5) @ k.transpose(-2, -1)
+    idx = sr_oracle.relative_position_index(ws).reshape(-1).to(table.device)
+    attn = attn + table[idx].reshape(ws * ws, ws * ws, nh).permute(2, 0, 1).unsqueeze(0)
+    if shift:
+        mask = sr_oracle.calculate_mask(h, w, ws, shift).to(table.device)
+        nw = mask.shape[0]
+        attn = (attn.reshape(b, nw, nh, ws * ws, ws * ws) + mask[None, :, None]).reshape(-1, nh, ws * ws, ws * ws)
+    out = (torch.softmax(attn, -1) @ v).transpose(1, 2).reshape(-1, ws, ws, nh * hd)
+    out = sr_oracle.window_reverse(out, ws, h, w)
+    if shift:
+        out = torch.roll(out, shifts=(shift, shift), dims=(1, 2))
+    return out.reshape(b, h, w, nh, hd)
+
+
+@pytest.mark.parametrize('b,h,w,nh,hd,shift', [(2, 16, 24, 6, 30, 0), (2, 16, 24, 6, 30, 4), (1, 8, 8, 6, 10, 0),
+                                               (1, 64, 64, 6, 30, 4), (1, 24, 16, 2, 32, 3)])
+def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift):
+    so = _ops()
+    g = torch.Generator().manual_seed(1)
+    ca = nh * 32
+    qkv = torch.zeros((b, h, w, 3, nh, 32))
+    qkv[..., :hd] = torch.randn((b, h, w, 3, nh, hd), generator=g)
+    qkv = qkv.reshape(b, h, w, 3 * ca).to(cuda).to(torch.bfloat16)
+    table = (torch.randn((225, nh), generator=g) * 0.5).to(cuda)
+    out = so.window_attention_fwd(qkv, table, nh, 8, shift, hd**-0.5)
+    qr = qkv.float().requires_grad_(True)
+    tr = table.clone().requires_grad_(True)
+    ref = _ref_window_attention(qr, tr, nh, hd, 8, shift, h, w)
+    got = out.reshape(b, h, w, nh, 32)
+    assert torch.count_nonzero(got[..., hd:]) == 0
+    err = (got[..., :hd].float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item(), f'fwd err {err:.3e}'
+    go = torch.zeros((b, h, w, nh, 32))
+    go[..., :hd] = torch.randn((b, h, w, nh, hd), generator=g)
+    go = go.reshape(b, h, w, ca).to(cuda).to(torch.bfloat16)
+    ref.backward(go.reshape(b, h, w, nh, 32)[..., :hd].float())
+    gqkv, gtable = so.window_attention_bwd(qkv, go, table, nh, 8, shift, hd**-0.5)
+    want = qr.grad
+    rel = ((gqkv.float() - want).norm() / want.norm()).item()
+    assert rel <= 2e-2, f'gqkv rel-L2 {rel:.3e}'
+    relt = ((gtable - tr.grad).norm() / tr.grad.norm()).item()
+    assert relt <= 2e-2, f'gtable rel-L2 {relt:.3e}'
+
+
+def test_swin_block_vs_oracle(cuda):
+    """One shifted SwinTransformerBlock (C=180, 6 heads, ws 8, shift 4) forward + all gradients."""
+    so = _ops()
+    c, nh, hidden, b, h, w = 180, 6, 360, 2, 16, 24
+    g = torch.Generator().manual_seed(2)
+    shapes = {'norm1.weight': (c,), 'norm1.bias': (c,), 'attn.qkv.weight': (3 * c, c), 'attn.qkv.bias': (3 * c,),
+              'attn.relative_position_bias_table': (225, nh), 'attn.proj.weight': (c, c), 'attn.proj.bias': (c,),
+              'norm2.weight': (c,), 'norm2.bias': (c,), 'mlp.fc1.weight': (hidden, c), 'mlp.fc1.bias': (hidden,),
+              'mlp.fc2.weight': (c, hidden), 'mlp.fc2.bias': (c,)}
+    sd = sr_oracle.fill_state_dict_({'blk.' + k: torch.zeros(s) for k, s in shapes.items()})
+    x = torch.randn((b, h * w, c), generator=g)
+    for shift in (0, 4):
+        ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        xr = x.clone().requires_grad_(True)
+        ref = sr_oracle.swin_block(ref_sd, 'blk', xr, h, w, nh, 8, shift)
+        gy = torch.randn((b, h * w, c), generator=g)
+        ref.backward(gy)
+        p = {k[4:]: v.to(cuda).requires_grad_(True) for k, v in sd.items()}
+        xp = torch.zeros((b, h, w, 192))
+        xp[..., :c] = x.reshape(b, h, w, c)
+        xp = xp.to(cuda).to(torch.bfloat16).requires_grad_(True)
+        out = so.swin_block(xp, p['norm1.weight'], p['norm1.bias'], p['attn.qkv.weight'], p['attn.qkv.bias'],
+                            p['attn.relative_position_bias_table'], p['attn.proj.weight'], p['attn.proj.bias'],
+                            p['norm2.weight'], p['norm2.bias'], p['mlp.fc1.weight'], p['mlp.fc1.bias'],
+                            p['mlp.fc2.weight'], p['mlp.fc2.bias'], nh, 8, shift)
+        err = (out[..., :c].float().cpu().reshape(b, h * w, c) - ref.detach()).abs().max().item()
+        assert err <= 2e-2 * ref.abs().max().item(), f'shift {shift}: fwd err {err:.3e}'
+        assert torch.count_nonzero(out[..., c:]) == 0
+        gyp = torch.zeros((b, h, w, 192))
+        gyp[..., :c] = gy.reshape(b, h, w, c)
+        out.backward(gyp.to(cuda).to(torch.bfloat16))
+        rel = ((xp.grad[..., :c].float().cpu().reshape(b, h * w, c) - xr.grad).norm() / xr.grad.norm()).item()
+        assert rel <= 3e-2, f'shift {shift}: gx rel-L2 {rel:.3e}'
+        for k in shapes:
+            want = ref_sd['blk.' + k].grad
+            rel = ((p[k].grad.cpu() - want).norm() / want.norm()).item()
+            assert rel <= 3e-2, f'shift {shift}: {k} rel-L2 {rel:.3e}'
+
+
+@pytest.mark.parametrize('case', ['swinir_c180_d2x2_x4', 'swinir_c60_d2_x2'])
+def test_swinir_matches_reference_golden(cuda, case):
+    fx = torch.load(os.path.join(GOLDEN, case + '.pt'), weights_only=False)
+    net = _build(fx, cuda)
+    out = net(fx['x'].to(cuda))
+    err = (out.detach().cpu() - fx['out']).abs().max().item()
+    assert err <= MAX_ABS, f'max-abs {err:.3e}'
+    assert abs(sr_oracle.psnr(out.detach().cpu(), fx['gt']) - sr_oracle.psnr(fx['out'], fx['gt'])) <= PSNR_TOL
+    ((out - fx['gt'].to(cuda))**2).mean().backward()
+    params = dict(net.named_parameters())
+    for k, want in fx['grads'].items():
+        _check_grad(params[k].grad, want)
+
+
+def test_swinir_full_size_vs_oracle(cuda):
+    """BASELINE config 4: embed 180, 6 RSTB x 6 layers, window 8, 6 heads, x4, 64x64 LR, default seeded init."""
+    from basicsr4rs_b200.archs import build_network
+    kw = dict(upscale=4, in_chans=3, img_size=64, window_size=8, img_range=1., depths=[6] * 6, embed_dim=180,
+              num_heads=[6] * 6, mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv')
+    torch.manual_seed(0)
+    net = build_network(dict(type='SwinIR', **kw))
+    assert sum(p.numel() for p in net.parameters()) == 11900199 and len(net.state_dict()) == 550
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(cuda).eval()
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand((1, 3, 64, 64), generator=g)
+    with torch.no_grad():
+        out = net(x.to(cuda)).cpu()
+        ref = sr_oracle.swinir_forward(sd, x, embed_dim=180, depths=[6] * 6, num_heads=[6] * 6, window_size=8,
+                                       upscale=4, img_range=1.)
+    err = (out - ref).abs().max().item()
+    print(f'SwinIR full: max-abs {err:.3e}, PSNR vs oracle {sr_oracle.psnr(out, ref, crop=1):.1f} dB')
+    assert err <= MAX_ABS, f'max-abs {err:.3e}'
+    # training mode with stochastic depth runs and produces finite gradients
+    net.train()
+    o = net(torch.rand((2, 3, 64, 64), device=cuda))
+    o.mean().backward()
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
