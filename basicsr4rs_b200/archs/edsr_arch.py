@@ -6,23 +6,14 @@ from torch import nn as nn
 from ..ops import sr_b200 as ops
 from ..utils.registry import ARCH_REGISTRY
 from .arch_util import ResidualBlockNoBN, Upsample, make_layer, require_cuda
-from .graphed import GRAPHS, GraphedSegments, Segment
+from .graphed import GRAPHS, ArchMixin, GraphedSegments, Segment
 
 
-class _MeanShiftMixin:
-    """``self.mean`` stays a plain tensor attribute (absent from the state dict, edsr_arch.py:42,51);
-    a device copy is cached for the fused entry / exit kernels."""
-
-    def _device_mean(self, x):
-        m = getattr(self, '_mean_dev', None)
-        if m is None or m.device != x.device:
-            m = self.mean.detach().to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
-            self._mean_dev = m
-        return m
+_MeanShiftMixin = ArchMixin  # ``self.mean`` stays a plain tensor attribute (edsr_arch.py:42,51)
 
 
 @ARCH_REGISTRY.register()
-class EDSR(nn.Module, _MeanShiftMixin):
+class EDSR(ArchMixin, nn.Module):
     """EDSR: mean-shift -> conv_first -> num_block x ResidualBlockNoBN -> conv_after_body + skip -> Upsample
     -> conv_last -> inverse shift.
 
@@ -42,10 +33,12 @@ class EDSR(nn.Module, _MeanShiftMixin):
                  img_range=255.,
                  rgb_mean=(0.4488, 0.4371, 0.4040),
                  cuda_graph=False,
-                 graph_segments=4):
+                 graph_segments=4,
+                 graph_input_shape=None):
         super(EDSR, self).__init__()
         self.cuda_graph = cuda_graph
         self.graph_segments = max(1, int(graph_segments))
+        self.graph_input_shape = graph_input_shape  # e.g. [16, 3, 48, 48]: capture on .to(device), before DDP
 
         self.img_range = img_range
         self.mean = torch.Tensor(rgb_mean).view(1, 3, 1, 1)

@@ -69,10 +69,83 @@ class GraphedSegments:
 
         with torch.no_grad():  # one eager pass only to learn every segment's input signature
             self._wire(eager_call, x)
+        # the differentiable stream between segments is bf16; fp32 tensors (image input, fp32 skip twins) are
+        # carried along without gradients
         sample_args = tuple(
-            tuple(a.detach().clone().requires_grad_(a.is_floating_point() and i > 0) for a in record[i])
+            tuple(a.detach().clone().requires_grad_(a.dtype == torch.bfloat16 and i > 0) for a in record[i])
             for i in range(len(segs)))
         n0 = L.launch_count
         graphed = torch.cuda.make_graphed_callables(tuple(segs), sample_args, num_warmup_iters=self.WARMUP)
         self.kernels_per_step[key] = (L.launch_count - n0) // (self.WARMUP + 1)
         return list(graphed)
+
+
+def graphed_forward(module, x, build_segments, wire):
+    """Replay ``module``'s training forward/backward for input ``x`` from CUDA graphs (captured on first use)."""
+    graphs = GRAPHS.get(module)
+    if graphs is None:
+        graphs = GRAPHS[module] = GraphedSegments(build_segments, wire)
+    return graphs(x.contiguous().float(), True)
+
+
+def chain_wire(nseg, carry=1):
+    """wire() for the common shape: segment 0 returns (stream..., *carry); middle segments map stream -> stream;
+    the last segment consumes (stream..., *carry).  ``carry`` = how many trailing outputs of segment 0 skip
+    straight to the last segment (the long skip connection)."""
+
+    def wire(call, x):
+        out = call(0, x)
+        stream, kept = out[:-carry], out[-carry:]
+        for i in range(1, nseg - 1):
+            stream = call(i, *stream)
+            if not isinstance(stream, tuple):
+                stream = (stream,)
+        return call(nseg - 1, *stream, *kept)
+
+    return wire
+
+
+def split_even(items, n):
+    n = min(max(1, n), max(1, len(items)))
+    cuts = [round(i * len(items) / n) for i in range(n + 1)]
+    return [items[cuts[i]:cuts[i + 1]] for i in range(n)]
+
+
+def precapture(module):
+    """Capture ``module``'s training graphs for ``module.graph_input_shape`` right after it lands on the GPU.
+
+    DDP stashes an AccumulateGrad node per parameter on the stream it was constructed on; capturing a backward
+    afterwards would make that (legacy) stream wait on the capturing stream, which CUDA rejects.  The reference
+    wraps with DDP right after ``net.to(device)`` (base_model.py:94-99), so the archs call this from
+    ``nn.Module._apply`` -- i.e. between ``.to(device)`` and the DDP wrap, with no change to the caller."""
+    shape = getattr(module, 'graph_input_shape', None)
+    if not getattr(module, 'cuda_graph', False) or not shape:
+        return
+    p = next(module.parameters(), None)
+    if p is None or not p.is_cuda:
+        return
+    key_done = ('precaptured', tuple(shape), str(p.device))
+    if module.__dict__.get('_srb200_precaptured') == key_done:
+        return
+    module.__dict__['_srb200_precaptured'] = key_done
+    was_training = module.training
+    module.train()
+    with torch.enable_grad(), torch.cuda.device(p.device):
+        module(torch.zeros(tuple(shape), dtype=torch.float32, device=p.device))
+    module.train(was_training)
+
+
+class ArchMixin:
+    """Shared by the three archs: device copy of the (non-buffer) mean, and graph pre-capture on ``.to(device)``."""
+
+    def _device_mean(self, x):
+        m = getattr(self, '_mean_dev', None)
+        if m is None or m.device != x.device:
+            m = self.mean.detach().to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+            self._mean_dev = m
+        return m
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        precapture(self)
+        return out

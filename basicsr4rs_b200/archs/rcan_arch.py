@@ -6,7 +6,7 @@ from torch import nn as nn
 from ..ops import sr_b200 as ops
 from ..utils.registry import ARCH_REGISTRY
 from .arch_util import Upsample, make_layer, nchw_roundtrip, require_cuda
-from .edsr_arch import _MeanShiftMixin
+from .graphed import ArchMixin, Segment, chain_wire, graphed_forward, split_even
 
 
 class ChannelAttention(nn.Module):
@@ -69,7 +69,7 @@ class ResidualGroup(nn.Module):
 
 
 @ARCH_REGISTRY.register()
-class RCAN(nn.Module, _MeanShiftMixin):
+class RCAN(ArchMixin, nn.Module):
     """Residual Channel Attention Network (reference rcan_arch.py:71-135).
 
     Args (identical to the reference): num_in_ch, num_out_ch, num_feat=64, num_group=10, num_block=16,
@@ -86,8 +86,14 @@ class RCAN(nn.Module, _MeanShiftMixin):
                  upscale=4,
                  res_scale=1,
                  img_range=255.,
-                 rgb_mean=(0.4488, 0.4371, 0.4040)):
+                 rgb_mean=(0.4488, 0.4371, 0.4040),
+                 cuda_graph=False,
+                 graph_segments=5,
+                 graph_input_shape=None):
         super(RCAN, self).__init__()
+        self.cuda_graph = cuda_graph          # optional: replay training fwd/bwd from CUDA graphs (archs/graphed.py)
+        self.graph_segments = graph_segments
+        self.graph_input_shape = graph_input_shape
 
         self.img_range = img_range
         self.mean = torch.Tensor(rgb_mean).view(1, 3, 1, 1)
@@ -104,19 +110,51 @@ class RCAN(nn.Module, _MeanShiftMixin):
         self.upsample = Upsample(upscale, num_feat)
         self.conv_last = nn.Conv2d(num_feat, num_out_ch, 3, 1, 1)
 
-    def forward(self, x):
-        require_cuda(x, 'RCAN')
+    # The skip stream is carried twice: bf16 (differentiable, feeds the tensor cores) and fp32 (what the skip
+    # adds read and write).  200 stacked res_scale=1 additions in bf16 alone drift past the 1e-2 output bar
+    # (1.16e-2 for bf16 autocast of the reference itself).
+    def _head(self, x):
         mean = self._device_mean(x)
         t = ops.image_to_nhwc(x, mean, self.img_range, ops.pad64(x.shape[1]))
-        # The skip stream is carried twice: bf16 (differentiable, feeds the tensor cores) and fp32 (what the
-        # skip adds read and write).  200 stacked res_scale=1 additions in bf16 alone drift past the 1e-2
-        # output bar (1.16e-2 for bf16 autocast of the reference itself).
-        first, first32 = ops.conv_nhwc(t, self.conv_first.weight, self.conv_first.bias, want_f32=True)
-        res, res32 = first, first32
-        for group in self.body:
-            res, res32 = group.forward_nhwc(res, res32)
+        return ops.conv_nhwc(t, self.conv_first.weight, self.conv_first.bias, want_f32=True)
+
+    def _tail(self, res, res32, first, first32):
         res = ops.conv_nhwc(res, self.conv_after_body.weight, self.conv_after_body.bias, residual=first,
                             residual32=first32)
         up = self.upsample.forward_nhwc(res)
-        out = ops.conv_to_image(up, self.conv_last.weight, self.conv_last.bias, 1.0 / self.img_range, mean)
+        return ops.conv_to_image(up, self.conv_last.weight, self.conv_last.bias, 1.0 / self.img_range,
+                                 self._mean_dev)
+
+    def _build_segments(self):
+        groups = split_even(list(self.body), self.graph_segments)
+
+        def run(gs):
+            def fn(res, res32):
+                for grp in gs:
+                    res, res32 = grp.forward_nhwc(res, res32)
+                return res, res32
+            return fn
+
+        def head_fn(x):
+            first, first32 = self._head(x)
+            res, res32 = run(groups[0])(first, first32)
+            return res, res32, first, first32
+
+        segs = [Segment(head_fn, [self.conv_first] + groups[0])]
+        segs += [Segment(run(g), g) for g in groups[1:]]
+        segs.append(Segment(self._tail, [self.conv_after_body, self.upsample, self.conv_last]))
+        return segs
+
+    def forward(self, x):
+        require_cuda(x, 'RCAN')
+        if self.cuda_graph and self.training and torch.is_grad_enabled():
+            self._device_mean(x)
+            nseg = len(split_even(list(self.body), self.graph_segments)) + 1
+            out = graphed_forward(self, x, self._build_segments, chain_wire(nseg, carry=2))
+            return out if out.dtype == x.dtype else out.to(x.dtype)
+        first, first32 = self._head(x)
+        res, res32 = first, first32
+        for group in self.body:
+            res, res32 = group.forward_nhwc(res, res32)
+        out = self._tail(res, res32, first, first32)
         return out if out.dtype == x.dtype else out.to(x.dtype)

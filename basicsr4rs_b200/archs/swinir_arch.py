@@ -23,7 +23,7 @@ from ..ops import sr_b200 as ops
 from ..ops.sr_b200 import swin_ops
 from ..utils.registry import ARCH_REGISTRY
 from .arch_util import Upsample, require_cuda, to_2tuple, trunc_normal_
-from .edsr_arch import _MeanShiftMixin
+from .graphed import ArchMixin, Segment, chain_wire, graphed_forward, split_even
 
 KERNEL_WINDOW = 8  # the fused attention kernel is specialised for 8x8 windows (64 tokens)
 
@@ -287,7 +287,7 @@ class UpsampleOneStep(nn.Sequential):
 
 
 @ARCH_REGISTRY.register()
-class SwinIR(nn.Module, _MeanShiftMixin):
+class SwinIR(ArchMixin, nn.Module):
     """SwinIR (classical / lightweight / real-world SR, denoising) -- same constructor as the reference."""
 
     def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=96, depths=(6, 6, 6, 6),
@@ -295,6 +295,11 @@ class SwinIR(nn.Module, _MeanShiftMixin):
                  attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
                  use_checkpoint=False, upscale=2, img_range=1., upsampler='', resi_connection='1conv', **kwargs):
         super(SwinIR, self).__init__()
+        # optional extras tolerated through **kwargs like any unknown key of the reference (:744):
+        # cuda_graph / graph_segments replay the training fwd/bwd from CUDA graphs (archs/graphed.py)
+        self.cuda_graph = bool(kwargs.get('cuda_graph', False))
+        self.graph_segments = int(kwargs.get('graph_segments', 6))
+        self.graph_input_shape = kwargs.get('graph_input_shape', None)
         num_in_ch = in_chans
         num_out_ch = in_chans
         num_feat = 64
@@ -396,22 +401,58 @@ class SwinIR(nn.Module, _MeanShiftMixin):
             t = layer.forward_nhwc(t)
         return swin_ops.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps)
 
-    def forward(self, x):
-        require_cuda(x, 'SwinIR')
+    def _head(self, x):
         mean = self._device_mean(x) if self.mean.numel() == x.shape[1] else None
         t = ops.image_to_nhwc(x, mean, self.img_range, ops.pad64(x.shape[1]))
-        first = ops.conv_nhwc(t, self.conv_first.weight, self.conv_first.bias)
-        feat = _resi_conv(self.conv_after_body, self.forward_features_nhwc(first), first)
+        return ops.conv_nhwc(t, self.conv_first.weight, self.conv_first.bias)
+
+    def _tail(self, t, first, x=None):
+        mean = getattr(self, '_mean_dev', None) if self.mean.numel() == self.conv_first.weight.shape[1] else None
+        t = swin_ops.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps)
+        feat = _resi_conv(self.conv_after_body, t, first)
         inv = 1.0 / self.img_range
         if self.upsampler == 'pixelshuffle':
             c = self.conv_before_upsample[0]
             u = ops.conv_nhwc(feat, c.weight, c.bias, act='lrelu', slope=self.conv_before_upsample[1].negative_slope)
             u = self.upsample.forward_nhwc(u)
-            out = ops.conv_to_image(u, self.conv_last.weight, self.conv_last.bias, inv, mean)
-        elif self.upsampler == '':
+            return ops.conv_to_image(u, self.conv_last.weight, self.conv_last.bias, inv, mean)
+        if self.upsampler == '':
             # denoising / JPEG-CAR: x + conv_last(res) in normalised space == x + conv_last(res) / img_range
-            out = x.float() + ops.conv_to_image(feat, self.conv_last.weight, self.conv_last.bias, inv, None)
-        else:
-            raise NotImplementedError(f"srb200 SwinIR: upsampler '{self.upsampler}' is not on the B200 path yet "
-                                      "(classical 'pixelshuffle' and '' are); there is no PyTorch fallback")
+            return x.float() + ops.conv_to_image(feat, self.conv_last.weight, self.conv_last.bias, inv, None)
+        raise NotImplementedError(f"srb200 SwinIR: upsampler '{self.upsampler}' is not on the B200 path yet "
+                                  "(classical 'pixelshuffle' and '' are); there is no PyTorch fallback")
+
+    def _build_segments(self):
+        groups = split_even(list(self.layers), self.graph_segments)
+
+        def run(gs):
+            def fn(t):
+                for layer in gs:
+                    t = layer.forward_nhwc(t)
+                return t
+            return fn
+
+        def head_fn(x):
+            first = self._head(x)
+            return run(groups[0])(self.patch_embed.forward_nhwc(first)), first
+
+        tail_mods = [self.norm, self.conv_after_body] + [getattr(self, n) for n in
+                                                         ('conv_before_upsample', 'upsample', 'conv_last')
+                                                         if hasattr(self, n)]
+        segs = [Segment(head_fn, [self.conv_first, self.patch_embed] + groups[0])]
+        segs += [Segment(run(g), g) for g in groups[1:]]
+        segs.append(Segment(self._tail, tail_mods))
+        return segs
+
+    def forward(self, x):
+        require_cuda(x, 'SwinIR')
+        if self.cuda_graph and self.training and torch.is_grad_enabled() and self.upsampler == 'pixelshuffle':
+            nseg = len(split_even(list(self.layers), self.graph_segments)) + 1
+            out = graphed_forward(self, x, self._build_segments, chain_wire(nseg, carry=1))
+            return out if out.dtype == x.dtype else out.to(x.dtype)
+        first = self._head(x)
+        t = self.patch_embed.forward_nhwc(first)
+        for layer in self.layers:
+            t = layer.forward_nhwc(t)
+        out = self._tail(t, first, x)
         return out if out.dtype == x.dtype else out.to(x.dtype)

@@ -34,6 +34,23 @@ CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; loss + Adam eage
 FLOP_PER_PATCH_FWD_BWD = 694.66e9
 
 
+def synthetic_batch(rank, batch=BATCH, lr=LR, scale=4):
+    """Per-rank synthetic shard: LR patches in [0,1) and GT, seeded 1234 + rank."""
+    g = torch.Generator().manual_seed(1234 + rank)
+    lq = torch.rand((batch, 3, lr, lr), generator=g)
+    gt = torch.rand((batch, 3, scale * lr, scale * lr), generator=g)
+    return lq, gt
+
+
+def max_over_ranks(ms, device, world):
+    """Device-timed milliseconds -> max over ranks (the job is as slow as its slowest rank)."""
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -153,15 +170,14 @@ def main():
     L.check(L.load().srb200_check_device(local_rank), 'srb200_check_device')
 
     torch.manual_seed(0)
-    net = build_network(dict(EDSR_L, cuda_graph=not args.no_graph, graph_segments=4)).to(dev)
+    net = build_network(dict(EDSR_L, cuda_graph=not args.no_graph, graph_segments=4,
+                             graph_input_shape=[BATCH, 3, LR, LR])).to(dev)  # graphs captured here, before DDP
     model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True) \
         if world > 1 else net
     optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99))
     crit = nn.L1Loss()
 
-    g = torch.Generator().manual_seed(1234 + rank)
-    lq_h = torch.rand((BATCH, 3, LR, LR), generator=g).pin_memory()
-    gt_h = torch.rand((BATCH, 3, 4 * LR, 4 * LR), generator=g).pin_memory()
+    lq_h, gt_h = (t.pin_memory() for t in synthetic_batch(rank))
     lq_d, gt_d = lq_h.to(dev), gt_h.to(dev)
 
     def train_step(lq, gt):
@@ -184,10 +200,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+        return max_over_ranks(e0.elapsed_time(e1), dev, world)
 
     for _ in range(args.warmup):
         train_step(lq_d, gt_d)
@@ -249,7 +262,7 @@ def main():
                          'peak_kind': f'{pk_kind} bf16 sustained (timed inside a long step)',
                          'launches_timed': len(kernel_ms), 'avg_ms': k_avg},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (torchrun pins OMP threads to 1)
             threads = os.cpu_count() or 1
             t = cpu_oracle_step_time(1, threads, iters=1)
             line['cpu_baseline'] = {'value': 1.0 / t, 'unit': 'patches/s', 'cores': threads, 'kind': 'port',
