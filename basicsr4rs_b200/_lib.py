@@ -92,11 +92,17 @@ def load():
 
 
 launch_count = 0  # every successful C-ABI compute call enqueues exactly one CUDA kernel
+TRACE = None      # optional list: (what, cuda event recorded right after the launch) -- tools/trace_step.py
 
 
 def check(status, what):
     global launch_count
     launch_count += 1
+    if TRACE is not None:
+        import torch
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        TRACE.append((what, ev))
     if status != 0:
         msg = load().srb200_strerror(status).decode()
         raise RuntimeError(f'{what} failed: {msg} (status {status})')

@@ -567,10 +567,10 @@ extern "C" int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int 
                              srb200_stream_t stream) {
   if (!dy_bf16 || !out || rows <= 0 || C <= 0 || C % 8 != 0 || r < 1 || r > 3) return SRB200_EINVAL;
   if (C / 8 > 256 || (r > 1 && Wf <= 0)) return SRB200_EINVAL;
-  // >= 4 blocks per SM when the tensor allows it; each block covers a contiguous slab of rows
-  long long rpb = rows / (static_cast<long long>(num_sms()) * 4);
-  if (rpb < 32) rpb = 32;
-  if (rpb > 512) rpb = 512;
+  // ~2 blocks per SM, each covering a contiguous slab of rows: every block ends with one global atomic per
+  // column onto the SAME C addresses, so the block count (not the row count) bounds the serialised tail
+  long long rpb = (rows + static_cast<long long>(num_sms()) * 2 - 1) / (static_cast<long long>(num_sms()) * 2);
+  if (rpb < 64) rpb = 64;
   const int rows_per_block = static_cast<int>(rpb);
   const int grid = static_cast<int>((rows + rows_per_block - 1) / rows_per_block);
   const size_t smem = static_cast<size_t>(r) * r * C * sizeof(float);

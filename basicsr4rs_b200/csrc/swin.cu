@@ -39,52 +39,65 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                      __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                                      float* __restrict__ rstd_out, long long T, int C, int Cp,
                                      float eps) {
+  constexpr int TOK = (NVEC == 1) ? 2 : 1;  // tokens per warp iteration (independent loads in flight)
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int nv = Cp / 8;
-  for (long long t = warp_global; t < T; t += nwarps) {
-    float v[NVEC][8];
-    float sum = 0.0f;
+  // per-lane affine parameters live in registers for the whole kernel
+  float gm[NVEC][8], bt[NVEC][8];
 #pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      const int vec = lane + 32 * i;
-      if (vec < nv) {
-        ln_unpack(__ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec), v[i]);
+  for (int i = 0; i < NVEC; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sum += (vec * 8 + e < C) ? v[i][e] : 0.0f;
-      }
+    for (int e = 0; e < 8; ++e) {
+      const int c = (lane + 32 * i) * 8 + e;
+      gm[i][e] = (c < C) ? __ldg(gamma + c) : 0.0f;
+      bt[i][e] = (c < C) ? __ldg(beta + c) : 0.0f;
     }
-    const float mean = warp_sum(sum) / static_cast<float>(C);
-    float sq = 0.0f;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (long long t0 = warp_global * TOK; t0 < T; t0 += nwarps * TOK) {
+    float v[TOK][NVEC][8];
 #pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      const int vec = lane + 32 * i;
-      if (vec < nv) {
+    for (int k = 0; k < TOK; ++k)
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        const int vec = lane + 32 * i;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[k][i][e] = 0.0f;
+        if (vec < nv && t0 + k < T) ln_unpack(__ldg(reinterpret_cast<const uint4*>(x + (t0 + k) * Cp) + vec), v[k][i]);
+      }
+#pragma unroll
+    for (int k = 0; k < TOK; ++k) {
+      if (t0 + k >= T) break;
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[k][i][e];  // pad channels are zero by the layout invariant
+      const float mean = warp_sum(sum) * inv_c;
+      float sq = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i)
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float d = v[i][e] - mean;
-          sq += (vec * 8 + e < C) ? d * d : 0.0f;
+          const float d = v[k][i][e] - mean;
+          sq += ((lane + 32 * i) * 8 + e < C) ? d * d : 0.0f;
+        }
+      const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        const int vec = lane + 32 * i;
+        if (vec < nv) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (v[k][i][e] - mean) * rstd * gm[i][e] + bt[i][e];
+          *(reinterpret_cast<uint4*>(y + (t0 + k) * Cp) + vec) = ln_pack(o);
         }
       }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
-#pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      const int vec = lane + 32 * i;
-      if (vec < nv) {
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = vec * 8 + e;
-          o[e] = (c < C) ? (v[i][e] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) : 0.0f;
-        }
-        *(reinterpret_cast<uint4*>(y + t * Cp) + vec) = ln_pack(o);
+      if (lane == 0) {
+        if (mean_out) mean_out[t0 + k] = mean;
+        if (rstd_out) rstd_out[t0 + k] = rstd;
       }
-    }
-    if (lane == 0) {
-      if (mean_out) mean_out[t] = mean;
-      if (rstd_out) rstd_out[t] = rstd;
     }
   }
 }

@@ -12,8 +12,8 @@
 //   are drained by 4 epilogue warps with tcgen05.ld while the next tile's MMAs run.
 // * persistent CTAs (one per SM), static round-robin tile schedule.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue: TMEM lane quarter
+// = warp_idx % 4, and the two warps of a quarter split every 64-column chunk in halves.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -23,8 +23,11 @@
 namespace srb {
 
 struct TapGemmParams {
-  CUtensorMap tmap_a[9];  // one per source view (src_r^2 <= 9)
+  CUtensorMap tmap_a[9];    // one per source view (src_r^2 <= 9)
   CUtensorMap tmap_w;
+  CUtensorMap tmap_out[9];  // output views for the TMA-store epilogue (out_r^2 views for the fused PixelShuffle)
+  CUtensorMap tmap_aux;
+  int tma_store;            // 1: bf16 results leave through smem staging + cp.async.bulk.tensor stores
   int B, H, W;
   int tile_w, tile_h, tiles_x, tiles_y;
   int m_tiles, n_tiles;
@@ -56,7 +59,9 @@ struct TapCfg {
   static constexpr int A_BYTES = BLOCK_M * 128;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  // epilogue staging: 2 x [128 rows x 64 ch] bf16 tiles in the TMA 128B-swizzle layout
+  static constexpr int STORE_BYTES = BLOCK_N >= 64 ? 2 * 128 * 128 : 0;
+  static constexpr int STAGES_RAW = (232448 - 1024 - 256 - 1024 - STORE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
@@ -64,33 +69,50 @@ struct TapCfg {
                                    : (2 * BLOCK_N <= 256) ? 256
                                                           : 512;
   static constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;  // epilogue columns per tcgen05.ld
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): one ex2 + one rcp + 5 FMA
+// instead of libdevice's branchy erff -- the GELU epilogues are ALU-bound otherwise.
+// Returns e = exp(-z^2) as well, which d/dx GELU needs anyway.
+__device__ __forceinline__ float erf_as(float z_signed, float& e) {
+  const float z = fabsf(z_signed);
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  e = exp2f(-1.4426950408889634f * z * z);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float r = fmaf(-poly * t, e, 1.0f);
+  return copysignf(r, z_signed);
+}
+__device__ __forceinline__ float gelu_erf(float x) {  // nn.GELU() exact (erf) form, swinir_arch.py:46,57
+  float e;
+  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f, e));
 }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;  // e = exp(-x^2/2)
+  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f, e));
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+__global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   using Cfg = TapCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CHUNK = Cfg::CHUNK;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t store_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = store_base + Cfg::STORE_BYTES;
   // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));  // [BLOCK_N]
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
@@ -108,7 +130,7 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_barrier_init();
   }
@@ -196,10 +218,16 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
+    // ===================================================== epilogue (warps 2..9)
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;  // tile row == TMEM lane
+    const int half = (warp - 2) >> 2;     // which 32-column half of every 64-column chunk
+    const int row = quarter * 32 + lane;  // tile row == TMEM lane == smem staging row
     const int ly = row / p.tile_w, lx = row - ly * p.tile_w;
+    const bool use_tma = (BLOCK_N >= 64) && p.tma_store != 0;
+    const bool issuer = (warp == 2 && lane == 0);
+    const int etid = threadIdx.x - 64;    // 0..255
+    auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    uint32_t store_iter = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int n_t = t % p.n_tiles;
@@ -207,7 +235,8 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
       const int tx = m_t % p.tiles_x;
       const int ty = (m_t / p.tiles_x) % p.tiles_y;
       const int b = m_t / (p.tiles_x * p.tiles_y);
-      const int x = tx * p.tile_w + lx, y = ty * p.tile_h + ly;
+      const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+      const int x = x0 + lx, y = y0 + ly;
       const int n0 = n_t * BLOCK_N;
       const bool valid = (x < p.W) && (y < p.H);
       const int acc = it & 1;
@@ -216,123 +245,192 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+      const float al = p.alpha_b != nullptr ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
+      // bias of this N tile -> smem (every epilogue warp has passed the last barrier of the previous tile)
+      for (int i = etid; i < BLOCK_N; i += 256) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.0f;
+      epi_sync();
 
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / CHUNK; ++c) {
-        uint32_t r[CHUNK];
-        if constexpr (CHUNK == 32) {
-          tmem_ld32(taddr + c * CHUNK, r);
-        } else {
-          tmem_ld16(taddr + c * CHUNK, r);
+      // element offset of (this thread's pixel, channel nc) in an NHWC tensor shaped like `out`
+      auto out_offset = [&](int nc) -> size_t {
+        if (p.out_mode == SRB200_OUT_SHUFFLE) {
+          const int r2 = p.out_r * p.out_r;
+          const int C = p.Cout / r2;
+          const int ij = nc / C, cc = nc - ij * C;
+          const int i = ij / p.out_r, j = ij - i * p.out_r;
+          return ((static_cast<size_t>(b) * p.H * p.out_r + static_cast<size_t>(y) * p.out_r + i) *
+                      (static_cast<size_t>(p.W) * p.out_r) +
+                  static_cast<size_t>(x) * p.out_r + j) *
+                     C +
+                 cc;
         }
-        tmem_ld_wait();
-        float v[CHUNK];
+        return pix * p.Cout + nc;
+      };
+      // v: accumulators of CHUNK channels starting at nc -> final values (everything between MMA and store)
+      auto finish = [&](float (&v)[CHUNK], size_t off) {
+        if (p.act == SRB200_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(r[j]);
-        const int nc = n0 + c * CHUNK;
-        if (p.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + nc);
+          for (int j = 0; j < CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (p.act == SRB200_ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * p.act_slope;
+        } else if (p.act == SRB200_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) v[j] = gelu_erf(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) v[j] *= al;
+        if (!valid) return;  // out-of-image rows of a partial tile: never stored, never loaded
+        if (p.mask_mode != SRB200_MASK_NONE) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
+#pragma unroll
+          for (int j = 0; j < CHUNK / 8; ++j) {
+            const uint4 m = __ldg(mp + j);
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float m0 = bf16_lo(mw[q]), m1 = bf16_hi(mw[q]);
+              if (p.mask_mode == SRB200_MASK_SIGN) {
+                v[8 * j + 2 * q + 0] *= (m0 > 0.0f) ? 1.0f : p.mask_slope;
+                v[8 * j + 2 * q + 1] *= (m1 > 0.0f) ? 1.0f : p.mask_slope;
+              } else {
+                v[8 * j + 2 * q + 0] *= dgelu_erf(m0);
+                v[8 * j + 2 * q + 1] *= dgelu_erf(m1);
+              }
+            }
+          }
+        }
+        if (p.residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+          for (int j = 0; j < CHUNK / 8; ++j) {
+            const uint4 m = __ldg(rp + j);
+            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              v[8 * j + 2 * q + 0] += bf16_lo(mw[q]);
+              v[8 * j + 2 * q + 1] += bf16_hi(mw[q]);
+            }
+          }
+        }
+        if (p.residual_f32 != nullptr) {
+          const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + off);
 #pragma unroll
           for (int j = 0; j < CHUNK / 4; ++j) {
-            const float4 bv = __ldg(bp + j);
-            v[4 * j + 0] += bv.x;
-            v[4 * j + 1] += bv.y;
-            v[4 * j + 2] += bv.z;
-            v[4 * j + 3] += bv.w;
+            const float4 m = __ldg(rp + j);
+            v[4 * j + 0] += m.x;
+            v[4 * j + 1] += m.y;
+            v[4 * j + 2] += m.z;
+            v[4 * j + 3] += m.w;
           }
         }
-        if (valid) {
-          // element offset of (pixel, channel nc) in an NHWC tensor shaped like `out`
-          size_t off;
-          if (p.out_mode == SRB200_OUT_SHUFFLE) {
-            const int r2 = p.out_r * p.out_r;
-            const int C = p.Cout / r2;
-            const int ij = nc / C, cc = nc - ij * C;
-            const int i = ij / p.out_r, j = ij - i * p.out_r;
-            off = ((static_cast<size_t>(b) * p.H * p.out_r + static_cast<size_t>(y) * p.out_r + i) *
-                       (static_cast<size_t>(p.W) * p.out_r) +
-                   static_cast<size_t>(x) * p.out_r + j) *
-                      C +
-                  cc;
-          } else {
-            off = pix * p.Cout + nc;
-          }
-          if (p.aux_out != nullptr) {
-            uint4* ap = reinterpret_cast<uint4*>(p.aux_out + off);
+        if (p.out_f32 != nullptr) {
+          float4* fp = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
-            for (int j = 0; j < CHUNK / 8; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              ap[j] = o;
+          for (int j = 0; j < CHUNK / 4; ++j)
+            fp[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      };
+      auto load_acc = [&](int col, float (&v)[CHUNK]) {
+        uint32_t r[CHUNK];
+        if constexpr (CHUNK == 32) {
+          tmem_ld32(taddr + col, r);
+        } else {
+          tmem_ld16(taddr + col, r);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(r[j]);
+        const float4* bp = reinterpret_cast<const float4*>(s_bias + col);
+#pragma unroll
+        for (int j = 0; j < CHUNK / 4; ++j) {
+          const float4 bv = bp[j];
+          v[4 * j + 0] += bv.x;
+          v[4 * j + 1] += bv.y;
+          v[4 * j + 2] += bv.z;
+          v[4 * j + 3] += bv.w;
+        }
+      };
+
+      if (use_tma) {
+        // -------- results leave through swizzled smem staging + TMA tensor stores (full 128-byte lines,
+        // partial tiles clipped by the tensor map); the store of chunk c overlaps the math of chunk c+1
+        if constexpr (BLOCK_N >= 64) {
+          const bool has_aux = p.aux_out != nullptr;
+#pragma unroll 1
+          for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+            uint32_t buf_out, buf_aux = 0;
+            if (has_aux) {
+              buf_aux = store_base;
+              buf_out = store_base + 16384;
+              if (issuer) tma_store_wait_read<0>();
+            } else {
+              buf_out = store_base + (store_iter & 1u) * 16384;
+              if (issuer) tma_store_wait_read<1>();
             }
-          }
-          if (p.act == SRB200_ACT_RELU) {
+            epi_sync();
+            {
+              const int hf = half;
+              float v[CHUNK];
+              const int col = cc * 64 + hf * 32;
+              load_acc(col, v);
+              if (has_aux) {
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
-          } else if (p.act == SRB200_ACT_LRELU) {
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * p.act_slope;
-          } else if (p.act == SRB200_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) v[j] = gelu_erf(v[j]);
-          }
-          {
-            const float al = p.alpha_b != nullptr ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) v[j] *= al;
-          }
-          if (p.mask_mode != SRB200_MASK_NONE) {
-            const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
-#pragma unroll
-            for (int j = 0; j < CHUNK / 8; ++j) {
-              const uint4 m = __ldg(mp + j);
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float m0 = bf16_lo(mw[q]), m1 = bf16_hi(mw[q]);
-                if (p.mask_mode == SRB200_MASK_SIGN) {
-                  v[8 * j + 2 * q + 0] *= (m0 > 0.0f) ? 1.0f : p.mask_slope;
-                  v[8 * j + 2 * q + 1] *= (m1 > 0.0f) ? 1.0f : p.mask_slope;
-                } else {
-                  v[8 * j + 2 * q + 0] *= dgelu_erf(m0);
-                  v[8 * j + 2 * q + 1] *= dgelu_erf(m1);
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t dst = buf_aux + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                               "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])),
+                               "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                               "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                               "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                               : "memory");
                 }
               }
-            }
-          }
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+              finish(v, out_offset(n0 + col));
 #pragma unroll
-            for (int j = 0; j < CHUNK / 8; ++j) {
-              const uint4 m = __ldg(rp + j);
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[8 * j + 2 * q + 0] += bf16_lo(mw[q]);
-                v[8 * j + 2 * q + 1] += bf16_hi(mw[q]);
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t dst = buf_out + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                             "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])),
+                             "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                             "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                             "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                             : "memory");
               }
             }
-          }
-          if (p.residual_f32 != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + off);
-#pragma unroll
-            for (int j = 0; j < CHUNK / 4; ++j) {
-              const float4 m = __ldg(rp + j);
-              v[4 * j + 0] += m.x;
-              v[4 * j + 1] += m.y;
-              v[4 * j + 2] += m.z;
-              v[4 * j + 3] += m.w;
+            fence_proxy_async_smem();
+            epi_sync();
+            if (issuer) {
+              const int nc = n0 + cc * 64;
+              int view = 0, c0 = nc;
+              if (p.out_mode == SRB200_OUT_SHUFFLE) {
+                const int C = p.Cout / (p.out_r * p.out_r);
+                view = nc / C;
+                c0 = nc - view * C;
+              }
+              if (has_aux) tma_store_4d(&p.tmap_aux, buf_aux, c0, x0, y0, b);
+              tma_store_4d(&p.tmap_out[view], buf_out, c0, x0, y0, b);
+              tma_store_commit();
             }
+            ++store_iter;
           }
-          if (p.out_f32 != nullptr) {
-            float4* fp = reinterpret_cast<float4*>(p.out_f32 + off);
+        }
+      } else {
+        // -------- direct stores: final NCHW fp32 image (conv_last), or N < 64
+#pragma unroll 1
+        for (int c = half; c < BLOCK_N / CHUNK; c += 2) {
+          float v[CHUNK];
+          load_acc(c * CHUNK, v);
+          const int nc = n0 + c * CHUNK;
+          const size_t off = out_offset(nc);
+          if (valid && p.aux_out != nullptr) {
+            uint4* ap = reinterpret_cast<uint4*>(p.aux_out + off);
 #pragma unroll
-            for (int j = 0; j < CHUNK / 4; ++j)
-              fp[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < CHUNK / 8; ++j)
+              ap[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
+          finish(v, off);
+          if (!valid) continue;
           if (p.out_mode == SRB200_OUT_NCHW_F32) {
             float* op = reinterpret_cast<float*>(p.out);
             const size_t plane = static_cast<size_t>(p.H) * p.W;
@@ -341,21 +439,16 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
               const int ch = nc + j;
               if (ch < p.out_c) {
                 const float sh = p.out_shift != nullptr ? __ldg(p.out_shift + ch) : 0.0f;
-                op[(static_cast<size_t>(b) * p.out_c + ch) * plane + static_cast<size_t>(y) * p.W +
-                   x] = v[j] * p.out_scale + sh;
+                op[(static_cast<size_t>(b) * p.out_c + ch) * plane + static_cast<size_t>(y) * p.W + x] =
+                    v[j] * p.out_scale + sh;
               }
             }
           } else {
             uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
 #pragma unroll
-            for (int j = 0; j < CHUNK / 8; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              op[j] = o;
-            }
+            for (int j = 0; j < CHUNK / 8; ++j)
+              op[j] = make_uint4(pack_bf16x2(v[8 * j + 0], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
         }
       }
@@ -363,6 +456,7 @@ __global__ void __launch_bounds__(192, 1) tapgemm_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    if (use_tma && issuer) tma_store_wait_all<0>();  // smem must outlive the last bulk stores
   }
 
   tc_fence_before();
@@ -382,7 +476,7 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  tapgemm_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+  tapgemm_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(p);
   return launch_status();
 }
 
@@ -490,6 +584,29 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
     const uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
     const int rc = make_tmap_bf16(&p.tmap_w, w_packed, 2, dims, strides, box);
     if (rc != SRB200_OK) return rc;
+  }
+  // output views for the TMA-store epilogue: NHWC [B,H,W,Cout], or the out_r^2 phases of [B,H*r,W*r,Cout/r^2]
+  p.tma_store = (bn >= 64 && d->out_mode != SRB200_OUT_NCHW_F32) ? 1 : 0;
+  if (p.tma_store) {
+    const int ro = d->out_mode == SRB200_OUT_SHUFFLE ? d->out_r : 1;
+    const uint64_t Co = static_cast<uint64_t>(d->Cout) / (ro * ro);
+    const uint64_t Wo = static_cast<uint64_t>(d->W) * ro, Ho = static_cast<uint64_t>(d->H) * ro;
+    const uint64_t dims[4] = {Co, static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H),
+                              static_cast<uint64_t>(d->B)};
+    const uint64_t strides[3] = {ro * Co * 2, ro * Wo * Co * 2, Ho * Wo * Co * 2};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
+    for (int i = 0; i < ro; ++i)
+      for (int j = 0; j < ro; ++j) {
+        const size_t eoff = (static_cast<uint64_t>(i) * Wo + j) * Co;
+        int rc = make_tmap_bf16(&p.tmap_out[i * ro + j], static_cast<__nv_bfloat16*>(out) + eoff, 4, dims,
+                                strides, box);
+        if (rc != SRB200_OK) return rc;
+        if (aux_out && i == 0 && j == 0) {
+          rc = make_tmap_bf16(&p.tmap_aux, static_cast<__nv_bfloat16*>(aux_out), 4, dims, strides, box);
+          if (rc != SRB200_OK) return rc;
+        }
+      }
+    if (aux_out && ro != 1) return SRB200_EINVAL;
   }
   switch (bn) {
     case 256: return launch_tapgemm<256>(p, stream);

@@ -6,6 +6,7 @@ status into ``RuntimeError`` -- the same contract as the reference's pybind shim
 (basicsr/ops/fused_act/src/fused_bias_act.cpp:10-26, CHECK_CUDA / CHECK_CONTIGUOUS).
 """
 import ctypes
+import threading
 
 import torch
 
@@ -41,6 +42,39 @@ class EventProbe:
 
 
 PROBE = None
+
+_arena = threading.local()
+
+
+class zero_arena:
+    """All fp32 zero-initialised scratch (split-K accumulators, column sums, ...) requested by the wrappers
+    inside the ``with`` block is carved out of ONE ``torch.zeros`` -- one fill kernel instead of one per buffer."""
+
+    def __init__(self, device, n_floats):
+        self.device, self.n = device, int(n_floats) + 64
+
+    def __enter__(self):
+        self.prev = getattr(_arena, 'cur', None)
+        _arena.cur = [torch.zeros((self.n,), dtype=torch.float32, device=self.device), 0]
+        return self
+
+    def __exit__(self, *exc):
+        _arena.cur = self.prev
+        return False
+
+
+def zeros_f32(shape, device):
+    """fp32 zeros, 16-byte aligned, from the active :class:`zero_arena` when it has room."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    cur = getattr(_arena, 'cur', None)
+    if cur is not None and cur[0].device == device:
+        start = (cur[1] + 3) // 4 * 4
+        if start + n <= cur[0].numel():
+            cur[1] = start + n
+            return cur[0][start:start + n].view(shape)
+    return torch.zeros(shape, dtype=torch.float32, device=device)
 
 
 def _ptr(t):
@@ -225,7 +259,7 @@ def wgrad(dy, x, *, ksize, dy_r=1):
     b, h, w, k = x.shape
     n = dy.shape[-1] * dy_r * dy_r
     assert dy.shape[0] == b and dy.shape[1] == h * dy_r and dy.shape[2] == w * dy_r
-    acc = torch.zeros((ksize * ksize, n, k), dtype=torch.float32, device=x.device)
+    acc = zeros_f32((ksize * ksize, n, k), x.device)
     L.check(L.load().srb200_wgrad(_ptr(dy), _ptr(x), _ptr(acc), b, h, w, n, k, ksize, dy_r, _stream()), 'wgrad')
     return acc
 
@@ -235,7 +269,7 @@ def colsum(dy, r=1):
     _chk(dy, 'dy', torch.bfloat16)
     c = dy.shape[-1]
     rows = dy.numel() // c
-    out = torch.zeros((r * r * c,), dtype=torch.float32, device=dy.device)
+    out = zeros_f32((r * r * c,), dy.device)
     L.check(L.load().srb200_colsum(_ptr(dy), _ptr(out), rows, c, r, dy.shape[2] if dy.dim() == 4 else 0, _stream()),
             'colsum')
     return out
@@ -255,7 +289,7 @@ def channel_pool(t):
     """AdaptiveAvgPool2d(1) (rcan_arch.py:19) of NHWC bf16 -> fp32 [B, C]."""
     _chk(t, 't', torch.bfloat16)
     b, h, w, c = t.shape
-    out = torch.zeros((b, c), dtype=torch.float32, device=t.device)
+    out = zeros_f32((b, c), t.device)
     L.check(L.load().srb200_channel_pool(_ptr(t), _ptr(out), b, h * w, c, _stream()), 'channel_pool')
     return out
 
@@ -265,7 +299,7 @@ def channel_dot(a, m, scale=1.0):
     _chk(a, 'a', torch.bfloat16)
     _chk(m, 'm', torch.bfloat16)
     b, h, w, c = a.shape
-    out = torch.zeros((b, c), dtype=torch.float32, device=a.device)
+    out = zeros_f32((b, c), a.device)
     L.check(L.load().srb200_channel_dot(_ptr(a), _ptr(m), _ptr(out), b, h * w, c, float(scale), _stream()),
             'channel_dot')
     return out

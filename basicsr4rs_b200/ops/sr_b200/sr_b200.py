@@ -169,11 +169,15 @@ class _ConvNHWC(Function):
             assert act in ('relu', 'lrelu'), 'gelu backward goes through the fused MLP function'
             g = raw.act_bwd(g, y, slope if act == 'lrelu' else 0.0)
         gx = gw = gb = None
+        with raw.zero_arena(x.device, ksize * ksize * n_pad * k_pad + n_pad + 32):
+            if ctx.needs_input_grad[1]:
+                acc = raw.wgrad(g, x, ksize=ksize, dy_r=shuffle_r)
+            if bias is not None and ctx.needs_input_grad[2]:
+                gbp = raw.colsum(g, r=shuffle_r)
         if ctx.needs_input_grad[1]:
-            acc = raw.wgrad(g, x, ksize=ksize, dy_r=shuffle_r)
             gw = raw.unpack_wgrad(acc, weight.shape, perm_out=perm, alpha=alpha)
         if bias is not None and ctx.needs_input_grad[2]:
-            gb = _unpad_bias_grad(raw.colsum(g, r=shuffle_r), bias, perm) * alpha
+            gb = _unpad_bias_grad(gbp, bias, perm) * alpha
         if ctx.needs_input_grad[0]:
             wpt = _packed(weight, 'dgrad', n_pad, k_pad, perm_out=perm)
             gx = raw.tapgemm(g, wpt, ksize=ksize, cout=k_pad, alpha=alpha, flip=True, src_r=shuffle_r)
@@ -215,6 +219,11 @@ class _ResBlockNoBN(Function):
         s = ctx.res_scale
         cp = x.shape[-1]
         g = g.contiguous()
+        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 2 * cp + 32):
+            return _ResBlockNoBN._backward(ctx, g, x, h, w1, b1, w2, b2, s, cp)
+
+    @staticmethod
+    def _backward(ctx, g, x, h, w1, b1, w2, b2, s, cp):
         gw1 = gb1 = gw2 = gb2 = gx = None
         if ctx.needs_input_grad[3]:
             gw2 = raw.unpack_wgrad(raw.wgrad(g, h, ksize=3), w2.shape, alpha=s)
@@ -312,6 +321,11 @@ class _RCAB(Function):
         rs = ctx.res_scale
         cp = x.shape[-1]
         g = g.contiguous()
+        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 2 * cp + x.shape[0] * cp + 64):
+            return _RCAB._backward(ctx, g, x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2, rs, cp)
+
+    @staticmethod
+    def _backward(ctx, g, x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2, rs, cp):
         gs = raw.channel_dot(g, t, scale=rs)                       # d s[b,c] = res_scale * sum_hw g * t
         gwa1, gba1, gwa2, gba2, gp = raw.ca_fc_bwd(gs, s, z, p, wa1.detach().contiguous(), wa2.detach().contiguous())
         gt = raw.ca_apply_bwd(g, s, gp, rs)                        # d t

@@ -41,8 +41,8 @@ def layernorm_bwd(gy, x, mean, rstd, gamma, c, gres=None):
     cp = x.shape[-1]
     t = x.numel() // cp
     gx = torch.empty_like(x)
-    gg = torch.zeros((c,), dtype=torch.float32, device=x.device)
-    gb = torch.zeros((c,), dtype=torch.float32, device=x.device)
+    gg = raw.zeros_f32((c,), x.device)
+    gb = raw.zeros_f32((c,), x.device)
     L.check(L.load().srb200_layernorm_bwd(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(gres), _ptr(gx),
                                           _ptr(gg), _ptr(gb), t, c, cp, _stream()), 'layernorm_bwd')
     return gx, gg, gb
@@ -72,7 +72,7 @@ def window_attention_bwd(qkv, gout, table, num_heads, ws, shift, scale):
     b, h, w, c3 = qkv.shape
     ca = c3 // 3
     gqkv = torch.empty_like(qkv)
-    gtable = torch.zeros_like(table)
+    gtable = raw.zeros_f32(tuple(table.shape), table.device)
     L.check(L.load().srb200_window_attention_bwd(_ptr(qkv), _ptr(gout), _ptr(table), _ptr(gqkv), _ptr(gtable), b, h, w,
                                                  num_heads, ca, ws, shift, float(scale), _stream()),
             'window_attention_bwd')
@@ -165,6 +165,19 @@ class _SwinBlock(Function):
         p_qkv = head_perm(num_heads, hd, 3, dev)
         p_o = head_perm(num_heads, hd, 1, dev)
         g2 = g2.contiguous()
+        arena = raw.zero_arena(dev, 2 * cs * ch + cs * ca + 3 * ca * cs + 2 * cs + ch + 3 * ca + 4 * c +
+                               table.numel() + 64)
+        with arena:
+            return _SwinBlock._backward(ctx, g2, arena)
+
+    @staticmethod
+    def _backward(ctx, g2, arena):
+        (x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table, proj_w, proj_b, n2w,
+         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = ctx.saved_tensors
+        c, cs, ca, ch, hd, num_heads, ws, shift, scale = ctx.cfg
+        dev = x.device
+        p_qkv = head_perm(num_heads, hd, 3, dev)
+        p_o = head_perm(num_heads, hd, 1, dev)
         # ---- MLP branch
         g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
         g_fc2_w = raw.unpack_wgrad(raw.wgrad(g2s, h, ksize=1), fc2_w.shape)
