@@ -28,6 +28,7 @@ struct TapGemmParams {
   CUtensorMap tmap_out[9];  // output views for the TMA-store epilogue (out_r^2 views for the fused PixelShuffle)
   CUtensorMap tmap_aux;
   int tma_store;            // 1: bf16 results leave through smem staging + cp.async.bulk.tensor stores
+  unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (NULL = off)
   int B, H, W;
   int tile_w, tile_h, tiles_x, tiles_y;
   int m_tiles, n_tiles;
@@ -59,8 +60,10 @@ struct TapCfg {
   static constexpr int A_BYTES = BLOCK_M * 128;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // epilogue staging: 2 x [128 rows x 64 ch] bf16 tiles in the TMA 128B-swizzle layout
-  static constexpr int STORE_BYTES = BLOCK_N >= 64 ? 2 * 128 * 128 : 0;
+  // epilogue staging: NBUF x [128 rows x 64 ch] bf16 tiles in the TMA 128B-swizzle layout.  A bulk tensor
+  // store holds its buffer for ~1.4k cycles, so 4 buffers (where the operand ring leaves room) keep 3 in flight.
+  static constexpr int NBUF = (BLOCK_N >= 64 && BLOCK_N <= 192) ? 4 : 2;
+  static constexpr int STORE_BYTES = BLOCK_N >= 64 ? NBUF * 128 * 128 : 0;
   static constexpr int STAGES_RAW = (232448 - 1024 - 256 - 1024 - STORE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
@@ -146,10 +149,17 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int kchunks = p.kchunks_per_src * p.num_src;
+  // trace layout: [role 0..3][64 slots] (role 3: sub-phases of the epilogue of tile 5, warp 2 lane 0); role 0 producer (first TMA of tile issued), 1 MMA (tile start / all
+  // MMAs issued), 2 epilogue warp 2 (accumulator ready / tile drained)
+  unsigned long long* trc = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
+  auto stamp = [&](int role, int slot) {
+    if (trc != nullptr && slot < 64) trc[role * 64 + slot] = clock64();
+  };
+  if (threadIdx.x == 0) stamp(0, 63);
   const int num_kb = p.taps * kchunks;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (one elected lane)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -160,6 +170,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
         const int ty = (m_t / p.tiles_x) % p.tiles_y;
         const int b = m_t / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.tile_w, y0 = ty * p.tile_h, n0 = n_t * BLOCK_N;
+        stamp(0, (t - blockIdx.x) / gridDim.x);
         for (int tap = 0; tap < p.taps; ++tap) {
           int dy = 0, dx = 0;
           if (p.ksize == 3) {
@@ -197,6 +208,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        stamp(1, 2 * it);
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
@@ -215,6 +227,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           }
         }
         umma_commit(tfull_bar(acc));
+        stamp(1, 2 * it + 1);
       }
     }
   } else {
@@ -243,6 +256,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (issuer) stamp(2, 2 * it);
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
       const float al = p.alpha_b != nullptr ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
@@ -364,15 +378,17 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               buf_out = store_base + 16384;
               if (issuer) tma_store_wait_read<0>();
             } else {
-              buf_out = store_base + (store_iter & 1u) * 16384;
-              if (issuer) tma_store_wait_read<1>();
+              buf_out = store_base + (store_iter % Cfg::NBUF) * 16384;
+              if (issuer) tma_store_wait_read<Cfg::NBUF - 1>();
             }
             epi_sync();
+            if (issuer && it == 5) stamp(3, cc * 8 + 0);
             {
               const int hf = half;
               float v[CHUNK];
               const int col = cc * 64 + hf * 32;
               load_acc(col, v);
+              if (issuer && it == 5) stamp(3, cc * 8 + 1);
               if (has_aux) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -386,6 +402,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                 }
               }
               finish(v, out_offset(n0 + col));
+              if (issuer && it == 5) stamp(3, cc * 8 + 2);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint32_t dst = buf_out + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4);
@@ -397,8 +414,11 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                              : "memory");
               }
             }
+            if (issuer && it == 5) stamp(3, cc * 8 + 3);
             fence_proxy_async_smem();
+            if (issuer && it == 5) stamp(3, cc * 8 + 4);
             epi_sync();
+            if (issuer && it == 5) stamp(3, cc * 8 + 5);
             if (issuer) {
               const int nc = n0 + cc * 64;
               int view = 0, c0 = nc;
@@ -410,6 +430,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               if (has_aux) tma_store_4d(&p.tmap_aux, buf_aux, c0, x0, y0, b);
               tma_store_4d(&p.tmap_out[view], buf_out, c0, x0, y0, b);
               tma_store_commit();
+              if (it == 5) stamp(3, cc * 8 + 6);
             }
             ++store_iter;
           }
@@ -455,6 +476,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (issuer) stamp(2, 2 * it + 1);
     }
     if (use_tma && issuer) tma_store_wait_all<0>();  // smem must outlive the last bulk stores
   }
@@ -479,6 +501,8 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   tapgemm_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(p);
   return launch_status();
 }
+
+static unsigned long long* g_trace = nullptr;
 
 static int pick_block_n(int Cout) {
   if (Cout % 256 == 0) return 256;
@@ -560,6 +584,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.out_r = d->out_r;
   p.out_c = d->out_c;
   p.out_scale = d->out_scale;
+  p.trace = g_trace;
 
   // A views: in[B, H*r, W*r, Cin], view (i,j): element (b,y,x,c) at ((b*H*r + y*r+i)*W*r + x*r+j)*Cin + c
   const int r = d->src_r;
@@ -616,4 +641,10 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
     case 16: return launch_tapgemm<16>(p, stream);
   }
   return SRB200_EINVAL;
+}
+
+/* debug only: device buffer of 3*64 uint64 receiving CTA 0's per-role clock64 timeline of subsequent launches */
+extern "C" int srb200_debug_set_trace(void* dev_buf) {
+  g_trace = static_cast<unsigned long long*>(dev_buf);
+  return SRB200_OK;
 }

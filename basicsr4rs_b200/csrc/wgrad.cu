@@ -12,6 +12,7 @@
 // atomics into `acc` (zeroed by the caller), so any split count is legal.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -30,6 +31,8 @@ struct WgradParams {
   int m_tiles, n_tiles;
   int taps, ksize;
   int dy_c;      // channels per dY view (N / dy_r^2)
+  unsigned long long* trace;  // debug timeline of CTA 0 (NULL = off)
+  int exp_skip;  // debug: 1 = skip dY loads, 2 = skip X loads
 };
 
 template <int BLOCK_N>
@@ -72,6 +75,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int kb_begin = static_cast<int>((static_cast<long long>(p.total_kb) * split) / p.splits);
   const int kb_end = static_cast<int>((static_cast<long long>(p.total_kb) * (split + 1)) / p.splits);
   const int m0 = m_t * 128, n0 = n_t * BLOCK_N;
+  unsigned long long* trc = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
+  if (trc != nullptr && threadIdx.x == 0) trc[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_x);
@@ -96,38 +101,40 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
   if (warp == 0) {
-    if (lane == 0) {
-      int dy = 0, dx = 0;
-      if (p.ksize == 3) {
-        dy = tap / 3 - 1;
-        dx = tap % 3 - 1;
+    // TMA producer.  One cp.async.bulk.tensor costs its issuing thread ~170 cycles, so the 2 + BLOCK_N/64 boxes
+    // of a stage are issued by as many lanes in parallel (measured: 1070 -> MMA-bound cycles per k-block).
+    int dy = 0, dx = 0;
+    if (p.ksize == 3) {
+      dy = tap / 3 - 1;
+      dx = tap % 3 - 1;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int tx = kb % p.tiles_x;
+      const int ty = (kb / p.tiles_x) % p.tiles_y;
+      const int b = kb / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (lane == 0)
+        mbar_expect_tx(full_bar(stage), p.exp_skip == 1 ? Cfg::B_BYTES : p.exp_skip == 2 ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
+      __syncwarp();
+      if (lane < 2 && p.exp_skip == 1) {
+      } else if (lane >= 2 && p.exp_skip == 2) {
+      } else if (lane < 2) {
+        const int n = m0 + lane * 64;      // packed dY channel
+        const int view = n / p.dy_c;       // pixel-unshuffle view (0 when dy_r == 1)
+        const int c = n - view * p.dy_c;
+        // channels beyond N fall outside the tensor map and are zero-filled
+        tma_load_4d(smem_a(stage) + lane * 8192, &p.tmap_dy[n < p.N ? view : 0], full_bar(stage),
+                    n < p.N ? c : p.dy_c, x0, y0, b);
+      } else if (lane < 2 + BLOCK_N / 64) {
+        const int nb = lane - 2;
+        tma_load_4d(smem_b(stage) + nb * 8192, &p.tmap_x, full_bar(stage), n0 + nb * 64, x0 + dx, y0 + dy, b);
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int tx = kb % p.tiles_x;
-        const int ty = (kb / p.tiles_x) % p.tiles_y;
-        const int b = kb / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-#pragma unroll
-        for (int mb = 0; mb < 2; ++mb) {
-          const int n = m0 + mb * 64;        // packed dY channel
-          const int view = n / p.dy_c;       // pixel-unshuffle view (0 when dy_r == 1)
-          const int c = n - view * p.dy_c;
-          // channels beyond N fall outside the tensor map and are zero-filled
-          tma_load_4d(smem_a(stage) + mb * 8192, &p.tmap_dy[n < p.N ? view : 0], full_bar(stage),
-                      n < p.N ? c : p.dy_c, x0, y0, b);
-        }
-#pragma unroll
-        for (int nb = 0; nb < BLOCK_N / 64; ++nb)
-          tma_load_4d(smem_b(stage) + nb * 8192, &p.tmap_x, full_bar(stage), n0 + nb * 64, x0 + dx,
-                      y0 + dy, b);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
   } else if (warp == 1) {
@@ -138,6 +145,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
+        if (trc != nullptr && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
         const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         }
       }
       umma_commit(tfull_bar);
+      if (trc != nullptr) trc[1] = clock64();
     }
   } else {
     const int quarter = warp & 3;
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     if (kb_end > kb_begin) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
+      if (trc != nullptr && threadIdx.x == 64) trc[2] = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const int n = m0 + row;
       float* dst = p.acc + (static_cast<size_t>(tap) * p.N + n) * p.K + n0;
@@ -180,7 +190,179 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   }
   tc_fence_before();
   __syncthreads();
+  if (trc != nullptr && threadIdx.x == 64) trc[3] = clock64();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ 2-CTA variant (cta_group::2)
+// One CTA pair per work unit computes a 256 (out-ch) x 256 (in-ch) block: each CTA stages only ITS 128 output
+// channels of dY and ITS 128 input channels of X (32 KB / stage instead of 48 KB -> 6 stages instead of 4 and
+// 1/3 less L2->smem traffic per SM); the leader issues M=256 UMMAs that write both CTAs' TMEM.  The 1-CTA
+// kernel is load-latency bound (~1000 cycles per k-block vs 512 of MMA work); this one is not.
+struct Wg2Cfg {
+  static constexpr int A_BYTES = 128 * 128;   // own 128 out-ch: 2 boxes [64 px][64 ch]
+  static constexpr int B_BYTES = 128 * 128;   // own 128 in-ch : 2 boxes
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+    wgrad2_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = Wg2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 1);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  int u = blockIdx.x >> 1;  // work unit of the pair
+  const int split = u % p.splits;
+  u /= p.splits;
+  const int n_t = u % p.n_tiles;   // 256-wide in-channel tiles
+  u /= p.n_tiles;
+  const int m_t = u % p.m_tiles;   // 256-wide out-channel tiles
+  const int tap = u / p.m_tiles;
+  const int kb_begin = static_cast<int>((static_cast<long long>(p.total_kb) * split) / p.splits);
+  const int kb_end = static_cast<int>((static_cast<long long>(p.total_kb) * (split + 1)) / p.splits);
+  const int m0 = m_t * 256 + static_cast<int>(rank) * 128;  // this CTA's out channels
+  const int n0 = n_t * 256;                                 // the pair's in channels
+  const int nb0 = n0 + static_cast<int>(rank) * 128;        // this CTA's in channels (its half of B)
+  unsigned long long* trc = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
+  if (trc != nullptr && threadIdx.x == 0) trc[0] = clock64();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_x);
+    tma_prefetch_desc(&p.tmap_dy[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote signal can arrive
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    int dy = 0, dx = 0;
+    if (p.ksize == 3) {
+      dy = tap / 3 - 1;
+      dx = tap % 3 - 1;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      const int tx = kb % p.tiles_x;
+      const int ty = (kb / p.tiles_x) % p.tiles_y;
+      const int b = kb / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+      if (trc != nullptr && lane == 0 && kb - kb_begin < 20) trc[64 + 3 * (kb - kb_begin)] = clock64();
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (trc != nullptr && lane == 0 && kb - kb_begin < 20) trc[64 + 3 * (kb - kb_begin) + 1] = clock64();
+      // the leader's barrier collects the bytes of BOTH CTAs' loads
+      if (rank == 0 && lane == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+      __syncwarp();
+      if (lane < 2) {
+        const int n = m0 + lane * 64;
+        const int view = n / p.dy_c;
+        const int c = n - view * p.dy_c;
+        tma_load_4d_2cta(smem_a(stage) + lane * 8192, &p.tmap_dy[view], full_bar(stage), c, x0, y0, b);
+      } else if (lane < 4) {
+        const int nb = lane - 2;
+        tma_load_4d_2cta(smem_b(stage) + nb * 8192, &p.tmap_x, full_bar(stage), nb0 + nb * 64, x0 + dx, y0 + dy, b);
+      }
+      __syncwarp();
+      if (trc != nullptr && lane == 0 && kb - kb_begin < 20) trc[64 + 3 * (kb - kb_begin) + 2] = clock64();
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, 256, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (trc != nullptr && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
+        const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, 8192, 1024);
+          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, 8192, 1024);
+          umma_bf16_2cta(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit_2cta(tfull_bar);
+      if (trc != nullptr) trc[1] = clock64();
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    if (kb_end > kb_begin) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      float* dst = p.acc + (static_cast<size_t>(tap) * p.N + (m0 + row)) * p.K + n0;
+#pragma unroll 1
+      for (int c = 0; c < 256 / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + 4 * j), v);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be signalling our barriers / reading our TMEM allocation state
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+}
+
+static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Wg2Cfg::SMEM_BYTES) !=
+        cudaSuccess)
+      return SRB200_ELAUNCH;
+    configured = true;
+  }
+  const int grid = 2 * p.taps * p.m_tiles * p.n_tiles * p.splits;
+  wgrad2_kernel<<<grid, 192, Wg2Cfg::SMEM_BYTES, stream>>>(p);
+  return launch_status();
 }
 
 template <int BLOCK_N>
@@ -202,6 +384,12 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
 
 using namespace srb;
 
+static unsigned long long* g_wgrad_trace = nullptr;
+extern "C" int srb200_debug_set_wgrad_trace(void* dev_buf) {
+  g_wgrad_trace = static_cast<unsigned long long*>(dev_buf);
+  return SRB200_OK;
+}
+
 extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc, int B, int H,
                             int W, int N, int K, int ksize, int dy_r, srb200_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -218,11 +406,15 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   else bn = 64;
 
   WgradParams p;
+  p.trace = g_wgrad_trace;
   p.acc = acc;
   p.B = B;
   p.H = H;
   p.W = W;
   pick_tile(H, W, 64, &p.tile_w, &p.tile_h);
+  p.exp_skip = 0;
+  if (const char* e = getenv("SRB_WG_TILEW")) { p.tile_w = atoi(e); p.tile_h = 64 / p.tile_w; }
+  if (const char* e = getenv("SRB_WG_SKIP")) p.exp_skip = atoi(e);
   p.tiles_x = (W + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
   p.total_kb = B * p.tiles_x * p.tiles_y;
@@ -241,6 +433,17 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   while (splits > 1 && p.total_kb / splits < 8) --splits;
   p.splits = splits;
 
+  const bool two_cta = (N % 256 == 0) && (K % 256 == 0) && getenv("SRB_WGRAD_1CTA") == nullptr;
+  if (two_cta) {
+    p.m_tiles = N / 256;
+    p.n_tiles = K / 256;
+    const int units2 = p.taps * p.m_tiles * p.n_tiles;
+    int s2 = (num_sms() / 2) / units2;
+    if (s2 < 1) s2 = 1;
+    if (s2 > p.total_kb) s2 = p.total_kb;
+    while (s2 > 1 && p.total_kb / s2 < 8) --s2;
+    p.splits = s2;
+  }
   const uint32_t box[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
   {
     const uint64_t C = static_cast<uint64_t>(K);
@@ -266,6 +469,7 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
         if (rc != SRB200_OK) return rc;
       }
   }
+  if (two_cta) return launch_wgrad2(p, stream);
   switch (bn) {
     case 256: return launch_wgrad<256>(p, stream);
     case 192: return launch_wgrad<192>(p, stream);

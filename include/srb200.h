@@ -203,6 +203,11 @@ int srb200_window_attention_bwd(const void* qkv_bf16, const void* gout_bf16, con
 int srb200_act_bwd(const void* g_bf16, const void* y_bf16, void* out_bf16, int64_t n, float slope,
                    srb200_stream_t stream);
 
+/* debug only: device buffer of 3*64 uint64 that receives CTA 0's per-warp-role clock64 timeline of the
+ * following srb200_tapgemm launches (NULL switches it off). */
+int srb200_debug_set_trace(void* dev_buf);
+int srb200_debug_set_wgrad_trace(void* dev_buf); /* same for srb200_wgrad: 64 uint64 */
+
 #ifdef __cplusplus
 }
 #endif

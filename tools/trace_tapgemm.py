@@ -1,0 +1,39 @@
+"""Per-role clock64 timeline of CTA 0 for one tap-GEMM launch (debug aid)."""
+import ctypes, os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from basicsr4rs_b200 import _lib as L
+from basicsr4rs_b200.ops.sr_b200 import raw
+dev = torch.device('cuda:0')
+def run(name, b, h, w, cin, cout, ks, **kw):
+    x = torch.randn((b, h, w, cin), device=dev).to(torch.bfloat16)
+    wt = torch.randn((cout, cin, ks, ks), device=dev) * 0.02
+    wp = raw.pack_weight(wt, cout, cin); bias = torch.zeros(cout, device=dev)
+    for _ in range(3): raw.tapgemm(x, wp, ksize=ks, cout=cout, bias=bias, **kw)
+    buf = torch.zeros(4 * 64, dtype=torch.int64, device=dev)
+    L.load().srb200_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
+    raw.tapgemm(x, wp, ksize=ks, cout=cout, bias=bias, **kw)
+    torch.cuda.synchronize(); L.load().srb200_debug_set_trace(None)
+    t = buf.cpu().view(4, 64); t0 = int(t[0, 63])
+    rel = lambda v: (int(v) - t0) if int(v) else None
+    print(f'== {name}: cycles relative to kernel start (CTA 0)')
+    print(' producer tile starts :', [rel(v) for v in t[0, :12]])
+    print(' mma tile start/end   :', [(rel(t[1, 2*i]), rel(t[1, 2*i+1])) for i in range(12) if int(t[1, 2*i])])
+    print(' epi tile5 phases (sync, ld, math, sts, fence, sync2, issued) per chunk:', [[rel(v) for v in t[3, 8*c:8*c+7]] for c in range(4) if int(t[3, 8*c])])
+    print(' epi  acc ready/drained:', [(rel(t[2, 2*i]), rel(t[2, 2*i+1])) for i in range(12) if int(t[2, 2*i])])
+run('qkv 65536x192 -> 576', 16, 64, 64, 192, 576, 1)
+run('edsr body 256->256 48x48 relu', 16, 48, 48, 256, 256, 3, act=L.ACT_RELU)
+run('rcan 64->64 48x48', 16, 48, 48, 64, 64, 3)
+
+def run_wgrad(name, b, h, w, cin, cout, ks):
+    x = torch.randn((b, h, w, cin), device=dev).to(torch.bfloat16)
+    dy = torch.randn((b, h, w, cout), device=dev).to(torch.bfloat16)
+    for _ in range(3): raw.wgrad(dy, x, ksize=ks)
+    buf = torch.zeros(128, dtype=torch.int64, device=dev)
+    L.load().srb200_debug_set_wgrad_trace(ctypes.c_void_p(buf.data_ptr()))
+    raw.wgrad(dy, x, ksize=ks)
+    torch.cuda.synchronize(); L.load().srb200_debug_set_wgrad_trace(None)
+    t = buf.cpu(); t0 = int(t[0]); rel = lambda v: int(v) - t0 if int(v) else None
+    print(f'== wgrad {name}: mma issued-all {rel(t[1])}, acc ready {rel(t[2])}, cta end {rel(t[3])}')
+    print('   k-block ready times:', [rel(v) for v in t[8:48]])
+    print('   producer (before wait, after wait, after issue):', [(rel(t[64+3*i]), rel(t[65+3*i]), rel(t[66+3*i])) for i in range(20)])
+run_wgrad('edsr body 256x256 48x48', 16, 48, 48, 256, 256, 3)
