@@ -29,7 +29,14 @@ class TapGemmDesc(ctypes.Structure):
 
 class TapGemmExt(ctypes.Structure):
     """Mirror of ``srb200_tapgemm_ext``."""
-    _fields_ = [('residual_f32', c_void_p), ('out_f32', c_void_p), ('alpha_per_sample', c_void_p)]
+    _fields_ = [('residual_f32', c_void_p), ('out_f32', c_void_p), ('alpha_per_sample', c_void_p),
+                ('colsum', c_void_p)]
+
+
+# numpy mirror of ``srb200_pack_item`` (one row per weight of a batched pack / unpack launch)
+PACK_ITEM_FIELDS = [('src', '<i8'), ('dst', '<i8'), ('perm_out', '<i8'), ('perm_in', '<i8'), ('Co', '<i8'),
+                    ('Ci', '<i8'), ('taps', '<i8'), ('Np', '<i8'), ('Kp', '<i8'), ('transpose', '<i8'),
+                    ('chunk_begin', '<i8'), ('alpha', '<f4'), ('reserved', '<i4')]
 
 
 # every symbol include/srb200.h declares: name -> (restype, argtypes)
@@ -52,6 +59,8 @@ SIGNATURES = {
                                    c_void_p]),
     'srb200_unpack_wgrad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                     c_float, c_void_p]),
+    'srb200_pack_weights': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    'srb200_unpack_wgrads': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     'srb200_tapgemm': (c_int, [POINTER(TapGemmDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, POINTER(TapGemmExt), c_void_p]),
     'srb200_wgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

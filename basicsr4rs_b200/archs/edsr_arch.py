@@ -86,7 +86,7 @@ class EDSR(ArchMixin, nn.Module):
         segs.append(Segment(self._tail, [self.conv_after_body, self.upsample, self.conv_last]))
         return segs
 
-    def forward(self, x):
+    def _forward(self, x):
         require_cuda(x, 'EDSR')
         if self.cuda_graph and self.training and torch.is_grad_enabled():
             graphs = GRAPHS.get(self)
@@ -100,7 +100,7 @@ class EDSR(ArchMixin, nn.Module):
                     return call(nseg - 1, res, first)
 
                 self._device_mean(x)
-                graphs = GRAPHS[self] = GraphedSegments(self._build_segments, wire)
+                graphs = GRAPHS[self] = GraphedSegments(self._build_segments, wire, book=self._pack_book())
             out = graphs(x.contiguous().float(), True)
             return out if out.dtype == x.dtype else out.to(x.dtype)
         first = self._head(x)

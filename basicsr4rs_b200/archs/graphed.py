@@ -14,10 +14,12 @@ import torch
 from torch import nn as nn
 
 from .. import _lib as L
+from ..ops.sr_b200.sr_b200 import PackBook, pack_book
 
 # arch instance -> GraphedSegments; kept outside the module so that copy.deepcopy (EMA copy, sr_model.py:51),
 # state_dict and pickling never see CUDA graph objects
 GRAPHS = weakref.WeakKeyDictionary()
+BOOKS = weakref.WeakKeyDictionary()  # arch instance -> PackBook (bf16 GEMM operands of all its weights)
 
 
 def capturing():
@@ -31,8 +33,13 @@ class Segment(nn.Module):
         super().__init__()
         self.mods = nn.ModuleList(modules)
         self._fn = fn
+        self.book = None  # set on the FIRST segment: its forward graph starts with the batched weight repack
 
     def forward(self, *tensors):
+        if self.book is not None:
+            with pack_book(self.book):
+                self.book.refresh()
+                return self._fn(*tensors)
         return self._fn(*tensors)
 
 
@@ -44,9 +51,10 @@ class GraphedSegments:
 
     WARMUP = 3
 
-    def __init__(self, build_segments, wire):
+    def __init__(self, build_segments, wire, book=None):
         self._build = build_segments
         self._wire = wire
+        self._book = book
         self._cache = {}
         self.kernels_per_step = {}
 
@@ -62,6 +70,7 @@ class GraphedSegments:
         for s in segs:
             s.train(training)
         record = {}
+        segs[0].book = self._book
 
         def eager_call(i, *args):
             record[i] = args
@@ -74,6 +83,23 @@ class GraphedSegments:
         sample_args = tuple(
             tuple(a.detach().clone().requires_grad_(a.dtype == torch.bfloat16 and i > 0) for a in record[i])
             for i in range(len(segs)))
+        if self._book is not None:
+            # one warm-up forward+backward of every segment (side stream, like make_graphed_callables' own
+            # warm-up) so that every packed operand -- fprop and dgrad layouts -- is registered in the PackBook
+            # and the device table of pack items exists before anything is captured
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for seg, args in zip(segs, sample_args):
+                    outs = seg(*args)
+                    outs = tuple(o for o in (outs if isinstance(outs, tuple) else (outs,)) if o.requires_grad)
+                    ins = [a for a in args if a.requires_grad] + [p for p in seg.parameters() if p.requires_grad]
+                    if training and outs and ins:
+                        torch.autograd.grad(outs, ins, [torch.ones_like(o) for o in outs], allow_unused=True)
+                    del outs
+                self._book.refresh(force=True)
+            torch.cuda.current_stream().wait_stream(side)
+            self._book.capture_ok = True
         n0 = L.launch_count
         graphed = torch.cuda.make_graphed_callables(tuple(segs), sample_args, num_warmup_iters=self.WARMUP)
         self.kernels_per_step[key] = (L.launch_count - n0) // (self.WARMUP + 1)
@@ -84,7 +110,7 @@ def graphed_forward(module, x, build_segments, wire):
     """Replay ``module``'s training forward/backward for input ``x`` from CUDA graphs (captured on first use)."""
     graphs = GRAPHS.get(module)
     if graphs is None:
-        graphs = GRAPHS[module] = GraphedSegments(build_segments, wire)
+        graphs = GRAPHS[module] = GraphedSegments(build_segments, wire, book=module._pack_book())
     return graphs(x.contiguous().float(), True)
 
 
@@ -149,3 +175,15 @@ class ArchMixin:
         out = super()._apply(fn, *args, **kwargs)
         precapture(self)
         return out
+
+    def _pack_book(self):
+        book = BOOKS.get(self)
+        if book is None:
+            book = BOOKS[self] = PackBook()
+        return book
+
+    def forward(self, x):
+        """nn.Module contract of the reference archs (NCHW float in / out); every packed weight requested below
+        belongs to this network's :class:`PackBook`."""
+        with pack_book(self._pack_book()):
+            return self._forward(x)

@@ -145,7 +145,7 @@ class RCAN(ArchMixin, nn.Module):
         segs.append(Segment(self._tail, [self.conv_after_body, self.upsample, self.conv_last]))
         return segs
 
-    def forward(self, x):
+    def _forward(self, x):
         require_cuda(x, 'RCAN')
         if self.cuda_graph and self.training and torch.is_grad_enabled():
             self._device_mean(x)

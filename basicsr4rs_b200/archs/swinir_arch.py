@@ -444,7 +444,7 @@ class SwinIR(ArchMixin, nn.Module):
         segs.append(Segment(self._tail, tail_mods))
         return segs
 
-    def forward(self, x):
+    def _forward(self, x):
         require_cuda(x, 'SwinIR')
         if self.cuda_graph and self.training and torch.is_grad_enabled() and self.upsampler == 'pixelshuffle':
             nseg = len(split_even(list(self.layers), self.graph_segments)) + 1

@@ -316,6 +316,78 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __rest
   }
 }
 
+// Batched variants: ONE launch packs (or unpacks) every weight of a network.  `items` is a device table; item i
+// owns the 256-pair chunks [chunk_begin_i, chunk_begin_{i+1}) of the flattened work list, so a block never
+// straddles two items and finds its item with a binary search over `chunk_begin`.
+__device__ __forceinline__ int find_item(const srb200_pack_item* __restrict__ items, int n_items, long long chunk) {
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&items[mid].chunk_begin) <= chunk) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const srb200_pack_item* __restrict__ items, int n_items,
+                                                           long long total_chunks) {
+  __shared__ int s_item;
+  for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    if (threadIdx.x == 0) s_item = find_item(items, n_items, chunk);
+    __syncthreads();
+    const srb200_pack_item it = items[s_item];
+    __syncthreads();
+    const int Np = static_cast<int>(it.Np), Kp = static_cast<int>(it.Kp), Co = static_cast<int>(it.Co),
+              Ci = static_cast<int>(it.Ci), taps = static_cast<int>(it.taps);
+    const size_t pairs = static_cast<size_t>(Np) * Kp;
+    const size_t idx = static_cast<size_t>(chunk - it.chunk_begin) * 256 + threadIdx.x;
+    if (idx >= pairs) continue;
+    int n, k;
+    if (!it.transpose) {
+      n = static_cast<int>(idx / Kp);
+      k = static_cast<int>(idx % Kp);
+    } else {
+      k = static_cast<int>(idx / Np);
+      n = static_cast<int>(idx % Np);
+    }
+    const int32_t* perm_out = reinterpret_cast<const int32_t*>(it.perm_out);
+    const int32_t* perm_in = reinterpret_cast<const int32_t*>(it.perm_in);
+    const int o = perm_out != nullptr ? perm_out[n] : (n < Co ? n : -1);
+    const int i = perm_in != nullptr ? perm_in[k] : (k < Ci ? k : -1);
+    const bool live = (o >= 0 && i >= 0);
+    const float* src = reinterpret_cast<const float*>(it.src) + (static_cast<size_t>(live ? o : 0) * Ci + (live ? i : 0)) * taps;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(it.dst);
+    for (int t = 0; t < taps; ++t)
+      out[static_cast<size_t>(t) * pairs + idx] = __float2bfloat16_rn(live ? __ldg(src + t) : 0.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrads_kernel(const srb200_pack_item* __restrict__ items, int n_items,
+                                                            long long total_chunks) {
+  __shared__ int s_item;
+  for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    if (threadIdx.x == 0) s_item = find_item(items, n_items, chunk);
+    __syncthreads();
+    const srb200_pack_item it = items[s_item];
+    __syncthreads();
+    const int Np = static_cast<int>(it.Np), Kp = static_cast<int>(it.Kp), Co = static_cast<int>(it.Co),
+              Ci = static_cast<int>(it.Ci), taps = static_cast<int>(it.taps);
+    const size_t pairs = static_cast<size_t>(Np) * Kp;
+    const size_t idx = static_cast<size_t>(chunk - it.chunk_begin) * 256 + threadIdx.x;
+    if (idx >= pairs) continue;
+    const int n = static_cast<int>(idx / Kp);
+    const int k = static_cast<int>(idx % Kp);
+    const int32_t* perm_out = reinterpret_cast<const int32_t*>(it.perm_out);
+    const int32_t* perm_in = reinterpret_cast<const int32_t*>(it.perm_in);
+    const int o = perm_out != nullptr ? perm_out[n] : (n < Co ? n : -1);
+    const int i = perm_in != nullptr ? perm_in[k] : (k < Ci ? k : -1);
+    if (o < 0 || i < 0) continue;
+    const float* acc = reinterpret_cast<const float*>(it.src);
+    float* dst = reinterpret_cast<float*>(it.dst) + (static_cast<size_t>(o) * Ci + i) * taps;
+    for (int t = 0; t < taps; ++t) dst[t] = it.alpha * __ldg(acc + static_cast<size_t>(t) * pairs + idx);
+  }
+}
+
 // ------------------------------------------------------------------ column sums (bias gradient)
 // dy [rows, C] bf16 -> out[view*C + c] += sum; view = pixel-unshuffle phase of the row (R > 1).
 // thread = one 8-channel group x one row lane; R*R register accumulator sets, one smem reduction and
@@ -560,6 +632,24 @@ extern "C" int srb200_unpack_wgrad(const float* acc, float* gw, int Co, int Ci, 
   const size_t work = static_cast<size_t>(Np) * Kp;
   unpack_wgrad_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       acc, gw, Co, Ci, taps, perm_out, Np, perm_in, Kp, alpha);
+  return launch_status();
+}
+
+extern "C" int srb200_pack_weights(const srb200_pack_item* items_dev, int n_items, int64_t total_chunks,
+                                   srb200_stream_t stream) {
+  if (!items_dev || n_items <= 0 || total_chunks <= 0) return SRB200_EINVAL;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  const int grid = static_cast<int>(total_chunks < cap ? total_chunks : cap);
+  pack_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(items_dev, n_items, total_chunks);
+  return launch_status();
+}
+
+extern "C" int srb200_unpack_wgrads(const srb200_pack_item* items_dev, int n_items, int64_t total_chunks,
+                                    srb200_stream_t stream) {
+  if (!items_dev || n_items <= 0 || total_chunks <= 0) return SRB200_EINVAL;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  const int grid = static_cast<int>(total_chunks < cap ? total_chunks : cap);
+  unpack_wgrads_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(items_dev, n_items, total_chunks);
   return launch_status();
 }
 

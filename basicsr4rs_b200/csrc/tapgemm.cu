@@ -16,6 +16,7 @@
 // = warp_idx % 4, and the two warps of a quarter split every 64-column chunk in halves.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -46,6 +47,7 @@ struct TapGemmParams {
   const float* residual_f32;  // optional fp32 residual (layout of out)
   float* out_f32;             // optional fp32 copy of the result (layout of out)
   const float* alpha_b;       // optional per-sample scale [B] (stochastic depth)
+  float* colsum;              // optional fp32 [Cout]: += column sums of the stored result (bias gradient)
   int act;
   float act_slope, alpha;
   int mask_mode;
@@ -54,11 +56,15 @@ struct TapGemmParams {
   float out_scale;
 };
 
-template <int BLOCK_N>
+// TWO = CTA pair (cluster of 2, tcgen05 cta_group::2): one M=256 tile per pair, every CTA stages its own 128
+// rows of A but only HALF of B -- 32 KB instead of 48 KB of TMA traffic per 512-cycle k-block (N=256), which is
+// what a single SM's TMA path cannot sustain (measured ~80 B/cycle/SM: 616 cycles per k-block with one CTA).
+template <int BLOCK_N, bool TWO = false>
 struct TapCfg {
   static constexpr int BLOCK_M = 128;
   static constexpr int A_BYTES = BLOCK_M * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_ROWS = TWO ? BLOCK_N / 2 : BLOCK_N;  // rows of the weight box this CTA loads
+  static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging: NBUF x [128 rows x 64 ch] bf16 tiles in the TMA 128B-swizzle layout.  A bulk tensor
   // store holds its buffer for ~1.4k cycles, so 4 buffers (where the operand ring leaves room) keep 3 in flight.
@@ -99,9 +105,25 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
-template <int BLOCK_N>
+// Column sums over the 32 rows a warp owns: butterfly reduce-scatter (31 shuffles); lane l returns the sum of
+// column l.  w is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&w)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? w[i] : w[i + s];
+      const float keep = up ? w[i + s] : w[i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return w[0];
+}
+
+template <int BLOCK_N, bool TWO = false>
 __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
-  using Cfg = TapCfg<BLOCK_N>;
+  using Cfg = TapCfg<BLOCK_N, TWO>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CHUNK = Cfg::CHUNK;
 
@@ -121,6 +143,11 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // work units: one M tile (x N tile) per CTA, or one PAIR of consecutive M tiles per CTA pair
+  const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit0 = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_stride = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int m_units = TWO ? (p.m_tiles + 1) / 2 : p.m_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
@@ -133,29 +160,41 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), TWO ? 16 : 8);  // the leader's MMA thread waits for both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc_2cta(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / complete_tx
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = m_units * p.n_tiles;
   const int kchunks = p.kchunks_per_src * p.num_src;
-  // trace layout: [role 0..3][64 slots] (role 3: sub-phases of the epilogue of tile 5, warp 2 lane 0); role 0 producer (first TMA of tile issued), 1 MMA (tile start / all
+  // trace layout: [role 0..3][64 slots] (role 3: producer k-blocks of the first tile: before wait / after A issue); role 0 producer (first TMA of tile issued), 1 MMA (tile start / all
   // MMAs issued), 2 epilogue warp 2 (accumulator ready / tile drained)
   unsigned long long* trc = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
   auto stamp = [&](int role, int slot) {
     if (trc != nullptr && slot < 64) trc[role * 64 + slot] = clock64();
   };
   if (threadIdx.x == 0) stamp(0, 63);
+  if (p.trace != nullptr && threadIdx.x == 0) {  // per-CTA wall/cycle start (debug)
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[256 + 4 * blockIdx.x + 0] = gt;
+    p.trace[256 + 4 * blockIdx.x + 2] = clock64();
+  }
   const int num_kb = p.taps * kchunks;
 
   if (warp == 0) {
@@ -163,14 +202,15 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = unit0; t < total_tiles; t += unit_stride) {
         const int n_t = t % p.n_tiles;
-        const int m_t = t / p.n_tiles;
+        const int m_t = TWO ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
         const int tx = m_t % p.tiles_x;
         const int ty = (m_t / p.tiles_x) % p.tiles_y;
-        const int b = m_t / (p.tiles_x * p.tiles_y);
+        const int b = m_t / (p.tiles_x * p.tiles_y);  // == B for the missing half of an odd last pair: zero fill
         const int x0 = tx * p.tile_w, y0 = ty * p.tile_h, n0 = n_t * BLOCK_N;
-        stamp(0, (t - blockIdx.x) / gridDim.x);
+        stamp(0, (t - unit0) / unit_stride);
+        int kbi = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           int dy = 0, dx = 0;
           if (p.ksize == 3) {
@@ -181,13 +221,27 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               dx = -dx;
             }
           }
-          for (int kc = 0; kc < kchunks; ++kc) {
-            const int src = kc / p.kchunks_per_src;
-            const int c0 = (kc - src * p.kchunks_per_src) * 64;
+          int src = 0, c0 = 0;
+          for (int kc = 0; kc < kchunks; ++kc, ++kbi) {
+            if (t == unit0 && kbi < 16) stamp(3, 2 * kbi);
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-            tma_load_4d(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
-            tma_load_2d(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64, tap * p.Cout + n0);
+            if constexpr (TWO) {
+              // the leader's barrier collects the bytes of BOTH CTAs' loads
+              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+              tma_load_4d_2cta(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
+              tma_load_2d_2cta(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64,
+                               tap * p.Cout + n0 + rank * Cfg::B_ROWS);
+            } else {
+              mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+              tma_load_4d(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
+              tma_load_2d(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64, tap * p.Cout + n0);
+            }
+            if (t == unit0 && kbi < 16) stamp(3, 2 * kbi + 1);
+            c0 += 64;
+            if (c0 == p.kchunks_per_src * 64) {
+              c0 = 0;
+              ++src;
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -198,12 +252,12 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TWO ? 256 : 128, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = unit0; t < total_tiles; t += unit_stride, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -218,15 +272,18 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_smem_desc_sw128(a0 + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(b0 + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TWO) umma_bf16_2cta(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if constexpr (TWO) umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));
+        if constexpr (TWO) umma_commit_2cta(tfull_bar(acc));
+        else umma_commit(tfull_bar(acc));
         stamp(1, 2 * it + 1);
       }
     }
@@ -242,16 +299,36 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     uint32_t store_iter = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    // bias-gradient column sums of this warp's (32 rows x 32 columns) of every 64-column chunk; kept in
+    // registers across the CTA's tiles when there is a single N tile, flushed with one 128-byte red per chunk
+    constexpr int NCH = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
+    float csum[NCH];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) csum[q] = 0.0f;
+    int csum_n0 = -1;
+    auto flush_colsum = [&]() {
+      if (csum_n0 < 0) return;
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        atomicAdd(p.colsum + csum_n0 + q * 64 + half * 32 + lane, csum[q]);
+        csum[q] = 0.0f;
+      }
+      csum_n0 = -1;
+    };
+    for (int t = unit0; t < total_tiles; t += unit_stride, ++it) {
       const int n_t = t % p.n_tiles;
-      const int m_t = t / p.n_tiles;
+      const int m_t = TWO ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
       const int tx = m_t % p.tiles_x;
       const int ty = (m_t / p.tiles_x) % p.tiles_y;
       const int b = m_t / (p.tiles_x * p.tiles_y);
       const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
       const int x = x0 + lx, y = y0 + ly;
       const int n0 = n_t * BLOCK_N;
-      const bool valid = (x < p.W) && (y < p.H);
+      const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
+      if (p.colsum != nullptr) {
+        if (csum_n0 != n0) flush_colsum();
+        csum_n0 = n0;
+      }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -259,7 +336,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       if (issuer) stamp(2, 2 * it);
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
-      const float al = p.alpha_b != nullptr ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
+      const float al = (p.alpha_b != nullptr && b < p.B) ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
       // bias of this N tile -> smem (every epilogue warp has passed the last barrier of the previous tile)
       for (int i = etid; i < BLOCK_N; i += 256) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.0f;
       epi_sync();
@@ -382,13 +459,11 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               if (issuer) tma_store_wait_read<Cfg::NBUF - 1>();
             }
             epi_sync();
-            if (issuer && it == 5) stamp(3, cc * 8 + 0);
             {
               const int hf = half;
               float v[CHUNK];
               const int col = cc * 64 + hf * 32;
               load_acc(col, v);
-              if (issuer && it == 5) stamp(3, cc * 8 + 1);
               if (has_aux) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -402,7 +477,17 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                 }
               }
               finish(v, out_offset(n0 + col));
-              if (issuer && it == 5) stamp(3, cc * 8 + 2);
+              if constexpr (CHUNK == 32) {
+                if (p.colsum != nullptr) {
+                  float w[32];
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) w[j] = valid ? v[j] : 0.0f;
+                  const float cs = warp_colsum32(w, lane);
+#pragma unroll
+                  for (int q = 0; q < NCH; ++q)
+                    if (q == cc) csum[q] += cs;
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint32_t dst = buf_out + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4);
@@ -414,11 +499,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                              : "memory");
               }
             }
-            if (issuer && it == 5) stamp(3, cc * 8 + 3);
             fence_proxy_async_smem();
-            if (issuer && it == 5) stamp(3, cc * 8 + 4);
             epi_sync();
-            if (issuer && it == 5) stamp(3, cc * 8 + 5);
             if (issuer) {
               const int nc = n0 + cc * 64;
               int view = 0, c0 = nc;
@@ -430,7 +512,6 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               if (has_aux) tma_store_4d(&p.tmap_aux, buf_aux, c0, x0, y0, b);
               tma_store_4d(&p.tmap_out[view], buf_out, c0, x0, y0, b);
               tma_store_commit();
-              if (it == 5) stamp(3, cc * 8 + 6);
             }
             ++store_iter;
           }
@@ -475,15 +556,58 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(tempty_bar(acc), 0);  // the leader CTA issues the MMAs
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (issuer) stamp(2, 2 * it + 1);
     }
+    if (p.colsum != nullptr) flush_colsum();
     if (use_tma && issuer) tma_store_wait_all<0>();  // smem must outlive the last bulk stores
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if constexpr (TWO) {
+    cluster_sync_all();  // the peer may still be signalling our barriers / the pair's TMEM is released together
+    if (warp == 2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  } else {
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[256 + 4 * blockIdx.x + 1] = gt;
+    p.trace[256 + 4 * blockIdx.x + 3] = clock64();
+  }
+}
+
+template <int BLOCK_N>
+static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
+  using Cfg = TapCfg<BLOCK_N, true>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg::SMEM_BYTES) != cudaSuccess)
+      return SRB200_ELAUNCH;
+    configured = true;
+  }
+  const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, tapgemm_kernel<BLOCK_N, true>, p) != cudaSuccess) return SRB200_ELAUNCH;
+  return launch_status();
 }
 
 template <int BLOCK_N>
@@ -572,6 +696,8 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.residual_f32 = ext ? ext->residual_f32 : nullptr;
   p.out_f32 = ext ? ext->out_f32 : nullptr;
   p.alpha_b = ext ? ext->alpha_per_sample : nullptr;
+  p.colsum = ext ? ext->colsum : nullptr;
+  if (p.colsum && (bn < 64 || d->out_mode != SRB200_OUT_NHWC)) return SRB200_EINVAL;
   if ((p.residual_f32 || p.out_f32) && d->out_mode == SRB200_OUT_NCHW_F32) return SRB200_EINVAL;
   if ((reinterpret_cast<uintptr_t>(p.residual_f32) | reinterpret_cast<uintptr_t>(p.out_f32)) & 15u)
     return SRB200_EINVAL;
@@ -602,11 +728,13 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
       const int rc = make_tmap_bf16(&p.tmap_a[i * r + j], base, 4, dims, strides, box);
       if (rc != SRB200_OK) return rc;
     }
+  // CTA pairs (cta_group::2) for the wide layers: each CTA loads half of the weight box
+  const bool two_cta = (bn == 256) && p.m_tiles >= 2 && getenv("SRB_TAPGEMM_1CTA") == nullptr;
   {
     const uint64_t K = static_cast<uint64_t>(p.num_src) * C;
     const uint64_t dims[2] = {K, static_cast<uint64_t>(p.taps) * d->Cout};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(two_cta ? bn / 2 : bn)};
     const int rc = make_tmap_bf16(&p.tmap_w, w_packed, 2, dims, strides, box);
     if (rc != SRB200_OK) return rc;
   }
@@ -633,6 +761,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
       }
     if (aux_out && ro != 1) return SRB200_EINVAL;
   }
+  if (two_cta) return launch_tapgemm2<256>(p, stream);
   switch (bn) {
     case 256: return launch_tapgemm<256>(p, stream);
     case 192: return launch_tapgemm<192>(p, stream);

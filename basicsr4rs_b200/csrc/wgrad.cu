@@ -199,18 +199,25 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
 // channels of dY and ITS 128 input channels of X (32 KB / stage instead of 48 KB -> 6 stages instead of 4 and
 // 1/3 less L2->smem traffic per SM); the leader issues M=256 UMMAs that write both CTAs' TMEM.  The 1-CTA
 // kernel is load-latency bound (~1000 cycles per k-block vs 512 of MMA work); this one is not.
+// KPIX = pixels (GEMM-K) per stage.  A cp.async.bulk.tensor costs its issuing lane 400-500 cycles when four
+// lanes issue at once, whatever the box size, so with 64-pixel stages (4 x 8 KB boxes) the producer, not the
+// tensor pipe, paces the loop (~980 cycles per 512-cycle k-block); 128-pixel stages move twice the bytes per
+// instruction.
+template <int KPIX>
 struct Wg2Cfg {
-  static constexpr int A_BYTES = 128 * 128;   // own 128 out-ch: 2 boxes [64 px][64 ch]
-  static constexpr int B_BYTES = 128 * 128;   // own 128 in-ch : 2 boxes
+  static constexpr int BOX_BYTES = KPIX * 128;      // one box: [KPIX px][64 ch]
+  static constexpr int A_BYTES = 2 * BOX_BYTES;     // own 128 out-ch
+  static constexpr int B_BYTES = 2 * BOX_BYTES;     // own 128 in-ch
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = KPIX == 64 ? 6 : 3;
   static constexpr int TMEM_COLS = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+template <int KPIX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     wgrad2_kernel(const __grid_constant__ WgradParams p) {
-  using Cfg = Wg2Cfg;
+  using Cfg = Wg2Cfg<KPIX>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -287,10 +294,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
         const int n = m0 + lane * 64;
         const int view = n / p.dy_c;
         const int c = n - view * p.dy_c;
-        tma_load_4d_2cta(smem_a(stage) + lane * 8192, &p.tmap_dy[view], full_bar(stage), c, x0, y0, b);
+        tma_load_4d_2cta(smem_a(stage) + lane * Cfg::BOX_BYTES, &p.tmap_dy[view], full_bar(stage), c, x0, y0, b);
       } else if (lane < 4) {
         const int nb = lane - 2;
-        tma_load_4d_2cta(smem_b(stage) + nb * 8192, &p.tmap_x, full_bar(stage), nb0 + nb * 64, x0 + dx, y0 + dy, b);
+        tma_load_4d_2cta(smem_b(stage) + nb * Cfg::BOX_BYTES, &p.tmap_x, full_bar(stage), nb0 + nb * 64, x0 + dx,
+                         y0 + dy, b);
       }
       __syncwarp();
       if (trc != nullptr && lane == 0 && kb - kb_begin < 20) trc[64 + 3 * (kb - kb_begin) + 2] = clock64();
@@ -310,9 +318,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
         if (trc != nullptr && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
         const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, 8192, 1024);
-          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, 8192, 1024);
+        for (int k = 0; k < KPIX / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, Cfg::BOX_BYTES, 1024);
+          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, Cfg::BOX_BYTES, 1024);
           umma_bf16_2cta(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
@@ -352,16 +360,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   if (warp == 2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
 }
 
+template <int KPIX>
 static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Wg2Cfg::SMEM_BYTES) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(wgrad2_kernel<KPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Wg2Cfg<KPIX>::SMEM_BYTES) != cudaSuccess)
       return SRB200_ELAUNCH;
     configured = true;
   }
   const int grid = 2 * p.taps * p.m_tiles * p.n_tiles * p.splits;
-  wgrad2_kernel<<<grid, 192, Wg2Cfg::SMEM_BYTES, stream>>>(p);
+  wgrad2_kernel<KPIX><<<grid, 192, Wg2Cfg<KPIX>::SMEM_BYTES, stream>>>(p);
   return launch_status();
 }
 
@@ -434,7 +443,27 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   p.splits = splits;
 
   const bool two_cta = (N % 256 == 0) && (K % 256 == 0) && getenv("SRB_WGRAD_1CTA") == nullptr;
+  int kpix = 64;
   if (two_cta) {
+    // 128-pixel stages when every split still gets a few of them
+    const char* e = getenv("SRB_WG2_KPIX");
+    kpix = e ? atoi(e) : 128;
+    if (kpix == 128) {
+      int tw, th;
+      pick_tile(H, W, 128, &tw, &th);
+      const int kb128 = B * ((W + tw - 1) / tw) * ((H + th - 1) / th);
+      const int units2 = p.taps * (N / 256) * (K / 256);
+      int s2 = (num_sms() / 2) / units2;
+      if (s2 < 1) s2 = 1;
+      if (kb128 / s2 < 6 && !e) kpix = 64;
+      if (kpix == 128) {
+        p.tile_w = tw;
+        p.tile_h = th;
+        p.tiles_x = (W + tw - 1) / tw;
+        p.tiles_y = (H + th - 1) / th;
+        p.total_kb = kb128;
+      }
+    }
     p.m_tiles = N / 256;
     p.n_tiles = K / 256;
     const int units2 = p.taps * p.m_tiles * p.n_tiles;
@@ -469,7 +498,7 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
         if (rc != SRB200_OK) return rc;
       }
   }
-  if (two_cta) return launch_wgrad2(p, stream);
+  if (two_cta) return kpix == 128 ? launch_wgrad2<128>(p, stream) : launch_wgrad2<64>(p, stream);
   switch (bn) {
     case 256: return launch_wgrad<256>(p, stream);
     case 192: return launch_wgrad<192>(p, stream);

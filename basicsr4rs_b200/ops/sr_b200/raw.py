@@ -182,16 +182,50 @@ def nhwc_to_nchw(x, c, shift=None, scale=1.0):
 
 
 # ------------------------------------------------------------------ weights
-def pack_weight(w, n_pad, k_pad, perm_out=None, perm_in=None, transpose=False):
+def pack_weight(w, n_pad, k_pad, perm_out=None, perm_in=None, transpose=False, out=None):
     """fp32 [Co, Ci, kh, kw] (or [Co, Ci]) -> bf16 [taps, n_pad, k_pad] (or [taps, k_pad, n_pad])."""
     _chk(w, 'w', torch.float32)
     co, ci = w.shape[0], w.shape[1]
     taps = w.numel() // (co * ci)
     shape = (taps, k_pad, n_pad) if transpose else (taps, n_pad, k_pad)
-    out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
     L.check(L.load().srb200_pack_weight(_ptr(w), co, ci, taps, _ptr(perm_out), n_pad, _ptr(perm_in), k_pad,
                                         int(transpose), _ptr(out), _stream()), 'pack_weight')
     return out
+
+
+def pack_items(rows, device):
+    """Device table of ``srb200_pack_item`` rows for :func:`pack_weights` / :func:`unpack_wgrads`.
+
+    ``rows``: dicts with src, dst (tensors), Co, Ci, taps, Np, Kp and optional perm_out, perm_in (int32 tensors),
+    transpose, alpha.  Returns (table tensor, n_items, total_chunks); keep the tensors of ``rows`` alive."""
+    import numpy as np
+    tab = np.zeros(len(rows), dtype=np.dtype(L.PACK_ITEM_FIELDS))
+    chunk = 0
+    for i, r in enumerate(rows):
+        tab[i]['src'] = r['src'].data_ptr()
+        tab[i]['dst'] = r['dst'].data_ptr()
+        tab[i]['perm_out'] = r['perm_out'].data_ptr() if r.get('perm_out') is not None else 0
+        tab[i]['perm_in'] = r['perm_in'].data_ptr() if r.get('perm_in') is not None else 0
+        for k in ('Co', 'Ci', 'taps', 'Np', 'Kp'):
+            tab[i][k] = int(r[k])
+        tab[i]['transpose'] = int(bool(r.get('transpose', False)))
+        tab[i]['alpha'] = float(r.get('alpha', 1.0))
+        tab[i]['chunk_begin'] = chunk
+        chunk += (int(r['Np']) * int(r['Kp']) + 255) // 256
+    t = torch.from_numpy(tab.view(np.uint8).reshape(len(rows), -1).copy()).to(device)
+    return t, len(rows), chunk
+
+
+def pack_weights(table, n_items, total_chunks):
+    """One launch: every fp32 weight of the table -> its bf16 GEMM operand (srb200_pack_weights)."""
+    L.check(L.load().srb200_pack_weights(_ptr(table), n_items, total_chunks, _stream()), 'pack_weights')
+
+
+def unpack_wgrads(table, n_items, total_chunks):
+    """One launch: every fp32 [taps, Np, Kp] accumulator of the table -> gradient in the parameter layout."""
+    L.check(L.load().srb200_unpack_wgrads(_ptr(table), n_items, total_chunks, _stream()), 'unpack_wgrads')
 
 
 def unpack_wgrad(acc, w_shape, perm_out=None, perm_in=None, alpha=1.0):
@@ -210,7 +244,7 @@ def unpack_wgrad(acc, w_shape, perm_out=None, perm_in=None, alpha=1.0):
 def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alpha=1.0, mask_src=None,
             mask_mode=L.MASK_NONE, mask_slope=0.0, residual=None, flip=False, src_r=1, out_mode=L.OUT_NHWC,
             out_r=1, out_c=0, out_scale=1.0, out_shift=None, want_aux=False, residual_f32=None, want_f32=False,
-            alpha_per_sample=None):
+            alpha_per_sample=None, want_colsum=False):
     """conv3x3 / conv1x1 / Linear on NHWC bf16 (see include/srb200.h: srb200_tapgemm)."""
     _chk(x, 'x', torch.bfloat16)
     _chk(wp, 'wp', torch.bfloat16)
@@ -236,19 +270,25 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
         assert bias.numel() == cout
     out32 = torch.empty(out.shape, dtype=torch.float32, device=x.device) if want_f32 else None
     ext = None
-    if residual_f32 is not None or want_f32 or alpha_per_sample is not None:
+    csum = None
+    if want_colsum:  # fp32 [cout] column sums of the stored result, accumulated by the epilogue (bias gradient)
+        if out_mode != L.OUT_NHWC or cout % 64 != 0:
+            raise RuntimeError('want_colsum needs a plain NHWC output with cout % 64 == 0')
+        csum = zeros_f32((cout,), x.device)
+    if residual_f32 is not None or want_f32 or alpha_per_sample is not None or csum is not None:
         for t, name in ((residual_f32, 'residual_f32'), (alpha_per_sample, 'alpha_per_sample')):
             if t is not None:
                 _chk(t, name, torch.float32)
         ext = ctypes.byref(L.TapGemmExt(residual_f32.data_ptr() if residual_f32 is not None else None,
                                         out32.data_ptr() if out32 is not None else None,
-                                        alpha_per_sample.data_ptr() if alpha_per_sample is not None else None))
+                                        alpha_per_sample.data_ptr() if alpha_per_sample is not None else None,
+                                        csum.data_ptr() if csum is not None else None))
     ev = PROBE.begin('tapgemm', (b, h, w, cin * src_r * src_r, cout, ksize)) if PROBE is not None else None
     L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),
                                     _ptr(out_shift), _ptr(out), _ptr(aux), ext, _stream()), 'tapgemm')
     if ev is not None:
         PROBE.end(ev)
-    res = (out,) + ((aux,) if want_aux else ()) + ((out32,) if want_f32 else ())
+    res = (out,) + ((aux,) if want_aux else ()) + ((out32,) if want_f32 else ()) + ((csum,) if want_colsum else ())
     return res if len(res) > 1 else out
 
 

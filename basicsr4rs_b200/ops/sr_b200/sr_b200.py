@@ -7,6 +7,9 @@ Inside a network every activation is an NHWC bf16 tensor whose channel count is 
 of 64 ("NHWC64"); nn.Parameters stay fp32 in the reference's OIHW / [out,in] layout and are repacked
 to bf16 GEMM operands on the fly (cached per parameter version, never stored in the state dict).
 """
+import threading
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -34,9 +37,130 @@ def shuffle_perm(c_feat, r, device):
     return _perm_cache[key]
 
 
+class PackBook:
+    """All bf16 GEMM operands of ONE network, repacked by ONE kernel launch per optimizer step.
+
+    A training step of EDSR-L touches 137 packed operands (fprop + dgrad layouts of 69 weights), RCAN 829;
+    packing them one launch each costs more than the packing itself (8-13 us per launch against ~65 us of HBM
+    traffic in total).  The book owns a persistent bf16 buffer per (weight, layout) and a device table of
+    ``srb200_pack_item`` rows; :meth:`refresh` re-derives every buffer from the live fp32 parameters with
+    ``srb200_pack_weights``.  Entries register themselves the first time an arch asks for them
+    (:func:`_packed`), so the book needs no knowledge of the architecture.
+
+    Eager mode: the first :func:`_packed` call that finds a parameter newer than its pack refreshes the whole
+    book.  CUDA-graph mode: the refresh launch is captured at the head of the first segment's forward graph
+    (archs/graphed.py) and the captured kernels read the persistent buffers.
+    """
+
+    def __init__(self):
+        self.entries = {}     # key -> [weakref(weight), buf, spec dict, tag]
+        self.table = None     # (device tensor, n_items, total_chunks)
+        self.table_ptrs = None
+        self.capture_ok = False   # set by the graph capture driver once the refresh launch is part of the graph
+
+    def _rows(self):
+        rows, ptrs = [], []
+        for key in list(self.entries):
+            wref, buf, spec, _ = self.entries[key]
+            w = wref()
+            if w is None:
+                del self.entries[key]
+                continue
+            rows.append(dict(spec, src=w, dst=buf))
+            ptrs.append(w.data_ptr())
+        return rows, ptrs
+
+    def get(self, weight, kind, n_pad, k_pad, perm_out, perm_in):
+        key = (id(weight), kind, n_pad, k_pad, id(perm_out) if perm_out is not None else 0,
+               id(perm_in) if perm_in is not None else 0)
+        e = self.entries.get(key)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if e is None or e[0]() is not weight:
+            if capturing:
+                return None
+            w = weight.detach()
+            if not w.is_contiguous():
+                return None
+            co, ci = w.shape[0], w.shape[1]
+            taps = w.numel() // (co * ci)
+            buf = raw.pack_weight(w, n_pad, k_pad, perm_out=perm_out, perm_in=perm_in, transpose=(kind == 'dgrad'))
+            spec = dict(Co=co, Ci=ci, taps=taps, Np=n_pad, Kp=k_pad, perm_out=perm_out, perm_in=perm_in,
+                        transpose=(kind == 'dgrad'))
+            self.entries[key] = [weakref.ref(weight), buf, spec, (weight.data_ptr(), weight._version)]
+            self.table = None
+            return buf
+        if capturing:
+            return e[1] if self.capture_ok else None
+        if e[3] != (weight.data_ptr(), weight._version):
+            self.refresh()
+        return e[1]
+
+    def refresh(self, force=False):
+        """Repack every entry whose parameter changed (all of them after an optimizer step) in one launch."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            if self.table is None:
+                raise RuntimeError('PackBook: the item table must be built before CUDA-graph capture')
+            raw.pack_weights(*self.table)
+            return
+        stale = force
+        ptrs = []
+        for key in list(self.entries):
+            e = self.entries[key]
+            w = e[0]()
+            if w is None:
+                del self.entries[key]
+                self.table = None
+                continue
+            tag = (w.data_ptr(), w._version)
+            if tag != e[3]:
+                stale = True
+                e[3] = tag
+            ptrs.append(tag[0])
+        if not self.entries or not (stale or self.table is None):
+            return
+        if self.table is None or ptrs != self.table_ptrs:
+            rows, self.table_ptrs = self._rows()
+            self._keep = rows  # keeps perm tensors / buffers referenced by raw pointers alive
+            self.table = raw.pack_items(rows, rows[0]['dst'].device)
+        if stale:
+            raw.pack_weights(*self.table)
+
+
+_book_tls = threading.local()
+
+
+class pack_book:
+    """``with pack_book(book):`` -- operands requested inside (an arch's forward) are owned by ``book``; the
+    backward of those layers finds the same book through the parameter."""
+
+    def __init__(self, book):
+        self.book = book
+
+    def __enter__(self):
+        self.prev = getattr(_book_tls, 'book', None)
+        _book_tls.book = self.book
+        return self.book
+
+    def __exit__(self, *exc):
+        _book_tls.book = self.prev
+        return False
+
+
 def _packed(weight, kind, n_pad, k_pad, perm_out=None, perm_in=None):
-    """bf16 GEMM operand of an fp32 parameter, cached on the parameter until it is modified in place
+    """bf16 GEMM operand of an fp32 parameter.  Inside an arch (``pack_book``) it lives in the arch's
+    :class:`PackBook`; otherwise it is cached on the parameter until the parameter is modified in place
     (optimizer step bumps ``_version``) or re-allocated (``.to(device)`` / deepcopy change ``data_ptr``)."""
+    book = getattr(_book_tls, 'book', None)
+    if book is None:
+        ref = weight.__dict__.get('_srb200_book')
+        book = ref() if ref is not None else None
+    else:
+        weight.__dict__['_srb200_book'] = weakref.ref(book)
+    if book is not None:
+        buf = book.get(weight, kind, n_pad, k_pad, perm_out, perm_in)
+        if buf is not None:
+            return buf
     if torch.cuda.is_current_stream_capturing():
         # inside a CUDA-graph capture the repack kernel must be part of the graph (it re-reads the live
         # parameter storage on every replay), so the host-side cache is bypassed
@@ -83,6 +207,30 @@ def _padded_bias(bias, n_pad, perm_out=None):
             return bp
         cache['b'] = bp
     return cache['b']
+
+
+# The bias gradient of a layer is the column sum of its dY, and dY is almost always the OUTPUT of the previous
+# backward tap-GEMM.  That kernel's epilogue can accumulate the column sums for free (``want_colsum``); the
+# producer parks them here and the consumer -- the very next backward function of a sequential trunk -- picks
+# them up by the identity of the gradient tensor's storage.  One slot per thread: anything else falls back to
+# the standalone colsum kernel.
+_colsum_tls = threading.local()
+
+
+def _stash_colsum(t, csum):
+    # the slot keeps `t` alive, so no other tensor can be handed its storage while the entry is valid
+    _colsum_tls.slot = (t, t._version, csum)
+
+
+def _colsum_of(g):
+    """fp32 column sums of the NHWC bf16 gradient ``g``: taken from the producer's epilogue when available."""
+    slot = getattr(_colsum_tls, 'slot', None)
+    _colsum_tls.slot = None
+    if slot is not None:
+        t, ver, csum = slot
+        if t.data_ptr() == g.data_ptr() and t.shape == g.shape and t.stride() == g.stride() and t._version == ver:
+            return csum
+    return raw.colsum(g)
 
 
 def _unpad_bias_grad(gb_packed, bias, perm_out=None):
@@ -165,22 +313,34 @@ class _ConvNHWC(Function):
         perm = ctx.perm
         g = g.contiguous()
         g_res = g if ctx.has_res else None
+        gbp = None
         if act is not None:
             assert act in ('relu', 'lrelu'), 'gelu backward goes through the fused MLP function'
             g = raw.act_bwd(g, y, slope if act == 'lrelu' else 0.0)
+        elif bias is not None and ctx.needs_input_grad[2] and shuffle_r == 1:
+            gbp = _colsum_of(g)
+        _colsum_tls.slot = None
         gx = gw = gb = None
-        with raw.zero_arena(x.device, ksize * ksize * n_pad * k_pad + n_pad + 32):
+        with raw.zero_arena(x.device, ksize * ksize * n_pad * k_pad + n_pad + k_pad + 32):
             if ctx.needs_input_grad[1]:
                 acc = raw.wgrad(g, x, ksize=ksize, dy_r=shuffle_r)
-            if bias is not None and ctx.needs_input_grad[2]:
+            if bias is not None and ctx.needs_input_grad[2] and gbp is None:
                 gbp = raw.colsum(g, r=shuffle_r)
-        if ctx.needs_input_grad[1]:
-            gw = raw.unpack_wgrad(acc, weight.shape, perm_out=perm, alpha=alpha)
-        if bias is not None and ctx.needs_input_grad[2]:
-            gb = _unpad_bias_grad(gbp, bias, perm) * alpha
-        if ctx.needs_input_grad[0]:
-            wpt = _packed(weight, 'dgrad', n_pad, k_pad, perm_out=perm)
-            gx = raw.tapgemm(g, wpt, ksize=ksize, cout=k_pad, alpha=alpha, flip=True, src_r=shuffle_r)
+            if ctx.needs_input_grad[1]:
+                gw = raw.unpack_wgrad(acc, weight.shape, perm_out=perm, alpha=alpha)
+            if bias is not None and ctx.needs_input_grad[2]:
+                gb = _unpad_bias_grad(gbp, bias, perm)
+                if alpha != 1.0:
+                    gb = gb * alpha
+            if ctx.needs_input_grad[0]:
+                wpt = _packed(weight, 'dgrad', n_pad, k_pad, perm_out=perm)
+                if ksize == 3 and k_pad % 64 == 0:
+                    # the layer below is a conv with a bias: hand it the column sums of its dY
+                    gx, cs = raw.tapgemm(g, wpt, ksize=ksize, cout=k_pad, alpha=alpha, flip=True, src_r=shuffle_r,
+                                         want_colsum=True)
+                    _stash_colsum(gx, cs)
+                else:
+                    gx = raw.tapgemm(g, wpt, ksize=ksize, cout=k_pad, alpha=alpha, flip=True, src_r=shuffle_r)
         return gx, gw, gb, g_res, None, None, None, None, None, None, None
 
 
@@ -219,25 +379,30 @@ class _ResBlockNoBN(Function):
         s = ctx.res_scale
         cp = x.shape[-1]
         g = g.contiguous()
-        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 2 * cp + 32):
+        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 3 * cp + 32):
             return _ResBlockNoBN._backward(ctx, g, x, h, w1, b1, w2, b2, s, cp)
 
     @staticmethod
     def _backward(ctx, g, x, h, w1, b1, w2, b2, s, cp):
         gw1 = gb1 = gw2 = gb2 = gx = None
+        if b2 is not None and ctx.needs_input_grad[4]:
+            gb2 = _colsum_of(g)[:b2.numel()] * s   # from the epilogue that produced g, when it did
+        _colsum_tls.slot = None
         if ctx.needs_input_grad[3]:
             gw2 = raw.unpack_wgrad(raw.wgrad(g, h, ksize=3), w2.shape, alpha=s)
-        if b2 is not None and ctx.needs_input_grad[4]:
-            gb2 = raw.colsum(g)[:b2.numel()] * s
-        # d(pre-activation of conv1) = dgrad_conv2(s*g) masked by relu'(h)
+        # d(pre-activation of conv1) = dgrad_conv2(s*g) masked by relu'(h); its column sums = conv1's bias gradient
+        want_gb1 = b1 is not None and ctx.needs_input_grad[2]
         gh = raw.tapgemm(g, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, alpha=s, flip=True, mask_src=h,
-                         mask_mode=L.MASK_SIGN, mask_slope=0.0)
+                         mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=want_gb1)
+        if want_gb1:
+            gh, cs = gh
+            gb1 = cs[:b1.numel()].clone()
         if ctx.needs_input_grad[1]:
             gw1 = raw.unpack_wgrad(raw.wgrad(gh, x, ksize=3), w1.shape)
-        if b1 is not None and ctx.needs_input_grad[2]:
-            gb1 = raw.colsum(gh)[:b1.numel()].clone()
         if ctx.needs_input_grad[0]:
-            gx = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g)
+            gx, cs = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g,
+                                 want_colsum=True)
+            _stash_colsum(gx, cs)
         return gx, gw1, gb1, gw2, gb2, None
 
 
@@ -321,7 +486,7 @@ class _RCAB(Function):
         rs = ctx.res_scale
         cp = x.shape[-1]
         g = g.contiguous()
-        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 2 * cp + x.shape[0] * cp + 64):
+        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 3 * cp + x.shape[0] * cp + 64):
             return _RCAB._backward(ctx, g, x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2, rs, cp)
 
     @staticmethod
@@ -331,10 +496,10 @@ class _RCAB(Function):
         gt = raw.ca_apply_bwd(g, s, gp, rs)                        # d t
         gw2 = raw.unpack_wgrad(raw.wgrad(gt, h, ksize=3), w2.shape)
         gb2 = raw.colsum(gt)[:b2.numel()].clone()
-        gh = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
-                         mask_mode=L.MASK_SIGN, mask_slope=0.0)
+        gh, cs = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
+                             mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=True)
+        gb1 = cs[:b1.numel()].clone()
         gw1 = raw.unpack_wgrad(raw.wgrad(gh, x, ksize=3), w1.shape)
-        gb1 = raw.colsum(gh)[:b1.numel()].clone()
         gx = None
         if ctx.needs_input_grad[0]:
             gx = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g)

@@ -88,6 +88,27 @@ int srb200_unpack_wgrad(const float* acc, float* gw, int Co, int Ci, int taps,
                         const int32_t* perm_out, int Np, const int32_t* perm_in, int Kp,
                         float alpha, srb200_stream_t stream);
 
+/* Batched pack / unpack: one launch for every weight of a network (hundreds of layers).  `items_dev` is a
+ * DEVICE array; item i covers 256-pair chunks [chunk_begin, chunk_begin + ceil(Np*Kp/256)) of the work list
+ * (chunk_begin ascending, starting at 0; total_chunks = their sum).  Pack: src = fp32 weight, dst = bf16
+ * operand (semantics of srb200_pack_weight).  Unpack: src = fp32 [taps][Np][Kp] accumulator, dst = fp32
+ * gradient in the parameter layout, scaled by alpha (semantics of srb200_unpack_wgrad).                  */
+typedef struct {
+  const void* src;
+  void* dst;
+  const int32_t* perm_out; /* device, or NULL */
+  const int32_t* perm_in;  /* device, or NULL */
+  int64_t Co, Ci, taps, Np, Kp;
+  int64_t transpose;       /* pack only */
+  int64_t chunk_begin;
+  float alpha;             /* unpack only */
+  int32_t reserved;
+} srb200_pack_item;
+int srb200_pack_weights(const srb200_pack_item* items_dev, int n_items, int64_t total_chunks,
+                        srb200_stream_t stream);
+int srb200_unpack_wgrads(const srb200_pack_item* items_dev, int n_items, int64_t total_chunks,
+                         srb200_stream_t stream);
+
 /* ------------------------------------------------------------------ tap-GEMM (conv3x3 / conv1x1 / Linear)
  * out[b,y,x,n] = epi( sum_{t,k} A[b, y+dy(t), x+dx(t), k] * Wp[t][n][k] )
  * TMA-fed tcgen05 implicit GEMM, fp32 accumulation in TMEM.  Replaces nn.Conv2d(…,3,1,1)
@@ -119,6 +140,9 @@ typedef struct {
   const float* residual_f32;     /* fp32 residual, layout of out: v += residual_f32 (fp32 skip stream)  */
   float* out_f32;                /* additionally store the fp32 result (layout of out)                  */
   const float* alpha_per_sample; /* [B] extra scale per batch sample (DropPath, swinir_arch.py:14-26)   */
+  float* colsum;                 /* fp32 [Cout], zeroed by the caller: += sum over pixels of the stored
+                                    result (the bias gradient of the layer that consumes `out` as dY);
+                                    SRB200_OUT_NHWC with Cout % 64 == 0 only                            */
 } srb200_tapgemm_ext;
 
 int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16, const void* w_packed,

@@ -273,3 +273,112 @@ def test_wgrad_unshuffle_view(cuda):
     _assert_close(gw, wr.grad, 2e-3)
     gb = raw.colsum(dy_hr, r=r)  # packed order (ij, c)
     _assert_close(gb, br.grad[perm.long()], 1e-3)
+
+
+# ------------------------------------------------------------------ fused column sums / batched pack
+@pytest.mark.parametrize('b,h,w,cin,cout,ks', [(3, 16, 8, 64, 256, 3), (1, 8, 16, 128, 512, 3), (5, 20, 13, 64, 256, 1),
+                                               (2, 48, 48, 256, 256, 3)])
+def test_tapgemm_cta_pairs(cuda, b, h, w, cin, cout, ks, monkeypatch):
+    """cta_group::2 path (Cout % 256 == 0): odd tile counts (the pair's second half is out of range), partial
+    tiles, several N tiles; bit-identical to the single-CTA kernel (same accumulation order)."""
+    raw, L = _raw(), _L()
+    x, wt, bias = _mk_conv(cuda, b, h, w, cin, cout, ks, seed=21)
+    xb = _nhwc_bf16(x, cin)
+    wp = raw.pack_weight(wt, cout, cin)
+    res = torch.randn((b, h, w, cout), device=cuda).to(torch.bfloat16)
+    out, cs = raw.tapgemm(xb, wp, ksize=ks, cout=cout, bias=bias, act=L.ACT_RELU, alpha=0.5, residual=res,
+                          want_colsum=True)
+    ref = F.relu(F.conv2d(xb.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias, padding=ks // 2))
+    ref = ref.permute(0, 2, 3, 1) * 0.5 + res.float()
+    _assert_close(out, ref)
+    monkeypatch.setenv('SRB_TAPGEMM_1CTA', '1')
+    out1, cs1 = raw.tapgemm(xb, wp, ksize=ks, cout=cout, bias=bias, act=L.ACT_RELU, alpha=0.5, residual=res,
+                            want_colsum=True)
+    assert torch.equal(out.view(torch.int16), out1.view(torch.int16))
+    _assert_close(cs, cs1, 1e-5)
+
+
+@pytest.mark.parametrize('b,h,w,cin,cout,ks', [(2, 16, 16, 64, 64, 3), (1, 20, 13, 128, 192, 3), (2, 48, 48, 256, 256, 3),
+                                               (3, 24, 24, 64, 512, 3), (2, 16, 16, 192, 384, 1)])
+def test_tapgemm_fused_colsum(cuda, b, h, w, cin, cout, ks):
+    """The epilogue's column sums (bias gradient of the consuming layer) equal the sums of the stored tensor,
+    also with partial tiles (20x13), several N tiles (512, 384) and a masked + residual epilogue."""
+    raw, L = _raw(), _L()
+    x, wt, _ = _mk_conv(cuda, b, h, w, cin, cout, ks, seed=11)
+    xb = _nhwc_bf16(x, cin)
+    wp = raw.pack_weight(wt, cout, cin)
+    res = torch.randn((b, h, w, cout), device=cuda).to(torch.bfloat16)
+    msk = torch.randn((b, h, w, cout), device=cuda).to(torch.bfloat16)
+    plain = raw.tapgemm(xb, wp, ksize=ks, cout=cout, alpha=0.5, mask_src=msk, mask_mode=L.MASK_SIGN, residual=res)
+    out, cs = raw.tapgemm(xb, wp, ksize=ks, cout=cout, alpha=0.5, mask_src=msk, mask_mode=L.MASK_SIGN, residual=res,
+                          want_colsum=True)
+    assert torch.equal(out.view(torch.int16), plain.view(torch.int16))
+    ref = out.float().sum((0, 1, 2))
+    tol = 4e-3 * out.float().abs().sum((0, 1, 2)).max().item()  # bf16 store rounding, summed
+    assert (cs - ref).abs().max().item() <= tol
+    _assert_close(cs, raw.colsum(out), 4e-3)
+
+
+def test_batched_pack_and_unpack(cuda):
+    """srb200_pack_weights / srb200_unpack_wgrads (one launch, many weights) == the per-weight entry points."""
+    raw = _raw()
+    g = torch.Generator(device='cpu').manual_seed(3)
+    p = torch.arange(256, device=cuda)
+    perm = ((p % 64) * 4 + p // 64).to(torch.int32)
+    pad_in = torch.cat([torch.arange(180), torch.full((12,), -1)]).to(torch.int32).to(cuda)
+    specs = [  # (co, ci, taps, Np, Kp, perm_out, perm_in, transpose)
+        (64, 64, 9, 64, 64, None, None, False), (64, 64, 9, 64, 64, None, None, True),
+        (256, 64, 9, 256, 64, perm, None, False), (256, 64, 9, 256, 64, perm, None, True),
+        (3, 64, 9, 16, 64, None, None, False), (360, 180, 1, 384, 192, None, pad_in, False),
+        (180, 180, 9, 192, 192, None, None, True), (256, 256, 9, 256, 256, None, None, False),
+    ]
+    ws, rows, refs = [], [], []
+    for co, ci, taps, Np, Kp, po, pi, tr in specs:
+        shape = (co, ci, 3, 3) if taps == 9 else (co, ci)
+        w = torch.randn(shape, generator=g).to(cuda)
+        ref = raw.pack_weight(w, Np, Kp, perm_out=po, perm_in=pi, transpose=tr)
+        dst = torch.full_like(ref, float('nan'))
+        ws.append(w)
+        refs.append(ref)
+        rows.append(dict(src=w, dst=dst, Co=co, Ci=ci, taps=taps, Np=Np, Kp=Kp, perm_out=po, perm_in=pi, transpose=tr))
+    raw.pack_weights(*raw.pack_items(rows, cuda))
+    for r, ref in zip(rows, refs):
+        assert torch.equal(r['dst'].view(torch.int16), ref.view(torch.int16))
+    # unpack: fp32 [taps, Np, Kp] accumulators -> parameter layout (zero where the perms have no source)
+    urows, urefs = [], []
+    for (co, ci, taps, Np, Kp, po, pi, tr), w in zip(specs, ws):
+        if tr:
+            continue
+        acc = torch.randn((taps, Np, Kp), generator=g).to(cuda)
+        urefs.append(raw.unpack_wgrad(acc, w.shape, perm_out=po, perm_in=pi, alpha=0.25))
+        urows.append(dict(src=acc, dst=torch.zeros_like(w), Co=co, Ci=ci, taps=taps, Np=Np, Kp=Kp, perm_out=po,
+                          perm_in=pi, alpha=0.25))
+    raw.unpack_wgrads(*raw.pack_items(urows, cuda))
+    for r, ref in zip(urows, urefs):
+        assert torch.equal(r['dst'], ref)
+
+
+def test_pack_book_tracks_optimizer_steps(cuda):
+    """EDSR eager: after an in-place weight update the next forward sees the new weights (one batched repack)."""
+    from basicsr4rs_b200 import _lib as L
+    from basicsr4rs_b200.archs import build_network
+    from basicsr4rs_b200.archs.graphed import BOOKS
+    torch.manual_seed(0)
+    net = build_network(dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=64, num_block=2, upscale=2)).to(cuda)
+    x = torch.rand((1, 3, 16, 16), device=cuda)
+    y0 = net(x)
+    y0.square().mean().backward()
+    book = BOOKS[net]
+    assert len(book.entries) >= 2 * 5  # fprop + dgrad operands live in the book
+    n0 = L.launch_count
+    y1 = net(x)  # nothing changed: no repack
+    assert torch.equal(y0, y1)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.mul_(0.5)
+    y2 = net(x)
+    assert not torch.equal(y0, y2)
+    ref = build_network(dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=64, num_block=2, upscale=2)).to(cuda)
+    ref.load_state_dict(net.state_dict())
+    assert torch.equal(ref(x), y2)  # a fresh network (fresh packs) agrees bit for bit
+    assert L.launch_count > n0

@@ -9,16 +9,23 @@ def run(name, b, h, w, cin, cout, ks, **kw):
     wt = torch.randn((cout, cin, ks, ks), device=dev) * 0.02
     wp = raw.pack_weight(wt, cout, cin); bias = torch.zeros(cout, device=dev)
     for _ in range(3): raw.tapgemm(x, wp, ksize=ks, cout=cout, bias=bias, **kw)
-    buf = torch.zeros(4 * 64, dtype=torch.int64, device=dev)
+    buf = torch.zeros(4 * 64 + 4 * 148, dtype=torch.int64, device=dev)
     L.load().srb200_debug_set_trace(ctypes.c_void_p(buf.data_ptr()))
     raw.tapgemm(x, wp, ksize=ks, cout=cout, bias=bias, **kw)
     torch.cuda.synchronize(); L.load().srb200_debug_set_trace(None)
-    t = buf.cpu().view(4, 64); t0 = int(t[0, 63])
+    full = buf.cpu(); t = full[:256].view(4, 64); t0 = int(t[0, 63])
+    c = full[256:].view(148, 4)
+    c = c[c[:, 0] > 0]
+    g0 = int(c[:, 0].min())
+    dur_ns = (c[:, 1] - c[:, 0]).float(); dur_clk = (c[:, 3] - c[:, 2]).float()
+    print(f'== {name}: {c.shape[0]} CTAs; start spread {int(c[:,0].max())-g0} ns; kernel wall (first start -> last end) {int(c[:,1].max())-g0} ns;'
+          f' CTA duration ns min/mean/max {dur_ns.min():.0f}/{dur_ns.mean():.0f}/{dur_ns.max():.0f}; clk min/mean/max {dur_clk.min():.0f}/{dur_clk.mean():.0f}/{dur_clk.max():.0f};'
+          f' eff GHz {(dur_clk/dur_ns).mean():.3f}')
     rel = lambda v: (int(v) - t0) if int(v) else None
     print(f'== {name}: cycles relative to kernel start (CTA 0)')
     print(' producer tile starts :', [rel(v) for v in t[0, :12]])
     print(' mma tile start/end   :', [(rel(t[1, 2*i]), rel(t[1, 2*i+1])) for i in range(12) if int(t[1, 2*i])])
-    print(' epi tile5 phases (sync, ld, math, sts, fence, sync2, issued) per chunk:', [[rel(v) for v in t[3, 8*c:8*c+7]] for c in range(4) if int(t[3, 8*c])])
+    print(' producer k-block (before wait, after A issue) tile 0:', [(rel(t[3, 2*i]), rel(t[3, 2*i+1])) for i in range(16) if int(t[3, 2*i])])
     print(' epi  acc ready/drained:', [(rel(t[2, 2*i]), rel(t[2, 2*i+1])) for i in range(12) if int(t[2, 2*i])])
 run('qkv 65536x192 -> 576', 16, 64, 64, 192, 576, 1)
 run('edsr body 256->256 48x48 relu', 16, 48, 48, 256, 256, 3, act=L.ACT_RELU)
