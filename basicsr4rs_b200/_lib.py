@@ -61,6 +61,7 @@ SIGNATURES = {
                                     c_float, c_void_p]),
     'srb200_pack_weights': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     'srb200_unpack_wgrads': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    'srb200_unpack_wgrads_inline': (c_int, [c_void_p, c_int, c_void_p]),
     'srb200_tapgemm': (c_int, [POINTER(TapGemmDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, POINTER(TapGemmExt), c_void_p]),
     'srb200_wgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -653,6 +653,55 @@ extern "C" int srb200_unpack_wgrads(const srb200_pack_item* items_dev, int n_ite
   return launch_status();
 }
 
+// Up to SRB200_MAX_INLINE_ITEMS items passed BY VALUE (kernel parameters): no device table, so the launch can be
+// recorded into a CUDA graph and the per-layer backward needs ONE launch for all its weight and bias gradients
+// (a bias gradient is the [Np x 1] case: src = fp32 column sums, taps = 1, Kp = Ci = 1).
+struct InlineItems {
+  srb200_pack_item it[SRB200_MAX_INLINE_ITEMS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) unpack_inline_kernel(const __grid_constant__ InlineItems tab, long long total_chunks) {
+  for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    srb200_pack_item it = tab.it[0];  // statically indexed, predicated copies: the table stays in param space
+#pragma unroll
+    for (int j = 1; j < SRB200_MAX_INLINE_ITEMS; ++j)
+      if (j < tab.n && tab.it[j].chunk_begin <= chunk) it = tab.it[j];
+    const int Kp = static_cast<int>(it.Kp), Co = static_cast<int>(it.Co), Ci = static_cast<int>(it.Ci),
+              taps = static_cast<int>(it.taps);
+    const size_t pairs = static_cast<size_t>(it.Np) * Kp;
+    const size_t idx = static_cast<size_t>(chunk - it.chunk_begin) * 256 + threadIdx.x;
+    if (idx >= pairs) continue;
+    const int n = static_cast<int>(idx / Kp);
+    const int k = static_cast<int>(idx % Kp);
+    const int o = it.perm_out != nullptr ? it.perm_out[n] : (n < Co ? n : -1);
+    const int ii = it.perm_in != nullptr ? it.perm_in[k] : (k < Ci ? k : -1);
+    if (o < 0 || ii < 0) continue;
+    const float* acc = reinterpret_cast<const float*>(it.src);
+    float* dst = reinterpret_cast<float*>(it.dst) + (static_cast<size_t>(o) * Ci + ii) * taps;
+    for (int t = 0; t < taps; ++t) dst[t] = it.alpha * __ldg(acc + static_cast<size_t>(t) * pairs + idx);
+  }
+}
+
+extern "C" int srb200_unpack_wgrads_inline(const srb200_pack_item* items_host, int n_items,
+                                           srb200_stream_t stream) {
+  if (!items_host || n_items <= 0 || n_items > SRB200_MAX_INLINE_ITEMS) return SRB200_EINVAL;
+  InlineItems tab;
+  tab.n = n_items;
+  long long chunk = 0;
+  for (int i = 0; i < n_items; ++i) {
+    tab.it[i] = items_host[i];
+    if (!tab.it[i].src || !tab.it[i].dst || tab.it[i].Np <= 0 || tab.it[i].Kp <= 0) return SRB200_EINVAL;
+    tab.it[i].chunk_begin = chunk;
+    chunk += (tab.it[i].Np * tab.it[i].Kp + 255) / 256;
+  }
+  for (int i = n_items; i < SRB200_MAX_INLINE_ITEMS; ++i) tab.it[i] = tab.it[0];
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  const int grid = static_cast<int>(chunk < cap ? chunk : cap);
+  unpack_inline_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(tab, chunk);
+  return launch_status();
+}
+
 extern "C" int srb200_colsum(const void* dy_bf16, float* out, int64_t rows, int C, int r, int Wf,
                              srb200_stream_t stream) {
   if (!dy_bf16 || !out || rows <= 0 || C <= 0 || C % 8 != 0 || r < 1 || r > 3) return SRB200_EINVAL;

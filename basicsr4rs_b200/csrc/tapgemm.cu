@@ -85,9 +85,12 @@ struct TapCfg {
 // instead of libdevice's branchy erff -- the GELU epilogues are ALU-bound otherwise.
 // Returns e = exp(-z^2) as well, which d/dx GELU needs anyway.
 __device__ __forceinline__ float erf_as(float z_signed, float& e) {
+  // MUFU.RCP / MUFU.EX2 directly: the IEEE-rounded __frcp_rn and the range-checked exp2f expand to ~40 more
+  // instructions per element, which made the GELU epilogues ALU-bound (18k instead of 9.5k cycles per tile)
   const float z = fabsf(z_signed);
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  e = exp2f(-1.4426950408889634f * z * z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     uint32_t store_iter = 0;
     int it = 0;
+    int bias_n0 = -1;
     // bias-gradient column sums of this warp's (32 rows x 32 columns) of every 64-column chunk; kept in
     // registers across the CTA's tiles when there is a single N tile, flushed with one 128-byte red per chunk
     constexpr int NCH = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
@@ -337,9 +341,14 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
       const float al = (p.alpha_b != nullptr && b < p.B) ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
-      // bias of this N tile -> smem (every epilogue warp has passed the last barrier of the previous tile)
-      for (int i = etid; i < BLOCK_N; i += 256) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.0f;
-      epi_sync();
+      // bias of this N tile -> smem (every epilogue warp has passed the last barrier of the previous tile); the
+      // launch grid is a multiple of n_tiles, so a CTA keeps its N tile for all its tiles and this runs once
+      if (bias_n0 != n0) {
+        if (it > 0) epi_sync();  // every warp is done reading the previous tile's bias
+        for (int i = etid; i < BLOCK_N; i += 256) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.0f;
+        epi_sync();
+        bias_n0 = n0;
+      }
 
       // element offset of (this thread's pixel, channel nc) in an NHWC tensor shaped like `out`
       auto out_offset = [&](int nc) -> size_t {
@@ -593,7 +602,8 @@ static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
-  const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
+  int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
+  if (pairs >= p.n_tiles) pairs -= pairs % p.n_tiles;  // a CTA pair keeps its N tile for all its work units
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(320);
@@ -621,7 +631,8 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
+  int grid = total < num_sms() ? total : num_sms();
+  if (grid >= p.n_tiles) grid -= grid % p.n_tiles;  // a CTA keeps its N tile (bias, weight columns) for all its tiles
   tapgemm_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(p);
   return launch_status();
 }

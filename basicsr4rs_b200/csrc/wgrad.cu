@@ -35,20 +35,24 @@ struct WgradParams {
   int exp_skip;  // debug: 1 = skip dY loads, 2 = skip X loads
 };
 
-template <int BLOCK_N>
+// KPIX = pixels (GEMM-K) per stage: a cp.async.bulk.tensor costs its issuing lane 400-500 cycles whatever the box
+// size (several lanes issuing at once), so small stages leave the loop TMA-issue-bound (~1000 cycles per 64-pixel
+// k-block whose MMAs take 128-512); bigger boxes move more bytes per instruction.
+template <int BLOCK_N, int KPIX = 64>
 struct WgCfg {
-  static constexpr int A_BYTES = 128 * 128;          // 2 boxes of [64 px][64 ch]
-  static constexpr int B_BYTES = BLOCK_N * 128;      // BLOCK_N/64 boxes
+  static constexpr int BOX_BYTES = KPIX * 128;           // one box: [KPIX px][64 ch]
+  static constexpr int A_BYTES = 2 * BOX_BYTES;          // 128 out-ch
+  static constexpr int B_BYTES = (BLOCK_N / 64) * BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KPIX = 64>
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using Cfg = WgCfg<BLOCK_N>;
+  using Cfg = WgCfg<BLOCK_N, KPIX>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -116,21 +120,22 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       const int b = kb / (p.tiles_x * p.tiles_y);
       const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
       mbar_wait(empty_bar(stage), phase ^ 1u);
-      if (lane == 0)
-        mbar_expect_tx(full_bar(stage), p.exp_skip == 1 ? Cfg::B_BYTES : p.exp_skip == 2 ? Cfg::A_BYTES : Cfg::STAGE_BYTES);
+      // the upper 64 output channels of the tile may not exist (N = 64): their half of A is never loaded --
+      // whatever the MMA makes of the stale smem lands in accumulator rows the epilogue never reads
+      const bool upper = (m0 + 64) < p.N;
+      if (lane == 0) mbar_expect_tx(full_bar(stage), upper ? Cfg::STAGE_BYTES : Cfg::STAGE_BYTES - Cfg::BOX_BYTES);
       __syncwarp();
-      if (lane < 2 && p.exp_skip == 1) {
-      } else if (lane >= 2 && p.exp_skip == 2) {
-      } else if (lane < 2) {
-        const int n = m0 + lane * 64;      // packed dY channel
-        const int view = n / p.dy_c;       // pixel-unshuffle view (0 when dy_r == 1)
-        const int c = n - view * p.dy_c;
-        // channels beyond N fall outside the tensor map and are zero-filled
-        tma_load_4d(smem_a(stage) + lane * 8192, &p.tmap_dy[n < p.N ? view : 0], full_bar(stage),
-                    n < p.N ? c : p.dy_c, x0, y0, b);
+      if (lane < 2) {
+        if (lane == 0 || upper) {
+          const int n = m0 + lane * 64;      // packed dY channel
+          const int view = n / p.dy_c;       // pixel-unshuffle view (0 when dy_r == 1)
+          const int c = n - view * p.dy_c;
+          tma_load_4d(smem_a(stage) + lane * Cfg::BOX_BYTES, &p.tmap_dy[view], full_bar(stage), c, x0, y0, b);
+        }
       } else if (lane < 2 + BLOCK_N / 64) {
         const int nb = lane - 2;
-        tma_load_4d(smem_b(stage) + nb * 8192, &p.tmap_x, full_bar(stage), n0 + nb * 64, x0 + dx, y0 + dy, b);
+        tma_load_4d(smem_b(stage) + nb * Cfg::BOX_BYTES, &p.tmap_x, full_bar(stage), n0 + nb * 64, x0 + dx, y0 + dy,
+                    b);
       }
       if (++stage == STAGES) {
         stage = 0;
@@ -148,9 +153,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         if (trc != nullptr && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
         const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, 8192, 1024);
-          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, 8192, 1024);
+        for (int k = 0; k < KPIX / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, Cfg::BOX_BYTES, 1024);
+          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, Cfg::BOX_BYTES, 1024);
           umma_bf16(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(stage));
@@ -374,18 +379,18 @@ static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
   return launch_status();
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KPIX>
 static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
-  using Cfg = WgCfg<BLOCK_N>;
+  using Cfg = WgCfg<BLOCK_N, KPIX>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, KPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess)
       return SRB200_ELAUNCH;
     configured = true;
   }
   const int grid = p.taps * p.m_tiles * p.n_tiles * p.splits;
-  wgrad_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
+  wgrad_kernel<BLOCK_N, KPIX><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
   return launch_status();
 }
 
@@ -422,8 +427,6 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   p.W = W;
   pick_tile(H, W, 64, &p.tile_w, &p.tile_h);
   p.exp_skip = 0;
-  if (const char* e = getenv("SRB_WG_TILEW")) { p.tile_w = atoi(e); p.tile_h = 64 / p.tile_w; }
-  if (const char* e = getenv("SRB_WG_SKIP")) p.exp_skip = atoi(e);
   p.tiles_x = (W + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
   p.total_kb = B * p.tiles_x * p.tiles_y;
@@ -444,6 +447,29 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
 
   const bool two_cta = (N % 256 == 0) && (K % 256 == 0) && getenv("SRB_WGRAD_1CTA") == nullptr;
   int kpix = 64;
+  if (!two_cta) {
+    // largest stage (pixels per k-block) that still leaves every split a few k-blocks
+    const char* e = getenv("SRB_WG_KPIX");
+    const int cand[3] = {bn == 64 ? 256 : 128, 128, 64};
+    for (int ci = 0; ci < 3; ++ci) {
+      const int kp = e ? atoi(e) : cand[ci];
+      if (kp != 64 && kp != 128 && !(kp == 256 && bn == 64)) break;
+      int tw, th;
+      pick_tile(H, W, kp, &tw, &th);
+      const int kbs = B * ((W + tw - 1) / tw) * ((H + th - 1) / th);
+      if (kp == 64 || e || kbs / splits >= 4 || (splits == 1 && kbs >= 2)) {
+        kpix = kp;
+        p.tile_w = tw;
+        p.tile_h = th;
+        p.tiles_x = (W + tw - 1) / tw;
+        p.tiles_y = (H + th - 1) / th;
+        p.total_kb = kbs;
+        if (p.splits > p.total_kb) p.splits = p.total_kb;
+        while (p.splits > 1 && p.total_kb / p.splits < 4) --p.splits;
+        break;
+      }
+    }
+  }
   if (two_cta) {
     // 128-pixel stages when every split still gets a few of them
     const char* e = getenv("SRB_WG2_KPIX");
@@ -500,10 +526,13 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   }
   if (two_cta) return kpix == 128 ? launch_wgrad2<128>(p, stream) : launch_wgrad2<64>(p, stream);
   switch (bn) {
-    case 256: return launch_wgrad<256>(p, stream);
-    case 192: return launch_wgrad<192>(p, stream);
-    case 128: return launch_wgrad<128>(p, stream);
-    case 64: return launch_wgrad<64>(p, stream);
+    case 256: return kpix == 128 ? launch_wgrad<256, 128>(p, stream) : launch_wgrad<256, 64>(p, stream);
+    case 192: return kpix == 128 ? launch_wgrad<192, 128>(p, stream) : launch_wgrad<192, 64>(p, stream);
+    case 128: return kpix == 128 ? launch_wgrad<128, 128>(p, stream) : launch_wgrad<128, 64>(p, stream);
+    case 64:
+      return kpix == 256   ? launch_wgrad<64, 256>(p, stream)
+             : kpix == 128 ? launch_wgrad<64, 128>(p, stream)
+                           : launch_wgrad<64, 64>(p, stream);
   }
   return SRB200_EINVAL;
 }

@@ -195,11 +195,7 @@ def pack_weight(w, n_pad, k_pad, perm_out=None, perm_in=None, transpose=False, o
     return out
 
 
-def pack_items(rows, device):
-    """Device table of ``srb200_pack_item`` rows for :func:`pack_weights` / :func:`unpack_wgrads`.
-
-    ``rows``: dicts with src, dst (tensors), Co, Ci, taps, Np, Kp and optional perm_out, perm_in (int32 tensors),
-    transpose, alpha.  Returns (table tensor, n_items, total_chunks); keep the tensors of ``rows`` alive."""
+def _item_table(rows):
     import numpy as np
     tab = np.zeros(len(rows), dtype=np.dtype(L.PACK_ITEM_FIELDS))
     chunk = 0
@@ -214,6 +210,47 @@ def pack_items(rows, device):
         tab[i]['alpha'] = float(r.get('alpha', 1.0))
         tab[i]['chunk_begin'] = chunk
         chunk += (int(r['Np']) * int(r['Kp']) + 255) // 256
+    return tab, chunk
+
+
+MAX_INLINE_ITEMS = 8
+
+
+def finalize_grads(items):
+    """All weight and bias gradients of one layer's backward in ONE launch (srb200_unpack_wgrads_inline).
+
+    ``items``: list of ('w', acc [taps,Np,Kp] fp32, w_shape, perm_out, perm_in, alpha) or
+    ('b', colsum [Np] fp32, n_bias, perm_out, alpha).  Returns the gradients in the parameter layouts."""
+    rows, outs = [], []
+    for it in items:
+        if it[0] == 'w':
+            _, acc, w_shape, perm_out, perm_in, alpha = it
+            taps, n_pad, k_pad = acc.shape
+            alloc = torch.zeros if (perm_out is not None or perm_in is not None) else torch.empty
+            g = alloc(tuple(w_shape), dtype=torch.float32, device=acc.device)
+            rows.append(dict(src=acc, dst=g, Co=w_shape[0], Ci=w_shape[1], taps=taps, Np=n_pad, Kp=k_pad,
+                             perm_out=perm_out, perm_in=perm_in, alpha=alpha))
+        else:
+            _, cs, n_bias, perm_out, alpha = it
+            alloc = torch.zeros if perm_out is not None else torch.empty
+            g = alloc((n_bias,), dtype=torch.float32, device=cs.device)
+            rows.append(dict(src=cs, dst=g, Co=n_bias, Ci=1, taps=1, Np=cs.numel(), Kp=1, perm_out=perm_out,
+                             alpha=alpha))
+        outs.append(g)
+    for i in range(0, len(rows), MAX_INLINE_ITEMS):
+        tab, _ = _item_table(rows[i:i + MAX_INLINE_ITEMS])
+        L.check(L.load().srb200_unpack_wgrads_inline(tab.ctypes.data_as(ctypes.c_void_p), len(tab), _stream()),
+                'unpack_wgrads_inline')
+    return outs
+
+
+def pack_items(rows, device):
+    """Device table of ``srb200_pack_item`` rows for :func:`pack_weights` / :func:`unpack_wgrads`.
+
+    ``rows``: dicts with src, dst (tensors), Co, Ci, taps, Np, Kp and optional perm_out, perm_in (int32 tensors),
+    transpose, alpha.  Returns (table tensor, n_items, total_chunks); keep the tensors of ``rows`` alive."""
+    import numpy as np
+    tab, chunk = _item_table(rows)
     t = torch.from_numpy(tab.view(np.uint8).reshape(len(rows), -1).copy()).to(device)
     return t, len(rows), chunk
 

@@ -326,12 +326,17 @@ class _ConvNHWC(Function):
                 acc = raw.wgrad(g, x, ksize=ksize, dy_r=shuffle_r)
             if bias is not None and ctx.needs_input_grad[2] and gbp is None:
                 gbp = raw.colsum(g, r=shuffle_r)
+            items = []
             if ctx.needs_input_grad[1]:
-                gw = raw.unpack_wgrad(acc, weight.shape, perm_out=perm, alpha=alpha)
+                items.append(('w', acc, weight.shape, perm, None, alpha))
             if bias is not None and ctx.needs_input_grad[2]:
-                gb = _unpad_bias_grad(gbp, bias, perm)
-                if alpha != 1.0:
-                    gb = gb * alpha
+                items.append(('b', gbp, bias.numel(), perm, alpha))
+            if items:
+                grads = raw.finalize_grads(items)
+                if ctx.needs_input_grad[1]:
+                    gw = grads[0]
+                if bias is not None and ctx.needs_input_grad[2]:
+                    gb = grads[-1]
             if ctx.needs_input_grad[0]:
                 wpt = _packed(weight, 'dgrad', n_pad, k_pad, perm_out=perm)
                 if ksize == 3 and k_pad % 64 == 0:
@@ -385,24 +390,34 @@ class _ResBlockNoBN(Function):
     @staticmethod
     def _backward(ctx, g, x, h, w1, b1, w2, b2, s, cp):
         gw1 = gb1 = gw2 = gb2 = gx = None
+        items = []
         if b2 is not None and ctx.needs_input_grad[4]:
-            gb2 = _colsum_of(g)[:b2.numel()] * s   # from the epilogue that produced g, when it did
+            items.append(('b', _colsum_of(g), b2.numel(), None, s))  # from the epilogue that produced g, if any
         _colsum_tls.slot = None
         if ctx.needs_input_grad[3]:
-            gw2 = raw.unpack_wgrad(raw.wgrad(g, h, ksize=3), w2.shape, alpha=s)
+            items.append(('w', raw.wgrad(g, h, ksize=3), w2.shape, None, None, s))
         # d(pre-activation of conv1) = dgrad_conv2(s*g) masked by relu'(h); its column sums = conv1's bias gradient
         want_gb1 = b1 is not None and ctx.needs_input_grad[2]
         gh = raw.tapgemm(g, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, alpha=s, flip=True, mask_src=h,
                          mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=want_gb1)
         if want_gb1:
             gh, cs = gh
-            gb1 = cs[:b1.numel()].clone()
+            items.append(('b', cs, b1.numel(), None, 1.0))
         if ctx.needs_input_grad[1]:
-            gw1 = raw.unpack_wgrad(raw.wgrad(gh, x, ksize=3), w1.shape)
+            items.append(('w', raw.wgrad(gh, x, ksize=3), w1.shape, None, None, 1.0))
         if ctx.needs_input_grad[0]:
             gx, cs = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g,
                                  want_colsum=True)
             _stash_colsum(gx, cs)
+        grads = iter(raw.finalize_grads(items)) if items else iter(())  # one launch for all four gradients
+        if b2 is not None and ctx.needs_input_grad[4]:
+            gb2 = next(grads)
+        if ctx.needs_input_grad[3]:
+            gw2 = next(grads)
+        if want_gb1:
+            gb1 = next(grads)
+        if ctx.needs_input_grad[1]:
+            gw1 = next(grads)
         return gx, gw1, gb1, gw2, gb2, None
 
 
@@ -438,10 +453,17 @@ class _ConvToImage(Function):
         # dL/d(conv out) = g * out_scale, as NHWC bf16 padded to 64 channels (GEMM K/N granularity)
         gn = raw.nchw_to_nhwc(g.contiguous().float(), 64, shift=None, scale=ctx.out_scale)
         gx = gw = gb = None
+        items = []
         if ctx.needs_input_grad[1]:
-            gw = raw.unpack_wgrad(raw.wgrad(gn, x, ksize=ks), weight.shape)
+            items.append(('w', raw.wgrad(gn, x, ksize=ks), weight.shape, None, None, 1.0))
         if bias is not None and ctx.needs_input_grad[2]:
-            gb = raw.colsum(gn)[:cout].clone()
+            items.append(('b', raw.colsum(gn), cout, None, 1.0))
+        if items:
+            grads = raw.finalize_grads(items)
+            if ctx.needs_input_grad[1]:
+                gw = grads[0]
+            if bias is not None and ctx.needs_input_grad[2]:
+                gb = grads[-1]
         if ctx.needs_input_grad[0]:
             wpt = _packed(weight, 'dgrad', 64, k_pad)
             gx = raw.tapgemm(gn, wpt, ksize=ks, cout=k_pad, flip=True)
@@ -494,12 +516,13 @@ class _RCAB(Function):
         gs = raw.channel_dot(g, t, scale=rs)                       # d s[b,c] = res_scale * sum_hw g * t
         gwa1, gba1, gwa2, gba2, gp = raw.ca_fc_bwd(gs, s, z, p, wa1.detach().contiguous(), wa2.detach().contiguous())
         gt = raw.ca_apply_bwd(g, s, gp, rs)                        # d t
-        gw2 = raw.unpack_wgrad(raw.wgrad(gt, h, ksize=3), w2.shape)
-        gb2 = raw.colsum(gt)[:b2.numel()].clone()
-        gh, cs = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
-                             mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=True)
-        gb1 = cs[:b1.numel()].clone()
-        gw1 = raw.unpack_wgrad(raw.wgrad(gh, x, ksize=3), w1.shape)
+        acc2 = raw.wgrad(gt, h, ksize=3)
+        cs2 = raw.colsum(gt)
+        gh, cs1 = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
+                              mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=True)
+        acc1 = raw.wgrad(gh, x, ksize=3)
+        gw2, gb2, gw1, gb1 = raw.finalize_grads([('w', acc2, w2.shape, None, None, 1.0), ('b', cs2, b2.numel(), None, 1.0),
+                                                 ('w', acc1, w1.shape, None, None, 1.0), ('b', cs1, b1.numel(), None, 1.0)])
         gx = None
         if ctx.needs_input_grad[0]:
             gx = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g)

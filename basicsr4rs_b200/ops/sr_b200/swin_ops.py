@@ -180,24 +180,32 @@ class _SwinBlock(Function):
         p_o = head_perm(num_heads, hd, 1, dev)
         # ---- MLP branch
         g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
-        g_fc2_w = raw.unpack_wgrad(raw.wgrad(g2s, h, ksize=1), fc2_w.shape)
-        g_fc2_b = raw.colsum(g2s)[:fc2_b.numel()].clone()
-        ga = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
-                         mask_mode=L.MASK_DGELU)
-        g_fc1_w = raw.unpack_wgrad(raw.wgrad(ga, xn2, ksize=1), fc1_w.shape)
-        g_fc1_b = raw.colsum(ga)[:fc1_b.numel()].clone()
+        acc_fc2 = raw.wgrad(g2s, h, ksize=1)
+        cs_fc2 = raw.colsum(g2s)
+        ga, cs_fc1 = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
+                                 mask_mode=L.MASK_DGELU, want_colsum=True)  # column sums = fc1's bias gradient
+        acc_fc1 = raw.wgrad(ga, xn2, ksize=1)
         gxn2 = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True)
         gx1, g_n2w, g_n2b = layernorm_bwd(gxn2, x1, mean2, rstd2, n2w.detach(), c, gres=g2)
         # ---- attention branch
         g1s = scale_rows(gx1, alpha1) if alpha1 is not None else gx1
-        g_proj_w = raw.unpack_wgrad(raw.wgrad(g1s, o, ksize=1), proj_w.shape, perm_in=p_o)
-        g_proj_b = raw.colsum(g1s)[:proj_b.numel()].clone()
+        acc_proj = raw.wgrad(g1s, o, ksize=1)
+        cs_proj = raw.colsum(g1s)
         go = raw.tapgemm(g1s, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
         gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale)
-        g_qkv_w = raw.unpack_wgrad(raw.wgrad(gqkv, xn, ksize=1), qkv_w.shape, perm_out=p_qkv)
-        g_qkv_b = _unpad_bias_grad(raw.colsum(gqkv), qkv_b, p_qkv) if qkv_b is not None else None
+        acc_qkv = raw.wgrad(gqkv, xn, ksize=1)
         gxn = raw.tapgemm(gqkv, _packed(qkv_w, 'dgrad', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=cs, flip=True)
         gx, g_n1w, g_n1b = layernorm_bwd(gxn, x, mean1, rstd1, n1w.detach(), c, gres=gx1)
+        # ---- all eight parameter gradients of the four Linear layers leave through ONE launch
+        items = [('w', acc_fc2, fc2_w.shape, None, None, 1.0), ('b', cs_fc2, fc2_b.numel(), None, 1.0),
+                 ('w', acc_fc1, fc1_w.shape, None, None, 1.0), ('b', cs_fc1, fc1_b.numel(), None, 1.0),
+                 ('w', acc_proj, proj_w.shape, None, p_o, 1.0), ('b', cs_proj, proj_b.numel(), None, 1.0),
+                 ('w', acc_qkv, qkv_w.shape, p_qkv, None, 1.0)]
+        if qkv_b is not None:
+            items.append(('b', raw.colsum(gqkv), qkv_b.numel(), p_qkv, 1.0))
+        grads = raw.finalize_grads(items)
+        g_fc2_w, g_fc2_b, g_fc1_w, g_fc1_b, g_proj_w, g_proj_b, g_qkv_w = grads[:7]
+        g_qkv_b = grads[7] if qkv_b is not None else None
         return (gx, g_n1w, g_n1b, g_qkv_w, g_qkv_b, g_table, g_proj_w, g_proj_b, g_n2w, g_n2b, g_fc1_w, g_fc1_b,
                 g_fc2_w, g_fc2_b, None, None, None, None, None)
 

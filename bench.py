@@ -174,7 +174,7 @@ def main():
                              graph_input_shape=[BATCH, 3, LR, LR])).to(dev)  # graphs captured here, before DDP
     model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True) \
         if world > 1 else net
-    optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
     crit = nn.L1Loss()
 
     lq_h, gt_h = (t.pin_memory() for t in synthetic_batch(rank))

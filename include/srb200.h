@@ -108,6 +108,12 @@ int srb200_pack_weights(const srb200_pack_item* items_dev, int n_items, int64_t 
                         srb200_stream_t stream);
 int srb200_unpack_wgrads(const srb200_pack_item* items_dev, int n_items, int64_t total_chunks,
                          srb200_stream_t stream);
+/* Same as srb200_unpack_wgrads for up to SRB200_MAX_INLINE_ITEMS items given in HOST memory (copied into the
+ * kernel parameters; chunk_begin is computed by the library): all weight and bias gradients of one layer's
+ * backward in one launch, recordable into a CUDA graph.  A bias gradient is an item with taps = Kp = Ci = 1
+ * whose src is the fp32 column-sum vector.                                                                */
+#define SRB200_MAX_INLINE_ITEMS 8
+int srb200_unpack_wgrads_inline(const srb200_pack_item* items_host, int n_items, srb200_stream_t stream);
 
 /* ------------------------------------------------------------------ tap-GEMM (conv3x3 / conv1x1 / Linear)
  * out[b,y,x,n] = epi( sum_{t,k} A[b, y+dy(t), x+dx(t), k] * Wp[t][n][k] )

@@ -59,7 +59,7 @@ def main():
             continue
         torch.manual_seed(0)
         net = build_network(dict(opt, cuda_graph=not args.no_graph)).to(dev).train()
-        optim = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
+        optim = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
         lq = torch.rand((batch, 3, lr, lr), device=dev)
         gt = torch.rand((batch, 3, 4 * lr, 4 * lr), device=dev)
 

@@ -26,8 +26,12 @@ def run(name, b, h, w, cin, cout, ks, **kw):
     print(' producer tile starts :', [rel(v) for v in t[0, :12]])
     print(' mma tile start/end   :', [(rel(t[1, 2*i]), rel(t[1, 2*i+1])) for i in range(12) if int(t[1, 2*i])])
     print(' producer k-block (before wait, after A issue) tile 0:', [(rel(t[3, 2*i]), rel(t[3, 2*i+1])) for i in range(16) if int(t[3, 2*i])])
+    print(' epi tile 2 chunk phases (start, slot free, acc loaded, math done, staged, fenced, arrived):', [[rel(v) for v in t[3, 32+7*c:39+7*c]] for c in range(4) if int(t[3, 32+7*c])])
     print(' epi  acc ready/drained:', [(rel(t[2, 2*i]), rel(t[2, 2*i+1])) for i in range(12) if int(t[2, 2*i])])
 run('qkv 65536x192 -> 576', 16, 64, 64, 192, 576, 1)
+run('fc1 192->384 gelu+aux', 16, 64, 64, 192, 384, 1, act=L.ACT_GELU, want_aux=True)
+run('fc1 192->384 plain', 16, 64, 64, 192, 384, 1)
+run('fc1 192->384 gelu no aux', 16, 64, 64, 192, 384, 1, act=L.ACT_GELU)
 run('edsr body 256->256 48x48 relu', 16, 48, 48, 256, 256, 3, act=L.ACT_RELU)
 run('rcan 64->64 48x48', 16, 48, 48, 64, 64, 3)
 
