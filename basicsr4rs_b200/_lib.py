@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libsrb200.so')
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU = 0, 1, 2, 3
 OUT_NHWC, OUT_SHUFFLE, OUT_NCHW_F32 = 0, 1, 2
-MASK_NONE, MASK_SIGN, MASK_DGELU = 0, 1, 2
+MASK_NONE, MASK_SIGN, MASK_DGELU, MASK_MUL = 0, 1, 2, 3
 
 
 class TapGemmDesc(ctypes.Structure):
@@ -30,7 +30,7 @@ class TapGemmDesc(ctypes.Structure):
 class TapGemmExt(ctypes.Structure):
     """Mirror of ``srb200_tapgemm_ext``."""
     _fields_ = [('residual_f32', c_void_p), ('out_f32', c_void_p), ('alpha_per_sample', c_void_p),
-                ('colsum', c_void_p)]
+                ('aux_mode', ctypes.c_int32), ('reserved', ctypes.c_int32), ('colsum', c_void_p)]
 
 
 # numpy mirror of ``srb200_pack_item`` (one row per weight of a batched pack / unpack launch)

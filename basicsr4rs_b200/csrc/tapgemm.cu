@@ -33,6 +33,9 @@ struct TapGemmParams {
   int B, H, W;
   int tile_w, tile_h, tiles_x, tiles_y;
   int m_tiles, n_tiles;
+  // ceil(2^40 / d) for d = n_tiles, tiles_x, tiles_x * tiles_y: the per-tile index arithmetic of all three warp
+  // roles without the ~60-cycle integer division sequences (exact for operands < 2^20)
+  unsigned long long magic_n, magic_x, magic_xy;
   int kchunks_per_src;  // Cin / 64
   int num_src;          // src_r^2
   int Cout;             // packed N
@@ -48,6 +51,7 @@ struct TapGemmParams {
   float* out_f32;             // optional fp32 copy of the result (layout of out)
   const float* alpha_b;       // optional per-sample scale [B] (stochastic depth)
   float* colsum;              // optional fp32 [Cout]: += column sums of the stored result (bias gradient)
+  int aux_mode;               // 1: aux_out = act'(pre-activation) instead of the pre-activation (GELU only)
   int act;
   float act_slope, alpha;
   int mask_mode;
@@ -106,6 +110,18 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   float e;  // e = exp(-x^2/2)
   const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f, e));
   return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+// gelu(x) and gelu'(x) from one erf / exp evaluation (fc1 forward stores the derivative for the backward)
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& d) {
+  float e;
+  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f, e));
+  g = x * cdf;
+  d = fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+__device__ __forceinline__ int fast_div(int n, unsigned long long magic) {
+  return static_cast<int>(__umul64hi(static_cast<unsigned long long>(static_cast<unsigned>(n)) << 24, magic));
 }
 
 // Column sums over the 32 rows a warp owns: butterfly reduce-scatter (31 shuffles); lane l returns the sum of
@@ -206,11 +222,13 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int t = unit0; t < total_tiles; t += unit_stride) {
-        const int n_t = t % p.n_tiles;
-        const int m_t = TWO ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
-        const int tx = m_t % p.tiles_x;
-        const int ty = (m_t / p.tiles_x) % p.tiles_y;
-        const int b = m_t / (p.tiles_x * p.tiles_y);  // == B for the missing half of an odd last pair: zero fill
+        const int t_div = fast_div(t, p.magic_n);
+        const int n_t = t - t_div * p.n_tiles;
+        const int m_t = TWO ? 2 * t_div + rank : t_div;
+        const int b = fast_div(m_t, p.magic_xy);  // == B for the missing half of an odd last pair: zero fill
+        const int m_in = m_t - b * (p.tiles_x * p.tiles_y);
+        const int ty = fast_div(m_in, p.magic_x);
+        const int tx = m_in - ty * p.tiles_x;
         const int x0 = tx * p.tile_w, y0 = ty * p.tile_h, n0 = n_t * BLOCK_N;
         stamp(0, (t - unit0) / unit_stride);
         int kbi = 0;
@@ -303,6 +321,23 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     uint32_t store_iter = 0;
     int it = 0;
     int bias_n0 = -1;
+    // Which optional epilogue stages are on, in a REGISTER the optimizer cannot see through: tested straight from
+    // the kernel parameters every stage costs a dependent constant-bank load + uniform compare + branch (~60
+    // cycles each, ~8 of them per 32-column chunk even when every stage is off).
+    enum : uint32_t { F_ACT = 3u, F_MASK_SIGN = 4u, F_MASK_DGELU = 8u, F_RES = 16u, F_RES32 = 32u, F_OUT32 = 64u,
+                      F_COLSUM = 128u, F_SHUFFLE = 256u, F_MASK_MUL = 512u, F_AUX_GRAD = 1024u,
+                      F_MASK = F_MASK_SIGN | F_MASK_DGELU | F_MASK_MUL, F_TAIL = F_MASK | F_RES | F_RES32 | F_OUT32 };
+    uint32_t ef = static_cast<uint32_t>(p.act) & F_ACT;
+    if (p.mask_mode == SRB200_MASK_SIGN) ef |= F_MASK_SIGN;
+    else if (p.mask_mode == SRB200_MASK_MUL) ef |= F_MASK_MUL;
+    else if (p.mask_mode != SRB200_MASK_NONE) ef |= F_MASK_DGELU;
+    if (p.aux_mode == 1) ef |= F_AUX_GRAD;
+    if (p.residual != nullptr) ef |= F_RES;
+    if (p.residual_f32 != nullptr) ef |= F_RES32;
+    if (p.out_f32 != nullptr) ef |= F_OUT32;
+    if (p.colsum != nullptr) ef |= F_COLSUM;
+    if (p.out_mode == SRB200_OUT_SHUFFLE) ef |= F_SHUFFLE;
+    asm volatile("mov.b32 %0, %0;" : "+r"(ef));
     // bias-gradient column sums of this warp's (32 rows x 32 columns) of every 64-column chunk; kept in
     // registers across the CTA's tiles when there is a single N tile, flushed with one 128-byte red per chunk
     constexpr int NCH = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
@@ -320,11 +355,13 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       csum_n0 = -1;
     };
     for (int t = unit0; t < total_tiles; t += unit_stride, ++it) {
-      const int n_t = t % p.n_tiles;
-      const int m_t = TWO ? 2 * (t / p.n_tiles) + rank : t / p.n_tiles;
-      const int tx = m_t % p.tiles_x;
-      const int ty = (m_t / p.tiles_x) % p.tiles_y;
-      const int b = m_t / (p.tiles_x * p.tiles_y);
+      const int t_div = fast_div(t, p.magic_n);
+      const int n_t = t - t_div * p.n_tiles;
+      const int m_t = TWO ? 2 * t_div + rank : t_div;
+      const int b = fast_div(m_t, p.magic_xy);  // == B for the missing half of an odd last pair: zero fill
+      const int m_in = m_t - b * (p.tiles_x * p.tiles_y);
+      const int ty = fast_div(m_in, p.magic_x);
+      const int tx = m_in - ty * p.tiles_x;
       const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
       const int x = x0 + lx, y = y0 + ly;
       const int n0 = n_t * BLOCK_N;
@@ -352,7 +389,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 
       // element offset of (this thread's pixel, channel nc) in an NHWC tensor shaped like `out`
       auto out_offset = [&](int nc) -> size_t {
-        if (p.out_mode == SRB200_OUT_SHUFFLE) {
+        if (ef & F_SHUFFLE) {
           const int r2 = p.out_r * p.out_r;
           const int C = p.Cout / r2;
           const int ij = nc / C, cc = nc - ij * C;
@@ -367,20 +404,23 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       };
       // v: accumulators of CHUNK channels starting at nc -> final values (everything between MMA and store)
       auto finish = [&](float (&v)[CHUNK], size_t off) {
-        if (p.act == SRB200_ACT_RELU) {
+        const uint32_t act = ef & F_ACT;
+        if (act != SRB200_ACT_NONE && !(ef & F_AUX_GRAD)) {  // (with F_AUX_GRAD the activation is already applied)
+          if (act == SRB200_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
-        } else if (p.act == SRB200_ACT_LRELU) {
+            for (int j = 0; j < CHUNK; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (act == SRB200_ACT_LRELU) {
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * p.act_slope;
-        } else if (p.act == SRB200_ACT_GELU) {
+            for (int j = 0; j < CHUNK; ++j) v[j] = v[j] > 0.0f ? v[j] : v[j] * p.act_slope;
+          } else {
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < CHUNK; ++j) v[j] = gelu_erf(v[j]);
+          }
         }
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) v[j] *= al;
-        if (!valid) return;  // out-of-image rows of a partial tile: never stored, never loaded
-        if (p.mask_mode != SRB200_MASK_NONE) {
+        if (!valid || (ef & F_TAIL) == 0) return;  // out-of-image rows of a partial tile: never stored / loaded
+        if (ef & F_MASK) {
           const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
 #pragma unroll
           for (int j = 0; j < CHUNK / 8; ++j) {
@@ -389,9 +429,12 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float m0 = bf16_lo(mw[q]), m1 = bf16_hi(mw[q]);
-              if (p.mask_mode == SRB200_MASK_SIGN) {
+              if (ef & F_MASK_SIGN) {
                 v[8 * j + 2 * q + 0] *= (m0 > 0.0f) ? 1.0f : p.mask_slope;
                 v[8 * j + 2 * q + 1] *= (m1 > 0.0f) ? 1.0f : p.mask_slope;
+              } else if (ef & F_MASK_MUL) {
+                v[8 * j + 2 * q + 0] *= m0;
+                v[8 * j + 2 * q + 1] *= m1;
               } else {
                 v[8 * j + 2 * q + 0] *= dgelu_erf(m0);
                 v[8 * j + 2 * q + 1] *= dgelu_erf(m1);
@@ -399,7 +442,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
             }
           }
         }
-        if (p.residual != nullptr) {
+        if (ef & F_RES) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
           for (int j = 0; j < CHUNK / 8; ++j) {
@@ -412,7 +455,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
             }
           }
         }
-        if (p.residual_f32 != nullptr) {
+        if (ef & F_RES32) {
           const float4* rp = reinterpret_cast<const float4*>(p.residual_f32 + off);
 #pragma unroll
           for (int j = 0; j < CHUNK / 4; ++j) {
@@ -423,7 +466,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
             v[4 * j + 3] += m.w;
           }
         }
-        if (p.out_f32 != nullptr) {
+        if (ef & F_OUT32) {
           float4* fp = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
           for (int j = 0; j < CHUNK / 4; ++j)
@@ -474,20 +517,28 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               const int col = cc * 64 + hf * 32;
               load_acc(col, v);
               if (has_aux) {
+                float a[CHUNK];
+                if (ef & F_AUX_GRAD) {
+#pragma unroll
+                  for (int j = 0; j < CHUNK; ++j) gelu_and_grad(v[j], v[j], a[j]);  // v <- gelu, aux <- gelu'
+                } else {
+#pragma unroll
+                  for (int j = 0; j < CHUNK; ++j) a[j] = v[j];
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const uint32_t dst = buf_aux + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4);
                   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                               "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])),
-                               "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
-                               "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
-                               "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                               "r"(pack_bf16x2(a[8 * j + 0], a[8 * j + 1])),
+                               "r"(pack_bf16x2(a[8 * j + 2], a[8 * j + 3])),
+                               "r"(pack_bf16x2(a[8 * j + 4], a[8 * j + 5])),
+                               "r"(pack_bf16x2(a[8 * j + 6], a[8 * j + 7]))
                                : "memory");
                 }
               }
               finish(v, out_offset(n0 + col));
               if constexpr (CHUNK == 32) {
-                if (p.colsum != nullptr) {
+                if (ef & F_COLSUM) {
                   float w[32];
 #pragma unroll
                   for (int j = 0; j < 32; ++j) w[j] = valid ? v[j] : 0.0f;
@@ -692,6 +743,11 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.tiles_y = (d->H + p.tile_h - 1) / p.tile_h;
   p.m_tiles = d->B * p.tiles_x * p.tiles_y;
   p.n_tiles = d->Cout / bn;
+  auto magic = [](long long dv) { return static_cast<unsigned long long>(((1ULL << 40) + dv - 1) / dv); };
+  p.magic_n = magic(p.n_tiles);
+  p.magic_x = magic(p.tiles_x);
+  p.magic_xy = magic(static_cast<long long>(p.tiles_x) * p.tiles_y);
+  if (static_cast<long long>(p.m_tiles) * p.n_tiles >= (1LL << 20)) return SRB200_EINVAL;
   p.kchunks_per_src = d->Cin / 64;
   p.num_src = d->src_r * d->src_r;
   p.Cout = d->Cout;
@@ -708,6 +764,10 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.out_f32 = ext ? ext->out_f32 : nullptr;
   p.alpha_b = ext ? ext->alpha_per_sample : nullptr;
   p.colsum = ext ? ext->colsum : nullptr;
+  p.aux_mode = ext ? ext->aux_mode : 0;
+  if (p.aux_mode != 0 && (p.aux_mode != 1 || d->act != SRB200_ACT_GELU || !aux_out || bn < 64 ||
+                          d->out_mode != SRB200_OUT_NHWC))
+    return SRB200_EINVAL;
   if (p.colsum && (bn < 64 || d->out_mode != SRB200_OUT_NHWC)) return SRB200_EINVAL;
   if ((p.residual_f32 || p.out_f32) && d->out_mode == SRB200_OUT_NCHW_F32) return SRB200_EINVAL;
   if ((reinterpret_cast<uintptr_t>(p.residual_f32) | reinterpret_cast<uintptr_t>(p.out_f32)) & 15u)

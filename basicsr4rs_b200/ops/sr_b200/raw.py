@@ -281,7 +281,7 @@ def unpack_wgrad(acc, w_shape, perm_out=None, perm_in=None, alpha=1.0):
 def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alpha=1.0, mask_src=None,
             mask_mode=L.MASK_NONE, mask_slope=0.0, residual=None, flip=False, src_r=1, out_mode=L.OUT_NHWC,
             out_r=1, out_c=0, out_scale=1.0, out_shift=None, want_aux=False, residual_f32=None, want_f32=False,
-            alpha_per_sample=None, want_colsum=False):
+            alpha_per_sample=None, want_colsum=False, aux_grad=False):
     """conv3x3 / conv1x1 / Linear on NHWC bf16 (see include/srb200.h: srb200_tapgemm)."""
     _chk(x, 'x', torch.bfloat16)
     _chk(wp, 'wp', torch.bfloat16)
@@ -312,13 +312,14 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
         if out_mode != L.OUT_NHWC or cout % 64 != 0:
             raise RuntimeError('want_colsum needs a plain NHWC output with cout % 64 == 0')
         csum = zeros_f32((cout,), x.device)
-    if residual_f32 is not None or want_f32 or alpha_per_sample is not None or csum is not None:
+    if residual_f32 is not None or want_f32 or alpha_per_sample is not None or csum is not None or aux_grad:
         for t, name in ((residual_f32, 'residual_f32'), (alpha_per_sample, 'alpha_per_sample')):
             if t is not None:
                 _chk(t, name, torch.float32)
         ext = ctypes.byref(L.TapGemmExt(residual_f32.data_ptr() if residual_f32 is not None else None,
                                         out32.data_ptr() if out32 is not None else None,
                                         alpha_per_sample.data_ptr() if alpha_per_sample is not None else None,
+                                        1 if aux_grad else 0, 0,
                                         csum.data_ptr() if csum is not None else None))
     ev = PROBE.begin('tapgemm', (b, h, w, cin * src_r * src_r, cout, ksize)) if PROBE is not None else None
     L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),

@@ -148,7 +148,7 @@ class _SwinBlock(Function):
                          bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1)
         xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c)
         h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=_padded_bias(fc1_b, ch),
-                           act=L.ACT_GELU, want_aux=True)
+                           act=L.ACT_GELU, want_aux=True, aux_grad=True)  # a = gelu'(fc1 out): all the backward needs
         x2 = raw.tapgemm(h, _packed(fc2_w, 'fprop', cs, ch), ksize=1, cout=cs, bias=_padded_bias(fc2_b, cs),
                          residual=x1, alpha_per_sample=alpha2)
         ctx.save_for_backward(x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table,
@@ -183,7 +183,7 @@ class _SwinBlock(Function):
         acc_fc2 = raw.wgrad(g2s, h, ksize=1)
         cs_fc2 = raw.colsum(g2s)
         ga, cs_fc1 = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
-                                 mask_mode=L.MASK_DGELU, want_colsum=True)  # column sums = fc1's bias gradient
+                                 mask_mode=L.MASK_MUL, want_colsum=True)  # column sums = fc1's bias gradient
         acc_fc1 = raw.wgrad(ga, xn2, ksize=1)
         gxn2 = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True)
         gx1, g_n2w, g_n2b = layernorm_bwd(gxn2, x1, mean2, rstd2, n2w.detach(), c, gres=g2)

@@ -40,7 +40,8 @@ enum {
   SRB200_OUT_SHUFFLE = 1,  /* bf16 [B,H*r,W*r,Cout/r^2]: nn.PixelShuffle fused in store */
   SRB200_OUT_NCHW_F32 = 2  /* fp32 [B,out_c,H,W], v*out_scale + out_shift[c]            */
 };
-enum { SRB200_MASK_NONE = 0, SRB200_MASK_SIGN = 1, SRB200_MASK_DGELU = 2 };
+enum { SRB200_MASK_NONE = 0, SRB200_MASK_SIGN = 1, SRB200_MASK_DGELU = 2,
+       SRB200_MASK_MUL = 3 /* v *= mask_src: the saved activation derivative (aux_mode 1) */ };
 
 const char* srb200_version(void);
 const char* srb200_strerror(int code);
@@ -146,6 +147,10 @@ typedef struct {
   const float* residual_f32;     /* fp32 residual, layout of out: v += residual_f32 (fp32 skip stream)  */
   float* out_f32;                /* additionally store the fp32 result (layout of out)                  */
   const float* alpha_per_sample; /* [B] extra scale per batch sample (DropPath, swinir_arch.py:14-26)   */
+  int32_t aux_mode;              /* what aux_out receives: 0 = the pre-activation (bias added), 1 = the DERIVATIVE of
+                                    the activation at the pre-activation (SRB200_ACT_GELU: gelu'(a), computed from
+                                    the same erf / exp as gelu(a)); the backward then needs SRB200_MASK_MUL only   */
+  int32_t reserved;
   float* colsum;                 /* fp32 [Cout], zeroed by the caller: += sum over pixels of the stored
                                     result (the bias gradient of the layer that consumes `out` as dY);
                                     SRB200_OUT_NHWC with Cout % 64 == 0 only                            */

@@ -382,3 +382,24 @@ def test_pack_book_tracks_optimizer_steps(cuda):
     ref.load_state_dict(net.state_dict())
     assert torch.equal(ref(x), y2)  # a fresh network (fresh packs) agrees bit for bit
     assert L.launch_count > n0
+
+
+def test_tapgemm_gelu_derivative_aux_and_mask_mul(cuda):
+    """fc1's epilogue stores gelu'(a) next to gelu(a) (aux_mode 1); the backward multiplies by it (MASK_MUL)."""
+    raw, L = _raw(), _L()
+    b, h, w, cin, cout = 2, 16, 24, 192, 384
+    x, wt, bias = _mk_conv(cuda, b, h, w, cin, cout, 1, seed=31)
+    xb = _nhwc_bf16(x, cin)
+    wp = raw.pack_weight(wt, cout, cin)
+    out, d = raw.tapgemm(xb, wp, ksize=1, cout=cout, bias=bias, act=L.ACT_GELU, want_aux=True, aux_grad=True)
+    a = (F.conv2d(xb.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float(), bias)).permute(0, 2, 3, 1)
+    a = a.clone().requires_grad_(True)
+    g = F.gelu(a)
+    g.sum().backward()
+    _assert_close(out, g)
+    _assert_close(d, a.grad, 1e-2)
+    # backward side: v * saved derivative == v * gelu'(pre-activation)
+    dy = torch.randn((b, h, w, cin), device=cuda).to(torch.bfloat16)
+    ga = raw.tapgemm(dy, raw.pack_weight(wt, cout, cin), ksize=1, cout=cout, mask_src=d, mask_mode=L.MASK_MUL)
+    ref = F.conv2d(dy.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float()).permute(0, 2, 3, 1) * d.float()
+    _assert_close(ga, ref)
