@@ -11,6 +11,7 @@
 // Backward recomputes S / P, then dP = dO V^T, dS = P o (dP - rowsum(P o dP)), dQ = scale dS K,
 // dK = scale dS^T Q, dV = P^T dO and the bias-table gradient (smem histogram -> global atomics).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -267,7 +268,6 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
   __shared__ int sRegion[NTOK];
   int b, wy, wx, head;
   setup_window(g, b, wy, wx, head, sBias, sRegion, table);
-  for (int i = threadIdx.x; i < NBIAS; i += blockDim.x) sdBias[i] = 0.0f;
   const int ld = 3 * g.Cp;
   load_tile(sQ, qkv, g, b, wy, wx, ld, head * HD);
   load_tile(sK, qkv, g, b, wy, wx, ld, g.Cp + head * HD);
@@ -310,9 +310,6 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       ds[e] = s[nt][e] * (dp[nt][e] - delta[e >> 1]);
-      const int row = 16 * warp + gq + ((e & 2) ? 8 : 0);
-      const int col = nt * 8 + 2 * t + (e & 1);
-      atomicAdd(&sdBias[rel_index(row, col)], ds[e]);
     }
     const int r0 = 16 * warp + gq, c0 = nt * 8 + 2 * t;
     const uint32_t p01 = pack_bf16x2(s[nt][0], s[nt][1]), p23 = pack_bf16x2(s[nt][2], s[nt][3]);
@@ -334,6 +331,17 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
       dk[i][e] = 0.0f;
       dv[i][e] = 0.0f;
     }
+  // Bias-table gradient: bin (dy, dx) collects dS[(ry,rx),(ry-dy,rx-dx)].  One thread per bin sums its <= 64
+  // entries of the staged dS tile -- no shared-memory float atomics (4096 contended CAS loops per CTA were the
+  // bulk of this kernel's time), then one global atomic per bin as before.
+  for (int bin = threadIdx.x; bin < NBIAS; bin += blockDim.x) {
+    const int dy = bin / (2 * WS - 1) - (WS - 1), dx = bin % (2 * WS - 1) - (WS - 1);
+    float acc = 0.0f;
+    for (int ry = (dy > 0 ? dy : 0); ry < (dy < 0 ? WS + dy : WS); ++ry)
+      for (int rx = (dx > 0 ? dx : 0); rx < (dx < 0 ? WS + dx : WS); ++rx)
+        acc += __bfloat162float(sdS[(ry * WS + rx) * PROW + (ry - dy) * WS + (rx - dx)]);
+    sdBias[bin] = acc;
+  }
   gemm_regA_16x32x64(dq, dsf, sK, lane);          // dQ = dS K      (rows = this warp's queries)
   gemm_tA_16x32x64(dk, sdS, sQ, warp, lane);      // dK = dS^T Q    (rows = keys 16w..)
   gemm_tA_16x32x64(dv, sP, sdO, warp, lane);      // dV = P^T dO
@@ -352,6 +360,7 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
   store_tile(sQ, gqkv, g, b, wy, wx, ld, head * HD);
   store_tile(sK, gqkv, g, b, wy, wx, ld, g.Cp + head * HD);
   store_tile(sV, gqkv, g, b, wy, wx, ld, 2 * g.Cp + head * HD);
+  if (gtable == nullptr) return;  // (timing experiments only)
   for (int i = threadIdx.x; i < NBIAS; i += blockDim.x) atomicAdd(gtable + i * g.nH + head, sdBias[i]);
 }
 
@@ -394,6 +403,6 @@ extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gou
   if (grid > 0x7FFFFFFF) return SRB200_EINVAL;
   window_attn_bwd_kernel<<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<const __nv_bfloat16*>(gout_bf16),
-      rpb_table, static_cast<__nv_bfloat16*>(gqkv_bf16), g_rpb_table, g);
+      rpb_table, static_cast<__nv_bfloat16*>(gqkv_bf16), getenv("SRB_ATTN_NOTABLE") ? nullptr : g_rpb_table, g);
   return launch_status();
 }

@@ -273,6 +273,87 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float*
   }
 }
 
+// ------------------------------------------------------------------ few-channel exit conv (conv_last, F -> 3)
+// A 3x3 conv with C <= 7 output channels is HBM-bound on its INPUT, yet as a 9-tap implicit GEMM it re-reads every
+// input pixel nine times through L2 (EDSR-L: 2.7 GB of L2->SM traffic for a 302 MB tensor, 330 us).  It is linear:
+//   out[c](p) = sum_tap (X . Wtap[c])(p + tap)
+// so ONE 1x1 GEMM T[p][tap*C + c] = X[p] . W[c][:][tap] reads X once, and this kernel adds the nine shifted taps
+// of the tiny T tensor (zero outside the image, exactly the conv's zero padding), the bias and the image affine.
+__global__ void tap_stencil_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int C, int H, int W,
+                                   int Tp, const float* __restrict__ bias, const float* __restrict__ shift,
+                                   float scale) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * plane;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = pix / plane;
+    const int yx = static_cast<int>(pix - b * plane);
+    const int y = yx / W, x = yx - y * W;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const float* src = t + ((b * H + yy) * W + xx) * Tp + tap * C;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < C) acc[c] += __ldg(src + c);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) {
+        const float bv = bias != nullptr ? __ldg(bias + c) : 0.0f;
+        const float sh = shift != nullptr ? __ldg(shift + c) : 0.0f;
+        out[(b * C + c) * plane + yx] = (acc[c] + bv) * scale + sh;
+      }
+  }
+}
+
+// Backward twin: G[p][tap*C + c] = scale * g[c](p - tap) (zero outside the image; channels >= 9C are zero), bf16.
+// With it the data gradient dX = G . Wf and the weight gradient dWf = G^T X are single-tap GEMMs as well.
+template <int C>
+__global__ void tap_im2col_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                  int Gp, float scale) {
+  // thread = one pixel: gathers its 3x3xC neighbourhood (coalesced along x across the warp, L1-resident re-use) and
+  // writes the pixel's whole Gp-channel row (full 128-byte lines)
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * plane;
+  for (size_t pix = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = pix / plane;
+    const int yx = static_cast<int>(pix - b * plane);
+    const int y = yx / W, x = yx - y * W;
+    float v[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = 0.0f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y - (tap / 3 - 1), xx = x - (tap % 3 - 1);
+      const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (in) v[tap * C + c] = scale * __ldg(g + (b * C + c) * plane + yy * W + xx);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * Gp);
+    for (int grp = 0; grp < Gp / 8; ++grp) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (grp < 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q == grp) {
+            o.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+            o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+            o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+            o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+          }
+      }
+      dst[grp] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ weight pack / unpack
 __global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int taps,
                                    const int32_t* __restrict__ perm_out, int Np,
@@ -612,6 +693,36 @@ extern "C" int srb200_nhwc_to_nchw(const void* in_bf16, float* out, int B, int C
   const size_t work = static_cast<size_t>(B) * H * W * C;
   nhwc_to_nchw_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in_bf16), out, B, C, H, W, C_pad, shift, scale);
+  return launch_status();
+}
+
+extern "C" int srb200_tap_stencil(const float* t_f32, float* out, int B, int C, int H, int W, int Tp,
+                                  const float* bias, const float* shift, float scale, srb200_stream_t stream) {
+  if (!t_f32 || !out || B <= 0 || C <= 0 || C > 7 || H <= 0 || W <= 0 || Tp < 9 * C) return SRB200_EINVAL;
+  const size_t work = static_cast<size_t>(B) * H * W;
+  tap_stencil_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(t_f32, out, B, C, H, W, Tp,
+                                                                                        bias, shift, scale);
+  return launch_status();
+}
+
+extern "C" int srb200_tap_im2col(const float* g, void* out_bf16, int B, int C, int H, int W, int Gp, float scale,
+                                 srb200_stream_t stream) {
+  if (!g || !out_bf16 || B <= 0 || C <= 0 || C > 7 || H <= 0 || W <= 0 || Gp < 9 * C || Gp % 8 != 0)
+    return SRB200_EINVAL;
+  if (reinterpret_cast<uintptr_t>(out_bf16) & 15u) return SRB200_EINVAL;
+  const size_t work = static_cast<size_t>(B) * H * W;
+  const int grid = grid_for(work, 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+  switch (C) {
+    case 1: tap_im2col_kernel<1><<<grid, 256, 0, st>>>(g, o, B, H, W, Gp, scale); break;
+    case 2: tap_im2col_kernel<2><<<grid, 256, 0, st>>>(g, o, B, H, W, Gp, scale); break;
+    case 3: tap_im2col_kernel<3><<<grid, 256, 0, st>>>(g, o, B, H, W, Gp, scale); break;
+    case 4: tap_im2col_kernel<4><<<grid, 256, 0, st>>>(g, o, B, H, W, Gp, scale); break;
+    case 5: tap_im2col_kernel<5><<<grid, 256, 0, st>>>(g, o, B, H, W, Gp, scale); break;
+    case 6: tap_im2col_kernel<6><<<grid, 256, 0, st>>>(g, o, B, H, W, Gp, scale); break;
+    default: tap_im2col_kernel<7><<<grid, 256, 0, st>>>(g, o, B, H, W, Gp, scale); break;
+  }
   return launch_status();
 }
 

@@ -4,6 +4,7 @@
 //   per-sample row scaling (DropPath backward, swinir_arch.py:14-26).
 // HBM-bound: fwd moves 2*T*C*2 B, bwd 3*T*C*2 B (+ residual-gradient add fused).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "host_util.h"
 #include "ptx.cuh"
@@ -103,8 +104,8 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
 }
 
 // gx = LN'(gy) (+ gres);  ggamma[c] += sum_t gy*xhat;  gbeta[c] += sum_t gy
-template <int NVEC>
-__global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
+template <int NVEC, int TOK>
+__global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
                                      const __nv_bfloat16* __restrict__ x,
                                      const float* __restrict__ mean_in,
                                      const float* __restrict__ rstd_in,
@@ -129,46 +130,69 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
       const int c = (lane + 32 * i) * 8 + e;
       gm[i][e] = (c < C) ? __ldg(gamma + c) : 0.0f;
     }
-  for (long long t = warp_global; t < T; t += nwarps) {
-    const float mean = __ldg(mean_in + t), rstd = __ldg(rstd_in + t);
-    float g[NVEC][8], xh[NVEC][8];
-    float s1 = 0.0f, s2 = 0.0f;
+  // TOK tokens per warp iteration: all their 16-byte loads (gy, x, gres) are issued before the first reduction, so
+  // a warp keeps 3 * TOK * NVEC requests in flight instead of 2 (the one-token loop ran at 1.9 TB/s)
+  for (long long t0 = warp_global * TOK; t0 < T; t0 += nwarps * TOK) {
+    uint4 rg[TOK][NVEC], rx[TOK][NVEC], rr[TOK][NVEC];
+    float mean[TOK], rstd[TOK];
 #pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      const int vec = lane + 32 * i;
-      if (vec < nv) {
-        float xv[8];
-        ln_unpack(__ldg(reinterpret_cast<const uint4*>(gy + t * Cp) + vec), g[i]);
-        ln_unpack(__ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec), xv);
+    for (int k = 0; k < TOK; ++k) {
+      const long long t = t0 + k;
+      const bool tv = t < T;
+      mean[k] = tv ? __ldg(mean_in + t) : 0.0f;
+      rstd[k] = tv ? __ldg(rstd_in + t) : 0.0f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool live = vec * 8 + e < C;
-          xh[i][e] = live ? (xv[e] - mean) * rstd : 0.0f;
-          const float gv = live ? g[i][e] : 0.0f;
-          ag[i][e] += gv * xh[i][e];
-          ab[i][e] += gv;
-          g[i][e] = gv * gm[i][e];  // d xhat
-          s1 += g[i][e];
-          s2 += g[i][e] * xh[i][e];
+      for (int i = 0; i < NVEC; ++i) {
+        const int vec = lane + 32 * i;
+        rg[k][i] = rx[k][i] = rr[k][i] = make_uint4(0u, 0u, 0u, 0u);
+        if (tv && vec < nv) {
+          rg[k][i] = __ldg(reinterpret_cast<const uint4*>(gy + t * Cp) + vec);
+          rx[k][i] = __ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec);
+          if (gres != nullptr) rr[k][i] = __ldg(reinterpret_cast<const uint4*>(gres + t * Cp) + vec);
         }
       }
     }
-    s1 = warp_sum(s1) / static_cast<float>(C);
-    s2 = warp_sum(s2) / static_cast<float>(C);
 #pragma unroll
-    for (int i = 0; i < NVEC; ++i) {
-      const int vec = lane + 32 * i;
-      if (vec < nv) {
-        float o[8], r[8];
-        if (gres != nullptr) ln_unpack(__ldg(reinterpret_cast<const uint4*>(gres + t * Cp) + vec), r);
+    for (int k = 0; k < TOK; ++k) {
+      const long long t = t0 + k;
+      if (t >= T) break;
+      float g[NVEC][8], xh[NVEC][8];
+      float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool live = vec * 8 + e < C;
-          float d = live ? rstd * (g[i][e] - s1 - xh[i][e] * s2) : 0.0f;
-          if (gres != nullptr) d += r[e];
-          o[e] = d;
+      for (int i = 0; i < NVEC; ++i) {
+        const int vec = lane + 32 * i;
+        if (vec < nv) {
+          float xv[8];
+          ln_unpack(rg[k][i], g[i]);
+          ln_unpack(rx[k][i], xv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool live = vec * 8 + e < C;
+            xh[i][e] = live ? (xv[e] - mean[k]) * rstd[k] : 0.0f;
+            const float gv = live ? g[i][e] : 0.0f;
+            ag[i][e] += gv * xh[i][e];
+            ab[i][e] += gv;
+            g[i][e] = gv * gm[i][e];  // d xhat
+            s1 += g[i][e];
+            s2 += g[i][e] * xh[i][e];
+          }
         }
-        *(reinterpret_cast<uint4*>(gx + t * Cp) + vec) = ln_pack(o);
+      }
+      s1 = warp_sum(s1) / static_cast<float>(C);
+      s2 = warp_sum(s2) / static_cast<float>(C);
+#pragma unroll
+      for (int i = 0; i < NVEC; ++i) {
+        const int vec = lane + 32 * i;
+        if (vec < nv) {
+          float o[8], r[8];
+          ln_unpack(rr[k][i], r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool live = vec * 8 + e < C;
+            o[e] = (live ? rstd[k] * (g[i][e] - s1 - xh[i][e] * s2) : 0.0f) + r[e];
+          }
+          *(reinterpret_cast<uint4*>(gx + t * Cp) + vec) = ln_pack(o);
+        }
       }
     }
   }
@@ -184,6 +208,7 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ gy,
     }
   }
   __syncthreads();
+  if (ggamma == nullptr) return;  // (timing experiments only)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomicAdd(ggamma + c, s_red[c]);
     atomicAdd(gbeta + c, s_red[Cp + c]);
@@ -237,7 +262,10 @@ extern "C" int srb200_layernorm_bwd(const void* gy_bf16, const void* x_bf16, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int block = 256;
   long long blocks = (T + 63) / 64;  // >= 8 tokens per warp so the column atomics amortise
-  const long long cap = static_cast<long long>(num_sms()) * 4;
+  // persistent: as many blocks as stay resident (per-block prologue / column-sum epilogue is not free)
+  long long cap = static_cast<long long>(num_sms()) * (Cp <= 256 ? 3 : 1);
+  if (const char* e = getenv("SRB_LN_BPS")) cap = static_cast<long long>(num_sms()) * atoi(e);
+  if (getenv("SRB_LN_NOATOM")) ggamma = nullptr;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const size_t smem = 2 * static_cast<size_t>(Cp) * sizeof(float);
@@ -247,11 +275,11 @@ extern "C" int srb200_layernorm_bwd(const void* gy_bf16, const void* x_bf16, con
   __nv_bfloat16* gx = static_cast<__nv_bfloat16*>(gx_bf16);
   const int g = static_cast<int>(blocks);
   if (Cp <= 256)
-    layernorm_bwd_kernel<1><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+    layernorm_bwd_kernel<1, 2><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
   else if (Cp <= 512)
-    layernorm_bwd_kernel<2><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+    layernorm_bwd_kernel<2, 2><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
   else
-    layernorm_bwd_kernel<4><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+    layernorm_bwd_kernel<4, 1><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
   return launch_status();
 }
 

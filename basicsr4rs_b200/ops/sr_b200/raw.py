@@ -181,6 +181,25 @@ def nhwc_to_nchw(x, c, shift=None, scale=1.0):
     return out
 
 
+def tap_stencil(t32, c, bias=None, shift=None, scale=1.0):
+    """fp32 [B,H,W,Tp] per-tap partial products -> NCHW fp32 image: sum of the 9 shifted taps + bias, affine."""
+    _chk(t32, 't32', torch.float32)
+    b, h, w, tp = t32.shape
+    out = torch.empty((b, c, h, w), dtype=torch.float32, device=t32.device)
+    L.check(L.load().srb200_tap_stencil(_ptr(t32), _ptr(out), b, c, h, w, tp, _ptr(bias), _ptr(shift), float(scale),
+                                        _stream()), 'tap_stencil')
+    return out
+
+
+def tap_im2col(g, gp, scale=1.0):
+    """NCHW fp32 image gradient [B,C,H,W] -> NHWC bf16 [B,H,W,gp] with channel tap*C+c = scale * g[c] shifted by -tap."""
+    _chk(g, 'g', torch.float32)
+    b, c, h, w = g.shape
+    out = torch.empty((b, h, w, gp), dtype=torch.bfloat16, device=g.device)
+    L.check(L.load().srb200_tap_im2col(_ptr(g), _ptr(out), b, c, h, w, gp, float(scale), _stream()), 'tap_im2col')
+    return out
+
+
 # ------------------------------------------------------------------ weights
 def pack_weight(w, n_pad, k_pad, perm_out=None, perm_in=None, transpose=False, out=None):
     """fp32 [Co, Ci, kh, kw] (or [Co, Ci]) -> bf16 [taps, n_pad, k_pad] (or [taps, k_pad, n_pad])."""

@@ -426,20 +426,35 @@ def res_block_nobn(x, w1, b1, w2, b2, res_scale):
 
 
 # ------------------------------------------------------------------ conv_last + exit
+def _tap_folded_weight(weight, k_pad, tp):
+    """fp32 [tp, k_pad]: row tap*C + c = weight[c, :, ky, kx] (tap = 3*ky + kx), zero padded."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    wf = torch.zeros((tp, k_pad), dtype=torch.float32, device=weight.device)
+    wf[:9 * cout, :cin] = weight.detach().permute(2, 3, 0, 1).reshape(9 * cout, cin)
+    return wf
+
+
 class _ConvToImage(Function):
-    """conv_last (F -> num_out_ch) fused with ``x / img_range + mean`` and the NHWC bf16 -> NCHW fp32
-    exit (edsr_arch.py:58-59; rcan_arch.py:132-133; swinir_arch.py:900,920)."""
+    """conv_last (F -> num_out_ch <= 7, 3x3) fused with ``x / img_range + mean`` and the NHWC bf16 -> NCHW fp32 exit
+    (edsr_arch.py:58-59; rcan_arch.py:132-133; swinir_arch.py:900,920).
+
+    The conv is HBM-bound on its input, so it runs as ONE 1x1 tap-GEMM producing the nine per-tap partial products
+    of every pixel (T[p][tap*C+c], fp32) followed by a 9-tap stencil sum over the tiny T tensor
+    (srb200_tap_stencil) -- the input is read once, not nine times.  Backward: the image gradient is spread to the
+    same tap-major channel layout (srb200_tap_im2col), after which the data and weight gradients are single-tap
+    GEMMs too and the bias gradient is three of its column sums."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, out_scale, out_shift):
         cout, cin = weight.shape[0], weight.shape[1]
-        assert cout <= 16, 'fused image exit supports up to 16 output channels'
+        assert cout <= 7 and weight.shape[-1] == 3, 'fused image exit: 3x3 conv with up to 7 output channels'
         k_pad = x.shape[-1]
         assert k_pad == pad64(cin)
-        wp = _packed(weight, 'fprop', 16, k_pad)
-        bp = _padded_bias(bias, 16)
-        y = raw.tapgemm(x, wp, ksize=weight.shape[-1], cout=16, bias=bp, out_mode=L.OUT_NCHW_F32, out_c=cout,
-                        out_scale=out_scale, out_shift=out_shift)
+        tp = pad64(9 * cout)
+        wf = _tap_folded_weight(weight, k_pad, tp)
+        _, t32 = raw.tapgemm(x, wf.to(torch.bfloat16).view(1, tp, k_pad), ksize=1, cout=tp, want_f32=True)
+        y = raw.tap_stencil(t32, cout, bias=bias.detach() if bias is not None else None, shift=out_shift,
+                            scale=out_scale)
         ctx.save_for_backward(x, weight, bias)
         ctx.out_scale = out_scale
         return y
@@ -447,26 +462,22 @@ class _ConvToImage(Function):
     @staticmethod
     def backward(ctx, g):
         x, weight, bias = ctx.saved_tensors
-        cout = weight.shape[0]
+        cout, cin = weight.shape[0], weight.shape[1]
         k_pad = x.shape[-1]
-        ks = weight.shape[-1]
-        # dL/d(conv out) = g * out_scale, as NHWC bf16 padded to 64 channels (GEMM K/N granularity)
-        gn = raw.nchw_to_nhwc(g.contiguous().float(), 64, shift=None, scale=ctx.out_scale)
+        tp = pad64(9 * cout)
+        # G[p][tap*C + c] = out_scale * g[c](p - tap): d(conv out) in the tap-major layout of the forward's T
+        gn = raw.tap_im2col(g.contiguous().float(), tp, scale=ctx.out_scale)
         gx = gw = gb = None
-        items = []
-        if ctx.needs_input_grad[1]:
-            items.append(('w', raw.wgrad(gn, x, ksize=ks), weight.shape, None, None, 1.0))
-        if bias is not None and ctx.needs_input_grad[2]:
-            items.append(('b', raw.colsum(gn), cout, None, 1.0))
-        if items:
-            grads = raw.finalize_grads(items)
+        with raw.zero_arena(x.device, tp * k_pad + tp + k_pad + 64):
             if ctx.needs_input_grad[1]:
-                gw = grads[0]
+                acc = raw.wgrad(gn, x, ksize=1)  # [1, tp, k_pad] = G^T X
+                gw = acc[0, :9 * cout, :cin].reshape(3, 3, cout, cin).permute(2, 3, 0, 1).contiguous()
             if bias is not None and ctx.needs_input_grad[2]:
-                gb = grads[-1]
-        if ctx.needs_input_grad[0]:
-            wpt = _packed(weight, 'dgrad', 64, k_pad)
-            gx = raw.tapgemm(gn, wpt, ksize=ks, cout=k_pad, flip=True)
+                gb = raw.colsum(gn)[4 * cout:5 * cout].clone()  # centre tap: every pixel of g exactly once
+            if ctx.needs_input_grad[0]:
+                wd = _tap_folded_weight(weight, k_pad, tp).t().contiguous().to(torch.bfloat16).view(1, k_pad, tp)
+                gx, cs = raw.tapgemm(gn, wd, ksize=1, cout=k_pad, want_colsum=True)
+                _stash_colsum(gx, cs)
         return gx, gw, gb, None, None
 
 

@@ -76,6 +76,19 @@ int srb200_nchw_to_nhwc(const float* in, void* out_bf16, int B, int C, int H, in
 int srb200_nhwc_to_nchw(const void* in_bf16, float* out, int B, int C, int H, int W, int C_pad,
                         const float* shift, float scale, srb200_stream_t stream);
 
+/* ------------------------------------------------------------------ few-channel exit conv (conv_last, F -> C <= 7)
+ * nn.Conv2d(F, C, 3, 1, 1) + `x / img_range + mean` (edsr_arch.py:48,58-59; rcan_arch.py:122,132-133;
+ * swinir_arch.py:839,900,920) as ONE 1x1 tap-GEMM  T[p][tap*C + c] = X[p] . W[c][:][tap]  (reads X once instead of
+ * nine times) followed by srb200_tap_stencil:
+ *   out[b,c,y,x] = (sum_tap T[b, y+dy(tap), x+dx(tap), tap*C + c] + bias[c]) * scale + shift[c]     (NCHW fp32)
+ * T is fp32 [B,H,W,Tp] (Tp >= 9*C); taps outside the image contribute zero (the conv's zero padding).            */
+int srb200_tap_stencil(const float* t_f32, float* out, int B, int C, int H, int W, int Tp, const float* bias,
+                       const float* shift, float scale, srb200_stream_t stream);
+/* Backward twin: G[b,y,x, tap*C + c] = scale * g[b,c, y-dy(tap), x-dx(tap)] as NHWC bf16 with Gp channels (zero
+ * beyond 9*C and outside the image).  Then dX = G . Wf (1x1 tap-GEMM) and dWf = G^T X (1x1 srb200_wgrad).       */
+int srb200_tap_im2col(const float* g, void* out_bf16, int B, int C, int H, int W, int Gp, float scale,
+                      srb200_stream_t stream);
+
 /* ------------------------------------------------------------------ weight packing
  * conv / linear weight fp32 [Co, Ci, taps] (OIHW flattened; taps = 1 or 9) -> bf16
  *   transpose=0: out[t][n][k] = w[perm_out[n]][perm_in[k]][t]   (fprop operand, [taps][Np][Kp])

@@ -403,3 +403,29 @@ def test_tapgemm_gelu_derivative_aux_and_mask_mul(cuda):
     ga = raw.tapgemm(dy, raw.pack_weight(wt, cout, cin), ksize=1, cout=cout, mask_src=d, mask_mode=L.MASK_MUL)
     ref = F.conv2d(dy.float().permute(0, 3, 1, 2), wt.to(torch.bfloat16).float()).permute(0, 2, 3, 1) * d.float()
     _assert_close(ga, ref)
+
+
+@pytest.mark.parametrize('b,c,h,w,cin', [(2, 3, 24, 20, 64), (1, 4, 17, 9, 128), (1, 6, 8, 8, 64)])
+def test_conv_to_image_tap_folded(cuda, b, c, h, w, cin):
+    """conv_last as 1x1 tap-GEMM + stencil sum / im2col backward == nn.Conv2d(cin, c, 3, 1, 1) * scale + shift,
+    including its input, weight and bias gradients (c = 3, and the 4/6-band remote-sensing variants)."""
+    from basicsr4rs_b200.ops import sr_b200 as ops
+    g = torch.Generator(device='cpu').manual_seed(41)
+    x = torch.randn((b, cin, h, w), generator=g).to(cuda)
+    wt = (torch.randn((c, cin, 3, 3), generator=g) / (cin * 9)**0.5).to(cuda).requires_grad_(True)
+    bias = torch.randn((c,), generator=g).to(cuda).requires_grad_(True)
+    shift = torch.randn((c,), generator=g).to(cuda)
+    xb = _nhwc_bf16(x, cin).requires_grad_(True)
+    y = ops.conv_to_image(xb, wt, bias, 0.25, shift)
+    gy = torch.randn(y.shape, generator=torch.Generator(device='cpu').manual_seed(42)).to(cuda)
+    y.backward(gy)
+    xr = xb.detach().float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = wt.detach().clone().requires_grad_(True)
+    br = bias.detach().clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr.to(torch.bfloat16).float(), br, padding=1) * 0.25 + shift.view(1, -1, 1, 1)
+    ref.backward(gy)
+    _assert_close(y, ref, 2e-3)
+    _assert_close(xb.grad, xr.grad.permute(0, 2, 3, 1))
+    _assert_close(wt.grad, wr.grad)
+    # sum of ~1e3 bf16-rounded, sign-cancelling terms: compare against the magnitude that was summed
+    assert (bias.grad - br.grad).abs().max().item() <= 1e-3 * 0.25 * gy.abs().sum((0, 2, 3)).max().item()

@@ -93,3 +93,23 @@ def test_seeded_init_identical_to_reference(arch, kwargs):
     assert list(ours.keys()) == list(theirs.keys())
     for k in ours:
         assert ours[k].dtype == theirs[k].dtype and torch.equal(ours[k], theirs[k]), k
+
+
+def test_pack_item_table_matches_the_c_struct():
+    """The numpy mirror of ``srb200_pack_item`` (include/srb200.h) has the C layout: 96-byte rows, 8-byte fields at
+    the offsets the header implies, chunk_begin = running sum of ceil(Np*Kp/256)."""
+    import numpy as np
+    from basicsr4rs_b200 import _lib as L
+    from basicsr4rs_b200.ops.sr_b200 import raw
+    dt = np.dtype(L.PACK_ITEM_FIELDS)
+    assert dt.itemsize == 96
+    assert [dt.fields[n][1] for n in ('src', 'dst', 'perm_out', 'perm_in', 'Co', 'Ci', 'taps', 'Np', 'Kp', 'transpose',
+                                      'chunk_begin', 'alpha', 'reserved')] == [0, 8, 16, 24, 32, 40, 48, 56, 64, 72, 80,
+                                                                               88, 92]
+    a, b = torch.zeros(4), torch.zeros(4)
+    rows = [dict(src=a, dst=b, Co=64, Ci=64, taps=9, Np=64, Kp=64),
+            dict(src=a, dst=b, Co=3, Ci=64, taps=9, Np=16, Kp=64, transpose=True, alpha=0.5),
+            dict(src=a, dst=b, Co=180, Ci=1, taps=1, Np=192, Kp=1)]
+    tab, total = raw._item_table(rows)
+    assert list(tab['chunk_begin']) == [0, 16, 20] and total == 21
+    assert tab[1]['transpose'] == 1 and tab[1]['alpha'] == 0.5 and tab[0]['src'] == a.data_ptr()

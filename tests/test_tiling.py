@@ -1,0 +1,106 @@
+"""Host logic of the tiled multi-GPU inference path (BASELINE.json config 5): tile grids, rank sharding,
+window padding and seam handling -- CPU, with a plain bicubic-free stand-in network (nearest x``s`` upscale),
+plus a world_size-2 gloo run in which two ranks fill disjoint tiles of the same scene."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from basicsr4rs_b200.utils import tiling  # noqa: E402
+
+
+class _Nearest(torch.nn.Module):
+    def __init__(self, s):
+        super().__init__()
+        self.s = s
+
+    def forward(self, x):
+        return x.repeat_interleave(self.s, 2).repeat_interleave(self.s, 3)
+
+
+@pytest.mark.parametrize('h,w,tile,overlap', [(1024, 1024, 256, 0), (100, 70, 32, 8), (48, 48, 64, 0), (65, 33, 32, 31),
+                                              (1, 1, 8, 0)])
+def test_tile_grid_covers_image(h, w, tile, overlap):
+    tiles = tiling.tile_grid(h, w, tile, overlap)
+    cover = torch.zeros((h, w), dtype=torch.int32)
+    for (y, x, th, tw) in tiles:
+        assert 0 < th <= tile and 0 < tw <= tile and y + th <= h and x + tw <= w
+        cover[y:y + th, x:x + tw] += 1
+    assert (cover > 0).all()
+    if overlap == 0 and h % tile == 0 and w % tile == 0:
+        assert (cover == 1).all() and len(tiles) == (h // tile) * (w // tile)
+
+
+def test_tile_grid_edge_cases():
+    assert tiling.tile_grid(0, 10, 8) == []
+    with pytest.raises(ValueError):
+        tiling.tile_grid(10, 10, 8, overlap=8)
+    with pytest.raises(ValueError):
+        tiling.shard([1, 2, 3], 2, 2)
+
+
+def test_shards_partition_the_work():
+    items = list(range(37))
+    for world in (1, 2, 4, 8):
+        parts = [tiling.shard(items, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == items
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_pad_to_multiple_matches_reference_reflect():
+    """Same flip-concatenate padding as SwinIRModel.test (swinir_model.py:16-24), window_size 8."""
+    x = torch.arange(2 * 3 * 13 * 21, dtype=torch.float32).view(2, 3, 13, 21)
+    y, (h, w) = tiling.pad_to_multiple(x, 8)
+    assert (h, w) == (13, 21) and y.shape[-2:] == (16, 24)
+    ref = torch.cat([x, torch.flip(x, [2])], 2)[:, :, :16, :]
+    ref = torch.cat([ref, torch.flip(ref, [3])], 3)[:, :, :, :24]
+    assert torch.equal(y, ref)
+    z, _ = tiling.pad_to_multiple(y, 8)
+    assert z is y
+
+
+@pytest.mark.parametrize('overlap', [0, 8])
+def test_tiled_forward_equals_whole_image(overlap):
+    net = _Nearest(4)
+    img = torch.rand((1, 3, 90, 61))
+    whole = net(img)
+    out, n = tiling.tiled_forward(net, img, tile=32, scale=4, overlap=overlap, multiple=8)
+    assert n == len(tiling.tile_grid(90, 61, 32, overlap))
+    assert torch.equal(out, whole)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    net = _Nearest(2)
+    img = torch.arange(3 * 48 * 64, dtype=torch.float32).view(1, 3, 48, 64) + 1.0
+    out, n = tiling.tiled_forward(net, img, tile=16, scale=2, rank=rank, world=world)
+    # replicas only: the test (not the product path) sums the disjoint partial scenes to check the partition
+    filled = (out != 0).to(torch.int32)
+    dist.all_reduce(out)
+    dist.all_reduce(filled)
+    counts = torch.tensor([n])
+    dist.all_reduce(counts)
+    ok = torch.equal(out, net(img)) and int(filled.max()) == 1 and int(filled.min()) == 1 and \
+        int(counts) == len(tiling.tile_grid(48, 64, 16)) == 12
+    if rank == 0:
+        q.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_fill_disjoint_tiles():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 400
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
