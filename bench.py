@@ -28,10 +28,15 @@ sys.path.insert(0, ROOT)
 EDSR_L = dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=256, num_block=32, upscale=4, res_scale=0.1,
               img_range=255., rgb_mean=[0.4488, 0.4371, 0.4040])
 BATCH, LR = 16, 48
-CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; loss + Adam eager', 'workload': 'EDSR-L x4 train step (fwd + L1 + bwd + Adam), 16x3x48x48 LR patches per GPU',
+CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; L1 loss + torch.optim.Adam(fused=True) eager', 'workload': 'EDSR-L x4 train step (fwd + L1 + bwd + Adam), 16x3x48x48 LR patches per GPU',
           'arch': 'EDSR num_feat=256 num_block=32 res_scale=0.1 upscale=4', 'batch_per_gpu': BATCH,
           'lr_patch': LR, 'parallelism': 'ddp', 'l2': 'per-step working set (>2 GB of activations) exceeds the 126 MB L2'}
 FLOP_PER_PATCH_FWD_BWD = 694.66e9
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, mean of the three 256->256 launches in
+# profiles/r01_ncu_full_tapgemm.txt (one `ncu --set full` capture of this script): 39.09 / 20.14 / 39.29 MB.  The
+# algorithmic bytes are 18.9 MB in + 18.9 MB out + 1.2 MB weights (+18.9 MB residual for conv2 / dgrad-conv1); the
+# output is still L2-resident when the kernel ends, so DRAM sees only the compulsory reads -- no wasted re-reads.
+ROOFLINE_TRAFFIC_BYTES = 32.84e6
 
 
 def synthetic_batch(rank, batch=BATCH, lr=LR, scale=4):
@@ -256,9 +261,10 @@ def main():
                     'h2d_bytes_per_step': (lq_h.numel() + gt_h.numel()) * 4, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches, 'clocks': clocks,
             'model_tflops': value * FLOP_PER_PATCH_FWD_BWD / world / 1e12,
-            'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<256> conv3x3 256->256 (fprop + dgrad launches)',
+            'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<256,true> (cta_group::2) conv3x3 256->256, fprop + dgrad launches',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak if achieved else None, 'traffic': None,
+                         'frac': achieved / peak if achieved else None, 'traffic': ROOFLINE_TRAFFIC_BYTES,
+                         'traffic_unit': 'bytes/launch (ncu --set full, profiles/r01_ncu_full_tapgemm.txt)',
                          'peak_kind': f'{pk_kind} bf16 sustained (timed inside a long step)',
                          'launches_timed': len(kernel_ms), 'avg_ms': k_avg},
         }
