@@ -30,7 +30,8 @@ class TapGemmDesc(ctypes.Structure):
 class TapGemmExt(ctypes.Structure):
     """Mirror of ``srb200_tapgemm_ext``."""
     _fields_ = [('residual_f32', c_void_p), ('out_f32', c_void_p), ('alpha_per_sample', c_void_p),
-                ('aux_mode', ctypes.c_int32), ('reserved', ctypes.c_int32), ('colsum', c_void_p)]
+                ('aux_mode', ctypes.c_int32), ('colsum_per_image', ctypes.c_int32), ('colsum', c_void_p),
+                ('colsum_scale', c_float), ('reserved', ctypes.c_int32)]
 
 
 # numpy mirror of ``srb200_pack_item`` (one row per weight of a batched pack / unpack launch)
@@ -83,7 +84,7 @@ SIGNATURES = {
     'srb200_ca_fc_bwd': (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_void_p]),
     'srb200_debug_set_trace': (c_int, [c_void_p]),
     'srb200_debug_set_wgrad_trace': (c_int, [c_void_p]),
-    'srb200_ca_apply_bwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p]),
+    'srb200_ca_apply_bwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 
 _lib = None

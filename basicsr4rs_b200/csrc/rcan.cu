@@ -138,27 +138,39 @@ __global__ void ca_fc_bwd_kernel(const float* __restrict__ gs, const float* __re
                                  float* __restrict__ gw1, float* __restrict__ gb1,
                                  float* __restrict__ gw2, float* __restrict__ gb2,
                                  float* __restrict__ gp, int B, int C, int Cr) {
-  extern __shared__ float sm[];  // ga2[B*C], ga1[B*Cr]
+  // Everything (a few KB) is staged in shared memory by ONE round of global loads; the five dependent phases
+  // then run out of smem -- as separate global-load phases the kernel paid ~6 DRAM/L2 latencies (17 us).
+  extern __shared__ float sm[];  // ga2[B*C], ga1[B*Cr], z[B*Cr], p[B*C], w1[Cr*C], w2[C*Cr]
   float* ga2 = sm;
-  float* ga1 = sm + static_cast<size_t>(B) * C;
+  float* ga1 = ga2 + static_cast<size_t>(B) * C;
+  float* sz = ga1 + static_cast<size_t>(B) * Cr;
+  float* sp = sz + static_cast<size_t>(B) * Cr;
+  float* sw1 = sp + static_cast<size_t>(B) * C;
+  float* sw2 = sw1 + static_cast<size_t>(C) * Cr;
   for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
-    const float sv = s[i];
-    ga2[i] = gs[i] * sv * (1.0f - sv);
+    const float sv = __ldg(s + i);
+    ga2[i] = __ldg(gs + i) * sv * (1.0f - sv);
+    sp[i] = __ldg(p + i);
+  }
+  for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) sz[i] = __ldg(z + i);
+  for (int i = threadIdx.x; i < C * Cr; i += blockDim.x) {
+    sw1[i] = __ldg(w1 + i);
+    sw2[i] = __ldg(w2 + i);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) {
     const int b = i / Cr, j = i - b * Cr;
     float acc = 0.0f;
-    for (int c = 0; c < C; ++c) acc += w2[static_cast<size_t>(c) * Cr + j] * ga2[b * C + c];
-    ga1[i] = z[i] > 0.0f ? acc : 0.0f;
+    for (int c = 0; c < C; ++c) acc += sw2[c * Cr + j] * ga2[b * C + c];
+    ga1[i] = sz[i] > 0.0f ? acc : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * Cr; i += blockDim.x) {  // gW2 [C][Cr], gW1 [Cr][C]
     const int c = i / Cr, j = i - c * Cr;
     float a2 = 0.0f, a1 = 0.0f;
     for (int b = 0; b < B; ++b) {
-      a2 += ga2[b * C + c] * z[b * Cr + j];
-      a1 += ga1[b * Cr + j] * p[b * C + c];
+      a2 += ga2[b * C + c] * sz[b * Cr + j];
+      a1 += ga1[b * Cr + j] * sp[b * C + c];
     }
     gw2[static_cast<size_t>(c) * Cr + j] = a2;
     gw1[static_cast<size_t>(j) * C + c] = a1;
@@ -176,7 +188,7 @@ __global__ void ca_fc_bwd_kernel(const float* __restrict__ gs, const float* __re
   for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
     const int b = i / C, c = i - b * C;
     float acc = 0.0f;
-    for (int j = 0; j < Cr; ++j) acc += w1[static_cast<size_t>(j) * C + c] * ga1[b * Cr + j];
+    for (int j = 0; j < Cr; ++j) acc += sw1[j * C + c] * ga1[b * Cr + j];
     gp[i] = acc;
   }
 }
@@ -184,9 +196,17 @@ __global__ void ca_fc_bwd_kernel(const float* __restrict__ gs, const float* __re
 // gt = res_scale * g * s[b,c] + gp[b,c] / HW
 __global__ void ca_apply_bwd_kernel(const uint4* __restrict__ g, const float* __restrict__ s,
                                     const float* __restrict__ gp, uint4* __restrict__ gt, size_t nvec,
-                                    int HW, int C, float res_scale) {
+                                    int HW, int C, float res_scale, float* __restrict__ colsum) {
+  extern __shared__ float s_cs[];  // [C] column sums of gt (only when colsum != NULL)
   const int groups = C / 8;
   const float inv_hw = 1.0f / static_cast<float>(HW);
+  if (colsum != nullptr) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_cs[i] = 0.0f;
+    __syncthreads();
+  }
+  // the grid stride is a multiple of `groups`, so a thread stays on one 8-channel group
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int my_group = -1;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < nvec;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int gg = static_cast<int>(idx % groups);
@@ -198,6 +218,17 @@ __global__ void ca_apply_bwd_kernel(const uint4* __restrict__ g, const float* __
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = res_scale * vg[e] * __ldg(sp + e) + __ldg(pp + e) * inv_hw;
     gt[idx] = pack8(o);
+    my_group = gg;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] += o[e];
+  }
+  if (colsum != nullptr) {
+    if (my_group >= 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[my_group * 8 + e], cs[e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(colsum + i, s_cs[i]);
   }
 }
 
@@ -264,19 +295,32 @@ extern "C" int srb200_ca_fc_bwd(const float* gs, const float* s, const float* z,
                                 const float* w1, const float* w2, float* gw1, float* gb1, float* gw2,
                                 float* gb2, float* gp, int B, int C, int Cr, srb200_stream_t stream) {
   if (!gs || !s || !z || !p || !w1 || !w2 || !gw1 || !gb1 || !gw2 || !gb2 || !gp) return SRB200_EINVAL;
-  const size_t smem = (static_cast<size_t>(B) * C + static_cast<size_t>(B) * Cr) * sizeof(float);
-  if (B <= 0 || C <= 0 || Cr <= 0 || smem > 48 * 1024) return SRB200_EINVAL;
+  if (B <= 0 || C <= 0 || Cr <= 0) return SRB200_EINVAL;
+  const size_t smem = (2 * static_cast<size_t>(B) * C + 2 * static_cast<size_t>(B) * Cr +
+                       2 * static_cast<size_t>(C) * Cr) * sizeof(float);
+  if (smem > 200 * 1024) return SRB200_EINVAL;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(ca_fc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return SRB200_ELAUNCH;
+    configured = 200 * 1024;
+  }
   ca_fc_bwd_kernel<<<1, 256, smem, static_cast<cudaStream_t>(stream)>>>(gs, s, z, p, w1, w2, gw1, gb1,
                                                                         gw2, gb2, gp, B, C, Cr);
   return launch_status();
 }
 
 extern "C" int srb200_ca_apply_bwd(const void* g_bf16, const float* s, const float* gp, void* gt_bf16,
-                                   int B, int HW, int C, float res_scale, srb200_stream_t stream) {
+                                   int B, int HW, int C, float res_scale, float* colsum,
+                                   srb200_stream_t stream) {
   if (!g_bf16 || !s || !gp || !gt_bf16 || B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0)
     return SRB200_EINVAL;
+  if (colsum != nullptr && 256 % (C / 8) != 0) return SRB200_EINVAL;  // a thread must stay on one channel group
   const size_t nvec = static_cast<size_t>(B) * HW * (C / 8);
-  ca_apply_bwd_kernel<<<grid1d(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(g_bf16), s, gp, static_cast<uint4*>(gt_bf16), nvec, HW, C, res_scale);
+  // with column sums: ~2 blocks per SM (every block ends with C global atomics onto the same addresses)
+  int grid = grid1d(nvec, 256);
+  if (colsum != nullptr && grid > 2 * num_sms()) grid = 2 * num_sms();
+  ca_apply_bwd_kernel<<<grid, 256, colsum ? C * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g_bf16), s, gp, static_cast<uint4*>(gt_bf16), nvec, HW, C, res_scale, colsum);
   return launch_status();
 }

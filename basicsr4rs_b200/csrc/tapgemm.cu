@@ -52,6 +52,8 @@ struct TapGemmParams {
   const float* alpha_b;       // optional per-sample scale [B] (stochastic depth)
   float* colsum;              // optional fp32 [Cout]: += column sums of the stored result (bias gradient)
   int aux_mode;               // 1: aux_out = act'(pre-activation) instead of the pre-activation (GELU only)
+  int colsum_per_image;       // 1: colsum is [B][Cout] (per-sample sums: RCAN's global average pool)
+  float colsum_scale;         // factor applied to the sums when they are flushed (1/HW for the pool)
   int act;
   float act_slope, alpha;
   int mask_mode;
@@ -344,12 +346,13 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     float csum[NCH];
 #pragma unroll
     for (int q = 0; q < NCH; ++q) csum[q] = 0.0f;
-    int csum_n0 = -1;
+    int csum_n0 = -1, csum_b = 0;
     auto flush_colsum = [&]() {
       if (csum_n0 < 0) return;
+      float* dst = p.colsum + (p.colsum_per_image ? static_cast<size_t>(csum_b) * p.Cout : 0) + csum_n0;
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
-        atomicAdd(p.colsum + csum_n0 + q * 64 + half * 32 + lane, csum[q]);
+        if (csum_b < p.B) atomicAdd(dst + q * 64 + half * 32 + lane, csum[q] * p.colsum_scale);
         csum[q] = 0.0f;
       }
       csum_n0 = -1;
@@ -367,8 +370,9 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       const int n0 = n_t * BLOCK_N;
       const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
       if (p.colsum != nullptr) {
-        if (csum_n0 != n0) flush_colsum();
+        if (csum_n0 != n0 || (p.colsum_per_image && csum_b != b)) flush_colsum();
         csum_n0 = n0;
+        csum_b = p.colsum_per_image ? b : 0;
       }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
@@ -765,6 +769,8 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.alpha_b = ext ? ext->alpha_per_sample : nullptr;
   p.colsum = ext ? ext->colsum : nullptr;
   p.aux_mode = ext ? ext->aux_mode : 0;
+  p.colsum_per_image = ext ? ext->colsum_per_image : 0;
+  p.colsum_scale = (ext && ext->colsum_scale != 0.0f) ? ext->colsum_scale : 1.0f;
   if (p.aux_mode != 0 && (p.aux_mode != 1 || d->act != SRB200_ACT_GELU || !aux_out || bn < 64 ||
                           d->out_mode != SRB200_OUT_NHWC))
     return SRB200_EINVAL;

@@ -327,10 +327,11 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
     out32 = torch.empty(out.shape, dtype=torch.float32, device=x.device) if want_f32 else None
     ext = None
     csum = None
+    per_image = want_colsum == 'image_mean'  # [B, cout] per-sample means (RCAN's AdaptiveAvgPool2d(1))
     if want_colsum:  # fp32 [cout] column sums of the stored result, accumulated by the epilogue (bias gradient)
         if out_mode != L.OUT_NHWC or cout % 64 != 0:
             raise RuntimeError('want_colsum needs a plain NHWC output with cout % 64 == 0')
-        csum = zeros_f32((cout,), x.device)
+        csum = zeros_f32((b, cout) if per_image else (cout,), x.device)
     if residual_f32 is not None or want_f32 or alpha_per_sample is not None or csum is not None or aux_grad:
         for t, name in ((residual_f32, 'residual_f32'), (alpha_per_sample, 'alpha_per_sample')):
             if t is not None:
@@ -338,8 +339,9 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
         ext = ctypes.byref(L.TapGemmExt(residual_f32.data_ptr() if residual_f32 is not None else None,
                                         out32.data_ptr() if out32 is not None else None,
                                         alpha_per_sample.data_ptr() if alpha_per_sample is not None else None,
-                                        1 if aux_grad else 0, 0,
-                                        csum.data_ptr() if csum is not None else None))
+                                        1 if aux_grad else 0, 1 if per_image else 0,
+                                        csum.data_ptr() if csum is not None else None,
+                                        1.0 / (h * w) if per_image else 1.0, 0))
     ev = PROBE.begin('tapgemm', (b, h, w, cin * src_r * src_r, cout, ksize)) if PROBE is not None else None
     L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),
                                     _ptr(out_shift), _ptr(out), _ptr(aux), ext, _stream()), 'tapgemm')
@@ -444,11 +446,12 @@ def ca_fc_bwd(gs, s, z, p, w1, w2):
     return gw1, gb1, gw2, gb2, gp
 
 
-def ca_apply_bwd(g, s, gp, res_scale):
-    """gt = res_scale * g * s[b, c] + gp[b, c] / HW."""
+def ca_apply_bwd(g, s, gp, res_scale, want_colsum=False):
+    """gt = res_scale * g * s[b, c] + gp[b, c] / HW  (+ its fp32 column sums: the bias gradient of conv2)."""
     _chk(g, 'g', torch.bfloat16)
     b, h, w, c = g.shape
     gt = torch.empty_like(g)
+    cs = zeros_f32((c,), g.device) if want_colsum else None
     L.check(L.load().srb200_ca_apply_bwd(_ptr(g), _ptr(s), _ptr(gp), _ptr(gt), b, h * w, c, float(res_scale),
-                                         _stream()), 'ca_apply_bwd')
-    return gt
+                                         _ptr(cs), _stream()), 'ca_apply_bwd')
+    return (gt, cs) if want_colsum else gt

@@ -502,8 +502,9 @@ class _RCAB(Function):
         cp = pad64(c)
         assert x.shape[-1] == cp == c, 'RCAB kernels need num_feat % 64 == 0'
         h = raw.tapgemm(x, _packed(w1, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b1, cp), act=L.ACT_RELU)
-        t = raw.tapgemm(h, _packed(w2, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b2, cp))
-        p = raw.channel_pool(t)
+        # conv2; its epilogue also accumulates the per-sample channel means = AdaptiveAvgPool2d(1) (rcan_arch.py:19)
+        t, p = raw.tapgemm(h, _packed(w2, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b2, cp),
+                           want_colsum='image_mean')
         z, s = raw.ca_fc(p, wa1.detach().contiguous(), ba1.detach(), wa2.detach().contiguous(), ba2.detach())
         ctx.save_for_backward(x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2)
         ctx.res_scale = res_scale
@@ -526,9 +527,8 @@ class _RCAB(Function):
     def _backward(ctx, g, x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2, rs, cp):
         gs = raw.channel_dot(g, t, scale=rs)                       # d s[b,c] = res_scale * sum_hw g * t
         gwa1, gba1, gwa2, gba2, gp = raw.ca_fc_bwd(gs, s, z, p, wa1.detach().contiguous(), wa2.detach().contiguous())
-        gt = raw.ca_apply_bwd(g, s, gp, rs)                        # d t
+        gt, cs2 = raw.ca_apply_bwd(g, s, gp, rs, want_colsum=True)  # d t and its column sums (conv2's bias grad)
         acc2 = raw.wgrad(gt, h, ksize=3)
-        cs2 = raw.colsum(gt)
         gh, cs1 = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
                               mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=True)
         acc1 = raw.wgrad(gh, x, ksize=3)

@@ -163,10 +163,13 @@ typedef struct {
   int32_t aux_mode;              /* what aux_out receives: 0 = the pre-activation (bias added), 1 = the DERIVATIVE of
                                     the activation at the pre-activation (SRB200_ACT_GELU: gelu'(a), computed from
                                     the same erf / exp as gelu(a)); the backward then needs SRB200_MASK_MUL only   */
-  int32_t reserved;
+  int32_t colsum_per_image;      /* 1: colsum is [B][Cout], one row per sample (RCAN's AdaptiveAvgPool2d(1),
+                                    rcan_arch.py:19, for free from the conv that produces its input)             */
   float* colsum;                 /* fp32 [Cout], zeroed by the caller: += sum over pixels of the stored
                                     result (the bias gradient of the layer that consumes `out` as dY);
                                     SRB200_OUT_NHWC with Cout % 64 == 0 only                            */
+  float colsum_scale;            /* the sums are multiplied by this when flushed (0 = 1.0; 1/HW for a mean)        */
+  int32_t reserved;
 } srb200_tapgemm_ext;
 
 int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16, const void* w_packed,
@@ -214,8 +217,10 @@ int srb200_ca_apply(const void* t_bf16, const void* x_bf16, const float* x_f32, 
 int srb200_ca_fc_bwd(const float* gs, const float* s, const float* z, const float* p, const float* w1,
                      const float* w2, float* gw1, float* gb1, float* gw2, float* gb2, float* gp,
                      int B, int C, int Cr, srb200_stream_t stream);
+/* gt = res_scale*g*s[b,c] + gp[b,c]/HW; colsum (optional fp32 [C], zeroed by the caller) += column sums of gt,
+ * the bias gradient of the conv that produced t.                                                          */
 int srb200_ca_apply_bwd(const void* g_bf16, const float* s, const float* gp, void* gt_bf16, int B,
-                        int HW, int C, float res_scale, srb200_stream_t stream);
+                        int HW, int C, float res_scale, float* colsum, srb200_stream_t stream);
 
 /* ------------------------------------------------------------------ SwinIR token kernels
  * nn.LayerNorm(C, eps) over the C real channels of NHWC bf16 rows padded to Cp (pads stay 0)
