@@ -142,9 +142,14 @@ __device__ __forceinline__ float warp_colsum32(float (&w)[32], int lane) {
   return w[0];
 }
 
-template <int BLOCK_N, bool TWO = false>
+// TEAMS: the 8 epilogue warps work as two independent teams of 4 (one warp per TMEM lane quarter), team a draining
+// accumulator buffer a.  For small-K layers (SwinIR's linears, 64-channel convs) a tile's MMAs take ~1.2k cycles but
+// its epilogue 4k, so both accumulators are usually full and two tiles' epilogues can run side by side -- each team
+// has its own named barrier, staging slots and TMA-store issuer.
+template <int BLOCK_N, bool TWO = false, bool TEAMS = false>
 __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   using Cfg = TapCfg<BLOCK_N, TWO>;
+  static_assert(!TEAMS || (!TWO && BLOCK_N >= 64 && BLOCK_N <= 192), "teams: single-CTA, TMA-store tile widths");
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CHUNK = Cfg::CHUNK;
 
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), TWO ? 16 : 8);  // the leader's MMA thread waits for both CTAs' epilogue warps
+      mbar_init(tempty_bar(a), TWO ? 16 : (TEAMS ? 4 : 8));  // (pair: both CTAs' epilogue warps; teams: one team)
     }
     fence_barrier_init();
   }
@@ -313,13 +318,20 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   } else {
     // ===================================================== epilogue (warps 2..9)
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;     // which 32-column half of every 64-column chunk
+    const int team = TEAMS ? (warp - 2) >> 2 : 0;   // which accumulator buffer this team drains
+    const int half0 = TEAMS ? 0 : (warp - 2) >> 2;  // first 32-column half of every 64-column chunk this warp owns
+    constexpr int NHALF = TEAMS ? 2 : 1;            // a team's warp covers both halves
     const int row = quarter * 32 + lane;  // tile row == TMEM lane == smem staging row
     const int ly = row / p.tile_w, lx = row - ly * p.tile_w;
     const bool use_tma = (BLOCK_N >= 64) && p.tma_store != 0;
-    const bool issuer = (warp == 2 && lane == 0);
+    const bool issuer = TEAMS ? (((warp - 2) & 3) == 0 && lane == 0) : (warp == 2 && lane == 0);
     const int etid = threadIdx.x - 64;    // 0..255
-    auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    auto epi_sync = [&] {
+      if constexpr (TEAMS) asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    constexpr int NSLOT = TEAMS ? Cfg::NBUF / 2 : Cfg::NBUF;  // staging slots per team
+    const uint32_t my_store_base = store_base + (TEAMS ? team * NSLOT * 16384 : 0);
     uint32_t store_iter = 0;
     int it = 0;
     int bias_n0 = -1;
@@ -343,21 +355,31 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     // bias-gradient column sums of this warp's (32 rows x 32 columns) of every 64-column chunk; kept in
     // registers across the CTA's tiles when there is a single N tile, flushed with one 128-byte red per chunk
     constexpr int NCH = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
-    float csum[NCH];
+    float csum[NCH * NHALF];
 #pragma unroll
-    for (int q = 0; q < NCH; ++q) csum[q] = 0.0f;
+    for (int q = 0; q < NCH * NHALF; ++q) csum[q] = 0.0f;
     int csum_n0 = -1, csum_b = 0;
     auto flush_colsum = [&]() {
       if (csum_n0 < 0) return;
       float* dst = p.colsum + (p.colsum_per_image ? static_cast<size_t>(csum_b) * p.Cout : 0) + csum_n0;
 #pragma unroll
-      for (int q = 0; q < NCH; ++q) {
-        if (csum_b < p.B) atomicAdd(dst + q * 64 + half * 32 + lane, csum[q] * p.colsum_scale);
+      for (int q = 0; q < NCH * NHALF; ++q) {
+        if (csum_b < p.B)
+          atomicAdd(dst + (q / NHALF) * 64 + (half0 + q % NHALF) * 32 + lane, csum[q] * p.colsum_scale);
         csum[q] = 0.0f;
       }
       csum_n0 = -1;
     };
+    if constexpr (TEAMS) {
+      // the launch grid is a multiple of n_tiles (host-checked): one N tile, one bias vector per CTA, loaded once
+      // by all eight warps -- the teams never meet again
+      const int n00 = (unit0 - fast_div(unit0, p.magic_n) * p.n_tiles) * BLOCK_N;
+      for (int i = etid; i < BLOCK_N; i += 256) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n00 + i) : 0.0f;
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      bias_n0 = n00;
+    }
     for (int t = unit0; t < total_tiles; t += unit_stride, ++it) {
+      if (TEAMS && (it & 1) != team) continue;
       const int t_div = fast_div(t, p.magic_n);
       const int n_t = t - t_div * p.n_tiles;
       const int m_t = TWO ? 2 * t_div + rank : t_div;
@@ -385,6 +407,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       // bias of this N tile -> smem (every epilogue warp has passed the last barrier of the previous tile); the
       // launch grid is a multiple of n_tiles, so a CTA keeps its N tile for all its tiles and this runs once
       if (bias_n0 != n0) {
+        if constexpr (TEAMS) __trap();  // N-tile affinity violated
         if (it > 0) epi_sync();  // every warp is done reading the previous tile's bias
         for (int i = etid; i < BLOCK_N; i += 256) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.0f;
         epi_sync();
@@ -507,16 +530,17 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
             uint32_t buf_out, buf_aux = 0;
             if (has_aux) {
-              buf_aux = store_base;
-              buf_out = store_base + 16384;
+              buf_aux = my_store_base;
+              buf_out = my_store_base + 16384;
               if (issuer) tma_store_wait_read<0>();
             } else {
-              buf_out = store_base + (store_iter % Cfg::NBUF) * 16384;
-              if (issuer) tma_store_wait_read<Cfg::NBUF - 1>();
+              buf_out = my_store_base + (store_iter % NSLOT) * 16384;
+              if (issuer) tma_store_wait_read<NSLOT - 1>();
             }
             epi_sync();
-            {
-              const int hf = half;
+#pragma unroll 1
+            for (int hh = 0; hh < NHALF; ++hh) {
+              const int hf = half0 + hh;
               float v[CHUNK];
               const int col = cc * 64 + hf * 32;
               load_acc(col, v);
@@ -548,8 +572,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                   for (int j = 0; j < 32; ++j) w[j] = valid ? v[j] : 0.0f;
                   const float cs = warp_colsum32(w, lane);
 #pragma unroll
-                  for (int q = 0; q < NCH; ++q)
-                    if (q == cc) csum[q] += cs;
+                  for (int q = 0; q < NCH * NHALF; ++q)
+                    if (q == cc * NHALF + hh) csum[q] += cs;
                 }
               }
 #pragma unroll
@@ -573,8 +597,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                 view = nc / C;
                 c0 = nc - view * C;
               }
-              if (has_aux) tma_store_4d(&p.tmap_aux, buf_aux, c0, x0, y0, b);
-              tma_store_4d(&p.tmap_out[view], buf_out, c0, x0, y0, b);
+              if (p.tma_store != 2) {  // (2 = SRB_DEBUG_SKIP_STORE timing experiment: results are not written)
+                if (has_aux) tma_store_4d(&p.tmap_aux, buf_aux, c0, x0, y0, b);
+                tma_store_4d(&p.tmap_out[view], buf_out, c0, x0, y0, b);
+              }
               tma_store_commit();
             }
             ++store_iter;
@@ -583,7 +609,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       } else {
         // -------- direct stores: final NCHW fp32 image (conv_last), or N < 64
 #pragma unroll 1
-        for (int c = half; c < BLOCK_N / CHUNK; c += 2) {
+        for (int c = half0; c < BLOCK_N / CHUNK; c += (TEAMS ? 1 : 2)) {
           float v[CHUNK];
           load_acc(c * CHUNK, v);
           const int nc = n0 + c * CHUNK;
@@ -675,12 +701,12 @@ static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
   return launch_status();
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TEAMS = false>
 static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   using Cfg = TapCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, false, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess)
       return SRB200_ELAUNCH;
     configured = true;
@@ -688,7 +714,8 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   const int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
   if (grid >= p.n_tiles) grid -= grid % p.n_tiles;  // a CTA keeps its N tile (bias, weight columns) for all its tiles
-  tapgemm_kernel<BLOCK_N><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(p);
+  if (TEAMS && grid % p.n_tiles != 0) return SRB200_EINVAL;
+  tapgemm_kernel<BLOCK_N, false, TEAMS><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(p);
   return launch_status();
 }
 
@@ -837,8 +864,19 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
         }
       }
     if (aux_out && ro != 1) return SRB200_EINVAL;
+    if (getenv("SRB_DEBUG_SKIP_STORE") != nullptr) p.tma_store = 2;
   }
   if (two_cta) return launch_tapgemm2<256>(p, stream);
+  // small-K, wide-N layers (SwinIR's linears) are epilogue-bound: two epilogue teams (needs the TMA-store path and
+  // N-tile affinity).  Not for 64-wide tiles: their 2-tiles-per-CTA kernels only see a longer last-tile epilogue.
+  {
+    const int total = p.m_tiles * p.n_tiles;
+    int grid = total < num_sms() ? total : num_sms();
+    if (grid >= p.n_tiles) grid -= grid % p.n_tiles;
+    const bool teams = p.tma_store != 0 && grid % p.n_tiles == 0 && getenv("SRB_TAPGEMM_NO_TEAMS") == nullptr;
+    if (teams && bn == 192) return launch_tapgemm<192, true>(p, stream);
+    if (teams && bn == 128) return launch_tapgemm<128, true>(p, stream);
+  }
   switch (bn) {
     case 256: return launch_tapgemm<256>(p, stream);
     case 192: return launch_tapgemm<192>(p, stream);
