@@ -60,6 +60,7 @@ SIGNATURES = {
                                    c_void_p]),
     'srb200_unpack_wgrad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                     c_float, c_void_p]),
+    'srb200_nearest_up2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'srb200_tap_stencil': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                                    c_void_p]),
     'srb200_tap_im2col': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

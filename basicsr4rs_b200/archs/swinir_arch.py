@@ -419,8 +419,22 @@ class SwinIR(ArchMixin, nn.Module):
         if self.upsampler == '':
             # denoising / JPEG-CAR: x + conv_last(res) in normalised space == x + conv_last(res) / img_range
             return x.float() + ops.conv_to_image(feat, self.conv_last.weight, self.conv_last.bias, inv, None)
-        raise NotImplementedError(f"srb200 SwinIR: upsampler '{self.upsampler}' is not on the B200 path yet "
-                                  "(classical 'pixelshuffle' and '' are); there is no PyTorch fallback")
+        if self.upsampler == 'pixelshuffledirect':
+            # lightweight SR (reference :901-905): one conv to scale^2 * num_out_ch channels + PixelShuffle(scale)
+            conv, shuffle = self.upsample[0], self.upsample[1]
+            u, u32 = ops.conv_nhwc(feat, conv.weight, conv.bias, want_f32=True)
+            return ops.shuffle_to_image(u, u32, conv.weight.shape[0] // shuffle.upscale_factor**2,
+                                        shuffle.upscale_factor, inv, mean)
+        if self.upsampler == 'nearest+conv':
+            # real-world SR (reference :906-913): conv+lrelu, 2 x (nearest x2 -> conv -> lrelu 0.2), conv_hr, conv_last
+            c = self.conv_before_upsample[0]
+            u = ops.conv_nhwc(feat, c.weight, c.bias, act='lrelu', slope=self.conv_before_upsample[1].negative_slope)
+            s02 = self.lrelu.negative_slope
+            u = ops.conv_nhwc(ops.nearest_up2(u), self.conv_up1.weight, self.conv_up1.bias, act='lrelu', slope=s02)
+            u = ops.conv_nhwc(ops.nearest_up2(u), self.conv_up2.weight, self.conv_up2.bias, act='lrelu', slope=s02)
+            u = ops.conv_nhwc(u, self.conv_hr.weight, self.conv_hr.bias, act='lrelu', slope=s02)
+            return ops.conv_to_image(u, self.conv_last.weight, self.conv_last.bias, inv, mean)
+        raise ValueError(f"unknown upsampler '{self.upsampler}'")
 
     def _build_segments(self):
         groups = split_even(list(self.layers), self.graph_segments)
@@ -437,8 +451,8 @@ class SwinIR(ArchMixin, nn.Module):
             return run(groups[0])(self.patch_embed.forward_nhwc(first)), first
 
         tail_mods = [self.norm, self.conv_after_body] + [getattr(self, n) for n in
-                                                         ('conv_before_upsample', 'upsample', 'conv_last')
-                                                         if hasattr(self, n)]
+                                                         ('conv_before_upsample', 'upsample', 'conv_up1', 'conv_up2',
+                                                          'conv_hr', 'conv_last') if hasattr(self, n)]
         segs = [Segment(head_fn, [self.conv_first, self.patch_embed] + groups[0])]
         segs += [Segment(run(g), g) for g in groups[1:]]
         segs.append(Segment(self._tail, tail_mods))
@@ -446,7 +460,7 @@ class SwinIR(ArchMixin, nn.Module):
 
     def _forward(self, x):
         require_cuda(x, 'SwinIR')
-        if self.cuda_graph and self.training and torch.is_grad_enabled() and self.upsampler == 'pixelshuffle':
+        if self.cuda_graph and self.training and torch.is_grad_enabled() and self.upsampler != '':
             nseg = len(split_even(list(self.layers), self.graph_segments)) + 1
             out = graphed_forward(self, x, self._build_segments, chain_wire(nseg, carry=1))
             return out if out.dtype == x.dtype else out.to(x.dtype)

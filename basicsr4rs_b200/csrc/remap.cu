@@ -273,6 +273,55 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float*
   }
 }
 
+// ------------------------------------------------------------------ nearest-neighbour x2 (SwinIR 'nearest+conv')
+// torch.nn.functional.interpolate(x, scale_factor=2, mode='nearest') on NHWC bf16 (swinir_arch.py:911-912):
+// out[b, Y, X, :] = in[b, Y/2, X/2, :] -- a pure index remap (bit-exact); backward sums each 2x2 block in fp32.
+__global__ void nearest_up2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
+                                   int vec) {
+  const size_t total = static_cast<size_t>(B) * (2 * H) * (2 * W) * vec;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % vec);
+    size_t pix = idx / vec;
+    const int X = static_cast<int>(pix % (2 * W));
+    pix /= (2 * W);
+    const int Y = static_cast<int>(pix % (2 * H));
+    const size_t b = pix / (2 * H);
+    out[idx] = __ldg(in + ((b * H + (Y >> 1)) * W + (X >> 1)) * vec + v);
+  }
+}
+
+__global__ void nearest_up2_bwd_kernel(const uint4* __restrict__ g, uint4* __restrict__ out, int B, int H, int W,
+                                       int vec) {
+  const size_t total = static_cast<size_t>(B) * H * W * vec;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % vec);
+    size_t pix = idx / vec;
+    const int x = static_cast<int>(pix % W);
+    pix /= W;
+    const int y = static_cast<int>(pix % H);
+    const size_t b = pix / H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint4 m = __ldg(g + ((b * 2 * H + 2 * y + i) * (2 * W) + 2 * x + j) * vec + v);
+        acc[0] += bf16_lo(m.x);
+        acc[1] += bf16_hi(m.x);
+        acc[2] += bf16_lo(m.y);
+        acc[3] += bf16_hi(m.y);
+        acc[4] += bf16_lo(m.z);
+        acc[5] += bf16_hi(m.z);
+        acc[6] += bf16_lo(m.w);
+        acc[7] += bf16_hi(m.w);
+      }
+    out[idx] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                          pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
 // ------------------------------------------------------------------ few-channel exit conv (conv_last, F -> 3)
 // A 3x3 conv with C <= 7 output channels is HBM-bound on its INPUT, yet as a 9-tap implicit GEMM it re-reads every
 // input pixel nine times through L2 (EDSR-L: 2.7 GB of L2->SM traffic for a 302 MB tensor, 330 us).  It is linear:
@@ -693,6 +742,24 @@ extern "C" int srb200_nhwc_to_nchw(const void* in_bf16, float* out, int B, int C
   const size_t work = static_cast<size_t>(B) * H * W * C;
   nhwc_to_nchw_kernel<<<grid_for(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in_bf16), out, B, C, H, W, C_pad, shift, scale);
+  return launch_status();
+}
+
+extern "C" int srb200_nearest_up2(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, int inverse,
+                                  srb200_stream_t stream) {
+  if (!in_bf16 || !out_bf16 || B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0) return SRB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(in_bf16) | reinterpret_cast<uintptr_t>(out_bf16)) & 15u) return SRB200_EINVAL;
+  const int vec = C / 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!inverse) {
+    const size_t work = static_cast<size_t>(B) * 4 * H * W * vec;
+    nearest_up2_kernel<<<grid_for(work, 256), 256, 0, st>>>(static_cast<const uint4*>(in_bf16),
+                                                           static_cast<uint4*>(out_bf16), B, H, W, vec);
+  } else {
+    const size_t work = static_cast<size_t>(B) * H * W * vec;
+    nearest_up2_bwd_kernel<<<grid_for(work, 256), 256, 0, st>>>(static_cast<const uint4*>(in_bf16),
+                                                               static_cast<uint4*>(out_bf16), B, H, W, vec);
+  }
   return launch_status();
 }
 

@@ -181,6 +181,20 @@ def nhwc_to_nchw(x, c, shift=None, scale=1.0):
     return out
 
 
+def nearest_up2(x, inverse=False):
+    """NHWC bf16 nearest-neighbour x2 (inverse=False) or its gradient, the 2x2 block sum (inverse=True)."""
+    _chk(x, 'x', torch.bfloat16)
+    b, h, w, c = x.shape
+    if not inverse:
+        out = torch.empty((b, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+        L.check(L.load().srb200_nearest_up2(_ptr(x), _ptr(out), b, h, w, c, 0, _stream()), 'nearest_up2')
+    else:
+        assert h % 2 == 0 and w % 2 == 0
+        out = torch.empty((b, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+        L.check(L.load().srb200_nearest_up2(_ptr(x), _ptr(out), b, h // 2, w // 2, c, 1, _stream()), 'nearest_up2_bwd')
+    return out
+
+
 def tap_stencil(t32, c, bias=None, shift=None, scale=1.0):
     """fp32 [B,H,W,Tp] per-tap partial products -> NCHW fp32 image: sum of the 9 shifted taps + bias, affine."""
     _chk(t32, 't32', torch.float32)

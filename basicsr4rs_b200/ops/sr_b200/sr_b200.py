@@ -481,6 +481,52 @@ class _ConvToImage(Function):
         return gx, gw, gb, None, None
 
 
+class _NearestUp2(Function):
+    """F.interpolate(scale_factor=2, mode='nearest') on NHWC bf16 (swinir_arch.py:911-912)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return raw.nearest_up2(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return raw.nearest_up2(g.contiguous(), inverse=True)
+
+
+def nearest_up2(x):
+    return _NearestUp2.apply(x)
+
+
+class _ShuffleToImage(Function):
+    """nn.PixelShuffle(r) of the first r*r*C channels of an NHWC tensor, fused exit to the NCHW fp32 image with
+    ``x * scale + shift`` -- the tail of SwinIR's 'pixelshuffledirect' branch (UpsampleOneStep, swinir_arch.py:669-690,
+    followed by :920).  ``x32`` carries the conv result in fp32 (never differentiated): the image is not rounded to
+    bf16 on its way out."""
+
+    @staticmethod
+    def forward(ctx, x, x32, c_img, r, scale, shift):
+        cc = c_img * r * r
+        ctx.cfg = (c_img, r, scale, x.shape[-1])
+        hr = raw.pixel_shuffle_nhwc(x32[..., :cc].contiguous(), r)        # fp32 [B, rH, rW, c_img], bit-exact remap
+        out = hr.permute(0, 3, 1, 2) * scale
+        if shift is not None:
+            out = out + shift.view(1, -1, 1, 1)
+        return out.contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        c_img, r, scale, cp = ctx.cfg
+        gn = raw.nchw_to_nhwc(g.contiguous().float(), 8, shift=None, scale=scale)[..., :c_img].contiguous()
+        lr = raw.pixel_shuffle_nhwc(gn, r, inverse=True)                  # bf16 [B, H, W, c_img*r*r]
+        gx = torch.zeros(lr.shape[:3] + (cp,), dtype=torch.bfloat16, device=g.device)
+        gx[..., :lr.shape[-1]] = lr
+        return gx, None, None, None, None, None
+
+
+def shuffle_to_image(x, x32, c_img, r, scale, shift):
+    return _ShuffleToImage.apply(x, x32, c_img, r, float(scale), shift)
+
+
 def conv_to_image(x, weight, bias, out_scale, out_shift):
     return _ConvToImage.apply(x, weight, bias, float(out_scale), out_shift)
 

@@ -76,6 +76,12 @@ int srb200_nchw_to_nhwc(const float* in, void* out_bf16, int B, int C, int H, in
 int srb200_nhwc_to_nchw(const void* in_bf16, float* out, int B, int C, int H, int W, int C_pad,
                         const float* shift, float scale, srb200_stream_t stream);
 
+/* Nearest-neighbour x2 on NHWC bf16 (C % 8 == 0): F.interpolate(scale_factor=2, mode='nearest') of SwinIR's
+ * 'nearest+conv' reconstruction (swinir_arch.py:911-912).  inverse=0: in [B,H,W,C] -> out [B,2H,2W,C] (bit-exact
+ * copy); inverse=1 (its gradient): in [B,2H,2W,C] -> out [B,H,W,C], each output = fp32 sum of its 2x2 block.     */
+int srb200_nearest_up2(const void* in_bf16, void* out_bf16, int B, int H, int W, int C, int inverse,
+                       srb200_stream_t stream);
+
 /* ------------------------------------------------------------------ few-channel exit conv (conv_last, F -> C <= 7)
  * nn.Conv2d(F, C, 3, 1, 1) + `x / img_range + mean` (edsr_arch.py:48,58-59; rcan_arch.py:122,132-133;
  * swinir_arch.py:839,900,920) as ONE 1x1 tap-GEMM  T[p][tap*C + c] = X[p] . W[c][:][tap]  (reads X once instead of

@@ -201,9 +201,20 @@ def swin_block(sd, prefix, x, h, w, num_heads, ws, shift, drop_keep=None):
 
 
 def swinir_forward(sd, x, embed_dim=180, depths=(6, 6, 6, 6, 6, 6), num_heads=(6, 6, 6, 6, 6, 6), window_size=8,
-                   upscale=4, img_range=1., in_chans=3):
-    """swinir_arch.py:891-900,920 -- classical-SR ('pixelshuffle', '1conv') branch, eval mode."""
+                   upscale=4, img_range=1., in_chans=3, upsampler='pixelshuffle', resi_connection='1conv'):
+    """swinir_arch.py:891-920, eval mode: the classical-SR ('pixelshuffle') branch and the three other
+    reconstruction branches ('pixelshuffledirect' :901-905, 'nearest+conv' :906-913, '' :914-918); conv_after_body as
+    '1conv' or '3conv' (:818-826)."""
+    def resi(prefix, v):
+        if resi_connection == '1conv':
+            return conv(sd, prefix, v)
+        # '3conv' (:533-538, :821-826): conv3x3 C->C/4, lrelu 0.2, conv1x1, lrelu 0.2, conv3x3 C/4->C
+        v = F.leaky_relu(conv(sd, prefix + '.0', v), 0.2)
+        v = F.leaky_relu(conv(sd, prefix + '.2', v, padding=0), 0.2)
+        return conv(sd, prefix + '.4', v)
+
     mean = _mean(x, RGB_MEAN) if in_chans == 3 else torch.zeros(1, 1, 1, 1)
+    x_in = x
     x = (x - mean) * img_range
     x = conv(sd, 'conv_first', x)
     b, c, h, w = x.shape
@@ -215,13 +226,26 @@ def swinir_forward(sd, x, embed_dim=180, depths=(6, 6, 6, 6, 6, 6), num_heads=(6
             shift = 0 if bi % 2 == 0 else window_size // 2
             r = swin_block(sd, f'layers.{li}.residual_group.blocks.{bi}', r, h, w, num_heads[li], window_size, shift)
         r = r.transpose(1, 2).reshape(b, c, h, w)  # PatchUnEmbed :638-640
-        r = conv(sd, f'layers.{li}.conv', r)
+        r = resi(f'layers.{li}.conv', r)  # RSTB.conv :530-538
         t = r.flatten(2).transpose(1, 2) + t  # RSTB :557-558
     t = F.layer_norm(t, (c,), sd['norm.weight'], sd['norm.bias'], 1e-5)
     feat = t.transpose(1, 2).reshape(b, c, h, w)
-    x = conv(sd, 'conv_after_body', feat) + x
-    x = F.leaky_relu(conv(sd, 'conv_before_upsample.0', x), 0.01)
-    x = conv(sd, 'conv_last', upsample(sd, 'upsample', x, upscale))
+    body = resi('conv_after_body', feat)
+    if upsampler == '':  # denoising / JPEG CAR: image-space residual
+        return ((x_in - mean) * img_range + conv(sd, 'conv_last', body + x)) / img_range + mean
+    x = body + x
+    if upsampler == 'pixelshuffle':
+        x = F.leaky_relu(conv(sd, 'conv_before_upsample.0', x), 0.01)
+        x = conv(sd, 'conv_last', upsample(sd, 'upsample', x, upscale))
+    elif upsampler == 'pixelshuffledirect':
+        x = F.pixel_shuffle(conv(sd, 'upsample.0', x), upscale)
+    elif upsampler == 'nearest+conv':
+        x = F.leaky_relu(conv(sd, 'conv_before_upsample.0', x), 0.01)
+        x = F.leaky_relu(conv(sd, 'conv_up1', F.interpolate(x, scale_factor=2, mode='nearest')), 0.2)
+        x = F.leaky_relu(conv(sd, 'conv_up2', F.interpolate(x, scale_factor=2, mode='nearest')), 0.2)
+        x = conv(sd, 'conv_last', F.leaky_relu(conv(sd, 'conv_hr', x), 0.2))
+    else:
+        raise ValueError(upsampler)
     return x / img_range + mean
 
 

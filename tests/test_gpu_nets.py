@@ -40,7 +40,9 @@ def _build(fx, dev):
     return net.to(dev).eval()
 
 
-def _check_grad(got, want):
+def _check_grad(got, want, calib=None):
+    """rel-L2 / cosine bars; ``calib`` = the error PyTorch's CPU bf16 autocast of the reference makes on this
+    gradient (fixture['autocast_rel']), which loosens the bar to 2x that when it is the larger one."""
     got = got.detach().float().cpu()
     if isinstance(want, dict):
         g, w = got.flatten()[::want['stride']], want['sample']
@@ -49,7 +51,9 @@ def _check_grad(got, want):
         g, w = got, want
     rel = ((g - w).norm() / (w.norm() + 1e-12)).item()
     cos = (torch.dot(g.flatten().double(), w.flatten().double()) / (g.double().norm() * w.double().norm() + 1e-30)).item()
-    assert rel <= GRAD_REL_L2 and cos >= GRAD_COS, f'relative L2 {rel:.3e}, cosine {cos:.5f}'
+    bar = max(GRAD_REL_L2, 2.0 * calib) if calib is not None else GRAD_REL_L2
+    cos_bar = GRAD_COS if bar == GRAD_REL_L2 else 1.0 - 0.5 * bar * bar * 1.5
+    assert rel <= bar and cos >= cos_bar, f'relative L2 {rel:.3e} (bar {bar:.3e}), cosine {cos:.5f}'
 
 
 def _golden_cases(prefix):

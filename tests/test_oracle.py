@@ -22,7 +22,9 @@ def oracle_forward(fx, sd, x):
         return sr_oracle.rcan_forward(sd, x, num_group=kw['num_group'], num_block=kw['num_block'],
                                       upscale=kw['upscale'], res_scale=kw['res_scale'], img_range=kw['img_range'])
     return sr_oracle.swinir_forward(sd, x, embed_dim=kw['embed_dim'], depths=kw['depths'], num_heads=kw['num_heads'],
-                                    window_size=kw['window_size'], upscale=kw['upscale'], img_range=kw['img_range'])
+                                    window_size=kw['window_size'], upscale=kw['upscale'], img_range=kw['img_range'],
+                                    upsampler=kw.get('upsampler', 'pixelshuffle'),
+                                    resi_connection=kw.get('resi_connection', '1conv'))
 
 
 def state_dict_from_fixture(fx):
