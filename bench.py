@@ -171,6 +171,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # keep stdout for the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     L.check(L.load().srb200_check_device(local_rank), 'srb200_check_device')
 
