@@ -64,6 +64,7 @@ SIGNATURES = {
     'srb200_tap_stencil': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                                    c_void_p]),
     'srb200_tap_im2col': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    'srb200_multi_axpby': (c_int, [c_void_p, c_int, c_int64, c_float, c_float, c_void_p]),
     'srb200_pack_weights': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     'srb200_unpack_wgrads': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     'srb200_unpack_wgrads_inline': (c_int, [c_void_p, c_int, c_void_p]),

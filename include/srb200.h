@@ -135,6 +135,19 @@ int srb200_unpack_wgrads(const srb200_pack_item* items_dev, int n_items, int64_t
 #define SRB200_MAX_INLINE_ITEMS 8
 int srb200_unpack_wgrads_inline(const srb200_pack_item* items_host, int n_items, srb200_stream_t stream);
 
+/* ------------------------------------------------------------------ multi-tensor EMA
+ * dst_i = a * dst_i + b * src_i for every fp32 tensor pair of a DEVICE table, one launch: the exponential moving
+ * average of BaseModel.model_ema (basicsr/models/base_model.py:75-82; a = decay, b = 1 - decay) without its two
+ * launches per parameter.  Item i covers 1024-float chunks [chunk_begin, chunk_begin + ceil(n/1024)).           */
+typedef struct {
+  const void* src;
+  void* dst;
+  int64_t n;
+  int64_t chunk_begin;
+} srb200_vec_item;
+int srb200_multi_axpby(const srb200_vec_item* items_dev, int n_items, int64_t total_chunks, float a, float b,
+                       srb200_stream_t stream);
+
 /* ------------------------------------------------------------------ tap-GEMM (conv3x3 / conv1x1 / Linear)
  * out[b,y,x,n] = epi( sum_{t,k} A[b, y+dy(t), x+dx(t), k] * Wp[t][n][k] )
  * TMA-fed tcgen05 implicit GEMM, fp32 accumulation in TMEM.  Replaces nn.Conv2d(…,3,1,1)

@@ -194,3 +194,30 @@ def test_edsr_cuda_graph_replay_matches_eager(cuda):
     assert y.shape == (1, 3, 36, 44)
     import copy
     copy.deepcopy(graphed)  # EMA copy must not trip over CUDA graph objects
+
+
+def test_fused_ema_matches_reference_loop(cuda):
+    """utils/ema.FusedEMA == BaseModel.model_ema's per-parameter loop (base_model.py:75-82), one launch."""
+    import copy
+    from basicsr4rs_b200 import _lib as L
+    from basicsr4rs_b200.archs import build_network
+    from basicsr4rs_b200.utils.ema import FusedEMA
+    torch.manual_seed(0)
+    net = build_network(dict(type='RCAN', num_in_ch=3, num_out_ch=3, num_feat=64, num_group=2, num_block=3,
+                             squeeze_factor=16, upscale=4)).to(cuda)
+    ema = copy.deepcopy(net)
+    ref = copy.deepcopy(net)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.add_(torch.randn_like(p_) * 0.1)
+    fused = FusedEMA(net, ema)
+    n0 = L.launch_count
+    for decay in (0.999, 0.9):
+        fused.step(decay)
+        src = dict(net.named_parameters())
+        with torch.no_grad():
+            for k, p_ in ref.named_parameters():
+                p_.data.mul_(decay).add_(src[k].data, alpha=1 - decay)
+    assert L.launch_count - n0 == 2
+    for (k, a), (_, b) in zip(ema.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), k
