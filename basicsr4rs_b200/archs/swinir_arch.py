@@ -25,7 +25,7 @@ from ..utils.registry import ARCH_REGISTRY
 from .arch_util import Upsample, require_cuda, to_2tuple, trunc_normal_
 from .graphed import ArchMixin, Segment, chain_wire, graphed_forward, split_even
 
-KERNEL_WINDOW = 8  # the fused attention kernel is specialised for 8x8 windows (64 tokens)
+KERNEL_WINDOW = 8  # the fused attention kernel holds a window in 64-row tiles: window sizes 2..8
 
 
 def drop_path_scale(batch, drop_prob, training, device):
@@ -152,9 +152,9 @@ class SwinTransformerBlock(nn.Module):
 
     def forward_nhwc(self, t):
         """t: [B, H, W, pad64(C)] bf16."""
-        if self.window_size != KERNEL_WINDOW:
-            raise NotImplementedError(f'srb200 fused window attention supports window_size {KERNEL_WINDOW} '
-                                      f'(got {self.window_size}); other sizes are a documented next step')
+        if not 2 <= self.window_size <= KERNEL_WINDOW:
+            raise NotImplementedError(f'srb200 fused window attention supports window_size 2..{KERNEL_WINDOW} '
+                                      f'(got {self.window_size})')
         b = t.shape[0]
         dp = self.drop_path
         a1 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None

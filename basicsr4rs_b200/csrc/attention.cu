@@ -18,12 +18,12 @@
 
 namespace srb {
 
-constexpr int WS = 8;
-constexpr int NTOK = 64;
+constexpr int WS_MAX = 8;   // window sizes 2..8: a window's ws*ws tokens occupy the first rows of the 64-row tiles,
+constexpr int NTOK = 64;    // the rest is padding (zero q/k/v, keys masked out of the softmax, rows never stored)
 constexpr int HD = 32;
 constexpr int QROW = 40;   // padded smem row (elements) of the 32-wide tiles: conflict-free ldmatrix
 constexpr int PROW = 72;   // padded smem row of the 64-wide P / dS tiles
-constexpr int NBIAS = (2 * WS - 1) * (2 * WS - 1);
+constexpr int NBIAS = (2 * WS_MAX - 1) * (2 * WS_MAX - 1);
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -47,13 +47,15 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 struct AttnGeom {
   int B, H, W, nH, Cp, shift;
   float scale;
+  int ws;  // window size (<= WS_MAX)
 };
 
 // global element offset of token n of window (b, wy, wx) in an NHWC tensor with `ld` channels
 __device__ __forceinline__ size_t token_offset(const AttnGeom& g, int b, int wy, int wx, int n,
                                                int ld) {
-  int y = wy * WS + (n >> 3) + g.shift;
-  int x = wx * WS + (n & 7) + g.shift;
+  const int ny = n / g.ws;
+  int y = wy * g.ws + ny + g.shift;
+  int x = wx * g.ws + (n - ny * g.ws) + g.shift;
   if (y >= g.H) y -= g.H;
   if (x >= g.W) x -= g.W;
   return ((static_cast<size_t>(b) * g.H + y) * g.W + x) * ld;
@@ -63,20 +65,24 @@ __device__ __forceinline__ size_t token_offset(const AttnGeom& g, int b, int wy,
 __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* gsrc,
                                           const AttnGeom& g, int b, int wy, int wx, int ld,
                                           int chan0) {
+  const int ntok = g.ws * g.ws;
   for (int c = threadIdx.x; c < NTOK * 4; c += blockDim.x) {
     const int n = c >> 2, part = c & 3;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(gsrc + token_offset(g, b, wy, wx, n, ld) +
-                                                         chan0 + part * 8));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < ntok)
+      v = __ldg(reinterpret_cast<const uint4*>(gsrc + token_offset(g, b, wy, wx, n, ld) + chan0 + part * 8));
     *reinterpret_cast<uint4*>(s + n * QROW + part * 8) = v;
   }
 }
 __device__ __forceinline__ void store_tile(const __nv_bfloat16* s, __nv_bfloat16* gdst,
                                            const AttnGeom& g, int b, int wy, int wx, int ld,
                                            int chan0) {
+  const int ntok = g.ws * g.ws;
   for (int c = threadIdx.x; c < NTOK * 4; c += blockDim.x) {
     const int n = c >> 2, part = c & 3;
-    *reinterpret_cast<uint4*>(gdst + token_offset(g, b, wy, wx, n, ld) + chan0 + part * 8) =
-        *reinterpret_cast<const uint4*>(s + n * QROW + part * 8);
+    if (n < ntok)
+      *reinterpret_cast<uint4*>(gdst + token_offset(g, b, wy, wx, n, ld) + chan0 + part * 8) =
+          *reinterpret_cast<const uint4*>(s + n * QROW + part * 8);
   }
 }
 
@@ -132,15 +138,17 @@ __device__ __forceinline__ void gemm_tA_16x32x64(float (&acc)[4][4], const __nv_
   }
 }
 
-__device__ __forceinline__ int rel_index(int row, int col) {
-  return ((row >> 3) - (col >> 3) + WS - 1) * (2 * WS - 1) + ((row & 7) - (col & 7) + WS - 1);
+__device__ __forceinline__ int rel_index(int row, int col, int ws) {
+  const int ry = row / ws, cy = col / ws;
+  return (ry - cy + ws - 1) * (2 * ws - 1) + ((row - ry * ws) - (col - cy * ws) + ws - 1);
 }
 
 // logits -> probabilities in place (unnormalised exp); returns 1/rowsum for the two rows of this thread
 __device__ __forceinline__ void softmax_rows(float (&s)[8][4], const float* sBias, const int* sRegion,
                                              bool masked, float scale, int warp, int lane,
-                                             float (&inv)[2]) {
+                                             float (&inv)[2], int ws) {
   const int g = lane >> 2, t = lane & 3;
+  const int ntok = ws * ws;
   float mx[2] = {-1e30f, -1e30f};
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
@@ -148,8 +156,14 @@ __device__ __forceinline__ void softmax_rows(float (&s)[8][4], const float* sBia
     for (int e = 0; e < 4; ++e) {
       const int row = 16 * warp + g + ((e & 2) ? 8 : 0);
       const int col = nt * 8 + 2 * t + (e & 1);
-      float v = s[nt][e] * scale + sBias[rel_index(row, col)];
-      if (masked && sRegion[row] != sRegion[col]) v += -100.0f;
+      float v = -1e30f;  // padding keys (ws < 8) drop out of the softmax; padding query rows are never stored
+      if (col < ntok) {
+        v = 0.0f;
+        if (row < ntok) {
+          v = s[nt][e] * scale + sBias[rel_index(row, col, ws)];
+          if (masked && sRegion[row] != sRegion[col]) v += -100.0f;
+        }
+      }
       s[nt][e] = v;
       mx[e >> 1] = fmaxf(mx[e >> 1], v);
     }
@@ -178,7 +192,7 @@ __device__ __forceinline__ void softmax_rows(float (&s)[8][4], const float* sBia
 __device__ __forceinline__ void setup_window(const AttnGeom& g, int& b, int& wy, int& wx, int& head,
                                              float* sBias, int* sRegion,
                                              const float* __restrict__ table) {
-  const int nWw = g.W / WS, nWh = g.H / WS;
+  const int nWw = g.W / g.ws, nWh = g.H / g.ws;
   int u = blockIdx.x;
   head = u % g.nH;
   u /= g.nH;
@@ -186,13 +200,15 @@ __device__ __forceinline__ void setup_window(const AttnGeom& g, int& b, int& wy,
   u /= nWw;
   wy = u % nWh;
   b = u / nWh;
-  for (int i = threadIdx.x; i < NBIAS; i += blockDim.x) sBias[i] = __ldg(table + i * g.nH + head);
+  for (int i = threadIdx.x; i < (2 * g.ws - 1) * (2 * g.ws - 1); i += blockDim.x)
+    sBias[i] = __ldg(table + i * g.nH + head);
   if (threadIdx.x < NTOK) {
     int id = 0;
-    if (g.shift > 0) {
-      const int ys = wy * WS + (threadIdx.x >> 3), xs = wx * WS + (threadIdx.x & 7);
-      const int rh = ys < g.H - WS ? 0 : (ys < g.H - g.shift ? 1 : 2);
-      const int rw = xs < g.W - WS ? 0 : (xs < g.W - g.shift ? 1 : 2);
+    if (g.shift > 0 && threadIdx.x < g.ws * g.ws) {
+      const int ty = threadIdx.x / g.ws;
+      const int ys = wy * g.ws + ty, xs = wx * g.ws + (threadIdx.x - ty * g.ws);
+      const int rh = ys < g.H - g.ws ? 0 : (ys < g.H - g.shift ? 1 : 2);
+      const int rw = xs < g.W - g.ws ? 0 : (xs < g.W - g.shift ? 1 : 2);
       id = rh * 3 + rw;
     }
     sRegion[threadIdx.x] = id;
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(128) window_attn_fwd_kernel(const __nv_bfloat1
     for (int e = 0; e < 4; ++e) s[i][e] = 0.0f;
   gemm_nt_16x64x32(s, sQ, sK, warp, lane);
   float inv[2];
-  softmax_rows(s, sBias, sRegion, g.shift > 0, g.scale, warp, lane, inv);
+  softmax_rows(s, sBias, sRegion, g.shift > 0, g.scale, warp, lane, inv, g.ws);
   uint32_t pf[4][4];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
     }
   gemm_nt_16x64x32(s, sQ, sK, warp, lane);
   float inv[2];
-  softmax_rows(s, sBias, sRegion, g.shift > 0, g.scale, warp, lane, inv);
+  softmax_rows(s, sBias, sRegion, g.shift > 0, g.scale, warp, lane, inv, g.ws);
   gemm_nt_16x64x32(dp, sdO, sV, warp, lane);  // dP = dO V^T
   float delta[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -334,12 +350,13 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
   // Bias-table gradient: bin (dy, dx) collects dS[(ry,rx),(ry-dy,rx-dx)].  One thread per bin sums its <= 64
   // entries of the staged dS tile -- no shared-memory float atomics (4096 contended CAS loops per CTA were the
   // bulk of this kernel's time), then one global atomic per bin as before.
-  for (int bin = threadIdx.x; bin < NBIAS; bin += blockDim.x) {
-    const int dy = bin / (2 * WS - 1) - (WS - 1), dx = bin % (2 * WS - 1) - (WS - 1);
+  const int ws = g.ws, nbias = (2 * ws - 1) * (2 * ws - 1);
+  for (int bin = threadIdx.x; bin < nbias; bin += blockDim.x) {
+    const int dy = bin / (2 * ws - 1) - (ws - 1), dx = bin % (2 * ws - 1) - (ws - 1);
     float acc = 0.0f;
-    for (int ry = (dy > 0 ? dy : 0); ry < (dy < 0 ? WS + dy : WS); ++ry)
-      for (int rx = (dx > 0 ? dx : 0); rx < (dx < 0 ? WS + dx : WS); ++rx)
-        acc += __bfloat162float(sdS[(ry * WS + rx) * PROW + (ry - dy) * WS + (rx - dx)]);
+    for (int ry = (dy > 0 ? dy : 0); ry < (dy < 0 ? ws + dy : ws); ++ry)
+      for (int rx = (dx > 0 ? dx : 0); rx < (dx < 0 ? ws + dx : ws); ++rx)
+        acc += __bfloat162float(sdS[(ry * ws + rx) * PROW + (ry - dy) * ws + (rx - dx)]);
     sdBias[bin] = acc;
   }
   gemm_regA_16x32x64(dq, dsf, sK, lane);          // dQ = dS K      (rows = this warp's queries)
@@ -361,12 +378,12 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
   store_tile(sK, gqkv, g, b, wy, wx, ld, g.Cp + head * HD);
   store_tile(sV, gqkv, g, b, wy, wx, ld, 2 * g.Cp + head * HD);
   if (gtable == nullptr) return;  // (timing experiments only)
-  for (int i = threadIdx.x; i < NBIAS; i += blockDim.x) atomicAdd(gtable + i * g.nH + head, sdBias[i]);
+  for (int i = threadIdx.x; i < nbias; i += blockDim.x) atomicAdd(gtable + i * g.nH + head, sdBias[i]);
 }
 
 static int check_geom(int B, int H, int W, int nH, int Cp, int ws, int shift) {
   if (B <= 0 || H <= 0 || W <= 0 || nH <= 0) return SRB200_EINVAL;
-  if (ws != WS || H % WS != 0 || W % WS != 0 || shift < 0 || shift >= WS) return SRB200_EINVAL;
+  if (ws < 2 || ws > WS_MAX || H % ws != 0 || W % ws != 0 || shift < 0 || shift >= ws) return SRB200_EINVAL;
   if (Cp != nH * HD) return SRB200_EINVAL;
   return SRB200_OK;
 }
@@ -382,8 +399,8 @@ extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rp
   if (!qkv_bf16 || !rpb_table || !out_bf16) return SRB200_EINVAL;
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
-  AttnGeom g{B, H, W, num_heads, Cp, shift, scale};
-  const long long grid = static_cast<long long>(B) * (H / WS) * (W / WS) * num_heads;
+  AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
+  const long long grid = static_cast<long long>(B) * (H / window_size) * (W / window_size) * num_heads;
   if (grid > 0x7FFFFFFF) return SRB200_EINVAL;
   window_attn_fwd_kernel<<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), rpb_table, static_cast<__nv_bfloat16*>(out_bf16), g);
@@ -398,8 +415,8 @@ extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gou
   if (!qkv_bf16 || !gout_bf16 || !rpb_table || !gqkv_bf16 || !g_rpb_table) return SRB200_EINVAL;
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
-  AttnGeom g{B, H, W, num_heads, Cp, shift, scale};
-  const long long grid = static_cast<long long>(B) * (H / WS) * (W / WS) * num_heads;
+  AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
+  const long long grid = static_cast<long long>(B) * (H / window_size) * (W / window_size) * num_heads;
   if (grid > 0x7FFFFFFF) return SRB200_EINVAL;
   window_attn_bwd_kernel<<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<const __nv_bfloat16*>(gout_bf16),

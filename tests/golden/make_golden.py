@@ -43,6 +43,10 @@ CASES = {
     'swinir_c60_d2_nearest_x4': ('SwinIR', dict(upscale=4, in_chans=3, img_size=16, window_size=8, img_range=1.,
                                                 depths=[2], embed_dim=60, num_heads=[6], mlp_ratio=2,
                                                 upsampler='nearest+conv', resi_connection='3conv'), (1, 3, 16, 16)),
+    # the fork's remote-sensing shape: 6-wide windows, 4 input bands (train_SwinIR_L2S288_scratch.yml:43-54)
+    'swinir_c60_ws6_in4_x2': ('SwinIR', dict(upscale=2, in_chans=4, img_size=12, window_size=6, img_range=1.,
+                                             depths=[2], embed_dim=60, num_heads=[6], mlp_ratio=2,
+                                             upsampler='pixelshuffle', resi_connection='1conv'), (1, 4, 12, 18)),
 }
 
 GRAD_KEYS = {

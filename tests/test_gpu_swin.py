@@ -74,20 +74,23 @@ def _ref_window_attention(qkv_pad, table, nh, hd, ws, shift, h, w):
     return out.reshape(b, h, w, nh, hd)
 
 
-@pytest.mark.parametrize('b,h,w,nh,hd,shift', [(2, 16, 24, 6, 30, 0), (2, 16, 24, 6, 30, 4), (1, 8, 8, 6, 10, 0),
-                                               (1, 64, 64, 6, 30, 4), (1, 24, 16, 2, 32, 3)])
-def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift):
+@pytest.mark.parametrize('b,h,w,nh,hd,shift,ws', [(2, 16, 24, 6, 30, 0, 8), (2, 16, 24, 6, 30, 4, 8), (1, 8, 8, 6, 10, 0, 8),
+                                                  (1, 64, 64, 6, 30, 4, 8), (1, 24, 16, 2, 32, 3, 8),
+                                                  # the fork's remote-sensing recipes: 6-wide windows; and 7 (Swin default)
+                                                  (2, 12, 18, 6, 30, 0, 6), (2, 12, 18, 6, 30, 3, 6), (1, 48, 48, 6, 30, 3, 6),
+                                                  (1, 14, 21, 3, 20, 3, 7), (1, 8, 12, 2, 16, 2, 4)])
+def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift, ws):
     so = _ops()
     g = torch.Generator().manual_seed(1)
     ca = nh * 32
     qkv = torch.zeros((b, h, w, 3, nh, 32))
     qkv[..., :hd] = torch.randn((b, h, w, 3, nh, hd), generator=g)
     qkv = qkv.reshape(b, h, w, 3 * ca).to(cuda).to(torch.bfloat16)
-    table = (torch.randn((225, nh), generator=g) * 0.5).to(cuda)
-    out = so.window_attention_fwd(qkv, table, nh, 8, shift, hd**-0.5)
+    table = (torch.randn(((2 * ws - 1)**2, nh), generator=g) * 0.5).to(cuda)
+    out = so.window_attention_fwd(qkv, table, nh, ws, shift, hd**-0.5)
     qr = qkv.float().requires_grad_(True)
     tr = table.clone().requires_grad_(True)
-    ref = _ref_window_attention(qr, tr, nh, hd, 8, shift, h, w)
+    ref = _ref_window_attention(qr, tr, nh, hd, ws, shift, h, w)
     got = out.reshape(b, h, w, nh, 32)
     assert torch.count_nonzero(got[..., hd:]) == 0
     err = (got[..., :hd].float() - ref).abs().max().item()
@@ -96,7 +99,7 @@ def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift):
     go[..., :hd] = torch.randn((b, h, w, nh, hd), generator=g)
     go = go.reshape(b, h, w, ca).to(cuda).to(torch.bfloat16)
     ref.backward(go.reshape(b, h, w, nh, 32)[..., :hd].float())
-    gqkv, gtable = so.window_attention_bwd(qkv, go, table, nh, 8, shift, hd**-0.5)
+    gqkv, gtable = so.window_attention_bwd(qkv, go, table, nh, ws, shift, hd**-0.5)
     want = qr.grad
     rel = ((gqkv.float() - want).norm() / want.norm()).item()
     assert rel <= 2e-2, f'gqkv rel-L2 {rel:.3e}'
@@ -144,7 +147,7 @@ def test_swin_block_vs_oracle(cuda):
 
 
 @pytest.mark.parametrize('case', ['swinir_c180_d2x2_x4', 'swinir_c60_d2_x2', 'swinir_c60_d2_direct_x2',
-                                  'swinir_c60_d2_nearest_x4'])
+                                  'swinir_c60_d2_nearest_x4', 'swinir_c60_ws6_in4_x2'])
 def test_swinir_matches_reference_golden(cuda, case):
     fx = torch.load(os.path.join(GOLDEN, case + '.pt'), weights_only=False)
     net = _build(fx, cuda)

@@ -23,7 +23,7 @@ def oracle_forward(fx, sd, x):
                                       upscale=kw['upscale'], res_scale=kw['res_scale'], img_range=kw['img_range'])
     return sr_oracle.swinir_forward(sd, x, embed_dim=kw['embed_dim'], depths=kw['depths'], num_heads=kw['num_heads'],
                                     window_size=kw['window_size'], upscale=kw['upscale'], img_range=kw['img_range'],
-                                    upsampler=kw.get('upsampler', 'pixelshuffle'),
+                                    in_chans=kw.get('in_chans', 3), upsampler=kw.get('upsampler', 'pixelshuffle'),
                                     resi_connection=kw.get('resi_connection', '1conv'))
 
 
