@@ -377,7 +377,6 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
   store_tile(sQ, gqkv, g, b, wy, wx, ld, head * HD);
   store_tile(sK, gqkv, g, b, wy, wx, ld, g.Cp + head * HD);
   store_tile(sV, gqkv, g, b, wy, wx, ld, 2 * g.Cp + head * HD);
-  if (gtable == nullptr) return;  // (timing experiments only)
   for (int i = threadIdx.x; i < nbias; i += blockDim.x) atomicAdd(gtable + i * g.nH + head, sdBias[i]);
 }
 
@@ -420,6 +419,6 @@ extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gou
   if (grid > 0x7FFFFFFF) return SRB200_EINVAL;
   window_attn_bwd_kernel<<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<const __nv_bfloat16*>(gout_bf16),
-      rpb_table, static_cast<__nv_bfloat16*>(gqkv_bf16), getenv("SRB_ATTN_NOTABLE") ? nullptr : g_rpb_table, g);
+      rpb_table, static_cast<__nv_bfloat16*>(gqkv_bf16), g_rpb_table, g);
   return launch_status();
 }

@@ -208,7 +208,6 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
     }
   }
   __syncthreads();
-  if (ggamma == nullptr) return;  // (timing experiments only)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomicAdd(ggamma + c, s_red[c]);
     atomicAdd(gbeta + c, s_red[Cp + c]);
@@ -264,8 +263,6 @@ extern "C" int srb200_layernorm_bwd(const void* gy_bf16, const void* x_bf16, con
   long long blocks = (T + 63) / 64;  // >= 8 tokens per warp so the column atomics amortise
   // persistent: as many blocks as stay resident (per-block prologue / column-sum epilogue is not free)
   long long cap = static_cast<long long>(num_sms()) * (Cp <= 256 ? 3 : 1);
-  if (const char* e = getenv("SRB_LN_BPS")) cap = static_cast<long long>(num_sms()) * atoi(e);
-  if (getenv("SRB_LN_NOATOM")) ggamma = nullptr;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const size_t smem = 2 * static_cast<size_t>(Cp) * sizeof(float);

@@ -597,10 +597,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                 view = nc / C;
                 c0 = nc - view * C;
               }
-              if (p.tma_store != 2) {  // (2 = SRB_DEBUG_SKIP_STORE timing experiment: results are not written)
-                if (has_aux) tma_store_4d(&p.tmap_aux, buf_aux, c0, x0, y0, b);
-                tma_store_4d(&p.tmap_out[view], buf_out, c0, x0, y0, b);
-              }
+              if (has_aux) tma_store_4d(&p.tmap_aux, buf_aux, c0, x0, y0, b);
+              tma_store_4d(&p.tmap_out[view], buf_out, c0, x0, y0, b);
               tma_store_commit();
             }
             ++store_iter;
@@ -864,7 +862,6 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
         }
       }
     if (aux_out && ro != 1) return SRB200_EINVAL;
-    if (getenv("SRB_DEBUG_SKIP_STORE") != nullptr) p.tma_store = 2;
   }
   if (two_cta) return launch_tapgemm2<256>(p, stream);
   // small-K, wide-N layers (SwinIR's linears) are epilogue-bound: two epilogue teams (needs the TMA-store path and

@@ -32,7 +32,6 @@ struct WgradParams {
   int taps, ksize;
   int dy_c;      // channels per dY view (N / dy_r^2)
   unsigned long long* trace;  // debug timeline of CTA 0 (NULL = off)
-  int exp_skip;  // debug: 1 = skip dY loads, 2 = skip X loads
 };
 
 // KPIX = pixels (GEMM-K) per stage: a cp.async.bulk.tensor costs its issuing lane 400-500 cycles whatever the box
@@ -426,7 +425,6 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   p.H = H;
   p.W = W;
   pick_tile(H, W, 64, &p.tile_w, &p.tile_h);
-  p.exp_skip = 0;
   p.tiles_x = (W + p.tile_w - 1) / p.tile_w;
   p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
   p.total_kb = B * p.tiles_x * p.tiles_y;

@@ -13,7 +13,12 @@
  *
  * Activation layout inside a network: NHWC, bf16, channel count padded to a multiple
  * of 64 with zeros ("NHWC64").  Weights are fp32 nn.Parameters on the host side and are
- * repacked to bf16 tap-major GEMM operands by srb200_pack_weight (derived cache).
+ * repacked to bf16 tap-major GEMM operands by srb200_pack_weight(s) (derived cache).
+ *
+ * Kernel-variant selectors read from the environment at call time (tuning / A-B measurements only; every
+ * variant computes the same result): SRB_TAPGEMM_1CTA (no cta_group::2 pairs), SRB_TAPGEMM_NO_TEAMS (one 8-warp
+ * epilogue instead of two 4-warp teams), SRB_WGRAD_1CTA, SRB_WG_KPIX / SRB_WG2_KPIX = 64 | 128 | 256 (pixels per
+ * weight-gradient pipeline stage).
  */
 #ifndef SRB200_H_
 #define SRB200_H_
