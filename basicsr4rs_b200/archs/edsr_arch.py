@@ -100,7 +100,7 @@ class EDSR(ArchMixin, nn.Module):
                     return call(nseg - 1, res, first)
 
                 self._device_mean(x)
-                graphs = GRAPHS[self] = GraphedSegments(self._build_segments, wire, book=self._pack_book())
+                graphs = GRAPHS[self] = GraphedSegments(self._build_segments, wire, book=self._pack_book(), pdl=True)
             out = graphs(x.contiguous().float(), True)
             return out if out.dtype == x.dtype else out.to(x.dtype)
         first = self._head(x)

@@ -51,10 +51,11 @@ class GraphedSegments:
 
     WARMUP = 3
 
-    def __init__(self, build_segments, wire, book=None):
+    def __init__(self, build_segments, wire, book=None, pdl=False):
         self._build = build_segments
         self._wire = wire
         self._book = book
+        self._pdl = pdl  # capture the GEMM launches with programmatic dependent launch (srb200_set_pdl)
         self._cache = {}
         self.kernels_per_step = {}
 
@@ -101,7 +102,11 @@ class GraphedSegments:
             torch.cuda.current_stream().wait_stream(side)
             self._book.capture_ok = True
         n0 = L.launch_count
-        graphed = torch.cuda.make_graphed_callables(tuple(segs), sample_args, num_warmup_iters=self.WARMUP)
+        prev = L.load().srb200_set_pdl(1 if self._pdl else 0)
+        try:
+            graphed = torch.cuda.make_graphed_callables(tuple(segs), sample_args, num_warmup_iters=self.WARMUP)
+        finally:
+            L.load().srb200_set_pdl(prev)
         self.kernels_per_step[key] = (L.launch_count - n0) // (self.WARMUP + 1)
         return list(graphed)
 
@@ -110,7 +115,8 @@ def graphed_forward(module, x, build_segments, wire):
     """Replay ``module``'s training forward/backward for input ``x`` from CUDA graphs (captured on first use)."""
     graphs = GRAPHS.get(module)
     if graphs is None:
-        graphs = GRAPHS[module] = GraphedSegments(build_segments, wire, book=module._pack_book())
+        graphs = GRAPHS[module] = GraphedSegments(build_segments, wire, book=module._pack_book(),
+                                                  pdl=getattr(module, 'graph_pdl', False))
     return graphs(x.contiguous().float(), True)
 
 

@@ -75,6 +75,7 @@ class RCAN(ArchMixin, nn.Module):
     Args (identical to the reference): num_in_ch, num_out_ch, num_feat=64, num_group=10, num_block=16,
     squeeze_factor=16, upscale=4, res_scale=1, img_range=255., rgb_mean=(0.4488, 0.4371, 0.4040).
     """
+    graph_pdl = True  # back-to-back GEMM chain: captured with programmatic dependent launch (archs/graphed.py)
 
     def __init__(self,
                  num_in_ch,

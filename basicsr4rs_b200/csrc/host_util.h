@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/srb200.h"
 
@@ -61,6 +62,52 @@ inline int num_sms() {
 
 inline int launch_status() {
   return cudaPeekAtLastError() == cudaSuccess ? SRB200_OK : SRB200_ELAUNCH;
+}
+
+// Programmatic dependent launch (SRB_PDL=1): the GEMM kernels call griddepcontrol.launch_dependents right after
+// their prologue and griddepcontrol.wait before touching global memory, so the barrier init / TMEM allocation /
+// tensor-map fetch of kernel N+1 overlaps the tail of kernel N on SMs that have already drained.
+// Off by default: it is a win for chains of GEMM kernels (EDSR, RCAN: +1..5 %) but when a multi-wave kernel such as
+// the window attention sits between them, the early-resident GEMM CTAs starve it (SwinIR: -15 %).  The archs switch
+// it on around their CUDA-graph capture with srb200_set_pdl(); SRB_PDL=0/1 in the environment overrides.
+inline int& pdl_flag() {
+  static int flag = 0;
+  return flag;
+}
+inline bool pdl_enabled() {
+  static const int env = [] {
+    const char* e = getenv("SRB_PDL");
+    return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
+  }();
+  return env >= 0 ? env == 1 : pdl_flag() != 0;
+}
+
+template <typename Kernel, typename Params>
+inline int launch_ex(Kernel kernel, int grid, int block, size_t smem, cudaStream_t stream, int cluster,
+                     const Params& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  if (cudaLaunchKernelEx(&cfg, kernel, p) != cudaSuccess) return SRB200_ELAUNCH;
+  return launch_status();
 }
 
 // spatial tile (tw x th pixels, tw*th == npix) minimising padded area for an H x W image

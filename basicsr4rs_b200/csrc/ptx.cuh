@@ -201,6 +201,16 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 
 }  // namespace srb
 
+// ================================================================ programmatic dependent launch
+namespace srb {
+// let the next kernel of the stream start its prologue; then wait until OUR prerequisite grid has completed and
+// flushed (both are no-ops unless the kernels were launched with programmatic stream serialization)
+__device__ __forceinline__ void pdl_handoff() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+}  // namespace srb
+
 // ================================================================ 2-CTA (cta_group::2) variants
 // A CTA pair (cluster of 2 on one TPC) executes one M=256 UMMA: each CTA stages its own 128 rows of A and
 // half of B, the leader (cluster rank 0) issues the MMA, accumulators land in both CTAs' TMEM.

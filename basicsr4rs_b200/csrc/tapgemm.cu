@@ -52,6 +52,7 @@ struct TapGemmParams {
   const float* alpha_b;       // optional per-sample scale [B] (stochastic depth)
   float* colsum;              // optional fp32 [Cout]: += column sums of the stored result (bias gradient)
   int aux_mode;               // 1: aux_out = act'(pre-activation) instead of the pre-activation (GELU only)
+  int pdl;                    // launched with programmatic stream serialization: do the griddepcontrol handoff
   int colsum_per_image;       // 1: colsum is [B][Cout] (per-sample sums: RCAN's global average pool)
   float colsum_scale;         // factor applied to the sums when they are flushed (1/HW for the pool)
   int act;
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   __syncthreads();
   if constexpr (TWO) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / complete_tx
   tc_fence_after();
+  if (p.pdl) pdl_handoff();  // everything above touched no global memory
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -683,20 +685,7 @@ static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
   const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
   int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
   if (pairs >= p.n_tiles) pairs -= pairs % p.n_tiles;  // a CTA pair keeps its N tile for all its work units
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(320);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, tapgemm_kernel<BLOCK_N, true>, p) != cudaSuccess) return SRB200_ELAUNCH;
-  return launch_status();
+  return launch_ex(tapgemm_kernel<BLOCK_N, true>, 2 * pairs, 320, Cfg::SMEM_BYTES, stream, 2, p);
 }
 
 template <int BLOCK_N, bool TEAMS = false>
@@ -713,8 +702,7 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   int grid = total < num_sms() ? total : num_sms();
   if (grid >= p.n_tiles) grid -= grid % p.n_tiles;  // a CTA keeps its N tile (bias, weight columns) for all its tiles
   if (TEAMS && grid % p.n_tiles != 0) return SRB200_EINVAL;
-  tapgemm_kernel<BLOCK_N, false, TEAMS><<<grid, 320, Cfg::SMEM_BYTES, stream>>>(p);
-  return launch_status();
+  return launch_ex(tapgemm_kernel<BLOCK_N, false, TEAMS>, grid, 320, Cfg::SMEM_BYTES, stream, 1, p);
 }
 
 static unsigned long long* g_trace = nullptr;
@@ -813,6 +801,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.out_c = d->out_c;
   p.out_scale = d->out_scale;
   p.trace = g_trace;
+  p.pdl = pdl_enabled() ? 1 : 0;
 
   // A views: in[B, H*r, W*r, Cin], view (i,j): element (b,y,x,c) at ((b*H*r + y*r+i)*W*r + x*r+j)*Cin + c
   const int r = d->src_r;
@@ -882,6 +871,12 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
     case 16: return launch_tapgemm<16>(p, stream);
   }
   return SRB200_EINVAL;
+}
+
+extern "C" int srb200_set_pdl(int on) {
+  const int prev = pdl_flag();
+  pdl_flag() = on ? 1 : 0;
+  return prev;
 }
 
 /* debug only: device buffer of 3*64 uint64 receiving CTA 0's per-role clock64 timeline of subsequent launches */

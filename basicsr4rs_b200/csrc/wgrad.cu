@@ -32,6 +32,7 @@ struct WgradParams {
   int taps, ksize;
   int dy_c;      // channels per dY view (N / dy_r^2)
   unsigned long long* trace;  // debug timeline of CTA 0 (NULL = off)
+  int pdl;       // launched with programmatic stream serialization: do the griddepcontrol handoff
 };
 
 // KPIX = pixels (GEMM-K) per stage: a cp.async.bulk.tensor costs its issuing lane 400-500 cycles whatever the box
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.pdl) pdl_handoff();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -272,6 +274,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote signal can arrive
   tc_fence_after();
+  if (p.pdl) pdl_handoff();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -374,8 +377,7 @@ static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = 2 * p.taps * p.m_tiles * p.n_tiles * p.splits;
-  wgrad2_kernel<KPIX><<<grid, 192, Wg2Cfg<KPIX>::SMEM_BYTES, stream>>>(p);
-  return launch_status();
+  return launch_ex(wgrad2_kernel<KPIX>, grid, 192, Wg2Cfg<KPIX>::SMEM_BYTES, stream, 1, p);  // (__cluster_dims__ 2)
 }
 
 template <int BLOCK_N, int KPIX>
@@ -389,8 +391,7 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.taps * p.m_tiles * p.n_tiles * p.splits;
-  wgrad_kernel<BLOCK_N, KPIX><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(p);
-  return launch_status();
+  return launch_ex(wgrad_kernel<BLOCK_N, KPIX>, grid, 192, Cfg::SMEM_BYTES, stream, 1, p);
 }
 
 }  // namespace srb
@@ -420,6 +421,7 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
 
   WgradParams p;
   p.trace = g_wgrad_trace;
+  p.pdl = pdl_enabled() ? 1 : 0;
   p.acc = acc;
   p.B = B;
   p.H = H;

@@ -280,6 +280,13 @@ int srb200_window_attention_bwd(const void* qkv_bf16, const void* gout_bf16, con
 int srb200_act_bwd(const void* g_bf16, const void* y_bf16, void* out_bf16, int64_t n, float slope,
                    srb200_stream_t stream);
 
+/* Programmatic dependent launch for the GEMM kernels (srb200_tapgemm, srb200_wgrad) launched from now on: their
+ * prologue (barrier init, TMEM allocation, tensor-map fetch) overlaps the tail of the previous kernel of the stream.
+ * Process-wide switch, returns the previous value; meant to bracket a CUDA-graph capture (the attribute is baked into
+ * the captured launches).  Helps back-to-back GEMM chains (EDSR, RCAN), hurts when multi-wave kernels sit between
+ * them (SwinIR) -- hence off by default.  SRB_PDL=0|1 in the environment overrides.                              */
+int srb200_set_pdl(int on);
+
 /* debug only: device buffer of 3*64 uint64 that receives CTA 0's per-warp-role clock64 timeline of the
  * following srb200_tapgemm launches (NULL switches it off). */
 int srb200_debug_set_trace(void* dev_buf);
