@@ -32,11 +32,11 @@ CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; L1 loss + torch.
           'arch': 'EDSR num_feat=256 num_block=32 res_scale=0.1 upscale=4', 'batch_per_gpu': BATCH,
           'lr_patch': LR, 'parallelism': 'ddp', 'l2': 'per-step working set (>2 GB of activations) exceeds the 126 MB L2'}
 FLOP_PER_PATCH_FWD_BWD = 694.66e9
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, mean of the three 256->256 launches in
-# profiles/r01_ncu_full_tapgemm.txt (one `ncu --set full` capture of this script): 39.09 / 20.14 / 39.29 MB.  The
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, mean of the four 256->256 launches in
+# profiles/r01_ncu_full_tapgemm.txt (one `ncu --set full` capture of this script): 39.09 / 20.14 / 39.29 / 20.14 MB.  The
 # algorithmic bytes are 18.9 MB in + 18.9 MB out + 1.2 MB weights (+18.9 MB residual for conv2 / dgrad-conv1); the
 # output is still L2-resident when the kernel ends, so DRAM sees only the compulsory reads -- no wasted re-reads.
-ROOFLINE_TRAFFIC_BYTES = 32.84e6
+ROOFLINE_TRAFFIC_BYTES = 29.66e6
 
 
 def synthetic_batch(rank, batch=BATCH, lr=LR, scale=4):
