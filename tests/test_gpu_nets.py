@@ -221,3 +221,36 @@ def test_fused_ema_matches_reference_loop(cuda):
     assert L.launch_count - n0 == 2
     for (k, a), (_, b) in zip(ema.named_parameters(), ref.named_parameters()):
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), k
+
+
+def test_amp_gradscaler_step_like_srrs_model(cuda):
+    """SRRSModel.optimize_parameters (srrs_model.py:24-88) wraps the forward in torch.cuda.amp.autocast and scales the
+    loss with a GradScaler.  The srb200 Functions compute in bf16 regardless of autocast and pass loss-scaled
+    gradients straight through (bf16 has fp32's exponent range), so after ``scaler.unscale_`` the parameter
+    gradients equal those of the plain step and ``scaler.step`` performs the update (no inf/nan skip)."""
+    from basicsr4rs_b200.archs import build_network
+    opt = dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=64, num_block=2, upscale=2, res_scale=1.0)
+    torch.manual_seed(0)
+    net_a = build_network(dict(opt)).to(cuda)
+    net_b = build_network(dict(opt)).to(cuda)
+    net_b.load_state_dict(net_a.state_dict())
+    x = torch.rand((2, 3, 16, 16), device=cuda)
+    gt = torch.rand((2, 3, 32, 32), device=cuda)
+    (net_a(x) - gt).abs().mean().backward()
+    optim = torch.optim.Adam(net_b.parameters(), lr=1e-3)
+    scaler = torch.amp.GradScaler('cuda', init_scale=65536.0)
+    before = [p.detach().clone() for p in net_b.parameters()]
+    with torch.autocast('cuda', dtype=torch.float16):
+        out = net_b(x)
+        loss = (out.float() - gt).abs().mean()
+    assert out.dtype == torch.float32  # the archs return the caller's dtype (fp32 image in -> fp32 image out)
+    scaler.scale(loss).backward()
+    scaler.unscale_(optim)
+    for (k, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        assert torch.isfinite(pb.grad).all(), k
+        rel = ((pa.grad - pb.grad).norm() / (pa.grad.norm() + 1e-12)).item()
+        assert rel <= 2e-2, f'{k}: {rel:.3e}'  # identical kernels; only the 2^16 pre-scaling of bf16 intermediates differs
+    scaler.step(optim)
+    scaler.update()
+    assert scaler.get_scale() == 65536.0  # no overflow was detected
+    assert any(not torch.equal(b, p.detach()) for b, p in zip(before, net_b.parameters()))
