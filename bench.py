@@ -140,7 +140,10 @@ def run_reference(args, rank):
             'cpu_baseline': {'value': value, 'unit': 'patches/s', 'cores': threads, 'kind': 'port',
                              'sample': f'{n} of 16 patches per step, EDSR-L x4 fwd+L1+bwd, oracle/sr_oracle.py fp32'},
             'e2e': {'value': value, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
+
+
+JSON_OUT = sys.stdout
 
 
 def main():
@@ -156,6 +159,12 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly ONE line, the JSON record: everything else a library may print there (NCCL prints its
+    # version banner to stdout when NCCL_DEBUG=VERSION|WARN) is routed to stderr at the file-descriptor level
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
 
     if args.impl == 'reference':
         run_reference(args, rank)
@@ -171,7 +180,6 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # keep stdout for the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     L.check(L.load().srb200_check_device(local_rank), 'srb200_check_device')
 
@@ -274,7 +282,7 @@ def main():
             t = cpu_oracle_step_time(4, threads, iters=2)
             line['cpu_baseline'] = {'value': 4.0 / t, 'unit': 'patches/s', 'cores': threads, 'kind': 'port',
                                     'sample': '4 of 16 patches, EDSR-L x4 fwd+L1+bwd, oracle/sr_oracle.py fp32, best of 3'}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

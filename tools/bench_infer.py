@@ -34,7 +34,6 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # keep stdout for the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     opt, _, gflop_px = INFER['edsr_l_infer_1024' if args.arch == 'edsr_l' else 'swinir_infer_1024']
     torch.manual_seed(0)
