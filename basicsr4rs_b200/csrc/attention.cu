@@ -61,27 +61,42 @@ __device__ __forceinline__ size_t token_offset(const AttnGeom& g, int b, int wy,
   return ((static_cast<size_t>(b) * g.H + y) * g.W + x) * ld;
 }
 
-// copy a [64 tokens x 32] head slice global -> smem (row stride QROW)
-__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* gsrc,
-                                          const AttnGeom& g, int b, int wy, int wx, int ld,
-                                          int chan0) {
+// Each of the 128 threads moves the same two 16-byte pieces (tokens tid/4 and tid/4 + 32, part tid%4) of every
+// [64 tokens x 32] head slice: their pixel indices are computed ONCE per CTA (TokenSlots) -- these kernels are
+// instruction-bound and the 64-bit offset arithmetic per piece was a fifth of their instructions.
+struct TokenSlots {
+  long long pix[2];  // pixel index ((b*H + y)*W + x) of the thread's two tokens, -1 = padding token (ws < 8)
+};
+__device__ __forceinline__ TokenSlots token_slots(const AttnGeom& g, int b, int wy, int wx) {
+  TokenSlots t;
   const int ntok = g.ws * g.ws;
-  for (int c = threadIdx.x; c < NTOK * 4; c += blockDim.x) {
-    const int n = c >> 2, part = c & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int n = (threadIdx.x >> 2) + 32 * i;
+    t.pix[i] = n < ntok ? static_cast<long long>(token_offset(g, b, wy, wx, n, 1)) : -1;
+  }
+  return t;
+}
+// copy a [64 tokens x 32] head slice global -> smem (row stride QROW)
+__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* gsrc, const TokenSlots& t, int ld,
+                                          int chan0) {
+  const int part = threadIdx.x & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int n = (threadIdx.x >> 2) + 32 * i;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (n < ntok)
-      v = __ldg(reinterpret_cast<const uint4*>(gsrc + token_offset(g, b, wy, wx, n, ld) + chan0 + part * 8));
+    if (t.pix[i] >= 0) v = __ldg(reinterpret_cast<const uint4*>(gsrc + t.pix[i] * ld + chan0 + part * 8));
     *reinterpret_cast<uint4*>(s + n * QROW + part * 8) = v;
   }
 }
-__device__ __forceinline__ void store_tile(const __nv_bfloat16* s, __nv_bfloat16* gdst,
-                                           const AttnGeom& g, int b, int wy, int wx, int ld,
+__device__ __forceinline__ void store_tile(const __nv_bfloat16* s, __nv_bfloat16* gdst, const TokenSlots& t, int ld,
                                            int chan0) {
-  const int ntok = g.ws * g.ws;
-  for (int c = threadIdx.x; c < NTOK * 4; c += blockDim.x) {
-    const int n = c >> 2, part = c & 3;
-    if (n < ntok)
-      *reinterpret_cast<uint4*>(gdst + token_offset(g, b, wy, wx, n, ld) + chan0 + part * 8) =
+  const int part = threadIdx.x & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int n = (threadIdx.x >> 2) + 32 * i;
+    if (t.pix[i] >= 0)
+      *reinterpret_cast<uint4*>(gdst + t.pix[i] * ld + chan0 + part * 8) =
           *reinterpret_cast<const uint4*>(s + n * QROW + part * 8);
   }
 }
@@ -192,14 +207,12 @@ __device__ __forceinline__ void softmax_rows(float (&s)[8][4], const float* sBia
 __device__ __forceinline__ void setup_window(const AttnGeom& g, int& b, int& wy, int& wx, int& head,
                                              float* sBias, int* sRegion,
                                              const float* __restrict__ table) {
-  const int nWw = g.W / g.ws, nWh = g.H / g.ws;
-  int u = blockIdx.x;
-  head = u % g.nH;
-  u /= g.nH;
-  wx = u % nWw;
-  u /= nWw;
-  wy = u % nWh;
-  b = u / nWh;
+  // grid = (heads, windows per image, batch): one integer division instead of four
+  const int nWw = g.W / g.ws;
+  head = blockIdx.x;
+  wy = blockIdx.y / nWw;
+  wx = blockIdx.y - wy * nWw;
+  b = blockIdx.z;
   for (int i = threadIdx.x; i < (2 * g.ws - 1) * (2 * g.ws - 1); i += blockDim.x)
     sBias[i] = __ldg(table + i * g.nH + head);
   if (threadIdx.x < NTOK) {
@@ -232,9 +245,10 @@ __global__ void __launch_bounds__(128) window_attn_fwd_kernel(const __nv_bfloat1
   int b, wy, wx, head;
   setup_window(g, b, wy, wx, head, sBias, sRegion, table);
   const int ld = 3 * g.Cp;
-  load_tile(sQ, qkv, g, b, wy, wx, ld, head * HD);
-  load_tile(sK, qkv, g, b, wy, wx, ld, g.Cp + head * HD);
-  load_tile(sV, qkv, g, b, wy, wx, ld, 2 * g.Cp + head * HD);
+  const TokenSlots slots = token_slots(g, b, wy, wx);
+  load_tile(sQ, qkv, slots, ld, head * HD);
+  load_tile(sK, qkv, slots, ld, g.Cp + head * HD);
+  load_tile(sV, qkv, slots, ld, 2 * g.Cp + head * HD);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float s[8][4];
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(128) window_attn_fwd_kernel(const __nv_bfloat1
         pack_bf16x2(o[nt][2] * inv[1], o[nt][3] * inv[1]);
   }
   __syncthreads();
-  store_tile(sQ, out, g, b, wy, wx, g.Cp, head * HD);
+  store_tile(sQ, out, slots, g.Cp, head * HD);
 }
 
 template <int WST>
@@ -293,10 +307,11 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
   int b, wy, wx, head;
   setup_window(g, b, wy, wx, head, sBias, sRegion, table);
   const int ld = 3 * g.Cp;
-  load_tile(sQ, qkv, g, b, wy, wx, ld, head * HD);
-  load_tile(sK, qkv, g, b, wy, wx, ld, g.Cp + head * HD);
-  load_tile(sV, qkv, g, b, wy, wx, ld, 2 * g.Cp + head * HD);
-  load_tile(sdO, gout, g, b, wy, wx, g.Cp, head * HD);
+  const TokenSlots slots = token_slots(g, b, wy, wx);
+  load_tile(sQ, qkv, slots, ld, head * HD);
+  load_tile(sK, qkv, slots, ld, g.Cp + head * HD);
+  load_tile(sV, qkv, slots, ld, 2 * g.Cp + head * HD);
+  load_tile(sdO, gout, slots, g.Cp, head * HD);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
@@ -382,9 +397,9 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
     *reinterpret_cast<uint32_t*>(sV + (r0 + 8) * QROW + c0) = pack_bf16x2(dv[nt][2], dv[nt][3]);
   }
   __syncthreads();
-  store_tile(sQ, gqkv, g, b, wy, wx, ld, head * HD);
-  store_tile(sK, gqkv, g, b, wy, wx, ld, g.Cp + head * HD);
-  store_tile(sV, gqkv, g, b, wy, wx, ld, 2 * g.Cp + head * HD);
+  store_tile(sQ, gqkv, slots, ld, head * HD);
+  store_tile(sK, gqkv, slots, ld, g.Cp + head * HD);
+  store_tile(sV, gqkv, slots, ld, 2 * g.Cp + head * HD);
   for (int i = threadIdx.x; i < nbias; i += blockDim.x) atomicAdd(gtable + i * g.nH + head, sdBias[i]);
 }
 
@@ -407,13 +422,14 @@ extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rp
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
   AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
-  const long long grid = static_cast<long long>(B) * (H / window_size) * (W / window_size) * num_heads;
-  if (grid > 0x7FFFFFFF) return SRB200_EINVAL;
+  const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
+  if (wins > 65535 || B > 65535) return SRB200_EINVAL;
+  const dim3 grid(num_heads, static_cast<unsigned>(wins), B);
   if (window_size == 8)
-    window_attn_fwd_kernel<8><<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    window_attn_fwd_kernel<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), rpb_table, static_cast<__nv_bfloat16*>(out_bf16), g);
   else
-    window_attn_fwd_kernel<0><<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    window_attn_fwd_kernel<0><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), rpb_table, static_cast<__nv_bfloat16*>(out_bf16), g);
   return launch_status();
 }
@@ -427,14 +443,15 @@ extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gou
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
   AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
-  const long long grid = static_cast<long long>(B) * (H / window_size) * (W / window_size) * num_heads;
-  if (grid > 0x7FFFFFFF) return SRB200_EINVAL;
+  const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
+  if (wins > 65535 || B > 65535) return SRB200_EINVAL;
+  const dim3 grid(num_heads, static_cast<unsigned>(wins), B);
   if (window_size == 8)
-    window_attn_bwd_kernel<8><<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    window_attn_bwd_kernel<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<const __nv_bfloat16*>(gout_bf16), rpb_table,
         static_cast<__nv_bfloat16*>(gqkv_bf16), g_rpb_table, g);
   else
-    window_attn_bwd_kernel<0><<<static_cast<int>(grid), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    window_attn_bwd_kernel<0><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<const __nv_bfloat16*>(gout_bf16), rpb_table,
         static_cast<__nv_bfloat16*>(gqkv_bf16), g_rpb_table, g);
   return launch_status();
