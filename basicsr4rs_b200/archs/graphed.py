@@ -14,6 +14,7 @@ import torch
 from torch import nn as nn
 
 from .. import _lib as L
+from ..ops.sr_b200 import raw
 from ..ops.sr_b200.sr_b200 import PackBook, pack_book
 
 # arch instance -> GraphedSegments; kept outside the module so that copy.deepcopy (EMA copy, sr_model.py:51),
@@ -34,13 +35,20 @@ class Segment(nn.Module):
         self.mods = nn.ModuleList(modules)
         self._fn = fn
         self.book = None  # set on the FIRST segment: its forward graph starts with the batched weight repack
+        self.arena_floats = 0  # > 0: all zero-initialised fp32 scratch of this segment's forward from ONE fill
+
+    def _run(self, *tensors):
+        if self.arena_floats > 0:
+            with raw.zero_arena(tensors[0].device, self.arena_floats):
+                return self._fn(*tensors)
+        return self._fn(*tensors)
 
     def forward(self, *tensors):
         if self.book is not None:
             with pack_book(self.book):
                 self.book.refresh()
-                return self._fn(*tensors)
-        return self._fn(*tensors)
+                return self._run(*tensors)
+        return self._run(*tensors)
 
 
 class GraphedSegments:

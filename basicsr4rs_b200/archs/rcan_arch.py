@@ -144,7 +144,14 @@ class RCAN(ArchMixin, nn.Module):
         segs = [Segment(head_fn, [self.conv_first] + groups[0])]
         segs += [Segment(run(g), g) for g in groups[1:]]
         segs.append(Segment(self._tail, [self.conv_after_body, self.upsample, self.conv_last]))
+        for seg, g in zip(segs, groups):  # the per-sample pool sums of every RCAB of the segment: one fill
+            seg.arena_floats = self._pool_floats(g)
         return segs
+
+    def _pool_floats(self, groups, batch=64):
+        """fp32 scratch the channel-attention pooling of ``groups`` needs (B x C per RCAB, B <= ``batch``)."""
+        n_rcab = sum(len(grp.residual_group) for grp in groups)
+        return n_rcab * (batch * self.conv_first.weight.shape[0] + 8)
 
     def _forward(self, x):
         require_cuda(x, 'RCAN')
@@ -153,9 +160,10 @@ class RCAN(ArchMixin, nn.Module):
             nseg = len(split_even(list(self.body), self.graph_segments)) + 1
             out = graphed_forward(self, x, self._build_segments, chain_wire(nseg, carry=2))
             return out if out.dtype == x.dtype else out.to(x.dtype)
-        first, first32 = self._head(x)
-        res, res32 = first, first32
-        for group in self.body:
-            res, res32 = group.forward_nhwc(res, res32)
-        out = self._tail(res, res32, first, first32)
+        with ops.raw.zero_arena(x.device, self._pool_floats(list(self.body), batch=x.shape[0])):
+            first, first32 = self._head(x)
+            res, res32 = first, first32
+            for group in self.body:
+                res, res32 = group.forward_nhwc(res, res32)
+            out = self._tail(res, res32, first, first32)
         return out if out.dtype == x.dtype else out.to(x.dtype)

@@ -486,6 +486,11 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const srb200_pack_ite
     const int i = perm_in != nullptr ? perm_in[k] : (k < Ci ? k : -1);
     const bool live = (o >= 0 && i >= 0);
     const float* src = reinterpret_cast<const float*>(it.src) + (static_cast<size_t>(live ? o : 0) * Ci + (live ? i : 0)) * taps;
+    if (it.transpose == 2) {  // fp32 copy (padded / permuted bias vectors ride in the same launch)
+      float* outf = reinterpret_cast<float*>(it.dst);
+      for (int t = 0; t < taps; ++t) outf[static_cast<size_t>(t) * pairs + idx] = live ? __ldg(src + t) : 0.0f;
+      continue;
+    }
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(it.dst);
     for (int t = 0; t < taps; ++t)
       out[static_cast<size_t>(t) * pairs + idx] = __float2bfloat16_rn(live ? __ldg(src + t) : 0.0f);

@@ -239,7 +239,7 @@ def _item_table(rows):
         tab[i]['perm_in'] = r['perm_in'].data_ptr() if r.get('perm_in') is not None else 0
         for k in ('Co', 'Ci', 'taps', 'Np', 'Kp'):
             tab[i][k] = int(r[k])
-        tab[i]['transpose'] = int(bool(r.get('transpose', False)))
+        tab[i]['transpose'] = int(r.get('transpose', 0))  # 0 / 1: bf16 operand layouts, 2: fp32 copy (bias)
         tab[i]['alpha'] = float(r.get('alpha', 1.0))
         tab[i]['chunk_begin'] = chunk
         chunk += (int(r['Np']) * int(r['Kp']) + 255) // 256

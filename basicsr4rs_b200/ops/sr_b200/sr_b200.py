@@ -95,6 +95,26 @@ class PackBook:
             self.refresh()
         return e[1]
 
+    def get_bias(self, bias, n_pad, perm_out):
+        """fp32 [n_pad] bias in the packed channel order (zero padded): an fp32 item of the same batched launch."""
+        key = (id(bias), 'bias', n_pad, 1, id(perm_out) if perm_out is not None else 0, 0)
+        e = self.entries.get(key)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if e is None or e[0]() is not bias:
+            if capturing or bias.dtype != torch.float32 or not bias.is_contiguous():
+                return None
+            buf = torch.empty((n_pad,), dtype=torch.float32, device=bias.device)
+            spec = dict(Co=bias.numel(), Ci=1, taps=1, Np=n_pad, Kp=1, perm_out=perm_out, perm_in=None, transpose=2)
+            self.entries[key] = [weakref.ref(bias), buf, spec, None]  # tag None: filled by the refresh below
+            self.table = None
+            self.refresh(force=True)
+            return buf
+        if capturing:
+            return e[1] if self.capture_ok else None
+        if e[3] != (bias.data_ptr(), bias._version):
+            self.refresh()
+        return e[1]
+
     def refresh(self, force=False):
         """Repack every entry whose parameter changed (all of them after an optimizer step) in one launch."""
         capturing = torch.cuda.is_current_stream_capturing()
@@ -183,6 +203,18 @@ def _packed(weight, kind, n_pad, k_pad, perm_out=None, perm_in=None):
 def _padded_bias(bias, n_pad, perm_out=None):
     if bias is None:
         return None
+    if perm_out is None and bias.numel() == n_pad and bias.dtype == torch.float32:
+        return bias.detach()  # already in the packed layout
+    book = getattr(_book_tls, 'book', None)
+    if book is None:
+        ref = bias.__dict__.get('_srb200_book')
+        book = ref() if ref is not None else None
+    else:
+        bias.__dict__['_srb200_book'] = weakref.ref(book)
+    if book is not None:
+        buf = book.get_bias(bias, n_pad, perm_out)
+        if buf is not None:
+            return buf
     capturing = torch.cuda.is_current_stream_capturing()  # see _packed: no host-side cache inside a capture
     cache = bias.__dict__.setdefault('_srb200_pack', {})
     tag = (bias.data_ptr(), bias._version)

@@ -124,7 +124,8 @@ typedef struct {
   const int32_t* perm_out; /* device, or NULL */
   const int32_t* perm_in;  /* device, or NULL */
   int64_t Co, Ci, taps, Np, Kp;
-  int64_t transpose;       /* pack only */
+  int64_t transpose;       /* pack only: 0 / 1 = bf16 operand layouts of srb200_pack_weight, 2 = fp32 copy
+                              out[n] = w[perm_out[n]] (zero padded): bias vectors (taps = Kp = Ci = 1) */
   int64_t chunk_begin;
   float alpha;             /* unpack only */
   int32_t reserved;
