@@ -259,14 +259,14 @@ def finalize_grads(items):
         if it[0] == 'w':
             _, acc, w_shape, perm_out, perm_in, alpha = it
             taps, n_pad, k_pad = acc.shape
-            alloc = torch.zeros if (perm_out is not None or perm_in is not None) else torch.empty
-            g = alloc(tuple(w_shape), dtype=torch.float32, device=acc.device)
+            # every parameter element has exactly one packed slot (the index maps are onto: padding only ADDS
+            # packed slots), so the scatter writes the whole gradient -- no zero fill needed
+            g = torch.empty(tuple(w_shape), dtype=torch.float32, device=acc.device)
             rows.append(dict(src=acc, dst=g, Co=w_shape[0], Ci=w_shape[1], taps=taps, Np=n_pad, Kp=k_pad,
                              perm_out=perm_out, perm_in=perm_in, alpha=alpha))
         else:
             _, cs, n_bias, perm_out, alpha = it
-            alloc = torch.zeros if perm_out is not None else torch.empty
-            g = alloc((n_bias,), dtype=torch.float32, device=cs.device)
+            g = torch.empty((n_bias,), dtype=torch.float32, device=cs.device)
             rows.append(dict(src=cs, dst=g, Co=n_bias, Ci=1, taps=1, Np=cs.numel(), Kp=1, perm_out=perm_out,
                              alpha=alpha))
         outs.append(g)
