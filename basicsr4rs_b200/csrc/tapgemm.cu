@@ -33,8 +33,8 @@ struct TapGemmParams {
   int B, H, W;
   int tile_w, tile_h, tiles_x, tiles_y;
   int m_tiles, n_tiles;
-  // ceil(2^40 / d) for d = n_tiles, tiles_x, tiles_x * tiles_y: the per-tile index arithmetic of all three warp
-  // roles without the ~60-cycle integer division sequences (exact for operands < 2^20)
+  // ceil(2^48 / d) for d = n_tiles, tiles_x, tiles_x * tiles_y: the per-tile index arithmetic of all three warp
+  // roles without the ~60-cycle integer division sequences (exact for operands < 2^24)
   unsigned long long magic_n, magic_x, magic_xy;
   int kchunks_per_src;  // Cin / 64
   int num_src;          // src_r^2
@@ -124,7 +124,7 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& d) {
 }
 
 __device__ __forceinline__ int fast_div(int n, unsigned long long magic) {
-  return static_cast<int>(__umul64hi(static_cast<unsigned long long>(static_cast<unsigned>(n)) << 24, magic));
+  return static_cast<int>(__umul64hi(static_cast<unsigned long long>(static_cast<unsigned>(n)) << 16, magic));
 }
 
 // Column sums over the 32 rows a warp owns: butterfly reduce-scatter (31 shuffles); lane l returns the sum of
@@ -760,11 +760,11 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.tiles_y = (d->H + p.tile_h - 1) / p.tile_h;
   p.m_tiles = d->B * p.tiles_x * p.tiles_y;
   p.n_tiles = d->Cout / bn;
-  auto magic = [](long long dv) { return static_cast<unsigned long long>(((1ULL << 40) + dv - 1) / dv); };
+  auto magic = [](long long dv) { return static_cast<unsigned long long>(((1ULL << 48) + dv - 1) / dv); };
   p.magic_n = magic(p.n_tiles);
   p.magic_x = magic(p.tiles_x);
   p.magic_xy = magic(static_cast<long long>(p.tiles_x) * p.tiles_y);
-  if (static_cast<long long>(p.m_tiles) * p.n_tiles >= (1LL << 20)) return SRB200_EINVAL;
+  if (static_cast<long long>(p.m_tiles) * p.n_tiles >= (1LL << 24)) return SRB200_EINVAL;
   p.kchunks_per_src = d->Cin / 64;
   p.num_src = d->src_r * d->src_r;
   p.Cout = d->Cout;
