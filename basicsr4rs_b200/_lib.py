@@ -83,6 +83,8 @@ SIGNATURES = {
     'srb200_channel_dot': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     'srb200_ca_fc': (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]),
     'srb200_ca_apply': (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_float, c_void_p]),
+    'srb200_ca_forward': (c_int, [c_void_p] * 12 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    'srb200_ca_backward': (c_int, [c_void_p] * 15 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
     'srb200_ca_fc_bwd': (c_int, [c_void_p] * 11 + [c_int, c_int, c_int, c_void_p]),
     'srb200_set_pdl': (c_int, [c_int]),
     'srb200_debug_set_trace': (c_int, [c_void_p]),

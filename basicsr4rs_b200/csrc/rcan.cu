@@ -232,6 +232,242 @@ __global__ void ca_apply_bwd_kernel(const uint4* __restrict__ g, const float* __
   }
 }
 
+// ------------------------------------------------------------------ fused channel attention (one launch each way)
+// forward:  s = sigmoid(W2 relu(W1 p + b1) + b2) for ALL images in every CTA's shared memory (B*C*Cr MACs: nothing),
+//           then y = x + res_scale * t * s[b,c].  CTA 0 also writes z, s for the backward.
+__global__ void __launch_bounds__(256) ca_forward_fused_kernel(
+    const uint4* __restrict__ t, const uint4* __restrict__ x, const float* __restrict__ x32,
+    const float* __restrict__ p, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ z_out,
+    float* __restrict__ s_out, uint4* __restrict__ y, float* __restrict__ y32, size_t nvec, int B, int HW, int C,
+    int Cr, float res_scale) {
+  extern __shared__ float sm[];  // s[B*C], z[B*Cr]
+  float* ss = sm;
+  float* sz = sm + static_cast<size_t>(B) * C;
+  for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) {
+    const int b = i / Cr, j = i - b * Cr;
+    float acc = __ldg(b1 + j);
+    for (int c = 0; c < C; ++c) acc += __ldg(w1 + static_cast<size_t>(j) * C + c) * __ldg(p + static_cast<size_t>(b) * C + c);
+    sz[i] = fmaxf(acc, 0.0f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
+    const int b = i / C, c = i - b * C;
+    float acc = __ldg(b2 + c);
+    for (int j = 0; j < Cr; ++j) acc += __ldg(w2 + static_cast<size_t>(c) * Cr + j) * sz[b * Cr + j];
+    ss[i] = 1.0f / (1.0f + __expf(-acc));
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) z_out[i] = sz[i];
+    for (int i = threadIdx.x; i < B * C; i += blockDim.x) s_out[i] = ss[i];
+  }
+  const int groups = C / 8;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < nvec;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    const size_t b = idx / (static_cast<size_t>(groups) * HW);
+    float vt[8], vx[8], o[8];
+    unpack8(__ldg(t + idx), vt);
+    if (x32 != nullptr) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x32 + idx * 8));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(x32 + idx * 8 + 4));
+      vx[0] = a.x; vx[1] = a.y; vx[2] = a.z; vx[3] = a.w;
+      vx[4] = c.x; vx[5] = c.y; vx[6] = c.z; vx[7] = c.w;
+    } else {
+      unpack8(__ldg(x + idx), vx);
+    }
+    const float* sv = ss + b * C + g * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = vx[e] + res_scale * vt[e] * sv[e];
+    y[idx] = pack8(o);
+    if (y32 != nullptr) {
+      *reinterpret_cast<float4*>(y32 + idx * 8) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(y32 + idx * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// backward, ONE persistent launch (all CTAs co-resident), phases joined by a device-wide arrive barrier instead
+// of three kernel boundaries.  Every CTA owns one contiguous slab of 16-byte vectors in phases 1 and 3:
+//   1. gs[b,c] += res_scale * sum_hw g*t   (registers -> warp shuffle -> smem -> global atomics), then arrive
+//   2. after ALL CTAs arrived: every CTA redoes the tiny FC backward in shared memory (B*C*Cr MACs) to get
+//      gp[b,c] for the <= 2 images its slab touches; CTA 0 also writes gW1, gb1, gW2, gb2
+//   3. gt = res_scale * g * s[b,c] + gp[b,c]/HW, plus its column sums (conv2's bias gradient)
+// sync[0] = arrival counter, zeroed by the caller.
+constexpr int kCaBatch = 4;  // independent 16-byte load pairs in flight per thread
+
+__device__ __forceinline__ void group_reduce8(float (&v)[8], int groups) {
+  // lanes l, l+groups, l+2*groups, ... hold the same channel group (groups is a power of two)
+  for (int off = groups; off < 32; off <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += __shfl_xor_sync(0xffffffffu, v[e], off);
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) ca_backward_fused_kernel(
+    const uint4* __restrict__ g, const uint4* __restrict__ t, const float* __restrict__ s,
+    const float* __restrict__ z, const float* __restrict__ p, const float* __restrict__ w1,
+    const float* __restrict__ w2, float* __restrict__ gs, float* __restrict__ gw1, float* __restrict__ gb1,
+    float* __restrict__ gw2, float* __restrict__ gb2, uint4* __restrict__ gt, float* __restrict__ colsum,
+    unsigned int* __restrict__ sync, size_t nvec, size_t slab, int B, int HW, int C, int Cr, float res_scale) {
+  extern __shared__ float sm[];  // ga2[B*C] (phase 1: partial sums), ga1[B*Cr], gp2[2*C], cs[C]
+  float* ga2 = sm;
+  float* ga1 = sm + static_cast<size_t>(B) * C;
+  float* gp2 = ga1 + static_cast<size_t>(B) * Cr;
+  float* s_cs = gp2 + 2 * C;
+  const int groups = C / 8;
+  const int grp = threadIdx.x % groups;  // blockDim and slab are multiples of groups: fixed per thread
+  const bool lead = (threadIdx.x & 31) < groups;
+  const size_t per_img = static_cast<size_t>(groups) * HW;
+  const size_t lo = blockIdx.x * slab;
+  const size_t hi = (lo + slab < nvec) ? lo + slab : nvec;
+  const int b_first = (lo < nvec) ? static_cast<int>(lo / per_img) : 0;
+  // ---- phase 1
+  for (int i = threadIdx.x; i < B * C; i += blockDim.x) sm[i] = 0.0f;
+  __syncthreads();
+  {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cur_b = b_first;
+    auto flush = [&]() {  // (warp-uniform: every lane of a warp sees the same image index)
+      group_reduce8(acc, groups);
+      if (lead) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&ga2[cur_b * C + grp * 8 + e], acc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    };
+    for (size_t base = lo + threadIdx.x; base < hi; base += static_cast<size_t>(kCaBatch) * blockDim.x) {
+      uint4 rg[kCaBatch], rt[kCaBatch];
+#pragma unroll
+      for (int u = 0; u < kCaBatch; ++u) {
+        const size_t idx = base + static_cast<size_t>(u) * blockDim.x;
+        if (idx < hi) {
+          rg[u] = __ldg(g + idx);
+          rt[u] = __ldg(t + idx);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kCaBatch; ++u) {
+        // a warp's 32 consecutive vectors never straddle two images (per_img % 32 == 0 is checked on the host)
+        const size_t idx = base + static_cast<size_t>(u) * blockDim.x;
+        const size_t idx0 = idx - (threadIdx.x & 31);
+        if (idx0 < hi) {
+          const int bb = static_cast<int>(idx0 / per_img);
+          if (bb != cur_b) {
+            flush();
+            cur_b = bb;
+          }
+          if (idx < hi) {
+            float vg[8], vt[8];
+            unpack8(rg[u], vg);
+            unpack8(rt[u], vt);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += vg[e] * vt[e];
+          }
+        }
+      }
+    }
+    flush();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * C; i += blockDim.x)
+    if (sm[i] != 0.0f) atomicAdd(gs + i, sm[i] * res_scale);
+  __threadfence();
+  __syncthreads();
+  // ---- device-wide barrier
+  if (threadIdx.x == 0) {
+    atomicAdd(&sync[0], 1u);
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(&sync[0]) < gridDim.x) {
+      __nanosleep(32);
+      if (++spins > (1u << 25)) __trap();  // a protocol bug traps instead of hanging the GPU
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- phase 2 (every CTA, redundantly; only CTA 0 writes the parameter gradients)
+  for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
+    const float sv = __ldg(s + i);
+    ga2[i] = __ldcg(gs + i) * sv * (1.0f - sv);  // (L2: written by other CTAs' atomics)
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_cs[i] = 0.0f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) {
+    const int b = i / Cr, j = i - b * Cr;
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) acc += __ldg(w2 + static_cast<size_t>(c) * Cr + j) * ga2[b * C + c];
+    ga1[i] = __ldg(z + i) > 0.0f ? acc : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {  // gp for the (at most two) images of this slab
+    const int which = i / C, c = i - which * C;
+    const int b = b_first + which;
+    float acc = 0.0f;
+    if (b < B)
+      for (int j = 0; j < Cr; ++j) acc += __ldg(w1 + static_cast<size_t>(j) * C + c) * ga1[b * Cr + j];
+    gp2[i] = acc / static_cast<float>(HW);
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < C * Cr; i += blockDim.x) {  // gW2 [C][Cr], gW1 [Cr][C]
+      const int c = i / Cr, j = i - c * Cr;
+      float a2 = 0.0f, a1 = 0.0f;
+      for (int b = 0; b < B; ++b) {
+        a2 += ga2[b * C + c] * __ldg(z + b * Cr + j);
+        a1 += ga1[b * Cr + j] * __ldg(p + b * C + c);
+      }
+      gw2[static_cast<size_t>(c) * Cr + j] = a2;
+      gw1[static_cast<size_t>(j) * C + c] = a1;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float a = 0.0f;
+      for (int b = 0; b < B; ++b) a += ga2[b * C + c];
+      gb2[c] = a;
+    }
+    for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
+      float a = 0.0f;
+      for (int b = 0; b < B; ++b) a += ga1[b * Cr + j];
+      gb1[j] = a;
+    }
+  }
+  __syncthreads();
+  // ---- phase 3 (g comes back from L2)
+  float cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (size_t base = lo + threadIdx.x; base < hi; base += static_cast<size_t>(kCaBatch) * blockDim.x) {
+    uint4 rg[kCaBatch];
+#pragma unroll
+    for (int u = 0; u < kCaBatch; ++u) {
+      const size_t idx = base + static_cast<size_t>(u) * blockDim.x;
+      if (idx < hi) rg[u] = __ldg(g + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < kCaBatch; ++u) {
+      const size_t idx = base + static_cast<size_t>(u) * blockDim.x;
+      if (idx < hi) {
+        const int b = static_cast<int>(idx / per_img);
+        float vg[8], o[8];
+        unpack8(rg[u], vg);
+        const float* sp = s + static_cast<size_t>(b) * C + grp * 8;
+        const float* pp = gp2 + (b - b_first) * C + grp * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[e] = res_scale * vg[e] * __ldg(sp + e) + pp[e];
+          cs[e] += o[e];
+        }
+        gt[idx] = pack8(o);
+      }
+    }
+  }
+  group_reduce8(cs, groups);
+  if (lead) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&s_cs[grp * 8 + e], cs[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(colsum + i, s_cs[i]);
+}
+
 static inline int grid1d(size_t work, int block) {
   size_t g = (work + block - 1) / block;
   const size_t cap = static_cast<size_t>(num_sms()) * 16;
@@ -322,5 +558,58 @@ extern "C" int srb200_ca_apply_bwd(const void* g_bf16, const float* s, const flo
   if (colsum != nullptr && grid > 2 * num_sms()) grid = 2 * num_sms();
   ca_apply_bwd_kernel<<<grid, 256, colsum ? C * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g_bf16), s, gp, static_cast<uint4*>(gt_bf16), nvec, HW, C, res_scale, colsum);
+  return launch_status();
+}
+
+extern "C" int srb200_ca_forward(const void* t_bf16, const void* x_bf16, const float* x_f32, const float* p,
+                                 const float* w1, const float* b1, const float* w2, const float* b2, float* z,
+                                 float* s, void* y_bf16, float* y_f32, int B, int HW, int C, int Cr,
+                                 float res_scale, srb200_stream_t stream) {
+  if (!t_bf16 || (!x_bf16 && !x_f32) || !p || !w1 || !b1 || !w2 || !b2 || !z || !s || !y_bf16) return SRB200_EINVAL;
+  if (B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || Cr <= 0) return SRB200_EINVAL;
+  const size_t smem = (static_cast<size_t>(B) * C + static_cast<size_t>(B) * Cr) * sizeof(float);
+  if (smem > 48 * 1024) return SRB200_EINVAL;
+  const size_t nvec = static_cast<size_t>(B) * HW * (C / 8);
+  int grid = grid1d(nvec, 256);
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();  // every CTA repeats the FC: keep them few and fat
+  ca_forward_fused_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(t_bf16), static_cast<const uint4*>(x_bf16), x_f32, p, w1, b1, w2, b2, z, s,
+      static_cast<uint4*>(y_bf16), y_f32, nvec, B, HW, C, Cr, res_scale);
+  return launch_status();
+}
+
+extern "C" int srb200_ca_backward(const void* g_bf16, const void* t_bf16, const float* s, const float* z,
+                                  const float* p, const float* w1, const float* w2, float* gs, float* gw1, float* gb1,
+                                  float* gw2, float* gb2, void* gt_bf16, float* colsum, unsigned int* sync, int B,
+                                  int HW, int C, int Cr, float res_scale, srb200_stream_t stream) {
+  if (!g_bf16 || !t_bf16 || !s || !z || !p || !w1 || !w2 || !gs || !gw1 || !gb1 || !gw2 || !gb2 || !gt_bf16 ||
+      !colsum || !sync)
+    return SRB200_EINVAL;
+  const int groups = C / 8;
+  if (B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || Cr <= 0) return SRB200_EINVAL;
+  if ((groups & (groups - 1)) != 0 || groups > 256) return SRB200_EINVAL;  // channel groups: a power of two
+  const size_t smem = (static_cast<size_t>(B) * C + static_cast<size_t>(B) * Cr + 3 * static_cast<size_t>(C)) *
+                      sizeof(float);
+  if (smem > 48 * 1024) return SRB200_EINVAL;
+  const size_t nvec = static_cast<size_t>(B) * HW * groups;
+  const size_t per_img = static_cast<size_t>(groups) * HW;
+  // all CTAs must be co-resident (device-wide barrier): use at most half of what the device can hold
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ca_backward_fused_kernel, 256, smem) != cudaSuccess || occ < 1)
+    return SRB200_ELAUNCH;
+  const int ctas_per_sm = occ >= 6 ? 3 : (occ >= 2 ? occ / 2 : 1);
+  size_t grid = static_cast<size_t>(num_sms()) * ctas_per_sm;
+  // slab: a multiple of the block size (so of `groups` and of a warp), no longer than one image (a slab then
+  // touches at most two images), warps never straddling an image
+  size_t slab = ((nvec + grid - 1) / grid + 255) / 256 * 256;
+  if (per_img % 32 != 0 || slab > per_img) {
+    // small or ragged feature maps: one CTA per image keeps every assumption trivially true
+    if (B > static_cast<int>(grid)) return SRB200_EINVAL;
+    slab = per_img;
+  }
+  grid = (nvec + slab - 1) / slab;
+  ca_backward_fused_kernel<<<static_cast<unsigned>(grid), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g_bf16), static_cast<const uint4*>(t_bf16), s, z, p, w1, w2, gs, gw1, gb1, gw2, gb2,
+      static_cast<uint4*>(gt_bf16), colsum, sync, nvec, slab, B, HW, C, Cr, res_scale);
   return launch_status();
 }

@@ -446,6 +446,52 @@ def ca_apply(t, x, s, res_scale, x32=None, want_f32=False):
     return (y, y32) if want_f32 else y
 
 
+def ca_forward(t, x, p, w1, b1, w2, b2, res_scale, x32=None, want_f32=False):
+    """Fused ``ca_fc`` + ``ca_apply`` (one launch): returns (y | (y, y32), z, s)."""
+    _chk(t, 't', torch.bfloat16)
+    if x32 is not None:
+        _chk(x32, 'x32', torch.float32)
+    else:
+        _chk(x, 'x', torch.bfloat16)
+    for tt, n in ((p, 'p'), (w1, 'w1'), (b1, 'b1'), (w2, 'w2'), (b2, 'b2')):
+        _chk(tt, n, torch.float32)
+    b, h, w, c = t.shape
+    cr = w1.shape[0]
+    zs = torch.empty((b * (cr + c),), dtype=torch.float32, device=t.device)
+    z, s = zs[:b * cr].view(b, cr), zs[b * cr:].view(b, c)
+    y = torch.empty_like(t)
+    y32 = torch.empty(t.shape, dtype=torch.float32, device=t.device) if want_f32 else None
+    L.check(L.load().srb200_ca_forward(_ptr(t), _ptr(x) if x32 is None else None, _ptr(x32), _ptr(p), _ptr(w1),
+                                       _ptr(b1), _ptr(w2), _ptr(b2), _ptr(z), _ptr(s), _ptr(y), _ptr(y32), b, h * w,
+                                       c, cr, float(res_scale), _stream()), 'ca_forward')
+    return ((y, y32) if want_f32 else y), z, s
+
+
+def ca_backward(g, t, s, z, p, w1, w2, res_scale):
+    """Fused ``channel_dot`` -> ``ca_fc_bwd`` -> ``ca_apply_bwd`` (one persistent launch).
+
+    Returns (gw1, gb1, gw2, gb2, gt, colsum(gt)).  Needs zeroed scratch: taken from the active zero arena."""
+    _chk(g, 'g', torch.bfloat16)
+    _chk(t, 't', torch.bfloat16)
+    b, h, w, c = g.shape
+    cr = z.shape[1]
+    dev = g.device
+    gs = zeros_f32((b, c), dev)
+    cs = zeros_f32((c,), dev)
+    sync = zeros_f32((4,), dev)
+    out = torch.empty((2 * cr * c + cr + c,), dtype=torch.float32, device=dev)
+    o = 0
+    gw1 = out[o:o + cr * c].view(cr, c, 1, 1); o += cr * c
+    gw2 = out[o:o + cr * c].view(c, cr, 1, 1); o += cr * c
+    gb1 = out[o:o + cr]; o += cr
+    gb2 = out[o:o + c]
+    gt = torch.empty_like(g)
+    L.check(L.load().srb200_ca_backward(_ptr(g), _ptr(t), _ptr(s), _ptr(z), _ptr(p), _ptr(w1), _ptr(w2), _ptr(gs),
+                                        _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2), _ptr(gt), _ptr(cs),
+                                        _ptr(sync), b, h * w, c, cr, float(res_scale), _stream()), 'ca_backward')
+    return gw1, gb1, gw2, gb2, gt, cs
+
+
 def ca_fc_bwd(gs, s, z, p, w1, w2):
     b, c = s.shape
     cr = z.shape[1]

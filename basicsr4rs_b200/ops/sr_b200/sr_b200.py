@@ -567,8 +567,8 @@ def conv_to_image(x, weight, bias, out_scale, out_shift):
 class _RCAB(Function):
     """x + res_scale * CA(conv2(relu(conv1(x))))  (rcan_arch.py:36-46, ChannelAttention :16-24).
 
-    forward : tap-GEMM(+bias+ReLU) ; tap-GEMM(+bias) ; pool ; FC+sigmoid ; fused scale+residual pass
-    backward: channel_dot (d s) ; FC backward ; fused d t pass ; wgrad/colsum/dgrad(+ReLU mask) for conv2 ;
+    forward : tap-GEMM(+bias+ReLU) ; tap-GEMM(+bias, +pool in the epilogue) ; fused FC+sigmoid+scale+residual pass
+    backward: one persistent launch (d s ; FC backward ; d t + colsum) ; wgrad/colsum/dgrad(+ReLU mask) for conv2 ;
               wgrad/colsum/dgrad(+skip gradient) for conv1
     """
 
@@ -583,12 +583,15 @@ class _RCAB(Function):
         # conv2; its epilogue also accumulates the per-sample channel means = AdaptiveAvgPool2d(1) (rcan_arch.py:19)
         t, p = raw.tapgemm(h, _packed(w2, 'fprop', cp, cp), ksize=3, cout=cp, bias=_padded_bias(b2, cp),
                            want_colsum='image_mean')
-        z, s = raw.ca_fc(p, wa1.detach().contiguous(), ba1.detach(), wa2.detach().contiguous(), ba2.detach())
+        # FC + sigmoid + scale + residual in one launch (every CTA recomputes the tiny FC in shared memory)
+        y, z, s = raw.ca_forward(t, x if x32 is None else None, p, wa1.detach().contiguous(), ba1.detach(),
+                                 wa2.detach().contiguous(), ba2.detach(), res_scale, x32=x32,
+                                 want_f32=x32 is not None)
         ctx.save_for_backward(x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2)
         ctx.res_scale = res_scale
         if x32 is None:
-            return raw.ca_apply(t, x, s, res_scale)
-        y, y32 = raw.ca_apply(t, None, s, res_scale, x32=x32, want_f32=True)
+            return y
+        y, y32 = y
         ctx.mark_non_differentiable(y32)
         return y, y32
 
@@ -603,9 +606,9 @@ class _RCAB(Function):
 
     @staticmethod
     def _backward(ctx, g, x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2, rs, cp):
-        gs = raw.channel_dot(g, t, scale=rs)                       # d s[b,c] = res_scale * sum_hw g * t
-        gwa1, gba1, gwa2, gba2, gp = raw.ca_fc_bwd(gs, s, z, p, wa1.detach().contiguous(), wa2.detach().contiguous())
-        gt, cs2 = raw.ca_apply_bwd(g, s, gp, rs, want_colsum=True)  # d t and its column sums (conv2's bias grad)
+        # d s = res_scale * sum_hw g*t  ->  FC backward  ->  d t (+ its column sums = conv2's bias grad): one launch
+        gwa1, gba1, gwa2, gba2, gt, cs2 = raw.ca_backward(g, t, s, z, p, wa1.detach().contiguous(),
+                                                         wa2.detach().contiguous(), rs)
         acc2 = raw.wgrad(gt, h, ksize=3)
         gh, cs1 = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
                               mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=True)

@@ -247,6 +247,21 @@ int srb200_ca_fc_bwd(const float* gs, const float* s, const float* z, const floa
 int srb200_ca_apply_bwd(const void* g_bf16, const float* s, const float* gp, void* gt_bf16, int B,
                         int HW, int C, float res_scale, float* colsum, srb200_stream_t stream);
 
+/* Fused forms (one launch each way) of the four / three calls above, used by the RCAB Function:
+ * srb200_ca_forward  = srb200_ca_fc + srb200_ca_apply (p = per-sample channel means, e.g. from srb200_tapgemm's
+ *                      per-image column sums); writes z [B,Cr], s [B,C] for the backward.
+ * srb200_ca_backward = srb200_channel_dot -> srb200_ca_fc_bwd -> srb200_ca_apply_bwd (+ column sums of gt) in one
+ *                      persistent kernel whose phases are joined by a device-wide arrive barrier (the grid is
+ *                      sized to at most half of what the device holds co-resident).  gs [B*C], colsum [C] and
+ *                      sync [1 x uint32] must be zeroed by the caller; C/8 must be a power of two.               */
+int srb200_ca_forward(const void* t_bf16, const void* x_bf16, const float* x_f32, const float* p, const float* w1,
+                      const float* b1, const float* w2, const float* b2, float* z, float* s, void* y_bf16,
+                      float* y_f32, int B, int HW, int C, int Cr, float res_scale, srb200_stream_t stream);
+int srb200_ca_backward(const void* g_bf16, const void* t_bf16, const float* s, const float* z, const float* p,
+                       const float* w1, const float* w2, float* gs, float* gw1, float* gb1, float* gw2, float* gb2,
+                       void* gt_bf16, float* colsum, unsigned int* sync, int B, int HW, int C, int Cr,
+                       float res_scale, srb200_stream_t stream);
+
 /* ------------------------------------------------------------------ SwinIR token kernels
  * nn.LayerNorm(C, eps) over the C real channels of NHWC bf16 rows padded to Cp (pads stay 0)
  * (swinir_arch.py:240,251,288,321,602,886).  mean/rstd [T] fp32 are saved for the backward.

@@ -47,6 +47,46 @@ def test_channel_attention_kernels(cuda):
         assert torch.allclose(got, want, rtol=1e-3, atol=1e-4 * want.abs().max().item())
     gt = raw.ca_apply_bwd(gy, s, gp, 0.5)
     assert torch.allclose(gt.float(), tf.grad, atol=2e-2 * tf.grad.abs().max().item())
+    # the fused one-launch forms the RCAB Function uses must agree with the pieces
+    for x32 in (None, x.float()):
+        yf, zf, sf = raw.ca_forward(t, x if x32 is None else None, p, w1, b1, w2, b2, 0.5, x32=x32,
+                                    want_f32=x32 is not None)
+        if x32 is not None:
+            yf, y32 = yf
+            assert torch.allclose(y32, y_ref, atol=1e-5, rtol=1e-5)
+        assert torch.equal(yf, y) and torch.allclose(zf, z, atol=1e-6) and torch.allclose(sf, s, atol=1e-6)
+    with raw.zero_arena(cuda, b * c + c + 64):
+        fw1, fb1, fw2, fb2, fgt, fcs = raw.ca_backward(gy, t, s, z, p, w1, w2, 0.5)
+    for got, want in ((fw1, gw1), (fb1, gb1), (fw2, gw2), (fb2, gb2)):
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5 * want.abs().max().item())
+    assert (fgt.float() - gt.float()).abs().max().item() <= 1e-2 * gt.float().abs().max().item()
+    assert torch.allclose(fcs, fgt.float().sum((0, 1, 2)), rtol=2e-3, atol=5e-2)  # (sums unrounded fp32)
+
+
+@pytest.mark.parametrize('b,hw,c,cr', [(16, 48, 64, 4), (1, 7, 128, 8), (5, 33, 64, 16)])
+def test_fused_channel_attention_backward_shapes(cuda, b, hw, c, cr):
+    """The persistent arrive / release kernel at the bench shape, a single tiny image and a ragged one."""
+    from basicsr4rs_b200.ops.sr_b200 import raw
+    g = torch.Generator().manual_seed(b * 131 + hw)
+    t = torch.randn((b, hw, hw, c), generator=g).to(cuda).to(torch.bfloat16)
+    gy = torch.randn((b, hw, hw, c), generator=g).to(cuda).to(torch.bfloat16)
+    w1 = (torch.randn((cr, c, 1, 1), generator=g) * 0.2).to(cuda)
+    b1 = (torch.randn((cr,), generator=g) * 0.1).to(cuda)
+    w2 = (torch.randn((c, cr, 1, 1), generator=g) * 0.5).to(cuda)
+    b2 = (torch.randn((c,), generator=g) * 0.1).to(cuda)
+    p = raw.channel_pool(t)
+    z, s = raw.ca_fc(p, w1, b1, w2, b2)
+    gs = raw.channel_dot(gy, t, scale=1.0)
+    gw1, gb1, gw2, gb2, gp = raw.ca_fc_bwd(gs, s, z, p, w1, w2)
+    gt = raw.ca_apply_bwd(gy, s, gp, 1.0)
+    for _ in range(3):  # repeated launches: the sync words come zeroed from the arena every time
+        with raw.zero_arena(cuda, b * c + c + 64):
+            fw1, fb1, fw2, fb2, fgt, fcs = raw.ca_backward(gy, t, s, z, p, w1, w2, 1.0)
+        for got, want in ((fw1, gw1), (fb1, gb1), (fw2, gw2), (fb2, gb2)):
+            assert torch.allclose(got, want, rtol=2e-3, atol=2e-4 * want.abs().max().item())
+        assert (fgt.float() - gt.float()).abs().max().item() <= 1e-2 * gt.float().abs().max().item()
+        want_cs = (gy.float() * s.view(b, 1, 1, c) + gp.view(b, 1, 1, c) / (hw * hw)).sum((0, 1, 2))  # unrounded
+        assert torch.allclose(fcs, want_cs, rtol=2e-3, atol=2e-3 * want_cs.abs().max().item())
 
 
 def test_rcan_matches_reference_golden(cuda):
