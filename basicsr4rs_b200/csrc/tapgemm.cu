@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
-  const int warp = threadIdx.x >> 5;
+  // (the shuffle tells the compiler the warp index is warp-uniform: the role branches below stay convergent and
+  // their address / descriptor arithmetic lives in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   // work units: one M tile (x N tile) per CTA, or one PAIR of consecutive M tiles per CTA pair
   const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   // MMAs issued), 2 epilogue warp 2 (accumulator ready / tile drained)
   unsigned long long* trc = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
   auto stamp = [&](int role, int slot) {
-    if (trc != nullptr && slot < 64) trc[role * 64 + slot] = clock64();
+    if (trc != nullptr && slot < 64 && lane == 0) trc[role * 64 + slot] = clock64();
   };
   if (threadIdx.x == 0) stamp(0, 63);
   if (p.trace != nullptr && threadIdx.x == 0) {  // per-CTA wall/cycle start (debug)
@@ -226,8 +228,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   const int num_kb = p.taps * kchunks;
 
   if (warp == 0) {
-    // ===================================================== TMA producer (one elected lane)
-    if (lane == 0) {
+    // ===================================================== TMA producer (convergent warp loop, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = unit0; t < total_tiles; t += unit_stride) {
@@ -255,17 +257,20 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           for (int kc = 0; kc < kchunks; ++kc, ++kbi) {
             if (t == unit0 && kbi < 16) stamp(3, 2 * kbi);
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            if constexpr (TWO) {
-              // the leader's barrier collects the bytes of BOTH CTAs' loads
-              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
-              tma_load_4d_2cta(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
-              tma_load_2d_2cta(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64,
-                               tap * p.Cout + n0 + rank * Cfg::B_ROWS);
-            } else {
-              mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-              tma_load_4d(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
-              tma_load_2d(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64, tap * p.Cout + n0);
+            if (elect_one()) {
+              if constexpr (TWO) {
+                // the leader's barrier collects the bytes of BOTH CTAs' loads
+                if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+                tma_load_4d_2cta(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
+                tma_load_2d_2cta(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64,
+                                 tap * p.Cout + n0 + rank * Cfg::B_ROWS);
+              } else {
+                mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                tma_load_4d(smem_a(stage), &p.tmap_a[src], full_bar(stage), c0, x0 + dx, y0 + dy, b);
+                tma_load_2d(smem_b(stage), &p.tmap_w, full_bar(stage), kc * 64, tap * p.Cout + n0);
+              }
             }
+            __syncwarp();
             if (t == unit0 && kbi < 16) stamp(3, 2 * kbi + 1);
             c0 += 64;
             if (c0 == p.kchunks_per_src * 64) {
@@ -282,8 +287,13 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop (convergent: barrier waits by all lanes, operands in uniform registers); one
+    // elected lane issues the MMAs and their commits.  Written as `if (lane == 0) { loop }` the compiler spends
+    // ~20 instructions (R2UR broadcasts inside an election loop, descriptor rebuilds) between two MMAs: measured
+    // ~150 cycles per MMA whatever its shape, i.e. above the 128-cycle floor of even the widest one.
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TWO ? 256 : 128, BLOCK_N, 0, 0);
+      constexpr uint32_t d_hi = smem_desc_hi_sw128(1024);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -297,23 +307,26 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+          const uint32_t a_lo = smem_desc_lo(smem_a(stage), 16);
+          const uint32_t b_lo = smem_desc_lo(smem_b(stage), 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a0 + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(b0 + k * 32, 16, 1024);
-            if constexpr (TWO) umma_bf16_2cta(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)  // (+32 bytes of K = +2 in the descriptor's address field)
+              umma_bf16_lh<TWO>(d_tmem, a_lo + 2 * k, d_hi, b_lo + 2 * k, d_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TWO) umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
+            else umma_commit(empty_bar(stage));
           }
-          if constexpr (TWO) umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
-          else umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if constexpr (TWO) umma_commit_2cta(tfull_bar(acc));
-        else umma_commit(tfull_bar(acc));
+        if (elect_one()) {
+          if constexpr (TWO) umma_commit_2cta(tfull_bar(acc));
+          else umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         stamp(1, 2 * it + 1);
       }
     }

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   // work unit
@@ -144,29 +144,34 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // convergent warp loop, one elected lane issues (see tapgemm.cu: a lane-0-only loop costs ~150 cycles per MMA)
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      constexpr uint32_t d_hi = smem_desc_hi_sw128(1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (trc != nullptr && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
-        const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+        if (trc != nullptr && lane == 0 && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
+        const uint32_t a_lo = smem_desc_lo(smem_a(stage), Cfg::BOX_BYTES);
+        const uint32_t b_lo = smem_desc_lo(smem_b(stage), Cfg::BOX_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KPIX / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, Cfg::BOX_BYTES, 1024);
-          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, Cfg::BOX_BYTES, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < KPIX / 16; ++k)  // (16 pixel rows = 2048 bytes = +128 in the address field)
+            umma_bf16_lh<false>(tmem_base, a_lo + 128 * k, d_hi, b_lo + 128 * k, d_hi, idesc,
+                                (kb > kb_begin || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
         }
-        umma_commit(empty_bar(stage));
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(tfull_bar);
-      if (trc != nullptr) trc[1] = clock64();
+      if (elect_one()) umma_commit(tfull_bar);
+      __syncwarp();
+      if (trc != nullptr && lane == 0) trc[1] = clock64();
     }
   } else {
     const int quarter = warp & 3;
@@ -235,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
 
@@ -315,29 +320,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, 256, 1, 1);
+      constexpr uint32_t d_hi = smem_desc_hi_sw128(1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (trc != nullptr && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
-        const uint32_t a0 = smem_a(stage), b0 = smem_b(stage);
+        if (trc != nullptr && lane == 0 && kb - kb_begin < 40) trc[8 + kb - kb_begin] = clock64();
+        const uint32_t a_lo = smem_desc_lo(smem_a(stage), Cfg::BOX_BYTES);
+        const uint32_t b_lo = smem_desc_lo(smem_b(stage), Cfg::BOX_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < KPIX / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a0 + k * 2048, Cfg::BOX_BYTES, 1024);
-          const uint64_t db = make_smem_desc_sw128(b0 + k * 2048, Cfg::BOX_BYTES, 1024);
-          umma_bf16_2cta(tmem_base, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < KPIX / 16; ++k)
+            umma_bf16_lh<true>(tmem_base, a_lo + 128 * k, d_hi, b_lo + 128 * k, d_hi, idesc,
+                               (kb > kb_begin || k > 0) ? 1u : 0u);
+          umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
         }
-        umma_commit_2cta(empty_bar(stage));  // frees the stage in both CTAs
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit_2cta(tfull_bar);
-      if (trc != nullptr) trc[1] = clock64();
+      if (elect_one()) umma_commit_2cta(tfull_bar);
+      __syncwarp();
+      if (trc != nullptr && lane == 0) trc[1] = clock64();
     }
   } else {
     const int quarter = warp & 3;
