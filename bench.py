@@ -249,6 +249,10 @@ def main():
     train_step(lq_d, gt_d)
     raw.PROBE = probe
     for _ in range(min(args.steps, 5)):
+        # an eager step is CPU-bound (one Python call per launch): queue it behind a device-side delay so that the
+        # kernels run back to back as they do in the graph replay -- otherwise every event pair also times the idle gap
+        # between the start event and a kernel the host has not launched yet
+        torch.cuda._sleep(int(0.08 * 1.9e9))
         train_step(lq_d, gt_d)
     raw.PROBE = None
     kernel_ms = probe.ms()
