@@ -331,6 +331,8 @@ def test_batched_pack_and_unpack(cuda):
         (256, 64, 9, 256, 64, perm, None, False), (256, 64, 9, 256, 64, perm, None, True),
         (3, 64, 9, 16, 64, None, None, False), (360, 180, 1, 384, 192, None, pad_in, False),
         (180, 180, 9, 192, 192, None, None, True), (256, 256, 9, 256, 256, None, None, False),
+        (3, 64, 9, 16, 64, None, None, True), (256, 256, 9, 256, 256, None, None, True),
+        (180, 180, 9, 192, 192, None, pad_in, False),
     ]
     ws, rows, refs = [], [], []
     for co, ci, taps, Np, Kp, po, pi, tr in specs:
