@@ -16,6 +16,8 @@ seeded random inits are interchangeable.  What differs is how ``forward`` comput
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -288,6 +290,8 @@ class UpsampleOneStep(nn.Sequential):
 
 @ARCH_REGISTRY.register()
 class SwinIR(ArchMixin, nn.Module):
+    # captured with programmatic dependent launch (archs/graphed.py): +0.7-1 %; SRB_SWIN_PDL=0 turns it off
+    graph_pdl = os.environ.get('SRB_SWIN_PDL', '1') != '0'
     """SwinIR (classical / lightweight / real-world SR, denoising) -- same constructor as the reference."""
 
     def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=96, depths=(6, 6, 6, 6),

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(128) window_attn_fwd_kernel(const __nv_bfloat1
                                                               const float* __restrict__ table,
                                                               __nv_bfloat16* __restrict__ out,
                                                               AttnGeom g_in) {
+  pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
   AttnGeom g = g_in;
   if (WST > 0) g.ws = WST;
   __shared__ __align__(16) __nv_bfloat16 sQ[NTOK * QROW];
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(128) window_attn_bwd_kernel(const __nv_bfloat1
                                                               const float* __restrict__ table,
                                                               __nv_bfloat16* __restrict__ gqkv,
                                                               float* __restrict__ gtable, AttnGeom g_in) {
+  pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
   AttnGeom g = g_in;
   if (WST > 0) g.ws = WST;
   __shared__ __align__(16) __nv_bfloat16 sQ[NTOK * QROW];

@@ -236,6 +236,9 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 namespace srb {
 // let the next kernel of the stream start its prologue; then wait until OUR prerequisite grid has completed and
 // flushed (both are no-ops unless the kernels were launched with programmatic stream serialization)
+// for kernels launched the ordinary way that precede a programmatically serialized one: let it start its
+// prologue right away (it still waits for this grid to complete and flush before touching global memory)
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_handoff() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");

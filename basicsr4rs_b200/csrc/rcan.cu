@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(256) ca_forward_fused_kernel(
     float* __restrict__ s_out, uint4* __restrict__ y, float* __restrict__ y32, size_t nvec, int B, int HW, int C,
     int Cr, float res_scale) {
   extern __shared__ float sm[];  // s[B*C], z[B*Cr]
+  pdl_trigger();  // the next (programmatically serialized) GEMM may start its prologue now
   float* ss = sm;
   float* sz = sm + static_cast<size_t>(B) * C;
   for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) {
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(256, 4) ca_backward_fused_kernel(
     float* __restrict__ gw2, float* __restrict__ gb2, uint4* __restrict__ gt, float* __restrict__ colsum,
     unsigned int* __restrict__ sync, size_t nvec, size_t slab, int B, int HW, int C, int Cr, float res_scale) {
   extern __shared__ float sm[];  // ga2[B*C] (phase 1: partial sums), ga1[B*Cr], gp2[2*C], cs[C]
+  pdl_trigger();  // the next (programmatically serialized) GEMM may start its prologue now
   float* ga2 = sm;
   float* ga1 = sm + static_cast<size_t>(B) * C;
   float* gp2 = ga1 + static_cast<size_t>(B) * Cr;

@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(256) multi_axpby_kernel(const srb200_vec_item*
 template <int R>
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ out,
                               long long rows, int C, int Wf, int rows_per_block) {
+  pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
   extern __shared__ float s_sum[];  // [R*R*C]
   constexpr int V = R * R;
   const int nsum = V * C;
@@ -875,6 +876,7 @@ struct InlineItems {
 };
 
 __global__ void __launch_bounds__(256) unpack_inline_kernel(const __grid_constant__ InlineItems tab, long long total_chunks) {
+  pdl_trigger();  // the next layer's first GEMM may start its prologue now
   for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     srb200_pack_item it = tab.it[0];  // statically indexed, predicated copies: the table stays in param space
 #pragma unroll

@@ -40,6 +40,7 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                      __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                                      float* __restrict__ rstd_out, long long T, int C, int Cp,
                                      float eps) {
+  pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
   constexpr int TOK = (NVEC == 1) ? 2 : 1;  // tokens per warp iteration (independent loads in flight)
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
                                      const __nv_bfloat16* __restrict__ gres,
                                      __nv_bfloat16* __restrict__ gx, float* __restrict__ ggamma,
                                      float* __restrict__ gbeta, long long T, int C, int Cp) {
+  pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
   extern __shared__ float s_red[];  // [2][Cp]
   for (int i = threadIdx.x; i < 2 * Cp; i += blockDim.x) s_red[i] = 0.0f;
   __syncthreads();
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
 
 __global__ void scale_rows_kernel(const uint4* __restrict__ g, const float* __restrict__ alpha,
                                   uint4* __restrict__ out, size_t nvec, size_t vec_per_sample) {
+  pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < nvec;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float a = __ldg(alpha + idx / vec_per_sample);

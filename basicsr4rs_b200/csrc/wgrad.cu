@@ -452,6 +452,11 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   if (splits > p.total_kb) splits = p.total_kb;
   // keep each split long enough to amortise the pipeline fill / atomic epilogue
   while (splits > 1 && p.total_kb / splits < 8) --splits;
+  if (const char* e = getenv("SRB_WG_SPLITS")) {  // tuning aid
+    splits = atoi(e);
+    if (splits < 1) splits = 1;
+    if (splits > p.total_kb) splits = p.total_kb;
+  }
   p.splits = splits;
 
   const bool two_cta = (N % 256 == 0) && (K % 256 == 0) && getenv("SRB_WGRAD_1CTA") == nullptr;
