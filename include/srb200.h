@@ -18,7 +18,7 @@
  * Kernel-variant selectors read from the environment at call time (tuning / A-B measurements only; every
  * variant computes the same result): SRB_TAPGEMM_1CTA (no cta_group::2 pairs), SRB_TAPGEMM_NO_TEAMS (one 8-warp
  * epilogue instead of two 4-warp teams), SRB_WGRAD_1CTA, SRB_WG_KPIX / SRB_WG2_KPIX = 64 | 128 | 256 (pixels per
- * weight-gradient pipeline stage).
+ * weight-gradient pipeline stage), SRB_WG_SPLITS (split-K factor of the 1-CTA weight-gradient kernel).
  */
 #ifndef SRB200_H_
 #define SRB200_H_
@@ -299,8 +299,10 @@ int srb200_act_bwd(const void* g_bf16, const void* y_bf16, void* out_bf16, int64
 /* Programmatic dependent launch for the GEMM kernels (srb200_tapgemm, srb200_wgrad) launched from now on: their
  * prologue (barrier init, TMEM allocation, tensor-map fetch) overlaps the tail of the previous kernel of the stream.
  * Process-wide switch, returns the previous value; meant to bracket a CUDA-graph capture (the attribute is baked into
- * the captured launches).  Helps back-to-back GEMM chains (EDSR, RCAN), hurts when multi-wave kernels sit between
- * them (SwinIR) -- hence off by default.  SRB_PDL=0|1 in the environment overrides.                              */
+ * the captured launches).  The library's other kernels (channel attention, gradient finalize, LayerNorm, window
+ * attention, column sums) execute griddepcontrol.launch_dependents on entry, so a GEMM that follows one of them
+ * starts its prologue early as well.  Off by default for eager launches (nothing to gain when the host paces the
+ * stream); the archs turn it on for their graph captures.  SRB_PDL=0|1 in the environment overrides.             */
 int srb200_set_pdl(int on);
 
 /* debug only: device buffer of 3*64 uint64 that receives CTA 0's per-warp-role clock64 timeline of the
