@@ -36,8 +36,22 @@ class Segment(nn.Module):
         self._fn = fn
         self.book = None  # set on the FIRST segment: its forward graph starts with the batched weight repack
         self.arena_floats = 0  # > 0: all zero-initialised fp32 scratch of this segment's forward from ONE fill
+        # the zero-initialised fp32 scratch of the BACKWARD of this segment's Functions, from one fill recorded in the
+        # forward (raw.backward_scratch); measured by the first grad-enabled run per input shape
+        self._bwd_floats = {}
 
     def _run(self, *tensors):
+        if not torch.is_grad_enabled():
+            return self._run_fwd(*tensors)
+        key = tuple(tuple(t.shape) for t in tensors)
+        need = self._bwd_floats.get(key)
+        with raw.backward_scratch(tensors[0].device, need) as scratch:
+            out = self._run_fwd(*tensors)
+        if need is None:
+            self._bwd_floats[key] = scratch.measured
+        return out
+
+    def _run_fwd(self, *tensors):
         if self.arena_floats > 0:
             with raw.zero_arena(tensors[0].device, self.arena_floats):
                 return self._fn(*tensors)
@@ -200,4 +214,14 @@ class ArchMixin:
         """nn.Module contract of the reference archs (NCHW float in / out); every packed weight requested below
         belongs to this network's :class:`PackBook`."""
         with pack_book(self._pack_book()):
-            return self._forward(x)
+            if not torch.is_grad_enabled():
+                return self._forward(x)
+            # eager training: the backward's zeroed scratch of every Function from one fill (raw.backward_scratch);
+            # sized by a measuring first pass per input shape (0 when CUDA-graph segments bring their own)
+            needs = self.__dict__.setdefault('_bwd_need', {})
+            need = needs.get(tuple(x.shape))
+            with raw.backward_scratch(x.device, need) as scratch:
+                out = self._forward(x)
+            if need is None:
+                needs[tuple(x.shape)] = scratch.measured
+            return out

@@ -50,17 +50,79 @@ class zero_arena:
     """All fp32 zero-initialised scratch (split-K accumulators, column sums, ...) requested by the wrappers
     inside the ``with`` block is carved out of ONE ``torch.zeros`` -- one fill kernel instead of one per buffer."""
 
-    def __init__(self, device, n_floats):
+    def __init__(self, device, n_floats, buf=None):
+        # buf: an already zeroed fp32 buffer to carve from instead of a fresh fill (see backward_scratch)
         self.device, self.n = device, int(n_floats) + 64
+        self.buf = buf if (buf is not None and buf.numel() >= self.n and buf.device == device) else None
 
     def __enter__(self):
         self.prev = getattr(_arena, 'cur', None)
-        _arena.cur = [torch.zeros((self.n,), dtype=torch.float32, device=self.device), 0]
+        buf = self.buf if self.buf is not None else torch.zeros((self.n,), dtype=torch.float32, device=self.device)
+        _arena.cur = [buf, 0]
         return self
 
     def __exit__(self, *exc):
         _arena.cur = self.prev
         return False
+
+
+_bwd_scratch = threading.local()
+
+
+class backward_scratch:
+    """Zeroed fp32 scratch for the BACKWARD of the Functions whose forward runs inside the block: one fill for all
+    of them (in the forward, where a CUDA-graph segment records it once) instead of one fill at the head of every
+    layer's backward, where it also breaks the programmatic-dependent-launch chain between two GEMMs.
+
+    ``n_floats=None`` only MEASURES: nothing is handed out, ``self.measured`` is what the block asked for."""
+
+    def __init__(self, device, n_floats):
+        self.device, self.n, self.measured = device, (None if n_floats is None else int(n_floats)), 0
+
+    def __enter__(self):
+        self.prev = getattr(_bwd_scratch, 'cur', None)
+        if self.n is None:
+            _bwd_scratch.cur = [None, 0]
+        elif self.n > 0:
+            _bwd_scratch.cur = [torch.zeros((self.n,), dtype=torch.float32, device=self.device), 0]
+        else:
+            _bwd_scratch.cur = None
+        return self
+
+    def __exit__(self, *exc):
+        cur = _bwd_scratch.cur
+        if cur is not None:
+            self.measured = cur[1]
+        _bwd_scratch.cur = self.prev
+        return False
+
+
+def take_backward_scratch(n_floats, device):
+    """A zeroed buffer big enough for ``zero_arena(device, n_floats, buf=...)``, or None (no provider / no room)."""
+    cur = getattr(_bwd_scratch, 'cur', None)
+    if cur is None:
+        return None
+    n = int(n_floats) + 64
+    start = (cur[1] + 3) // 4 * 4
+    if cur[0] is None:  # measuring pass
+        cur[1] = start + n
+        return None
+    if cur[0].device != device or start + n > cur[0].numel():
+        return None
+    cur[1] = start + n
+    return cur[0][start:start + n]
+
+
+def stash_backward_scratch(ctx, n_floats, device):
+    """Function.forward side: reserve the backward's zeroed scratch on ``ctx`` (None without a provider)."""
+    ctx.scratch = take_backward_scratch(n_floats, device) if any(ctx.needs_input_grad) else None
+
+
+def backward_arena(ctx, device, n_floats):
+    """Function.backward side: the zero arena of this backward, carved from the stashed scratch when there is one
+    (single use: a second backward through the same node falls back to its own fill)."""
+    scratch, ctx.scratch = getattr(ctx, 'scratch', None), None
+    return zero_arena(device, n_floats, buf=scratch)
 
 
 def zeros_f32(shape, device):

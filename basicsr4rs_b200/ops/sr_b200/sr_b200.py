@@ -331,6 +331,7 @@ class _ConvNHWC(Function):
             y, y32 = y
         ctx.save_for_backward(x, weight, bias, y if act is not None else None)
         ctx.cfg = (ksize, act, slope, alpha, shuffle_r, n_pad, k_pad)
+        raw.stash_backward_scratch(ctx, ksize * ksize * n_pad * k_pad + n_pad + k_pad + 32, x.device)
         ctx.perm = perm
         ctx.has_res = residual is not None
         if want_f32:
@@ -353,7 +354,7 @@ class _ConvNHWC(Function):
             gbp = _colsum_of(g)
         _colsum_tls.slot = None
         gx = gw = gb = None
-        with raw.zero_arena(x.device, ksize * ksize * n_pad * k_pad + n_pad + k_pad + 32):
+        with raw.backward_arena(ctx, x.device, ksize * ksize * n_pad * k_pad + n_pad + k_pad + 32):
             if ctx.needs_input_grad[1]:
                 acc = raw.wgrad(g, x, ksize=ksize, dy_r=shuffle_r)
             if bias is not None and ctx.needs_input_grad[2] and gbp is None:
@@ -408,6 +409,7 @@ class _ResBlockNoBN(Function):
                         residual=x)
         ctx.save_for_backward(x, h, w1, b1, w2, b2)
         ctx.res_scale = res_scale
+        raw.stash_backward_scratch(ctx, 2 * 9 * cp * cp + 3 * cp + 32, x.device)
         return y
 
     @staticmethod
@@ -416,7 +418,7 @@ class _ResBlockNoBN(Function):
         s = ctx.res_scale
         cp = x.shape[-1]
         g = g.contiguous()
-        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 3 * cp + 32):
+        with raw.backward_arena(ctx, x.device, 2 * 9 * cp * cp + 3 * cp + 32):
             return _ResBlockNoBN._backward(ctx, g, x, h, w1, b1, w2, b2, s, cp)
 
     @staticmethod
@@ -564,6 +566,11 @@ def conv_to_image(x, weight, bias, out_scale, out_shift):
 
 
 # ------------------------------------------------------------------ fused RCAB (RCAN)
+def rcab_backward_floats(batch, cp):
+    """Zeroed fp32 scratch of one RCAB backward: two split-K weight-gradient accumulators, column sums, d s, sync."""
+    return 2 * 9 * cp * cp + 3 * cp + batch * cp + 64
+
+
 class _RCAB(Function):
     """x + res_scale * CA(conv2(relu(conv1(x))))  (rcan_arch.py:36-46, ChannelAttention :16-24).
 
@@ -589,6 +596,8 @@ class _RCAB(Function):
                                  want_f32=x32 is not None)
         ctx.save_for_backward(x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2)
         ctx.res_scale = res_scale
+        # the backward's zero-initialised scratch, pre-zeroed by the segment-wide fill when the arch provides one
+        raw.stash_backward_scratch(ctx, rcab_backward_floats(x.shape[0], cp), x.device)
         if x32 is None:
             return y
         y, y32 = y
@@ -601,7 +610,7 @@ class _RCAB(Function):
         rs = ctx.res_scale
         cp = x.shape[-1]
         g = g.contiguous()
-        with raw.zero_arena(x.device, 2 * 9 * cp * cp + 3 * cp + x.shape[0] * cp + 64):
+        with raw.backward_arena(ctx, x.device, rcab_backward_floats(x.shape[0], cp)):
             return _RCAB._backward(ctx, g, x, h, t, p, z, s, w1, b1, w2, b2, wa1, wa2, rs, cp)
 
     @staticmethod

@@ -154,7 +154,12 @@ class _SwinBlock(Function):
         ctx.save_for_backward(x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table,
                               proj_w, proj_b, n2w, fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2)
         ctx.cfg = (c, cs, ca, ch, hd, num_heads, ws, shift, scale)
+        raw.stash_backward_scratch(ctx, _SwinBlock._scratch_floats(c, cs, ca, ch, table.numel()), dev)
         return x2
+
+    @staticmethod
+    def _scratch_floats(c, cs, ca, ch, table_numel):
+        return 2 * cs * ch + cs * ca + 3 * ca * cs + 2 * cs + ch + 3 * ca + 4 * c + table_numel + 64
 
     @staticmethod
     def backward(ctx, g2):
@@ -165,8 +170,7 @@ class _SwinBlock(Function):
         p_qkv = head_perm(num_heads, hd, 3, dev)
         p_o = head_perm(num_heads, hd, 1, dev)
         g2 = g2.contiguous()
-        arena = raw.zero_arena(dev, 2 * cs * ch + cs * ca + 3 * ca * cs + 2 * cs + ch + 3 * ca + 4 * c +
-                               table.numel() + 64)
+        arena = raw.backward_arena(ctx, dev, _SwinBlock._scratch_floats(c, cs, ca, ch, table.numel()))
         with arena:
             return _SwinBlock._backward(ctx, g2, arena)
 

@@ -33,10 +33,10 @@ CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; L1 loss + torch.
           'lr_patch': LR, 'parallelism': 'ddp', 'l2': 'per-step working set (>2 GB of activations) exceeds the 126 MB L2'}
 FLOP_PER_PATCH_FWD_BWD = 694.66e9
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, mean of the four 256->256 launches in
-# profiles/r01_ncu_full_tapgemm.txt (one `ncu --set full` capture of this script): 39.09 / 20.14 / 39.29 / 20.14 MB.  The
+# profiles/r01_ncu_full_tapgemm_v2.txt (one `ncu --set full` capture of this script): 39.09 / 20.14 / 40.10 / 20.14 MB.  The
 # algorithmic bytes are 18.9 MB in + 18.9 MB out + 1.2 MB weights (+18.9 MB residual for conv2 / dgrad-conv1); the
 # output is still L2-resident when the kernel ends, so DRAM sees only the compulsory reads -- no wasted re-reads.
-ROOFLINE_TRAFFIC_BYTES = 29.66e6
+ROOFLINE_TRAFFIC_BYTES = 29.87e6
 
 
 def synthetic_batch(rank, batch=BATCH, lr=LR, scale=4):
@@ -277,7 +277,7 @@ def main():
             'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<256,true> (cta_group::2) conv3x3 256->256, fprop + dgrad launches',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak if achieved else None, 'traffic': ROOFLINE_TRAFFIC_BYTES,
-                         'traffic_unit': 'bytes/launch (ncu --set full, profiles/r01_ncu_full_tapgemm.txt)',
+                         'traffic_unit': 'bytes/launch (ncu --set full, profiles/r01_ncu_full_tapgemm_v2.txt)',
                          'peak_kind': f'{pk_kind} bf16 sustained (timed inside a long step)',
                          'launches_timed': len(kernel_ms), 'avg_ms': k_avg},
         }
