@@ -113,3 +113,40 @@ def test_pack_item_table_matches_the_c_struct():
     tab, total = raw._item_table(rows)
     assert list(tab['chunk_begin']) == [0, 16, 20] and total == 21
     assert tab[1]['transpose'] == 1 and tab[1]['alpha'] == 0.5 and tab[0]['src'] == a.data_ptr()
+
+
+def test_backward_scratch_provider_measures_then_hands_out_zeroed_slices():
+    """raw.backward_scratch: a measuring pass sizes the one fill; slices are disjoint, 16-byte aligned, big enough
+    for the zero_arena they back, and a provider without room degrades to None (the Function then fills itself)."""
+    from basicsr4rs_b200.ops.sr_b200 import raw
+    cpu = torch.device('cpu')
+    assert raw.take_backward_scratch(100, cpu) is None  # no provider
+    with raw.backward_scratch(cpu, None) as m:
+        assert raw.take_backward_scratch(100, cpu) is None and raw.take_backward_scratch(7, cpu) is None
+    assert m.measured >= 100 + 64 + 7 + 64
+    with raw.backward_scratch(cpu, m.measured):
+        a = raw.take_backward_scratch(100, cpu)
+        b = raw.take_backward_scratch(7, cpu)
+        assert a.numel() == 164 and b.numel() == 71 and not a.any() and not b.any()
+        assert a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+        assert a.data_ptr() + 4 * a.numel() <= b.data_ptr()
+        assert raw.take_backward_scratch(1, cpu) is None  # exhausted
+        with raw.zero_arena(cpu, 100, buf=a):   # carves from the stashed slice, no new fill
+            z = raw.zeros_f32((10, 10), cpu)
+            assert z.data_ptr() == a.data_ptr()
+        with raw.zero_arena(cpu, 100, buf=b):   # too small: falls back to its own zeros
+            assert raw.zeros_f32((10, 10), cpu).data_ptr() != b.data_ptr()
+    assert raw.take_backward_scratch(100, cpu) is None
+
+    class Ctx:
+        needs_input_grad = (True, False)
+    ctx = Ctx()
+    with raw.backward_scratch(cpu, 1000):
+        raw.stash_backward_scratch(ctx, 100, cpu)
+    first = ctx.scratch
+    assert first is not None
+    with raw.backward_arena(ctx, cpu, 100):
+        assert raw.zeros_f32((4,), cpu).data_ptr() == first.data_ptr()
+    assert ctx.scratch is None  # single use
+    with raw.backward_arena(ctx, cpu, 100):
+        assert raw.zeros_f32((4,), cpu).data_ptr() != first.data_ptr()
