@@ -38,10 +38,16 @@ struct WgradParams {
 // KPIX = pixels (GEMM-K) per stage: a cp.async.bulk.tensor costs its issuing lane 400-500 cycles whatever the box
 // size (several lanes issuing at once), so small stages leave the loop TMA-issue-bound (~1000 cycles per 64-pixel
 // k-block whose MMAs take 128-512); bigger boxes move more bytes per instruction.
-template <int BLOCK_N, int KPIX = 64>
+// FOLD (3x3 layers with 64 input channels): the three taps of one stencil row share a work unit -- N = 3 x 64: box nb of
+// B is the SAME 64 input channels shifted by tap (row, nb), accumulator columns [64 nb, 64 nb + 64) belong to that tap.
+// An M=128 MMA costs >= ~118 cycles whatever its N (the A operand is read from shared memory at ~32 B/cycle), so
+// N = 64 units run the tensor core at a quarter of its rate; folded, one MMA does the work of three and dY is loaded
+// once per three taps.  A_BOXES = 1: the layer has only 64 output channels, the upper half of A is not even staged
+// (the MMA reads the first B box in its place; those accumulator rows are never stored).
+template <int BLOCK_N, int KPIX = 64, int A_BOXES = 2>
 struct WgCfg {
   static constexpr int BOX_BYTES = KPIX * 128;           // one box: [KPIX px][64 ch]
-  static constexpr int A_BYTES = 2 * BOX_BYTES;          // 128 out-ch
+  static constexpr int A_BYTES = A_BOXES * BOX_BYTES;    // 128 (64) out-ch
   static constexpr int B_BYTES = (BLOCK_N / 64) * BOX_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
@@ -50,9 +56,11 @@ struct WgCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BLOCK_N, int KPIX = 64>
+template <int BLOCK_N, int KPIX = 64, bool FOLD = false, int A_BOXES = 2>
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using Cfg = WgCfg<BLOCK_N, KPIX>;
+  using Cfg = WgCfg<BLOCK_N, KPIX, A_BOXES>;
+  static_assert(!FOLD || BLOCK_N == 192, "fold: three taps x 64 input channels");
+  static_assert(A_BOXES == 2 || FOLD, "single-box A only in the folded kernel");
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -78,7 +86,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
   const int tap = u / p.m_tiles;
   const int kb_begin = static_cast<int>((static_cast<long long>(p.total_kb) * split) / p.splits);
   const int kb_end = static_cast<int>((static_cast<long long>(p.total_kb) * (split + 1)) / p.splits);
-  const int m0 = m_t * 128, n0 = n_t * BLOCK_N;
+  const int m0 = m_t * 128, n0 = n_t * (FOLD ? 64 : BLOCK_N);
   unsigned long long* trc = (p.trace != nullptr && blockIdx.x == 0) ? p.trace : nullptr;
   if (trc != nullptr && threadIdx.x == 0) trc[0] = clock64();
 
@@ -109,7 +117,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
     // TMA producer.  One cp.async.bulk.tensor costs its issuing thread ~170 cycles, so the 2 + BLOCK_N/64 boxes
     // of a stage are issued by as many lanes in parallel (measured: 1070 -> MMA-bound cycles per k-block).
     int dy = 0, dx = 0;
-    if (p.ksize == 3) {
+    if (FOLD) {
+      dy = tap - 1;  // (`tap` is the stencil row; the column comes from the box index)
+    } else if (p.ksize == 3) {
       dy = tap / 3 - 1;
       dx = tap % 3 - 1;
     }
@@ -123,8 +133,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       mbar_wait(empty_bar(stage), phase ^ 1u);
       // the upper 64 output channels of the tile may not exist (N = 64): their half of A is never loaded --
       // whatever the MMA makes of the stale smem lands in accumulator rows the epilogue never reads
-      const bool upper = (m0 + 64) < p.N;
-      if (lane == 0) mbar_expect_tx(full_bar(stage), upper ? Cfg::STAGE_BYTES : Cfg::STAGE_BYTES - Cfg::BOX_BYTES);
+      const bool upper = A_BOXES == 2 && (m0 + 64) < p.N;
+      if (lane == 0)
+        mbar_expect_tx(full_bar(stage), (upper || A_BOXES == 1) ? Cfg::STAGE_BYTES : Cfg::STAGE_BYTES - Cfg::BOX_BYTES);
       __syncwarp();
       if (lane < 2) {
         if (lane == 0 || upper) {
@@ -135,8 +146,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
         }
       } else if (lane < 2 + BLOCK_N / 64) {
         const int nb = lane - 2;
-        tma_load_4d(smem_b(stage) + nb * Cfg::BOX_BYTES, &p.tmap_x, full_bar(stage), n0 + nb * 64, x0 + dx, y0 + dy,
-                    b);
+        if (FOLD)
+          tma_load_4d(smem_b(stage) + nb * Cfg::BOX_BYTES, &p.tmap_x, full_bar(stage), n0, x0 + nb - 1, y0 + dy, b);
+        else
+          tma_load_4d(smem_b(stage) + nb * Cfg::BOX_BYTES, &p.tmap_x, full_bar(stage), n0 + nb * 64, x0 + dx, y0 + dy,
+                      b);
       }
       if (++stage == STAGES) {
         stage = 0;
@@ -182,18 +196,20 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       if (trc != nullptr && threadIdx.x == 64) trc[2] = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const int n = m0 + row;
-      float* dst = p.acc + (static_cast<size_t>(tap) * p.N + n) * p.K + n0;
+      float* dst = p.acc + (static_cast<size_t>(FOLD ? 3 * tap : tap) * p.N + n) * p.K + n0;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
+        // folded: columns [64 nb, 64 nb + 64) are tap 3*row + nb; otherwise 32 more input channels of the same tap
+        float* d = FOLD ? dst + static_cast<size_t>(c >> 1) * p.N * p.K + (c & 1) * 32 : dst + c * 32;
         if (n < p.N) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                    __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + 4 * j), v);
+            atomicAdd(reinterpret_cast<float4*>(d + 4 * j), v);
           }
         }
       }
@@ -389,18 +405,18 @@ static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
   return launch_ex(wgrad2_kernel<KPIX>, grid, 192, Wg2Cfg<KPIX>::SMEM_BYTES, stream, 1, p);  // (__cluster_dims__ 2)
 }
 
-template <int BLOCK_N, int KPIX>
+template <int BLOCK_N, int KPIX, bool FOLD = false, int A_BOXES = 2>
 static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
-  using Cfg = WgCfg<BLOCK_N, KPIX>;
+  using Cfg = WgCfg<BLOCK_N, KPIX, A_BOXES>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, KPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, KPIX, FOLD, A_BOXES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              Cfg::SMEM_BYTES) != cudaSuccess)
       return SRB200_ELAUNCH;
     configured = true;
   }
-  const int grid = p.taps * p.m_tiles * p.n_tiles * p.splits;
-  return launch_ex(wgrad_kernel<BLOCK_N, KPIX>, grid, 192, Cfg::SMEM_BYTES, stream, 1, p);
+  const int grid = (FOLD ? 3 : p.taps) * p.m_tiles * p.n_tiles * p.splits;
+  return launch_ex(wgrad_kernel<BLOCK_N, KPIX, FOLD, A_BOXES>, grid, 192, Cfg::SMEM_BYTES, stream, 1, p);
 }
 
 }  // namespace srb
@@ -460,8 +476,36 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   p.splits = splits;
 
   const bool two_cta = (N % 256 == 0) && (K % 256 == 0) && getenv("SRB_WGRAD_1CTA") == nullptr;
+  // 64-wide input-channel tiles of a 3x3 layer: fold the three taps of a stencil row into one N = 192 unit (WgCfg)
+  // Measured (tools/sweep_fold.py, B16): 96x96 64->64 32.9 -> 24.7 us, but 48x48 14.5 -> 15.6 us and N = 256 23.1 ->
+  // 27.0 us: with few pixels per unit the fp32 atomics of the split-K merge (three taps' worth per CTA) outweigh the
+  // shorter mainloop, so it is used for 64-output-channel layers with >= 100k pixels.  SRB_WG_FOLD=1|0 forces.
+  const char* fold_env = getenv("SRB_WG_FOLD");
+  const bool fold_shape = ksize == 3 && bn == 64 && !two_cta;
+  const bool fold = fold_shape && (fold_env ? atoi(fold_env) != 0
+                                            : (N == 64 && static_cast<long long>(B) * H * W >= 100000));
+  const bool fold_a1 = fold && N == 64;
   int kpix = 64;
-  if (!two_cta) {
+  if (fold) {
+    const char* e = getenv("SRB_WG_KPIX");
+    kpix = fold_a1 ? 128 : 64;  // (stage = (A_BOXES + 3) boxes: 64 KB x 3 stages, or 40 KB x 5)
+    if (e && fold_a1 && (atoi(e) == 64 || atoi(e) == 128)) kpix = atoi(e);
+    pick_tile(H, W, kpix, &p.tile_w, &p.tile_h);
+    p.tiles_x = (W + p.tile_w - 1) / p.tile_w;
+    p.tiles_y = (H + p.tile_h - 1) / p.tile_h;
+    p.total_kb = B * p.tiles_x * p.tiles_y;
+    int s3 = num_sms() / (3 * p.m_tiles * p.n_tiles);
+    if (s3 < 1) s3 = 1;
+    if (s3 > p.total_kb) s3 = p.total_kb;
+    while (s3 > 1 && p.total_kb / s3 < 4) --s3;
+    if (const char* es = getenv("SRB_WG_SPLITS")) {
+      s3 = atoi(es);
+      if (s3 < 1) s3 = 1;
+      if (s3 > p.total_kb) s3 = p.total_kb;
+    }
+    p.splits = s3;
+  }
+  if (!two_cta && !fold) {
     // largest stage (pixels per k-block) that still leaves every split a few k-blocks
     const char* e = getenv("SRB_WG_KPIX");
     const int cand[3] = {bn == 64 ? 256 : 128, 128, 64};
@@ -539,6 +583,10 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
       }
   }
   if (two_cta) return kpix == 128 ? launch_wgrad2<128>(p, stream) : launch_wgrad2<64>(p, stream);
+  if (fold) {
+    if (!fold_a1) return launch_wgrad<192, 64, true, 2>(p, stream);
+    return kpix == 128 ? launch_wgrad<192, 128, true, 1>(p, stream) : launch_wgrad<192, 64, true, 1>(p, stream);
+  }
   switch (bn) {
     case 256: return kpix == 128 ? launch_wgrad<256, 128>(p, stream) : launch_wgrad<256, 64>(p, stream);
     case 192: return kpix == 128 ? launch_wgrad<192, 128>(p, stream) : launch_wgrad<192, 64>(p, stream);

@@ -18,7 +18,8 @@
  * Kernel-variant selectors read from the environment at call time (tuning / A-B measurements only; every
  * variant computes the same result): SRB_TAPGEMM_1CTA (no cta_group::2 pairs), SRB_TAPGEMM_NO_TEAMS (one 8-warp
  * epilogue instead of two 4-warp teams), SRB_WGRAD_1CTA, SRB_WG_KPIX / SRB_WG2_KPIX = 64 | 128 | 256 (pixels per
- * weight-gradient pipeline stage), SRB_WG_SPLITS (split-K factor of the 1-CTA weight-gradient kernel).
+ * weight-gradient pipeline stage), SRB_WG_SPLITS (split-K factor of the 1-CTA weight-gradient kernel), SRB_WG_FOLD = 0 | 1 (three taps of a stencil row per
+ * weight-gradient unit for 64-wide input-channel tiles; default: 64-output-channel layers with >= 100k pixels).
  */
 #ifndef SRB200_H_
 #define SRB200_H_

@@ -239,18 +239,25 @@ def test_tapgemm_dgrad_unshuffle_view(cuda):
 
 # ------------------------------------------------------------------ wgrad / colsum
 @pytest.mark.parametrize('b,h,w,cin,cout,ks', [(2, 16, 16, 64, 64, 3), (2, 48, 48, 256, 256, 3), (1, 20, 13, 128, 192, 3),
-                                               (2, 16, 16, 192, 384, 1), (4, 24, 24, 64, 256, 3)])
-def test_wgrad(cuda, b, h, w, cin, cout, ks):
+                                               (2, 16, 16, 192, 384, 1), (4, 24, 24, 64, 256, 3),
+                                               # 64-wide input tiles: the tap-folded kernel (1 / 2 A boxes, ragged, 5 tiles)
+                                               (16, 48, 48, 64, 64, 3), (1, 20, 13, 64, 192, 3), (1, 12, 12, 320, 64, 3)])
+def test_wgrad(cuda, b, h, w, cin, cout, ks, monkeypatch):
     raw = _raw()
     x, wt, _ = _mk_conv(cuda, b, h, w, cin, cout, ks, seed=5)
     xb = _nhwc_bf16(x, cin)
     dy = torch.randn((b, h, w, cout), device=cuda).to(torch.bfloat16)
-    acc = raw.wgrad(dy, xb, ksize=ks)
-    gw = raw.unpack_wgrad(acc, wt.shape, alpha=0.5)
     wr = wt.clone().requires_grad_(True)
     y = F.conv2d(xb.float().permute(0, 3, 1, 2), wr, None, padding=ks // 2)
     y.backward(dy.float().permute(0, 3, 1, 2))
-    _assert_close(gw, wr.grad * 0.5, 2e-3)
+    # 64-wide input tiles of a 3x3 layer have two kernels (per tap / three taps folded; the library picks by pixel
+    # count, SRB_WG_FOLD is read per call): both must agree with autograd
+    for fold in (('0', '1') if (cin % 128 != 0 and ks == 3) else (None,)):
+        if fold is not None:
+            monkeypatch.setenv('SRB_WG_FOLD', fold)
+        acc = raw.wgrad(dy, xb, ksize=ks)
+        gw = raw.unpack_wgrad(acc, wt.shape, alpha=0.5)
+        _assert_close(gw, wr.grad * 0.5, 2e-3)
     gb = raw.colsum(dy)
     _assert_close(gb, dy.float().sum((0, 1, 2)), 1e-3)
 
