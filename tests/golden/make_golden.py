@@ -43,6 +43,15 @@ CASES = {
     'swinir_c60_d2_nearest_x4': ('SwinIR', dict(upscale=4, in_chans=3, img_size=16, window_size=8, img_range=1.,
                                                 depths=[2], embed_dim=60, num_heads=[6], mlp_ratio=2,
                                                 upsampler='nearest+conv', resi_connection='3conv'), (1, 3, 16, 16)),
+    # denoising / JPEG-artifact branch: no upsampler, residual image (swinir_arch.py:915-918)
+    'swinir_c60_d2_denoise_x1': ('SwinIR', dict(upscale=1, in_chans=3, img_size=16, window_size=8, img_range=1.,
+                                                depths=[2], embed_dim=60, num_heads=[6], mlp_ratio=2, upsampler='',
+                                                resi_connection='1conv'), (1, 3, 16, 24)),
+    # the x3 (single PixelShuffle(3)) and x8 (three PixelShuffle(2) stages) Upsample heads (arch_util.py:119-138)
+    'rcan_f64_g1_b2_sq8_x3': ('RCAN', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_group=1, num_block=2,
+                                           squeeze_factor=8, upscale=3, res_scale=1.0, img_range=255.), (1, 3, 10, 14)),
+    'edsr_f64_b1_x8': ('EDSR', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=1, upscale=8, res_scale=1.0,
+                                    img_range=255.), (1, 3, 8, 8)),
     # the fork's remote-sensing shape: 6-wide windows, 4 input bands (train_SwinIR_L2S288_scratch.yml:43-54)
     'swinir_c60_ws6_in4_x2': ('SwinIR', dict(upscale=2, in_chans=4, img_size=12, window_size=6, img_range=1.,
                                              depths=[2], embed_dim=60, num_heads=[6], mlp_ratio=2,

@@ -78,7 +78,7 @@ def test_edsr_matches_reference_golden(cuda, case):
     ((out - fx['gt'].to(cuda))**2).mean().backward()
     params = dict(net.named_parameters())
     for k, want in fx['grads'].items():
-        _check_grad(params[k].grad, want)
+        _check_grad(params[k].grad, want, fx.get('autocast_rel', {}).get(k))
 
 
 def test_edsr_l_full_size_vs_oracle(cuda):

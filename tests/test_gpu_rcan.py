@@ -89,8 +89,9 @@ def test_fused_channel_attention_backward_shapes(cuda, b, hw, c, cr):
         assert torch.allclose(fcs, want_cs, rtol=2e-3, atol=2e-3 * want_cs.abs().max().item())
 
 
-def test_rcan_matches_reference_golden(cuda):
-    fx = torch.load(os.path.join(GOLDEN, 'rcan_f64_g2_b2_x4.pt'), weights_only=False)
+@pytest.mark.parametrize('case', ['rcan_f64_g2_b2_x4', 'rcan_f64_g1_b2_sq8_x3'])
+def test_rcan_matches_reference_golden(cuda, case):
+    fx = torch.load(os.path.join(GOLDEN, case + '.pt'), weights_only=False)
     net = _build(fx, cuda)
     out = net(fx['x'].to(cuda))
     err = (out.detach().cpu() - fx['out']).abs().max().item()
@@ -99,7 +100,7 @@ def test_rcan_matches_reference_golden(cuda):
     ((out - fx['gt'].to(cuda))**2).mean().backward()
     params = dict(net.named_parameters())
     for k, want in fx['grads'].items():
-        _check_grad(params[k].grad, want)
+        _check_grad(params[k].grad, want, fx.get('autocast_rel', {}).get(k))
 
 
 def test_rcan_full_depth_vs_oracle(cuda):

@@ -147,7 +147,7 @@ def test_swin_block_vs_oracle(cuda):
 
 
 @pytest.mark.parametrize('case', ['swinir_c180_d2x2_x4', 'swinir_c60_d2_x2', 'swinir_c60_d2_direct_x2',
-                                  'swinir_c60_d2_nearest_x4', 'swinir_c60_ws6_in4_x2'])
+                                  'swinir_c60_d2_nearest_x4', 'swinir_c60_ws6_in4_x2', 'swinir_c60_d2_denoise_x1'])
 def test_swinir_matches_reference_golden(cuda, case):
     fx = torch.load(os.path.join(GOLDEN, case + '.pt'), weights_only=False)
     net = _build(fx, cuda)

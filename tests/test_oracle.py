@@ -10,7 +10,7 @@ import torch
 from oracle import ref_shim, sr_oracle
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, '*_x[234].pt')))
+CASES = sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN, '*_x[1-8].pt')))
 
 
 def oracle_forward(fx, sd, x):
