@@ -150,3 +150,19 @@ def test_backward_scratch_provider_measures_then_hands_out_zeroed_slices():
     assert ctx.scratch is None  # single use
     with raw.backward_arena(ctx, cpu, 100):
         assert raw.zeros_f32((4,), cpu).data_ptr() != first.data_ptr()
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/srb200.h is the drop-in boundary: it must compile as C99 (and as C++) on its own -- no torch, no CUDA
+    headers, plain pointers and sizes only."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'srb200.h')
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    for lang, std in (('c', '-std=c99'), ('c++', '-std=c++17')):
+        r = subprocess.run(['gcc', std, '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only', '-x', lang, hdr],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    includes = re.findall(r'^\s*#\s*include\s*[<"]([^>"]+)[>"]', open(hdr).read(), flags=re.M)
+    assert set(includes) <= {'stdint.h', 'stddef.h'}, includes
