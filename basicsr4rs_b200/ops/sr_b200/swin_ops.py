@@ -163,8 +163,11 @@ class _SwinBlock(Function):
 
     @staticmethod
     def backward(ctx, g2):
+        # (read ONCE: under torch.utils.checkpoint(use_reentrant=False) -- SwinIR's use_checkpoint -- a second
+        # ctx.saved_tensors raises "already unpacked once")
+        saved = ctx.saved_tensors
         (x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table, proj_w, proj_b, n2w,
-         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = ctx.saved_tensors
+         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = saved
         c, cs, ca, ch, hd, num_heads, ws, shift, scale = ctx.cfg
         dev = x.device
         p_qkv = head_perm(num_heads, hd, 3, dev)
@@ -172,12 +175,12 @@ class _SwinBlock(Function):
         g2 = g2.contiguous()
         arena = raw.backward_arena(ctx, dev, _SwinBlock._scratch_floats(c, cs, ca, ch, table.numel()))
         with arena:
-            return _SwinBlock._backward(ctx, g2, arena)
+            return _SwinBlock._backward(ctx, g2, arena, saved)
 
     @staticmethod
-    def _backward(ctx, g2, arena):
+    def _backward(ctx, g2, arena, saved):
         (x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table, proj_w, proj_b, n2w,
-         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = ctx.saved_tensors
+         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = saved
         c, cs, ca, ch, hd, num_heads, ws, shift, scale = ctx.cfg
         dev = x.device
         p_qkv = head_perm(num_heads, hd, 3, dev)
