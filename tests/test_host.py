@@ -166,3 +166,30 @@ def test_public_header_is_plain_c(tmp_path):
         assert r.returncode == 0, r.stderr
     includes = re.findall(r'^\s*#\s*include\s*[<"]([^>"]+)[>"]', open(hdr).read(), flags=re.M)
     assert set(includes) <= {'stdint.h', 'stddef.h'}, includes
+
+
+def test_segment_sizes_its_backward_scratch_on_the_first_grad_enabled_run():
+    """archs/graphed.Segment: the first grad-enabled run per input shape only measures what its Functions ask for,
+    later runs hand the slices out of one fill; no_grad runs never allocate."""
+    from basicsr4rs_b200.archs.graphed import Segment
+    from basicsr4rs_b200.ops.sr_b200 import raw
+    got = []
+
+    def fn(t):
+        got.append((raw.take_backward_scratch(100, t.device), raw.take_backward_scratch(28, t.device)))
+        return t * 2
+
+    seg = Segment(fn, [torch.nn.Identity()])
+    x = torch.ones(2, 3)
+    seg(x)                                    # measuring pass
+    assert got[-1] == (None, None)
+    seg(x)                                    # sized pass
+    a, b = got[-1]
+    assert a is not None and b is not None and a.numel() == 164 and b.numel() == 92 and not a.any()
+    with torch.no_grad():
+        seg(x)
+    assert got[-1] == (None, None)
+    seg(torch.ones(4, 3))                     # new shape: measured again
+    assert got[-1] == (None, None)
+    seg(torch.ones(4, 3))
+    assert got[-1][0] is not None
