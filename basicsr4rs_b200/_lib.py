@@ -10,7 +10,13 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libsrb200.so')
+# this repo: basicsr4rs_b200/csrc/libsrb200.so; grafted into the reference (tools/graft_into_reference.py): the op
+# package holds the library next to this file and the sources under src/
+_SRC_DIR = os.path.join(_HERE, 'csrc') if os.path.isdir(os.path.join(_HERE, 'csrc')) else os.path.join(_HERE, 'src')
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libsrb200.so') if os.path.isdir(os.path.join(_HERE, 'csrc')) \
+    else os.path.join(_HERE, 'libsrb200.so')
+NVCC_FLAGS = ['-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-shared',
+              '-cudart', 'shared', '-Xcompiler', '-fPIC', '-Xlinker', '-rpath=/usr/local/cuda/lib64']
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU = 0, 1, 2, 3
 OUT_NHWC, OUT_SHUFFLE, OUT_NCHW_F32 = 0, 1, 2
@@ -95,11 +101,43 @@ SIGNATURES = {
 _lib = None
 
 
+def _include_dir():
+    for d in (os.path.join(os.path.dirname(_HERE), 'include'), os.path.join(_HERE, 'include')):
+        if os.path.exists(os.path.join(d, 'srb200.h')):
+            return d
+    raise RuntimeError('include/srb200.h not found next to the srb200 sources')
+
+
+def jit_build(force=False):
+    """``BASICSR_JIT=True`` (the reference's convention, ops/fused_act/fused_act.py:8-27): compile the library on first
+    import.  Rank-safe: an exclusive ``flock`` on a lock file next to the library serialises the ranks of a torchrun
+    job; the first one builds (into a temporary name, then an atomic rename), the others find it fresh."""
+    import fcntl
+    import subprocess
+    srcs = sorted(os.path.join(_SRC_DIR, f) for f in os.listdir(_SRC_DIR) if f.endswith('.cu'))
+    deps = srcs + [os.path.join(_SRC_DIR, f) for f in os.listdir(_SRC_DIR) if f.endswith(('.cuh', '.h'))]
+    with open(LIB_PATH + '.lock', 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            fresh = os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps)
+            if fresh and not force:
+                return LIB_PATH
+            nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+            tmp = f'{LIB_PATH}.{os.getpid()}.tmp'
+            subprocess.run([nvcc] + NVCC_FLAGS + ['-I', _include_dir(), '-o', tmp] + srcs, check=True, cwd=_SRC_DIR)
+            os.replace(tmp, LIB_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return LIB_PATH
+
+
 def load():
     """Load libsrb200.so once; raise (never fall back) when it is absent."""
     global _lib
     if _lib is not None:
         return _lib
+    if os.environ.get('BASICSR_JIT') == 'True':
+        jit_build()
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f'{LIB_PATH} is missing: build it with `python __graft_entry__.py build` '
                            '(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU/PyTorch fallback.')

@@ -57,9 +57,10 @@ def nchw_roundtrip(fn, x, who):
     """Run an NHWC-bf16 block on an NCHW float tensor (stand-alone use of a block)."""
     require_cuda(x, who)
     c = x.shape[1]
-    t = ops.image_to_nhwc(x, None, 1.0, ops.pad64(c))
-    y = fn(t)
-    out = _NHWCToImage.apply(y, c)
+    with torch.cuda.device(x.device):
+        t = ops.image_to_nhwc(x, None, 1.0, ops.pad64(c))
+        y = fn(t)
+        out = _NHWCToImage.apply(y, c)
     return out.to(x.dtype)
 
 

@@ -9,6 +9,7 @@ graph, weight repacking included in the capture) and replayed thereafter.  The m
 autograd, so DDP's bucket all-reduce overlaps the backward of the remaining segments.
 """
 import weakref
+from contextlib import nullcontext as _nullcontext
 
 import torch
 from torch import nn as nn
@@ -213,8 +214,16 @@ class ArchMixin:
     def forward(self, x):
         """nn.Module contract of the reference archs (NCHW float in / out); every packed weight requested below
         belongs to this network's :class:`PackBook`."""
-        with pack_book(self._pack_book()):
+        book = self._pack_book()
+        # (device guard: the C ABI launches on the current device's stream -- a net on cuda:1 must not launch on cuda:0)
+        with torch.cuda.device(x.device) if x.is_cuda else _nullcontext(), pack_book(book):
             if not torch.is_grad_enabled():
+                # evaluation (SRModel.test runs net_g_ema this way, sr_model.py:120-129): the EMA loop updates
+                # parameters through ``.data`` (base_model.py:81-82), which does not bump ``_version`` -- the version
+                # tags prove nothing here, so every packed operand is re-derived by ONE launch per forward
+                if book.entries and not capturing():
+                    book.invalidate()
+                    book.refresh()
                 return self._forward(x)
             # eager training: the backward's zeroed scratch of every Function from one fill (raw.backward_scratch);
             # sized by a measuring first pass per input shape (0 when CUDA-graph segments bring their own)

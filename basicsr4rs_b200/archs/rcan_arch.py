@@ -22,6 +22,13 @@ class ChannelAttention(nn.Module):
         a, b = self.attention[1], self.attention[3]
         return a.weight, a.bias, b.weight, b.bias
 
+    def forward_nhwc(self, t):
+        return ops.channel_attention(t, *self.fc_params())
+
+    def forward(self, x):
+        """Reference contract (rcan_arch.py:22-24): ``x * self.attention(x)`` on an NCHW float tensor."""
+        return nchw_roundtrip(self.forward_nhwc, x, 'ChannelAttention')
+
 
 class RCAB(nn.Module):
     """Residual channel attention block (reference rcan_arch.py:27-46), one fused autograd function."""

@@ -48,6 +48,11 @@ class DropPath(nn.Module):
     def scale(self, batch, device):
         return drop_path_scale(batch, self.drop_prob or 0., self.training, device)
 
+    def forward(self, x):
+        """Stand-alone use (reference :14-26, :39-40): x * floor(keep + U[0,1)) / keep per sample."""
+        a = self.scale(x.shape[0], x.device)
+        return x if a is None else x * a.to(x.dtype).view((-1,) + (1,) * (x.dim() - 1))
+
 
 class Mlp(nn.Module):
 
@@ -59,6 +64,27 @@ class Mlp(nn.Module):
         self.act = act_layer()
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
+
+    def _on_kernels(self):
+        return isinstance(self.act, nn.GELU) and getattr(self.act, 'approximate', 'none') == 'none' and \
+            not (self.training and self.drop.p > 0.)
+
+    def forward_nhwc(self, t):
+        """[..., pad64(C)] bf16 -> [..., pad64(out)] bf16: two tap-GEMMs with GELU in fc1's epilogue."""
+        if self._on_kernels():
+            return swin_ops.mlp(t, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+        # dropout > 0 / another activation: the reference expression (:54-60) on the un-padded channels
+        c, co = self.fc1.in_features, self.fc2.out_features
+        y = self.drop(self.fc2(self.drop(self.act(self.fc1(t[..., :c].float())))))
+        return nn.functional.pad(y, (0, ops.pad64(co) - co)).to(torch.bfloat16).contiguous()
+
+    def forward(self, x):
+        """Reference contract (:54-60): x [..., in_features] float -> [..., out_features]."""
+        require_cuda(x, 'Mlp')
+        lead = x.shape[:-1]
+        t = swin_ops.tokens_to_nhwc(x.reshape(1, -1, x.shape[-1]), 1, x.numel() // x.shape[-1])
+        y = self.forward_nhwc(t)
+        return swin_ops.nhwc_to_tokens(y, self.fc2.out_features, x.dtype).reshape(lead + (self.fc2.out_features,))
 
 
 def window_partition(x, window_size):
@@ -105,8 +131,54 @@ class WindowAttention(nn.Module):
         self.softmax = nn.Softmax(dim=-1)
         self._qk_scale_override = qk_scale
 
+    def on_kernels(self):
+        """True when the fused kernel covers this configuration; otherwise callers run the reference expression."""
+        hd = self.dim // self.num_heads
+        return (self.window_size[0] == self.window_size[1] and 2 <= self.window_size[0] <= KERNEL_WINDOW and
+                hd <= swin_ops.HD_PAD and self.num_heads % 2 == 0 and self.dim % self.num_heads == 0 and
+                self._qk_scale_override is None and
+                not (self.training and (self.attn_drop.p > 0. or self.proj_drop.p > 0.)))
+
+    def forward_nhwc(self, t, shift):
+        """t [B,H,W,pad64(C)] bf16 un-partitioned; partition / shift / mask / reverse happen inside the kernel."""
+        return swin_ops.window_attn(t, self.qkv.weight, self.qkv.bias, self.relative_position_bias_table,
+                                    self.proj.weight, self.proj.bias, self.num_heads, self.window_size[0], shift)
+
+    def torch_forward(self, x, mask=None):
+        """The reference expression (:144-175) on stock torch ops -- the fall-through for configurations the fused
+        kernel does not cover (window > 8, odd head counts, head_dim > 32, qk_scale, dropout > 0, explicit masks)."""
+        b_, n, c = x.shape
+        qkv = self.qkv(x).reshape(b_, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv[0] * self.scale, qkv[1], qkv[2]
+        attn = q @ k.transpose(-2, -1)
+        nt = self.window_size[0] * self.window_size[1]
+        bias = self.relative_position_bias_table[self.relative_position_index.view(-1)].view(nt, nt, -1)
+        attn = attn + bias.permute(2, 0, 1).contiguous().unsqueeze(0)
+        if mask is not None:
+            nw = mask.shape[0]
+            attn = attn.view(b_ // nw, nw, self.num_heads, n, n) + mask.unsqueeze(1).unsqueeze(0)
+            attn = attn.view(-1, self.num_heads, n, n)
+        attn = self.attn_drop(self.softmax(attn))
+        x = (attn @ v).transpose(1, 2).reshape(b_, n, c)
+        return self.proj_drop(self.proj(x))
+
+    def forward(self, x, mask=None):
+        """Reference contract (:144-175): x (num_windows*b, n, c) already partitioned; mask (nW, n, n) or None.
+        Without an explicit mask the windows run through the fused kernel as ws x ws images (one window each)."""
+        require_cuda(x, 'WindowAttention')
+        ws = self.window_size[0]
+        if mask is None and self.on_kernels() and x.shape[1] == ws * ws:
+            y = self.forward_nhwc(swin_ops.tokens_to_nhwc(x, ws, ws), 0)
+            return swin_ops.nhwc_to_tokens(y, self.dim, x.dtype)
+        return self.torch_forward(x, mask)
+
     def extra_repr(self) -> str:
         return f'dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}'
+
+    def flops(self, n):
+        """MACs of one window with n tokens (reference :180-191)."""
+        hd = self.dim // self.num_heads
+        return n * self.dim * 3 * self.dim + 2 * self.num_heads * n * hd * n + n * self.dim * self.dim
 
 
 class SwinTransformerBlock(nn.Module):
@@ -133,10 +205,6 @@ class SwinTransformerBlock(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
         self.register_buffer('attn_mask', self.calculate_mask(self.input_resolution) if self.shift_size > 0 else None)
-        if drop > 0. or attn_drop > 0.:
-            raise NotImplementedError('srb200 SwinIR: drop / attn_drop > 0 are not supported (all shipped YAMLs use 0)')
-        if qk_scale is not None:
-            raise NotImplementedError('srb200 SwinIR: qk_scale override is not supported')
 
     def calculate_mask(self, x_size):
         """0 / -100 SW-MSA mask; state-dict compatibility only (the kernel derives it analytically)."""
@@ -152,11 +220,17 @@ class SwinTransformerBlock(nn.Module):
         m = mw.unsqueeze(1) - mw.unsqueeze(2)
         return m.masked_fill(m != 0, float(-100.0)).masked_fill(m == 0, float(0.0))
 
+    def on_kernels(self):
+        """The fused block function needs the fused attention kernel, nn.LayerNorm, an exact-erf GELU Mlp and no
+        dropout; anything else takes :meth:`_forward_nhwc_general` (reference expression for the uncovered piece)."""
+        return (self.attn.on_kernels() and self.mlp._on_kernels() and type(self.norm1) is nn.LayerNorm and
+                type(self.norm2) is nn.LayerNorm and self.norm1.eps == self.norm2.eps and
+                self.norm1.elementwise_affine and self.norm2.elementwise_affine)
+
     def forward_nhwc(self, t):
         """t: [B, H, W, pad64(C)] bf16."""
-        if not 2 <= self.window_size <= KERNEL_WINDOW:
-            raise NotImplementedError(f'srb200 fused window attention supports window_size 2..{KERNEL_WINDOW} '
-                                      f'(got {self.window_size})')
+        if not self.on_kernels():
+            return self._forward_nhwc_general(t)
         b = t.shape[0]
         dp = self.drop_path
         a1 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None
@@ -165,7 +239,59 @@ class SwinTransformerBlock(nn.Module):
         return swin_ops.swin_block(t, self.norm1.weight, self.norm1.bias, at.qkv.weight, at.qkv.bias,
                                    at.relative_position_bias_table, at.proj.weight, at.proj.bias, self.norm2.weight,
                                    self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias,
-                                   self.num_heads, self.window_size, self.shift_size, a1, a2)
+                                   self.num_heads, self.window_size, self.shift_size, a1, a2, eps=self.norm1.eps)
+
+    def _forward_nhwc_general(self, t):
+        """Fall-through for configurations without a fused kernel (they must keep running, not
+        raise): window_size > 8, odd head counts, head_dim > 32, qk_scale, dropout > 0, a custom norm_layer / act_layer.
+        The uncovered piece is the reference expression (:283-323) on stock torch ops over the GPU tensors; everything
+        the kernels do cover (LayerNorm, Mlp, the attention of a supported shape) still goes through them."""
+        b, h, w, cp = t.shape
+        c, ws, sh = self.dim, self.window_size, self.shift_size
+
+        def norm(mod, z):
+            if type(mod) is nn.LayerNorm and mod.elementwise_affine:
+                return swin_ops.layer_norm(z, mod.weight, mod.bias, mod.eps)
+            y = mod(z[..., :c].float())
+            return nn.functional.pad(y, (0, cp - c)).to(torch.bfloat16).contiguous()
+
+        def residual(z, y):  # z + DropPath(y), both [B,H,W,cp] bf16 (padding channels stay zero)
+            y = self.drop_path(y) if isinstance(self.drop_path, DropPath) else y
+            return (z.float() + y.float()).to(torch.bfloat16)
+
+        xn = norm(self.norm1, t)
+        if self.attn.on_kernels():
+            y = self.attn.forward_nhwc(xn, sh)
+        else:
+            xs = xn[..., :c].float()
+            if sh > 0:
+                xs = torch.roll(xs, shifts=(-sh, -sh), dims=(1, 2))
+            win = xs.view(b, h // ws, ws, w // ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, c)
+            mask = None
+            if sh > 0:
+                mask = self.attn_mask if tuple(self.input_resolution) == (h, w) else self.calculate_mask((h, w))
+                mask = mask.to(t.device)
+            aw = self.attn.torch_forward(win, mask)
+            ys = aw.view(b, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c)
+            if sh > 0:
+                ys = torch.roll(ys, shifts=(sh, sh), dims=(1, 2))
+            y = nn.functional.pad(ys, (0, cp - c)).to(torch.bfloat16)
+        x1 = residual(t, y)
+        return residual(x1, self.mlp.forward_nhwc(norm(self.norm2, x1)))
+
+    def forward(self, x, x_size):
+        """Reference contract (:283-323): x [B, h*w, C] tokens, x_size = (h, w)."""
+        require_cuda(x, 'SwinTransformerBlock')
+        h, w = x_size
+        y = self.forward_nhwc(swin_ops.tokens_to_nhwc(x, h, w))
+        return swin_ops.nhwc_to_tokens(y, self.dim, x.dtype)
+
+    def flops(self):
+        """Reference :329-341."""
+        h, w = self.input_resolution
+        nw = h * w / self.window_size / self.window_size
+        return (2 * self.dim * h * w + nw * self.attn.flops(self.window_size * self.window_size) +
+                2 * h * w * self.dim * self.dim * self.mlp_ratio)
 
     def extra_repr(self) -> str:
         return (f'dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, '
@@ -200,8 +326,22 @@ class BasicLayer(nn.Module):
                 t = blk.forward_nhwc(t)
         return t
 
+    def forward(self, x, x_size):
+        """Reference contract (:458-466): x [B, h*w, C] tokens."""
+        require_cuda(x, 'BasicLayer')
+        y = self.forward_nhwc(swin_ops.tokens_to_nhwc(x, *x_size))
+        if self.downsample is not None:
+            return self.downsample(swin_ops.nhwc_to_tokens(y, self.dim, x.dtype))
+        return swin_ops.nhwc_to_tokens(y, self.dim, x.dtype)
+
     def extra_repr(self) -> str:
         return f'dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}'
+
+    def flops(self):
+        flops = sum(blk.flops() for blk in self.blocks)
+        if self.downsample is not None:
+            flops += self.downsample.flops()
+        return flops
 
 
 class PatchEmbed(nn.Module):
@@ -222,6 +362,19 @@ class PatchEmbed(nn.Module):
     def forward_nhwc(self, t):
         return swin_ops.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps) if self.norm is not None else t
 
+    def forward(self, x):
+        """Reference contract (:600-604): [B,C,H,W] -> [B,H*W,C] (+ LayerNorm)."""
+        b, c, h, w = x.shape
+        x = x.flatten(2).transpose(1, 2)
+        if self.norm is None:
+            return x
+        require_cuda(x, 'PatchEmbed')
+        return swin_ops.nhwc_to_tokens(self.forward_nhwc(swin_ops.tokens_to_nhwc(x, h, w)), c, x.dtype)
+
+    def flops(self):
+        h, w = self.img_size
+        return h * w * self.embed_dim if self.norm is not None else 0
+
 
 class PatchUnEmbed(nn.Module):
     """[B,H*W,C] -> [B,C,H,W]; the identity in NHWC."""
@@ -236,6 +389,13 @@ class PatchUnEmbed(nn.Module):
         self.num_patches = self.patches_resolution[0] * self.patches_resolution[1]
         self.in_chans = in_chans
         self.embed_dim = embed_dim
+
+    def forward(self, x, x_size):
+        """Reference contract (:638-640): [B,H*W,C] -> [B,C,H,W]."""
+        return x.transpose(1, 2).contiguous().view(x.shape[0], self.embed_dim, x_size[0], x_size[1])
+
+    def flops(self):
+        return 0
 
 
 class RSTB(nn.Module):
@@ -267,6 +427,17 @@ class RSTB(nn.Module):
     def forward_nhwc(self, t):
         return _resi_conv(self.conv, self.residual_group.forward_nhwc(t), t)
 
+    def forward(self, x, x_size):
+        """Reference contract (:557-558): x [B, h*w, C] tokens."""
+        require_cuda(x, 'RSTB')
+        y = self.forward_nhwc(swin_ops.tokens_to_nhwc(x, *x_size))
+        return swin_ops.nhwc_to_tokens(y, self.dim, x.dtype)
+
+    def flops(self):
+        h, w = self.input_resolution
+        return self.residual_group.flops() + h * w * self.dim * self.dim * 9 + self.patch_embed.flops() + \
+            self.patch_unembed.flops()
+
 
 def _resi_conv(conv, r, skip):
     """'1conv' / '3conv' residual connection (reference :532-539, :818-824) + skip, on NHWC bf16."""
@@ -286,6 +457,10 @@ class UpsampleOneStep(nn.Sequential):
         self.input_resolution = input_resolution
         m = [nn.Conv2d(num_feat, (scale**2) * num_out_ch, 3, 1, 1), nn.PixelShuffle(scale)]
         super(UpsampleOneStep, self).__init__(*m)
+
+    def flops(self):
+        h, w = self.input_resolution
+        return h * w * self.num_feat * 3 * 9
 
 
 @ARCH_REGISTRY.register()
@@ -378,8 +553,6 @@ class SwinIR(ArchMixin, nn.Module):
             self.conv_last = nn.Conv2d(embed_dim, num_out_ch, 3, 1, 1)
 
         self.apply(self._init_weights)
-        if ape:
-            raise NotImplementedError('srb200 SwinIR: ape=True is not supported (no shipped YAML uses it)')
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -398,12 +571,37 @@ class SwinIR(ArchMixin, nn.Module):
     def no_weight_decay_keywords(self):
         return {'relative_position_bias_table'}
 
+    def _embed(self, t):
+        """patch_embed(+norm) [+ absolute position embedding] [+ pos_drop] (reference :878-881)."""
+        t = self.patch_embed.forward_nhwc(t)
+        if self.ape:
+            b, h, w, cp = t.shape
+            pe = self.absolute_pos_embed
+            if pe.shape[1] != h * w:
+                raise RuntimeError(f'ape=True: absolute_pos_embed holds {pe.shape[1]} positions, the input has {h * w} '
+                                   '(same restriction as the reference, :880)')
+            pe = nn.functional.pad(pe.view(1, h, w, -1), (0, cp - pe.shape[-1]))
+            t = (t.float() + pe).to(torch.bfloat16)
+        if self.training and self.pos_drop.p > 0.:
+            t = self.pos_drop(t)
+        return t
+
     def forward_features_nhwc(self, t):
         """patch_embed(+norm) -> RSTBs -> norm -> patch_unembed, all on [B,H,W,pad64(C)] bf16 (reference :876-889)."""
-        t = self.patch_embed.forward_nhwc(t)
+        t = self._embed(t)
         for layer in self.layers:
             t = layer.forward_nhwc(t)
         return swin_ops.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps)
+
+    def flops(self):
+        """Reference :922-933."""
+        h, w = self.patches_resolution
+        flops = h * w * 3 * self.embed_dim * 9 + self.patch_embed.flops()
+        flops += sum(layer.flops() for layer in self.layers)
+        flops += h * w * 3 * self.embed_dim * self.embed_dim
+        if hasattr(self.upsample, 'flops') if hasattr(self, 'upsample') else False:
+            flops += self.upsample.flops()
+        return flops
 
     def _head(self, x):
         mean = self._device_mean(x) if self.mean.numel() == x.shape[1] else None
@@ -452,7 +650,7 @@ class SwinIR(ArchMixin, nn.Module):
 
         def head_fn(x):
             first = self._head(x)
-            return run(groups[0])(self.patch_embed.forward_nhwc(first)), first
+            return run(groups[0])(self._embed(first)), first
 
         tail_mods = [self.norm, self.conv_after_body] + [getattr(self, n) for n in
                                                          ('conv_before_upsample', 'upsample', 'conv_up1', 'conv_up2',
@@ -469,7 +667,7 @@ class SwinIR(ArchMixin, nn.Module):
             out = graphed_forward(self, x, self._build_segments, chain_wire(nseg, carry=1))
             return out if out.dtype == x.dtype else out.to(x.dtype)
         first = self._head(x)
-        t = self.patch_embed.forward_nhwc(first)
+        t = self._embed(first)
         for layer in self.layers:
             t = layer.forward_nhwc(t)
         out = self._tail(t, first, x)

@@ -207,11 +207,12 @@ __device__ __forceinline__ void softmax_rows(float (&s)[8][4], const float* sBia
 __device__ __forceinline__ void setup_window(const AttnGeom& g, int& b, int& wy, int& wx, int& head,
                                              float* sBias, int* sRegion,
                                              const float* __restrict__ table) {
-  // grid = (heads, windows per image, batch): one integer division instead of four
+  // grid = (heads * windows per image, batch): gridDim.x holds 2^31 - 1 blocks, so even a 16k x 16k scene fits
   const int nWw = g.W / g.ws;
-  head = blockIdx.x;
-  wy = blockIdx.y / nWw;
-  wx = blockIdx.y - wy * nWw;
+  const int win = blockIdx.x / g.nH;
+  head = blockIdx.x - win * g.nH;
+  wy = win / nWw;
+  wx = win - wy * nWw;
   b = blockIdx.z;
   for (int i = threadIdx.x; i < (2 * g.ws - 1) * (2 * g.ws - 1); i += blockDim.x)
     sBias[i] = __ldg(table + i * g.nH + head);
@@ -425,8 +426,8 @@ extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rp
   if (rc != SRB200_OK) return rc;
   AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
   const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
-  if (wins > 65535 || B > 65535) return SRB200_EINVAL;
-  const dim3 grid(num_heads, static_cast<unsigned>(wins), B);
+  if (wins * num_heads > 0x7fffffffLL || B > 65535) return SRB200_EINVAL;
+  const dim3 grid(static_cast<unsigned>(wins * num_heads), 1, B);
   if (window_size == 8)
     window_attn_fwd_kernel<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), rpb_table, static_cast<__nv_bfloat16*>(out_bf16), g);
@@ -446,8 +447,8 @@ extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gou
   if (rc != SRB200_OK) return rc;
   AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
   const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
-  if (wins > 65535 || B > 65535) return SRB200_EINVAL;
-  const dim3 grid(num_heads, static_cast<unsigned>(wins), B);
+  if (wins * num_heads > 0x7fffffffLL || B > 65535) return SRB200_EINVAL;
+  const dim3 grid(static_cast<unsigned>(wins * num_heads), 1, B);
   if (window_size == 8)
     window_attn_bwd_kernel<8><<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(qkv_bf16), static_cast<const __nv_bfloat16*>(gout_bf16), rpb_table,

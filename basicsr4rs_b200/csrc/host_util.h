@@ -6,7 +6,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#include "../../include/srb200.h"
+#include <atomic>
+
+#include "srb200.h"  // include/srb200.h (-I): the public C ABI
 
 namespace srb {
 
@@ -50,15 +52,47 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint
   return r == CUDA_SUCCESS ? SRB200_OK : SRB200_EDRIVER;
 }
 
-inline int num_sms() {
-  static int n = []() {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64) ? dev : 0;
 }
+
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs, e.g. tiled inference)
+inline int num_sms() {
+  static std::atomic<int> cache[64];
+  const int dev = current_device();
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remember it per device, thread-safely
+// (the entry points are called from the main thread in forward and from autograd worker threads in backward).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  template <typename Kernel>
+  int ensure(Kernel kernel, size_t smem_bytes) {
+    const unsigned long long bit = 1ULL << current_device();
+    if (mask.load(std::memory_order_acquire) & bit) return SRB200_OK;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)) !=
+        cudaSuccess)
+      return SRB200_ELAUNCH;
+    mask.fetch_or(bit, std::memory_order_release);
+    return SRB200_OK;
+  }
+};
+
+// a tuning / debugging environment variable, read ONCE per process (not on every launch)
+#define SRB_ENV(name)                        \
+  ([]() -> const char* {                     \
+    static const char* const v = getenv(name); \
+    return v;                                \
+  }())
 
 inline int launch_status() {
   return cudaPeekAtLastError() == cudaSuccess ? SRB200_OK : SRB200_ELAUNCH;
@@ -70,8 +104,8 @@ inline int launch_status() {
 // Off by default: it is a win for chains of GEMM kernels (EDSR, RCAN: +1..5 %) but when a multi-wave kernel such as
 // the window attention sits between them, the early-resident GEMM CTAs starve it (SwinIR: -15 %).  The archs switch
 // it on around their CUDA-graph capture with srb200_set_pdl(); SRB_PDL=0/1 in the environment overrides.
-inline int& pdl_flag() {
-  static int flag = 0;
+inline std::atomic<int>& pdl_flag() {
+  static std::atomic<int> flag{0};
   return flag;
 }
 inline bool pdl_enabled() {
@@ -79,7 +113,7 @@ inline bool pdl_enabled() {
     const char* e = getenv("SRB_PDL");
     return e == nullptr ? -1 : (e[0] == '1' ? 1 : 0);
   }();
-  return env >= 0 ? env == 1 : pdl_flag() != 0;
+  return env >= 0 ? env == 1 : pdl_flag().load(std::memory_order_relaxed) != 0;
 }
 
 template <typename Kernel, typename Params>

@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(256) ca_forward_fused_kernel(
   }
 }
 
-// backward, ONE persistent launch (all CTAs co-resident), phases joined by a device-wide arrive barrier instead
-// of three kernel boundaries.  Every CTA owns one contiguous slab of 16-byte vectors in phases 1 and 3:
+// backward, ONE persistent COOPERATIVE launch (the driver guarantees all CTAs co-resident), phases joined by a
+// device-wide arrive barrier instead of three kernel boundaries.  Every CTA owns one contiguous slab of 16-byte vectors in phases 1 and 3:
 //   1. gs[b,c] += res_scale * sum_hw g*t   (registers -> warp shuffle -> smem -> global atomics), then arrive
 //   2. after ALL CTAs arrived: every CTA redoes the tiny FC backward in shared memory (B*C*Cr MACs) to get
 //      gp[b,c] for the <= 2 images its slab touches; CTA 0 also writes gW1, gb1, gW2, gb2
@@ -537,12 +537,8 @@ extern "C" int srb200_ca_fc_bwd(const float* gs, const float* s, const float* z,
   const size_t smem = (2 * static_cast<size_t>(B) * C + 2 * static_cast<size_t>(B) * Cr +
                        2 * static_cast<size_t>(C) * Cr) * sizeof(float);
   if (smem > 200 * 1024) return SRB200_EINVAL;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(ca_fc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-      return SRB200_ELAUNCH;
-    configured = 200 * 1024;
-  }
+  static PerDeviceOnce configured;
+  if (smem > 48 * 1024 && configured.ensure(ca_fc_bwd_kernel, 200 * 1024) != SRB200_OK) return SRB200_ELAUNCH;
   ca_fc_bwd_kernel<<<1, 256, smem, static_cast<cudaStream_t>(stream)>>>(gs, s, z, p, w1, w2, gw1, gb1,
                                                                         gw2, gb2, gp, B, C, Cr);
   return launch_status();
@@ -610,8 +606,26 @@ extern "C" int srb200_ca_backward(const void* g_bf16, const void* t_bf16, const 
     slab = per_img;
   }
   grid = (nvec + slab - 1) / slab;
-  ca_backward_fused_kernel<<<static_cast<unsigned>(grid), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(g_bf16), static_cast<const uint4*>(t_bf16), s, z, p, w1, w2, gs, gw1, gb1, gw2, gb2,
-      static_cast<uint4*>(gt_bf16), colsum, sync, nvec, slab, B, HW, C, Cr, res_scale);
+  // COOPERATIVE launch: the driver either places all CTAs at once or rejects the launch -- the device-wide arrive
+  // barrier inside can then never spin on CTAs that were not scheduled (NCCL kernels of DDP, other streams or
+  // early-resident PDL CTAs may hold SMs when this kernel starts).  Works under stream capture (cooperative kernel
+  // nodes); the occupancy-derived grid above stays <= half of the co-resident capacity.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, ca_backward_fused_kernel, static_cast<const uint4*>(g_bf16),
+                         static_cast<const uint4*>(t_bf16), s, z, p, w1, w2, gs, gw1, gb1, gw2, gb2,
+                         static_cast<uint4*>(gt_bf16), colsum, sync, nvec, slab, B, HW, C, Cr,
+                         res_scale) != cudaSuccess) {
+    cudaGetLastError();
+    return SRB200_ELAUNCH;
+  }
   return launch_status();
 }

@@ -688,13 +688,8 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 template <int BLOCK_N>
 static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
   using Cfg = TapCfg<BLOCK_N, true>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg::SMEM_BYTES) != cudaSuccess)
-      return SRB200_ELAUNCH;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  if (configured.ensure(tapgemm_kernel<BLOCK_N, true>, Cfg::SMEM_BYTES) != SRB200_OK) return SRB200_ELAUNCH;
   const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
   int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
   if (pairs >= p.n_tiles) pairs -= pairs % p.n_tiles;  // a CTA pair keeps its N tile for all its work units
@@ -704,13 +699,8 @@ static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
 template <int BLOCK_N, bool TEAMS = false>
 static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   using Cfg = TapCfg<BLOCK_N>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tapgemm_kernel<BLOCK_N, false, TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg::SMEM_BYTES) != cudaSuccess)
-      return SRB200_ELAUNCH;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  if (configured.ensure(tapgemm_kernel<BLOCK_N, false, TEAMS>, Cfg::SMEM_BYTES) != SRB200_OK) return SRB200_ELAUNCH;
   const int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
   if (grid >= p.n_tiles) grid -= grid % p.n_tiles;  // a CTA keeps its N tile (bias, weight columns) for all its tiles
@@ -718,7 +708,7 @@ static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   return launch_ex(tapgemm_kernel<BLOCK_N, false, TEAMS>, grid, 320, Cfg::SMEM_BYTES, stream, 1, p);
 }
 
-static unsigned long long* g_trace = nullptr;
+static std::atomic<unsigned long long*> g_trace{nullptr};
 
 static int pick_block_n(int Cout) {
   if (Cout % 256 == 0) return 256;
@@ -813,7 +803,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.out_r = d->out_r;
   p.out_c = d->out_c;
   p.out_scale = d->out_scale;
-  p.trace = g_trace;
+  p.trace = g_trace.load(std::memory_order_relaxed);
   p.pdl = pdl_enabled() ? 1 : 0;
 
   // A views: in[B, H*r, W*r, Cin], view (i,j): element (b,y,x,c) at ((b*H*r + y*r+i)*W*r + x*r+j)*Cin + c
@@ -833,7 +823,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
       if (rc != SRB200_OK) return rc;
     }
   // CTA pairs (cta_group::2) for the wide layers: each CTA loads half of the weight box
-  const bool two_cta = (bn == 256) && p.m_tiles >= 2 && getenv("SRB_TAPGEMM_1CTA") == nullptr;
+  const bool two_cta = (bn == 256) && p.m_tiles >= 2 && SRB_ENV("SRB_TAPGEMM_1CTA") == nullptr;
   {
     const uint64_t K = static_cast<uint64_t>(p.num_src) * C;
     const uint64_t dims[2] = {K, static_cast<uint64_t>(p.taps) * d->Cout};
@@ -872,7 +862,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
     const int total = p.m_tiles * p.n_tiles;
     int grid = total < num_sms() ? total : num_sms();
     if (grid >= p.n_tiles) grid -= grid % p.n_tiles;
-    const bool teams = p.tma_store != 0 && grid % p.n_tiles == 0 && getenv("SRB_TAPGEMM_NO_TEAMS") == nullptr;
+    const bool teams = p.tma_store != 0 && grid % p.n_tiles == 0 && SRB_ENV("SRB_TAPGEMM_NO_TEAMS") == nullptr;
     if (teams && bn == 192) return launch_tapgemm<192, true>(p, stream);
     if (teams && bn == 128) return launch_tapgemm<128, true>(p, stream);
   }
@@ -887,13 +877,11 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
 }
 
 extern "C" int srb200_set_pdl(int on) {
-  const int prev = pdl_flag();
-  pdl_flag() = on ? 1 : 0;
-  return prev;
+  return pdl_flag().exchange(on ? 1 : 0);
 }
 
 /* debug only: device buffer of 3*64 uint64 receiving CTA 0's per-role clock64 timeline of subsequent launches */
 extern "C" int srb200_debug_set_trace(void* dev_buf) {
-  g_trace = static_cast<unsigned long long*>(dev_buf);
+  g_trace.store(static_cast<unsigned long long*>(dev_buf), std::memory_order_relaxed);
   return SRB200_OK;
 }

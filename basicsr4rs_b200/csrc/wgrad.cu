@@ -394,13 +394,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 
 template <int KPIX>
 static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(wgrad2_kernel<KPIX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Wg2Cfg<KPIX>::SMEM_BYTES) != cudaSuccess)
-      return SRB200_ELAUNCH;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  if (configured.ensure(wgrad2_kernel<KPIX>, Wg2Cfg<KPIX>::SMEM_BYTES) != SRB200_OK) return SRB200_ELAUNCH;
   const int grid = 2 * p.taps * p.m_tiles * p.n_tiles * p.splits;
   return launch_ex(wgrad2_kernel<KPIX>, grid, 192, Wg2Cfg<KPIX>::SMEM_BYTES, stream, 1, p);  // (__cluster_dims__ 2)
 }
@@ -408,13 +403,9 @@ static int launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
 template <int BLOCK_N, int KPIX, bool FOLD = false, int A_BOXES = 2>
 static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
   using Cfg = WgCfg<BLOCK_N, KPIX, A_BOXES>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, KPIX, FOLD, A_BOXES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             Cfg::SMEM_BYTES) != cudaSuccess)
-      return SRB200_ELAUNCH;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  if (configured.ensure(wgrad_kernel<BLOCK_N, KPIX, FOLD, A_BOXES>, Cfg::SMEM_BYTES) != SRB200_OK)
+    return SRB200_ELAUNCH;
   const int grid = (FOLD ? 3 : p.taps) * p.m_tiles * p.n_tiles * p.splits;
   return launch_ex(wgrad_kernel<BLOCK_N, KPIX, FOLD, A_BOXES>, grid, 192, Cfg::SMEM_BYTES, stream, 1, p);
 }
@@ -423,9 +414,9 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
 
 using namespace srb;
 
-static unsigned long long* g_wgrad_trace = nullptr;
+static std::atomic<unsigned long long*> g_wgrad_trace{nullptr};
 extern "C" int srb200_debug_set_wgrad_trace(void* dev_buf) {
-  g_wgrad_trace = static_cast<unsigned long long*>(dev_buf);
+  g_wgrad_trace.store(static_cast<unsigned long long*>(dev_buf), std::memory_order_relaxed);
   return SRB200_OK;
 }
 
@@ -445,7 +436,7 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   else bn = 64;
 
   WgradParams p;
-  p.trace = g_wgrad_trace;
+  p.trace = g_wgrad_trace.load(std::memory_order_relaxed);
   p.pdl = pdl_enabled() ? 1 : 0;
   p.acc = acc;
   p.B = B;
@@ -468,26 +459,26 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   if (splits > p.total_kb) splits = p.total_kb;
   // keep each split long enough to amortise the pipeline fill / atomic epilogue
   while (splits > 1 && p.total_kb / splits < 8) --splits;
-  if (const char* e = getenv("SRB_WG_SPLITS")) {  // tuning aid
+  if (const char* e = SRB_ENV("SRB_WG_SPLITS")) {  // tuning aid
     splits = atoi(e);
     if (splits < 1) splits = 1;
     if (splits > p.total_kb) splits = p.total_kb;
   }
   p.splits = splits;
 
-  const bool two_cta = (N % 256 == 0) && (K % 256 == 0) && getenv("SRB_WGRAD_1CTA") == nullptr;
+  const bool two_cta = (N % 256 == 0) && (K % 256 == 0) && SRB_ENV("SRB_WGRAD_1CTA") == nullptr;
   // 64-wide input-channel tiles of a 3x3 layer: fold the three taps of a stencil row into one N = 192 unit (WgCfg)
   // Measured (tools/sweep_fold.py, B16): 96x96 64->64 32.9 -> 24.7 us, but 48x48 14.5 -> 15.6 us and N = 256 23.1 ->
   // 27.0 us: with few pixels per unit the fp32 atomics of the split-K merge (three taps' worth per CTA) outweigh the
   // shorter mainloop, so it is used for 64-output-channel layers with >= 100k pixels.  SRB_WG_FOLD=1|0 forces.
-  const char* fold_env = getenv("SRB_WG_FOLD");
+  const char* fold_env = SRB_ENV("SRB_WG_FOLD");
   const bool fold_shape = ksize == 3 && bn == 64 && !two_cta;
   const bool fold = fold_shape && (fold_env ? atoi(fold_env) != 0
                                             : (N == 64 && static_cast<long long>(B) * H * W >= 100000));
   const bool fold_a1 = fold && N == 64;
   int kpix = 64;
   if (fold) {
-    const char* e = getenv("SRB_WG_KPIX");
+    const char* e = SRB_ENV("SRB_WG_KPIX");
     kpix = fold_a1 ? 128 : 64;  // (stage = (A_BOXES + 3) boxes: 64 KB x 3 stages, or 40 KB x 5)
     if (e && fold_a1 && (atoi(e) == 64 || atoi(e) == 128)) kpix = atoi(e);
     pick_tile(H, W, kpix, &p.tile_w, &p.tile_h);
@@ -498,7 +489,7 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
     if (s3 < 1) s3 = 1;
     if (s3 > p.total_kb) s3 = p.total_kb;
     while (s3 > 1 && p.total_kb / s3 < 4) --s3;
-    if (const char* es = getenv("SRB_WG_SPLITS")) {
+    if (const char* es = SRB_ENV("SRB_WG_SPLITS")) {
       s3 = atoi(es);
       if (s3 < 1) s3 = 1;
       if (s3 > p.total_kb) s3 = p.total_kb;
@@ -507,7 +498,7 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   }
   if (!two_cta && !fold) {
     // largest stage (pixels per k-block) that still leaves every split a few k-blocks
-    const char* e = getenv("SRB_WG_KPIX");
+    const char* e = SRB_ENV("SRB_WG_KPIX");
     const int cand[3] = {bn == 64 ? 256 : 128, 128, 64};
     for (int ci = 0; ci < 3; ++ci) {
       const int kp = e ? atoi(e) : cand[ci];
@@ -530,7 +521,7 @@ extern "C" int srb200_wgrad(const void* dy_bf16, const void* x_bf16, float* acc,
   }
   if (two_cta) {
     // 128-pixel stages when every split still gets a few of them
-    const char* e = getenv("SRB_WG2_KPIX");
+    const char* e = SRB_ENV("SRB_WG2_KPIX");
     kpix = e ? atoi(e) : 128;
     if (kpix == 128) {
       int tw, th;

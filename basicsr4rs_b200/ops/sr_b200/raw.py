@@ -19,15 +19,16 @@ def _stream():
 
 class EventProbe:
     """Times selected kernel launches with CUDA events on the launching stream (bench.py's roofline
-    leg): ``probe = EventProbe(lambda kind, info: ...)``; ``raw.PROBE = probe``; read ``probe.ms()``."""
+    leg): ``probe = EventProbe(lambda kind, info: ...)``; ``raw.PROBE = probe``; read ``probe.ms()`` (durations)
+    or ``probe.records()`` ((kind, info, ms) triples)."""
 
-    def __init__(self, predicate, limit=4096):
+    def __init__(self, predicate, limit=8192):
         self.predicate, self.limit, self.pairs = predicate, limit, []
 
     def begin(self, kind, info):
         if len(self.pairs) >= self.limit or not self.predicate(kind, info):
             return None
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), kind, info)
         ev[0].record()
         return ev
 
@@ -38,7 +39,20 @@ class EventProbe:
 
     def ms(self):
         torch.cuda.synchronize()
-        return [a.elapsed_time(b) for a, b in self.pairs]
+        return [p[0].elapsed_time(p[1]) for p in self.pairs]
+
+    def records(self):
+        torch.cuda.synchronize()
+        return [(p[2], p[3], p[0].elapsed_time(p[1])) for p in self.pairs]
+
+
+def probed(kind, info, launch):
+    """Run ``launch()`` (one C-ABI call) between two events when a probe is active and wants this kernel."""
+    ev = PROBE.begin(kind, info) if PROBE is not None else None
+    out = launch()
+    if ev is not None:
+        PROBE.end(ev)
+    return out
 
 
 PROBE = None
@@ -146,6 +160,10 @@ def _ptr(t):
 def _chk(t, name, dtype=None):
     if not t.is_cuda:
         raise RuntimeError(f'{name} must be a CUDA tensor')
+    if t.device.index != torch.cuda.current_device():
+        # the C ABI launches on the CURRENT device's stream (it never changes the device itself)
+        raise RuntimeError(f'{name} lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}: '
+                           'wrap the call in torch.cuda.device(tensor.device) (the archs\' forward does)')
     if not t.is_contiguous():
         raise RuntimeError(f'{name} must be contiguous')
     if dtype is not None and t.dtype != dtype:
@@ -435,7 +453,8 @@ def wgrad(dy, x, *, ksize, dy_r=1):
     n = dy.shape[-1] * dy_r * dy_r
     assert dy.shape[0] == b and dy.shape[1] == h * dy_r and dy.shape[2] == w * dy_r
     acc = zeros_f32((ksize * ksize, n, k), x.device)
-    L.check(L.load().srb200_wgrad(_ptr(dy), _ptr(x), _ptr(acc), b, h, w, n, k, ksize, dy_r, _stream()), 'wgrad')
+    probed('wgrad', (b, h, w, n, k, ksize), lambda: L.check(
+        L.load().srb200_wgrad(_ptr(dy), _ptr(x), _ptr(acc), b, h, w, n, k, ksize, dy_r, _stream()), 'wgrad'))
     return acc
 
 
@@ -523,9 +542,9 @@ def ca_forward(t, x, p, w1, b1, w2, b2, res_scale, x32=None, want_f32=False):
     z, s = zs[:b * cr].view(b, cr), zs[b * cr:].view(b, c)
     y = torch.empty_like(t)
     y32 = torch.empty(t.shape, dtype=torch.float32, device=t.device) if want_f32 else None
-    L.check(L.load().srb200_ca_forward(_ptr(t), _ptr(x) if x32 is None else None, _ptr(x32), _ptr(p), _ptr(w1),
-                                       _ptr(b1), _ptr(w2), _ptr(b2), _ptr(z), _ptr(s), _ptr(y), _ptr(y32), b, h * w,
-                                       c, cr, float(res_scale), _stream()), 'ca_forward')
+    probed('ca_forward', (b, h * w, c, x32 is not None), lambda: L.check(L.load().srb200_ca_forward(
+        _ptr(t), _ptr(x) if x32 is None else None, _ptr(x32), _ptr(p), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(z),
+        _ptr(s), _ptr(y), _ptr(y32), b, h * w, c, cr, float(res_scale), _stream()), 'ca_forward'))
     return ((y, y32) if want_f32 else y), z, s
 
 
@@ -548,9 +567,9 @@ def ca_backward(g, t, s, z, p, w1, w2, res_scale):
     gb1 = out[o:o + cr]; o += cr
     gb2 = out[o:o + c]
     gt = torch.empty_like(g)
-    L.check(L.load().srb200_ca_backward(_ptr(g), _ptr(t), _ptr(s), _ptr(z), _ptr(p), _ptr(w1), _ptr(w2), _ptr(gs),
-                                        _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2), _ptr(gt), _ptr(cs),
-                                        _ptr(sync), b, h * w, c, cr, float(res_scale), _stream()), 'ca_backward')
+    probed('ca_backward', (b, h * w, c), lambda: L.check(L.load().srb200_ca_backward(
+        _ptr(g), _ptr(t), _ptr(s), _ptr(z), _ptr(p), _ptr(w1), _ptr(w2), _ptr(gs), _ptr(gw1), _ptr(gb1), _ptr(gw2),
+        _ptr(gb2), _ptr(gt), _ptr(cs), _ptr(sync), b, h * w, c, cr, float(res_scale), _stream()), 'ca_backward'))
     return gw1, gb1, gw2, gb2, gt, cs
 
 

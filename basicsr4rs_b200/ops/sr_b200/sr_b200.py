@@ -115,6 +115,13 @@ class PackBook:
             self.refresh()
         return e[1]
 
+    def invalidate(self):
+        """Forget every version tag: the next :meth:`get` / :meth:`refresh` repacks the whole book.  For writers that
+        change parameters without bumping ``_version`` (``p.data.mul_()`` of the reference EMA loop,
+        base_model.py:81-82; raw-pointer kernels such as ``srb200_multi_axpby``)."""
+        for e in self.entries.values():
+            e[3] = None
+
     def refresh(self, force=False):
         """Repack every entry whose parameter changed (all of them after an optimizer step) in one launch."""
         capturing = torch.cuda.is_current_stream_capturing()
@@ -188,7 +195,9 @@ def _packed(weight, kind, n_pad, k_pad, perm_out=None, perm_in=None):
                                transpose=(kind == 'dgrad'))
     cache = weight.__dict__.setdefault('_srb200_pack', {})
     tag = (weight.data_ptr(), weight._version)
-    if cache.get('tag') != tag:
+    if cache.get('tag') != tag or not torch.is_grad_enabled():
+        # (no_grad = evaluation of a possibly EMA-updated copy: ``p.data.mul_()`` leaves ``_version`` alone, so the
+        # tag proves nothing there -- repack; one small launch per weight)
         cache.clear()
         cache['tag'] = tag
     if kind not in cache:
@@ -218,7 +227,7 @@ def _padded_bias(bias, n_pad, perm_out=None):
     capturing = torch.cuda.is_current_stream_capturing()  # see _packed: no host-side cache inside a capture
     cache = bias.__dict__.setdefault('_srb200_pack', {})
     tag = (bias.data_ptr(), bias._version)
-    if cache.get('tag') != tag:
+    if cache.get('tag') != tag or not torch.is_grad_enabled():
         cache.clear()
         cache['tag'] = tag
     if capturing or 'b' not in cache:
@@ -550,7 +559,7 @@ class _ShuffleToImage(Function):
     @staticmethod
     def backward(ctx, g):
         c_img, r, scale, cp = ctx.cfg
-        gn = raw.nchw_to_nhwc(g.contiguous().float(), 8, shift=None, scale=scale)[..., :c_img].contiguous()
+        gn = raw.nchw_to_nhwc(g.contiguous().float(), (c_img + 7) // 8 * 8, shift=None, scale=scale)[..., :c_img].contiguous()
         lr = raw.pixel_shuffle_nhwc(gn, r, inverse=True)                  # bf16 [B, H, W, c_img*r*r]
         gx = torch.zeros(lr.shape[:3] + (cp,), dtype=torch.bfloat16, device=g.device)
         gx[..., :lr.shape[-1]] = lr
@@ -562,7 +571,25 @@ def shuffle_to_image(x, x32, c_img, r, scale, shift):
 
 
 def conv_to_image(x, weight, bias, out_scale, out_shift):
-    return _ConvToImage.apply(x, weight, bias, float(out_scale), out_shift)
+    """conv_last + ``x * out_scale + out_shift`` + NCHW fp32 exit.  Up to 7 output bands take the fused tap-stencil
+    exit; more (hyperspectral stacks) run the generic tap-GEMM and a layout kernel, the affine on the small image."""
+    if weight.shape[0] <= 7 and weight.shape[-1] == 3:
+        return _ConvToImage.apply(x, weight, bias, float(out_scale), out_shift)
+    y = _NHWCToNCHW.apply(conv_nhwc(x, weight, bias), weight.shape[0]) * float(out_scale)
+    return y + out_shift.view(1, -1, 1, 1) if out_shift is not None else y
+
+
+class _NHWCToNCHW(Function):
+    """[B,H,W,Cp] bf16 -> [B,C,H,W] fp32 (first C channels) and back."""
+
+    @staticmethod
+    def forward(ctx, t, c):
+        ctx.c_pad = t.shape[-1]
+        return raw.nhwc_to_nchw(t.contiguous(), c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return raw.nchw_to_nhwc(g.contiguous().float(), ctx.c_pad), None
 
 
 # ------------------------------------------------------------------ fused RCAB (RCAN)
@@ -633,3 +660,30 @@ class _RCAB(Function):
 def rcab(x, w1, b1, w2, b2, wa1, ba1, wa2, ba2, res_scale, x32=None):
     """Returns y, or (y, y32) when the fp32 skip stream ``x32`` is carried along."""
     return _RCAB.apply(x, x32, w1, b1, w2, b2, wa1, ba1, wa2, ba2, float(res_scale))
+
+
+# ------------------------------------------------------------------ stand-alone ChannelAttention (RCAN)
+class _ChannelAttention(Function):
+    """x * sigmoid(W2 relu(W1 avgpool(x) + b1) + b2)  (rcan_arch.py:16-24) on an NHWC bf16 tensor, from the unfused
+    kernels (pool -> FC -> scale); inside an RCAB the fused :class:`_RCAB` is used instead."""
+
+    @staticmethod
+    def forward(ctx, t, wa1, ba1, wa2, ba2):
+        p = raw.channel_pool(t)
+        z, s = raw.ca_fc(p, wa1.detach().contiguous(), ba1.detach(), wa2.detach().contiguous(), ba2.detach())
+        y = raw.ca_apply(t, torch.zeros_like(t), s, 1.0)
+        ctx.save_for_backward(t, p, z, s, wa1, wa2)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        t, p, z, s, wa1, wa2 = ctx.saved_tensors
+        g = g.contiguous()
+        gs = raw.channel_dot(g, t)
+        gw1, gb1, gw2, gb2, gp = raw.ca_fc_bwd(gs, s, z, p, wa1.detach().contiguous(), wa2.detach().contiguous())
+        gt = raw.ca_apply_bwd(g, s, gp, 1.0)
+        return gt, gw1, gb1, gw2, gb2
+
+
+def channel_attention(t, wa1, ba1, wa2, ba2):
+    return _ChannelAttention.apply(t, wa1, ba1, wa2, ba2)

@@ -31,8 +31,9 @@ def layernorm_fwd(x, gamma, beta, c, eps=LN_EPS):
     y = torch.empty_like(x)
     mean = torch.empty((t,), dtype=torch.float32, device=x.device)
     rstd = torch.empty((t,), dtype=torch.float32, device=x.device)
-    L.check(L.load().srb200_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), t, c, cp,
-                                          float(eps), _stream()), 'layernorm_fwd')
+    raw.probed('layernorm_fwd', (t, c, cp), lambda: L.check(L.load().srb200_layernorm_fwd(
+        _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), t, c, cp, float(eps), _stream()),
+        'layernorm_fwd'))
     return y, mean, rstd
 
 
@@ -43,8 +44,9 @@ def layernorm_bwd(gy, x, mean, rstd, gamma, c, gres=None):
     gx = torch.empty_like(x)
     gg = raw.zeros_f32((c,), x.device)
     gb = raw.zeros_f32((c,), x.device)
-    L.check(L.load().srb200_layernorm_bwd(_ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(gres), _ptr(gx),
-                                          _ptr(gg), _ptr(gb), t, c, cp, _stream()), 'layernorm_bwd')
+    raw.probed('layernorm_bwd', (t, c, cp, gres is not None), lambda: L.check(L.load().srb200_layernorm_bwd(
+        _ptr(gy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(gres), _ptr(gx), _ptr(gg), _ptr(gb), t, c, cp,
+        _stream()), 'layernorm_bwd'))
     return gx, gg, gb
 
 
@@ -62,8 +64,9 @@ def window_attention_fwd(qkv, table, num_heads, ws, shift, scale):
     b, h, w, c3 = qkv.shape
     ca = c3 // 3
     out = torch.empty((b, h, w, ca), dtype=torch.bfloat16, device=qkv.device)
-    L.check(L.load().srb200_window_attention_fwd(_ptr(qkv), _ptr(table), _ptr(out), b, h, w, num_heads, ca, ws, shift,
-                                                 float(scale), _stream()), 'window_attention_fwd')
+    raw.probed('window_attn_fwd', (b, h, w, num_heads, ws), lambda: L.check(L.load().srb200_window_attention_fwd(
+        _ptr(qkv), _ptr(table), _ptr(out), b, h, w, num_heads, ca, ws, shift, float(scale), _stream()),
+        'window_attention_fwd'))
     return out
 
 
@@ -73,9 +76,9 @@ def window_attention_bwd(qkv, gout, table, num_heads, ws, shift, scale):
     ca = c3 // 3
     gqkv = torch.empty_like(qkv)
     gtable = raw.zeros_f32(tuple(table.shape), table.device)
-    L.check(L.load().srb200_window_attention_bwd(_ptr(qkv), _ptr(gout), _ptr(table), _ptr(gqkv), _ptr(gtable), b, h, w,
-                                                 num_heads, ca, ws, shift, float(scale), _stream()),
-            'window_attention_bwd')
+    raw.probed('window_attn_bwd', (b, h, w, num_heads, ws), lambda: L.check(L.load().srb200_window_attention_bwd(
+        _ptr(qkv), _ptr(gout), _ptr(table), _ptr(gqkv), _ptr(gtable), b, h, w, num_heads, ca, ws, shift, float(scale),
+        _stream()), 'window_attention_bwd'))
     return gqkv, gtable
 
 
@@ -126,7 +129,7 @@ class _SwinBlock(Function):
 
     @staticmethod
     def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
-                num_heads, ws, shift, alpha1, alpha2):
+                num_heads, ws, shift, alpha1, alpha2, eps=LN_EPS):
         c = n1w.numel()
         cs = x.shape[-1]
         assert cs == pad64(c)
@@ -140,13 +143,13 @@ class _SwinBlock(Function):
         p_o = head_perm(num_heads, hd, 1, dev)
         scale = hd**-0.5
 
-        xn, mean1, rstd1 = layernorm_fwd(x, n1w.detach(), n1b.detach(), c)
+        xn, mean1, rstd1 = layernorm_fwd(x, n1w.detach(), n1b.detach(), c, eps)
         qkv = raw.tapgemm(xn, _packed(qkv_w, 'fprop', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=3 * ca,
                           bias=_padded_bias(qkv_b, 3 * ca, p_qkv))
         o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale)
         x1 = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
                          bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1)
-        xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c)
+        xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c, eps)
         h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=_padded_bias(fc1_b, ch),
                            act=L.ACT_GELU, want_aux=True, aux_grad=True)  # a = gelu'(fc1 out): all the backward needs
         x2 = raw.tapgemm(h, _packed(fc2_w, 'fprop', cs, ch), ksize=1, cout=cs, bias=_padded_bias(fc2_b, cs),
@@ -214,10 +217,133 @@ class _SwinBlock(Function):
         g_fc2_w, g_fc2_b, g_fc1_w, g_fc1_b, g_proj_w, g_proj_b, g_qkv_w = grads[:7]
         g_qkv_b = grads[7] if qkv_b is not None else None
         return (gx, g_n1w, g_n1b, g_qkv_w, g_qkv_b, g_table, g_proj_w, g_proj_b, g_n2w, g_n2b, g_fc1_w, g_fc1_b,
-                g_fc2_w, g_fc2_b, None, None, None, None, None)
+                g_fc2_w, g_fc2_b, None, None, None, None, None, None)
 
 
 def swin_block(x, n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, num_heads, ws,
-               shift, alpha1=None, alpha2=None):
+               shift, alpha1=None, alpha2=None, eps=LN_EPS):
     return _SwinBlock.apply(x, n1w, n1b, qkv_w, qkv_b, table, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
-                            num_heads, ws, shift, alpha1, alpha2)
+                            num_heads, ws, shift, alpha1, alpha2, float(eps))
+
+
+# ------------------------------------------------------------------ stand-alone Mlp / WindowAttention
+class _Mlp(Function):
+    """fc2(GELU(fc1(x)))  (swinir_arch.py:54-60) on an NHWC64 bf16 tensor: two tap-GEMMs, GELU and its derivative in
+    fc1's epilogue -- the MLP branch of :class:`_SwinBlock` without the LayerNorm / skip around it."""
+
+    @staticmethod
+    def forward(ctx, x, fc1_w, fc1_b, fc2_w, fc2_b):
+        cs = x.shape[-1]
+        hidden, cout = fc1_w.shape[0], fc2_w.shape[0]
+        ch, co = pad64(hidden), pad64(cout)
+        assert cs == pad64(fc1_w.shape[1])
+        h, a = raw.tapgemm(x, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=_padded_bias(fc1_b, ch),
+                           act=L.ACT_GELU, want_aux=True, aux_grad=True)
+        y = raw.tapgemm(h, _packed(fc2_w, 'fprop', co, ch), ksize=1, cout=co, bias=_padded_bias(fc2_b, co))
+        ctx.save_for_backward(x, a, h, fc1_w, fc1_b, fc2_w, fc2_b)
+        raw.stash_backward_scratch(ctx, 2 * co * ch + 2 * cs * ch + 2 * (co + ch + cs) + 64, x.device)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, a, h, fc1_w, fc1_b, fc2_w, fc2_b = ctx.saved_tensors
+        cs, ch, co = x.shape[-1], h.shape[-1], g.shape[-1]
+        g = g.contiguous()
+        with raw.backward_arena(ctx, x.device, 2 * co * ch + 2 * cs * ch + 2 * (co + ch + cs) + 64):
+            acc2 = raw.wgrad(g, h, ksize=1)
+            cs2 = raw.colsum(g)
+            ga, cs1 = raw.tapgemm(g, _packed(fc2_w, 'dgrad', co, ch), ksize=1, cout=ch, flip=True, mask_src=a,
+                                  mask_mode=L.MASK_MUL, want_colsum=True)
+            acc1 = raw.wgrad(ga, x, ksize=1)
+            gx = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True) \
+                if ctx.needs_input_grad[0] else None
+            items = [('w', acc1, fc1_w.shape, None, None, 1.0), ('w', acc2, fc2_w.shape, None, None, 1.0)]
+            if fc1_b is not None:
+                items.append(('b', cs1, fc1_b.numel(), None, 1.0))
+            if fc2_b is not None:
+                items.append(('b', cs2, fc2_b.numel(), None, 1.0))
+            grads = raw.finalize_grads(items)
+        g1w, g2w = grads[0], grads[1]
+        rest = iter(grads[2:])
+        g1b = next(rest) if fc1_b is not None else None
+        g2b = next(rest) if fc2_b is not None else None
+        return gx, g1w, g1b, g2w, g2b
+
+
+def mlp(x, fc1_w, fc1_b, fc2_w, fc2_b):
+    return _Mlp.apply(x, fc1_w, fc1_b, fc2_w, fc2_b)
+
+
+class _WindowAttn(Function):
+    """proj(softmax(scale q k^T + rpb [+ analytic SW-MSA mask]) v) on an NHWC64 bf16 tensor (swinir_arch.py:144-175):
+    qkv tap-GEMM, the fused window-attention kernel (partition / shift / reverse are its addressing), proj tap-GEMM --
+    the attention branch of :class:`_SwinBlock` without the LayerNorm / skip around it."""
+
+    @staticmethod
+    def forward(ctx, x, qkv_w, qkv_b, table, proj_w, proj_b, num_heads, ws, shift):
+        c = qkv_w.shape[1]
+        cs = x.shape[-1]
+        assert cs == pad64(c)
+        hd = c // num_heads
+        assert hd <= HD_PAD and (num_heads * HD_PAD) % 64 == 0, 'window attention kernel: head_dim <= 32, even heads'
+        ca = num_heads * HD_PAD
+        p_qkv = head_perm(num_heads, hd, 3, x.device)
+        p_o = head_perm(num_heads, hd, 1, x.device)
+        scale = hd**-0.5
+        qkv = raw.tapgemm(x, _packed(qkv_w, 'fprop', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=3 * ca,
+                          bias=_padded_bias(qkv_b, 3 * ca, p_qkv))
+        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale)
+        y = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
+                        bias=_padded_bias(proj_b, cs))
+        ctx.save_for_backward(x, qkv, o, qkv_w, qkv_b, table, proj_w, proj_b)
+        ctx.cfg = (c, cs, ca, hd, num_heads, ws, shift, scale)
+        raw.stash_backward_scratch(ctx, cs * ca + 3 * ca * cs + 2 * cs + 3 * ca + table.numel() + 64, x.device)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, qkv, o, qkv_w, qkv_b, table, proj_w, proj_b = ctx.saved_tensors
+        c, cs, ca, hd, num_heads, ws, shift, scale = ctx.cfg
+        p_qkv = head_perm(num_heads, hd, 3, x.device)
+        p_o = head_perm(num_heads, hd, 1, x.device)
+        g = g.contiguous()
+        with raw.backward_arena(ctx, x.device, cs * ca + 3 * ca * cs + 2 * cs + 3 * ca + table.numel() + 64):
+            acc_proj = raw.wgrad(g, o, ksize=1)
+            cs_proj = raw.colsum(g)
+            go = raw.tapgemm(g, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
+            gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale)
+            acc_qkv = raw.wgrad(gqkv, x, ksize=1)
+            gx = raw.tapgemm(gqkv, _packed(qkv_w, 'dgrad', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=cs, flip=True) \
+                if ctx.needs_input_grad[0] else None
+            items = [('w', acc_proj, proj_w.shape, None, p_o, 1.0), ('w', acc_qkv, qkv_w.shape, p_qkv, None, 1.0)]
+            if proj_b is not None:
+                items.append(('b', cs_proj, proj_b.numel(), None, 1.0))
+            if qkv_b is not None:
+                items.append(('b', raw.colsum(gqkv), qkv_b.numel(), p_qkv, 1.0))
+            grads = raw.finalize_grads(items)
+        g_proj_w, g_qkv_w = grads[0], grads[1]
+        rest = iter(grads[2:])
+        g_proj_b = next(rest) if proj_b is not None else None
+        g_qkv_b = next(rest) if qkv_b is not None else None
+        return gx, g_qkv_w, g_qkv_b, g_table.clone(), g_proj_w, g_proj_b, None, None, None
+
+
+def window_attn(x, qkv_w, qkv_b, table, proj_w, proj_b, num_heads, ws, shift):
+    return _WindowAttn.apply(x, qkv_w, qkv_b, table, proj_w, proj_b, num_heads, ws, shift)
+
+
+# ------------------------------------------------------------------ token <-> NHWC64 plumbing (module boundaries only)
+def tokens_to_nhwc(x, h, w):
+    """[B, h*w, C] (any float dtype) -> [B, h, w, pad64(C)] bf16, differentiable.  Only the stand-alone ``forward`` of a
+    sub-module pays this; inside a SwinIR network the stream never leaves the NHWC64 layout."""
+    b, _, c = x.shape
+    cp = pad64(c)
+    t = x.reshape(b, h, w, c)
+    if cp != c:
+        t = torch.nn.functional.pad(t, (0, cp - c))
+    return t.to(torch.bfloat16).contiguous()
+
+
+def nhwc_to_tokens(t, c, dtype):
+    b, h, w, _ = t.shape
+    return t[..., :c].reshape(b, h * w, c).to(dtype)

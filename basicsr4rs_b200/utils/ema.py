@@ -24,6 +24,7 @@ _ITEM = np.dtype([('src', '<i8'), ('dst', '<i8'), ('n', '<i8'), ('chunk_begin', 
 class FusedEMA:
 
     def __init__(self, net, net_ema):
+        self._net_ema = net_ema
         src = dict(net.named_parameters())
         self.pairs = [(src[k], p) for k, p in net_ema.named_parameters()]  # same keys, like the reference loop
         for s, d in self.pairs:
@@ -52,3 +53,18 @@ class FusedEMA:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         L.check(L.load().srb200_multi_axpby(ctypes.c_void_p(self._table.data_ptr()), len(self.pairs), self._chunks,
                                             float(decay), float(1.0 - decay), stream), 'multi_axpby')
+        # the kernel wrote through raw pointers: ``_version`` of the EMA parameters did not move, so the bf16 operands
+        # packed from them (PackBook / per-parameter caches) must be told
+        invalidate_packs(self._net_ema)
+
+
+def invalidate_packs(net):
+    """Drop every cached bf16 operand derived from ``net``'s parameters (call after writing them through ``.data`` or
+    raw pointers while grad mode is on; no_grad forwards re-derive them anyway)."""
+    from ..archs.graphed import BOOKS
+    for m in net.modules():
+        book = BOOKS.get(m)
+        if book is not None:
+            book.invalidate()
+    for p in net.parameters():
+        p.__dict__.pop('_srb200_pack', None)

@@ -7,8 +7,9 @@ matplotlib / lmdb / a generated version.py), so this installs a 4-entry ``sys.mo
   rcan_arch,swinir_arch}.py
 from the read-only reference tree.  Used by ``tests/golden/make_golden.py`` (run in the build
 container, where /root/reference is mounted) and by the ``not gpu`` tests that pin ``oracle/sr_oracle.py``
-against the live reference.  /root/reference does not exist on the GPU box: nothing in the ``-m gpu``
-tests, smoke() or bench.py imports this module.
+against the live reference.  /root/reference does not exist on the GPU box; there the verbatim copies vendored
+by ``oracle/make_ref.py`` into ``oracle/_ref`` (git-ignored, shipped by gpurun) are loaded instead, by the
+``-m gpu`` parity tests and by ``bench.py --impl reference`` -- never by the product package.
 """
 import importlib
 import logging
@@ -16,7 +17,22 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('BASICSR_REF_ROOT', '/root/reference')
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+def _pick_root():
+    """$BASICSR_REF_ROOT, else the mounted reference tree, else the verbatim copies oracle/make_ref.py vendored
+    into oracle/_ref (the only form in which the reference reaches the GPU box)."""
+    env = os.environ.get('BASICSR_REF_ROOT')
+    if env:
+        return env
+    for root in ('/root/reference', _VENDORED):
+        if os.path.isdir(os.path.join(root, 'basicsr', 'archs')):
+            return root
+    return '/root/reference'
+
+
+REF_ROOT = _pick_root()
 
 
 def available():

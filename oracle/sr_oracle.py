@@ -200,11 +200,33 @@ def swin_block(sd, prefix, x, h, w, num_heads, ws, shift, drop_keep=None):
     return x + m
 
 
+def drop_path_masks(batch, depths, drop_path_rate, generator=None):
+    """Per-block stochastic-depth draws of a TRAINING forward, in the order the reference consumes its RNG
+    (swinir_arch.py:14-26 called twice per block from :320-321; rates from the linspace of :796): a dict
+    block prefix -> (mask1 [B,1,1], mask2 [B,1,1], keep_prob), masks = floor(keep_prob + U[0,1)).  With
+    ``generator=None`` the global CPU RNG is used, exactly like ``torch.rand`` inside the reference's ``drop_path``."""
+    rates = [r.item() for r in torch.linspace(0, drop_path_rate, sum(depths))]
+    out, i = {}, 0
+    for li, depth in enumerate(depths):
+        for bi in range(depth):
+            rate = rates[i]
+            i += 1
+            if rate == 0.:
+                continue
+            keep = 1 - rate
+            m1 = (keep + torch.rand((batch, 1, 1), generator=generator)).floor_()
+            m2 = (keep + torch.rand((batch, 1, 1), generator=generator)).floor_()
+            out[f'layers.{li}.residual_group.blocks.{bi}'] = (m1, m2, keep)
+    return out
+
+
 def swinir_forward(sd, x, embed_dim=180, depths=(6, 6, 6, 6, 6, 6), num_heads=(6, 6, 6, 6, 6, 6), window_size=8,
-                   upscale=4, img_range=1., in_chans=3, upsampler='pixelshuffle', resi_connection='1conv'):
-    """swinir_arch.py:891-920, eval mode: the classical-SR ('pixelshuffle') branch and the three other
+                   upscale=4, img_range=1., in_chans=3, upsampler='pixelshuffle', resi_connection='1conv',
+                   drop_masks=None, ape=False):
+    """swinir_arch.py:891-920: the classical-SR ('pixelshuffle') branch and the three other
     reconstruction branches ('pixelshuffledirect' :901-905, 'nearest+conv' :906-913, '' :914-918); conv_after_body as
-    '1conv' or '3conv' (:818-826)."""
+    '1conv' or '3conv' (:818-826).  Eval mode unless ``drop_masks`` (see :func:`drop_path_masks`) supplies the
+    stochastic-depth draws of a training forward; ``ape`` adds ``absolute_pos_embed`` (:879-880)."""
     def resi(prefix, v):
         if resi_connection == '1conv':
             return conv(sd, prefix, v)
@@ -220,11 +242,15 @@ def swinir_forward(sd, x, embed_dim=180, depths=(6, 6, 6, 6, 6, 6), num_heads=(6
     b, c, h, w = x.shape
     t = x.flatten(2).transpose(1, 2)  # PatchEmbed :600-604
     t = F.layer_norm(t, (c,), sd['patch_embed.norm.weight'], sd['patch_embed.norm.bias'], 1e-5)
+    if ape:
+        t = t + sd['absolute_pos_embed']
     for li, depth in enumerate(depths):
         r = t
         for bi in range(depth):
             shift = 0 if bi % 2 == 0 else window_size // 2
-            r = swin_block(sd, f'layers.{li}.residual_group.blocks.{bi}', r, h, w, num_heads[li], window_size, shift)
+            prefix = f'layers.{li}.residual_group.blocks.{bi}'
+            r = swin_block(sd, prefix, r, h, w, num_heads[li], window_size, shift,
+                           drop_keep=(drop_masks or {}).get(prefix))
         r = r.transpose(1, 2).reshape(b, c, h, w)  # PatchUnEmbed :638-640
         r = resi(f'layers.{li}.conv', r)  # RSTB.conv :530-538
         t = r.flatten(2).transpose(1, 2) + t  # RSTB :557-558

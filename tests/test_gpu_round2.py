@@ -1,0 +1,485 @@
+"""Round-2 parity holes (``-m gpu``): the configurations that were benchmarked or shipped without a numerical test.
+
+* SwinIR TRAINING mode with stochastic depth vs the oracle fed the same per-sample keep masks (the config bench.py
+  times), plus kernel tests of the two DropPath ingredients (``alpha_per_sample`` epilogue scale, ``scale_rows``);
+* RCAN and SwinIR CUDA-graph replay vs eager over optimizer steps (SwinIR with DropPath inside the capture);
+* ``use_checkpoint=True`` gradients vs ``False``;
+* full-size (BASELINE configs 3 / 4) GRADIENT parity for RCAN 10x20 and SwinIR 6x6 at batch 2, calibrated against
+  PyTorch's own bf16 autocast of the same oracle;
+* EMA updates (``p.data`` writes and ``FusedEMA``) must reach the next evaluation forward (packed-weight cache);
+* run-to-run reproducibility: what is bit-stable (forward) and what is not (fp32-atomic gradient merges);
+* the configurations that fall through to the reference expression (window 16, ape, dropout) and the reference's
+  sub-module ``forward`` contracts;
+* the live, unmodified reference (``oracle/_ref``, vendored by oracle/make_ref.py) run on the GPU in fp32 against ours.
+"""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ref_shim, sr_oracle
+
+from .test_gpu_nets import MAX_ABS, PSNR_TOL, _check_grad
+
+pytestmark = pytest.mark.gpu
+
+SWIN_S = dict(upscale=2, in_chans=3, img_size=16, window_size=8, img_range=1., depths=[2, 2], embed_dim=60,
+              num_heads=[6, 6], mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv')
+
+
+def _oracle_sd(net):
+    return {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
+
+
+def _swin_oracle(sd, x, kw, **extra):
+    return sr_oracle.swinir_forward(sd, x, embed_dim=kw['embed_dim'], depths=kw['depths'], num_heads=kw['num_heads'],
+                                    window_size=kw['window_size'], upscale=kw['upscale'], img_range=kw['img_range'],
+                                    in_chans=kw.get('in_chans', 3), upsampler=kw.get('upsampler', 'pixelshuffle'),
+                                    resi_connection=kw.get('resi_connection', '1conv'), **extra)
+
+
+class _InjectedDropPath:
+    """Replaces ``swinir_arch.drop_path_scale`` so that block i's two draws are the given masks (same order as the
+    reference's RNG consumption: two calls per block with drop_prob > 0)."""
+
+    def __init__(self, masks, device):
+        self.queue = []
+        for prefix in sorted(masks, key=lambda p: [int(t) for t in p.split('.') if t.isdigit()]):
+            m1, m2, keep = masks[prefix]
+            self.queue += [(m1.flatten() / keep).to(device).contiguous(), (m2.flatten() / keep).to(device).contiguous()]
+        self.i = 0
+
+    def __call__(self, batch, drop_prob, training, device):
+        if drop_prob == 0. or not training:
+            return None
+        a = self.queue[self.i]
+        self.i += 1
+        return a
+
+
+# ------------------------------------------------------------------ (i) DropPath
+def test_swinir_training_droppath_matches_oracle(cuda, monkeypatch):
+    from basicsr4rs_b200.archs import build_network, swinir_arch
+    kw = dict(SWIN_S, drop_path_rate=0.5)
+    torch.manual_seed(0)
+    net = build_network(dict(type='SwinIR', **kw))
+    sd0 = net.state_dict()
+    sr_oracle.fill_state_dict_(sd0)
+    net.load_state_dict(sd0)
+    sd = _oracle_sd(net)
+    net = net.to(cuda).train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((4, 3, 16, 16), generator=g)
+    gt = torch.rand((4, 3, 32, 32), generator=g)
+    masks = sr_oracle.drop_path_masks(4, kw['depths'], kw['drop_path_rate'], generator=g)
+    dropped = sum(int((m[0] == 0).sum() + (m[1] == 0).sum()) for m in masks.values())
+    assert 0 < dropped < 2 * 4 * len(masks)  # some, not all, branches dropped
+    inj = _InjectedDropPath(masks, cuda)
+    monkeypatch.setattr(swinir_arch, 'drop_path_scale', inj)
+    out = net(x.to(cuda))
+    assert inj.i == len(inj.queue)
+    ((out - gt.to(cuda))**2).mean().backward()
+    ref = _swin_oracle(sd, x, kw, drop_masks=masks)
+    ((ref - gt)**2).mean().backward()
+    err = (out.detach().cpu() - ref.detach()).abs().max().item()
+    assert err <= MAX_ABS, f'max-abs {err:.3e}'
+    # the same oracle in eval mode differs clearly: the masks really acted
+    with torch.no_grad():
+        assert (_swin_oracle(sd, x, kw) - ref).abs().max().item() > 10 * err
+    sd16 = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    with torch.autocast('cpu', dtype=torch.bfloat16):
+        ref16 = _swin_oracle(sd16, x, kw, drop_masks=masks)
+    ((ref16.float() - gt)**2).mean().backward()
+    for k, p in net.named_parameters():
+        want = sd[k].grad
+        if want is None or want.norm() == 0:
+            continue
+        calib = ((sd16[k].grad - want).norm() / want.norm()).item()
+        _check_grad(p.grad, want, calib)
+
+
+def test_alpha_per_sample_and_scale_rows_kernels(cuda):
+    """The two stochastic-depth ingredients: ``srb200_tapgemm_ext.alpha_per_sample`` (forward: x + a[b] * f(x)) and
+    ``srb200_scale_rows`` (backward: g * a[b]) against fp32 PyTorch, including dropped (a = 0) samples."""
+    from basicsr4rs_b200.ops.sr_b200 import raw, swin_ops
+    g = torch.Generator().manual_seed(0)
+    b, h, w, k, n = 5, 8, 16, 64, 192
+    x = torch.randn((b, h, w, k), generator=g).to(cuda).to(torch.bfloat16)
+    wt = (torch.randn((n, k), generator=g) * 0.1).to(cuda)
+    bias = torch.randn((n,), generator=g).to(cuda)
+    res = torch.randn((b, h, w, n), generator=g).to(cuda).to(torch.bfloat16)
+    alpha = torch.tensor([0.0, 1.25, 2.0, 0.0, 1.0], device=cuda)
+    wp = raw.pack_weight(wt.view(n, k, 1, 1).contiguous(), n, k)
+    y = raw.tapgemm(x, wp, ksize=1, cout=n, bias=bias, residual=res, alpha_per_sample=alpha)
+    want = res.float() + alpha.view(b, 1, 1, 1) * (x.float() @ wt.to(torch.bfloat16).float().t() + bias)
+    assert (y.float() - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+    # dropped samples pass the residual through bit-exactly
+    assert torch.equal(y[0].view(torch.int16), res[0].view(torch.int16))
+    assert torch.equal(y[3].view(torch.int16), res[3].view(torch.int16))
+    s = swin_ops.scale_rows(res, alpha)
+    want = (res.float() * alpha.view(b, 1, 1, 1)).to(torch.bfloat16)
+    assert torch.equal(s.view(torch.int16), want.view(torch.int16))
+
+
+# ------------------------------------------------------------------ (ii) CUDA-graph replay vs eager
+def _replay_vs_eager(cuda, kw, shape, scale, grad_keys, steps=3, before_forward=None):
+    from basicsr4rs_b200.archs import build_network
+    torch.manual_seed(0)
+    eager = build_network(kw).to(cuda).train()
+    graphed = build_network(dict(kw, cuda_graph=True, graph_segments=2)).to(cuda).train()
+    graphed.load_state_dict(eager.state_dict())
+    opt_e = torch.optim.SGD(eager.parameters(), lr=1e-3)
+    opt_g = torch.optim.SGD(graphed.parameters(), lr=1e-3)
+    g = torch.Generator().manual_seed(3)
+    b, c, h, w = shape
+    for step in range(steps):  # step 0 captures, later steps replay with UPDATED weights
+        x = torch.rand(shape, generator=g).to(cuda)
+        gt = torch.rand((b, c, h * scale, w * scale), generator=g).to(cuda)
+        outs = []
+        for net, opt in ((eager, opt_e), (graphed, opt_g)):
+            opt.zero_grad(set_to_none=True)
+            if before_forward is not None:
+                before_forward(step)
+            out = net(x)
+            ((out - gt)**2).mean().backward()
+            outs.append(out.detach().clone())
+            opt.step()
+        assert torch.allclose(outs[0], outs[1], atol=2e-5), f'step {step}: {(outs[0] - outs[1]).abs().max().item():.3e}'
+        pe, pg = dict(eager.named_parameters()), dict(graphed.named_parameters())
+        for k in grad_keys:
+            ge, gg = pe[k].grad, pg[k].grad
+            assert torch.allclose(ge, gg, rtol=2e-3, atol=2e-5 * ge.abs().max().item() + 1e-9), f'step {step}: {k}'
+    return eager, graphed
+
+
+def test_rcan_cuda_graph_replay_matches_eager(cuda):
+    """RCAN segments carry the fp32 skip twin across graph boundaries and capture with PDL (archs/graphed.py)."""
+    kw = dict(type='RCAN', num_in_ch=3, num_out_ch=3, num_feat=64, num_group=3, num_block=2, squeeze_factor=16,
+              upscale=4, res_scale=1)
+    _, graphed = _replay_vs_eager(cuda, kw, (2, 3, 16, 16), 4,
+                                  ['conv_first.weight', 'body.0.residual_group.1.rcab.0.weight',
+                                   'body.1.residual_group.0.rcab.3.attention.1.weight',
+                                   'body.2.residual_group.1.rcab.3.attention.3.bias', 'body.2.conv.bias',
+                                   'conv_last.weight'])
+    copy.deepcopy(graphed)
+
+
+def test_swinir_cuda_graph_replay_matches_eager(cuda):
+    kw = dict(type='SwinIR', **dict(SWIN_S, depths=[2, 2, 2], num_heads=[6, 6, 6], drop_path_rate=0.0))
+    _replay_vs_eager(cuda, kw, (2, 3, 16, 16), 2,
+                     ['conv_first.weight', 'layers.0.residual_group.blocks.1.attn.relative_position_bias_table',
+                      'layers.1.residual_group.blocks.0.attn.qkv.weight', 'layers.1.residual_group.blocks.1.mlp.fc1.bias',
+                      'layers.2.residual_group.blocks.1.norm2.weight', 'layers.2.conv.weight', 'conv_last.bias'])
+
+
+def test_swinir_cuda_graph_replay_with_droppath_inside_the_capture(cuda, monkeypatch):
+    """Stochastic depth inside a captured segment: (a) with the per-sample factors read from a persistent device
+    tensor the replay equals eager step by step (``alpha_per_sample`` is live data, not a captured constant);
+    (b) with the shipped ``torch.rand`` draw the masks are re-drawn on every replay, not frozen at capture time."""
+    from basicsr4rs_b200.archs import build_network, swinir_arch
+    depths = [2, 2, 2]
+    kw = dict(type='SwinIR', **dict(SWIN_S, depths=depths, num_heads=[6, 6, 6], drop_path_rate=0.5))
+    n_draws = 2 * (sum(depths) - 1)  # block 0 has rate 0 -> Identity
+    table = torch.ones((n_draws, 2), device=cuda)
+    rates = [r.item() for r in torch.linspace(0, 0.5, sum(depths))][1:]
+    state = {'i': 0}
+
+    def scale_from_table(batch, drop_prob, training, device):
+        if drop_prob == 0. or not training:
+            return None
+        row = table[state['i'] % n_draws]
+        state['i'] += 1
+        return row  # a VIEW of persistent memory: the captured kernels read whatever the table holds at replay time
+
+    monkeypatch.setattr(swinir_arch, 'drop_path_scale', scale_from_table)
+    g = torch.Generator().manual_seed(9)
+
+    def redraw(step):
+        if state.get('step') != step:  # once per step: both nets see the same factors
+            state['step'] = step
+            m = torch.stack([(1 - rates[i // 2] + torch.rand((2,), generator=g)).floor() / (1 - rates[i // 2])
+                             for i in range(n_draws)])
+            table.copy_(m.to(cuda))
+        state['i'] = 0
+
+    _replay_vs_eager(cuda, kw, (2, 3, 16, 16), 2,
+                     ['layers.0.residual_group.blocks.1.attn.proj.weight', 'layers.2.residual_group.blocks.1.mlp.fc2.weight',
+                      'layers.1.conv.weight'], steps=4, before_forward=redraw)
+    monkeypatch.undo()
+    # (b) the real draw
+    torch.manual_seed(0)
+    net = build_network(dict(kw, cuda_graph=True, graph_segments=2)).to(cuda).train()
+    x = torch.rand((8, 3, 16, 16), device=cuda)
+    outs = []
+    for _ in range(4):
+        out = net(x)
+        out.mean().backward()
+        outs.append(out.detach().clone())
+    assert any(not torch.equal(outs[0], o) for o in outs[1:]), 'DropPath masks frozen at capture time'
+
+
+# ------------------------------------------------------------------ (iii) use_checkpoint
+def test_swinir_use_checkpoint_matches_plain(cuda):
+    """use_checkpoint=True (swinir_arch.py:460-461) recomputes each block in the backward: same output, same gradients."""
+    from basicsr4rs_b200.archs import build_network
+    kw = dict(type='SwinIR', **dict(SWIN_S, drop_path_rate=0.0))
+    torch.manual_seed(0)
+    plain = build_network(kw).to(cuda).train()
+    ckpt = build_network(dict(kw, use_checkpoint=True)).to(cuda).train()
+    ckpt.load_state_dict(plain.state_dict())
+    x = torch.rand((2, 3, 16, 16), device=cuda)
+    gt = torch.rand((2, 3, 32, 32), device=cuda)
+    outs = []
+    for net in (plain, ckpt):
+        out = net(x)
+        ((out - gt)**2).mean().backward()
+        outs.append(out.detach())
+    assert torch.equal(outs[0], outs[1])
+    for (k, a), (_, b) in zip(plain.named_parameters(), ckpt.named_parameters()):
+        assert a.grad is not None and b.grad is not None, k
+        assert torch.allclose(a.grad, b.grad, rtol=2e-3, atol=2e-5 * a.grad.abs().max().item() + 1e-9), k
+
+
+# ------------------------------------------------------------------ (iv) full-size gradient parity
+def _full_size_grad_parity(cuda, arch, kw, oracle_fn, shape, scale, keys):
+    """ours (bf16 kernels) vs the oracle in fp32, both at the BASELINE size, batch 2.  The oracle runs on the GPU with
+    TF32 off (conftest) -- same arithmetic as on the CPU, seconds instead of minutes; the calibration run is the same
+    oracle under torch's CUDA bf16 autocast."""
+    from basicsr4rs_b200.archs import build_network
+    torch.manual_seed(0)
+    net = build_network(dict(type=arch, **kw))
+    sd = {k: v.detach().clone().to(cuda).requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
+    net = net.to(cuda).eval()  # eval: no stochastic depth (covered by the DropPath test above)
+    g = torch.Generator().manual_seed(1234)
+    b, c, h, w = shape
+    x = torch.rand(shape, generator=g).to(cuda)
+    gt = torch.rand((b, c, h * scale, w * scale), generator=g).to(cuda)
+    out = net(x)
+    ((out - gt)**2).mean().backward()
+    ref = oracle_fn(sd, x)
+    ((ref - gt)**2).mean().backward()
+    err = (out.detach() - ref.detach()).abs().max().item()
+    assert err <= MAX_ABS, f'max-abs {err:.3e}'
+    assert abs(sr_oracle.psnr(out.detach().cpu(), gt.cpu()) - sr_oracle.psnr(ref.detach().cpu(), gt.cpu())) <= PSNR_TOL
+    sd16 = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        ref16 = oracle_fn(sd16, x)
+    ((ref16.float() - gt)**2).mean().backward()
+    params = dict(net.named_parameters())
+    report = {}
+    for k in keys:
+        want = sd[k].grad
+        rel = ((params[k].grad - want).norm() / want.norm()).item()
+        rel16 = ((sd16[k].grad - want).norm() / want.norm()).item()
+        report[k] = (round(rel, 4), round(rel16, 4))
+        assert rel <= max(2.0 * rel16, 3e-2), f'{k}: relative L2 {rel:.3e} vs bf16 autocast {rel16:.3e}'
+    print(f'{arch} full size: max-abs {err:.3e}; grad rel-L2 (ours, bf16-autocast): {report}')
+
+
+def test_rcan_full_size_gradients_vs_oracle(cuda):
+    """BASELINE config 3 (10 groups x 20 RCAB, 64 ch, x4) at 48x48, batch 2: output AND gradients."""
+    kw = dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_group=10, num_block=20, squeeze_factor=16, upscale=4,
+              res_scale=1, img_range=255.)
+    _full_size_grad_parity(
+        cuda, 'RCAN', kw,
+        lambda sd, x: sr_oracle.rcan_forward(sd, x, num_group=10, num_block=20, upscale=4, res_scale=1, img_range=255.),
+        (2, 3, 48, 48), 4,
+        ['conv_first.weight', 'body.0.residual_group.0.rcab.0.weight', 'body.4.residual_group.10.rcab.2.weight',
+         'body.4.residual_group.10.rcab.3.attention.1.weight', 'body.9.residual_group.19.rcab.3.attention.3.weight',
+         'body.9.conv.weight', 'body.9.conv.bias', 'conv_after_body.weight', 'upsample.0.weight', 'conv_last.weight',
+         'conv_last.bias'])
+
+
+def test_swinir_full_size_gradients_vs_oracle(cuda):
+    """BASELINE config 4 (embed 180, 6 RSTB x 6, window 8, 6 heads, x4) at 64x64, batch 2: output AND gradients."""
+    kw = dict(upscale=4, in_chans=3, img_size=64, window_size=8, img_range=1., depths=[6] * 6, embed_dim=180,
+              num_heads=[6] * 6, mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv')
+    _full_size_grad_parity(
+        cuda, 'SwinIR', kw, lambda sd, x: _swin_oracle(sd, x, kw), (2, 3, 64, 64), 4,
+        ['conv_first.weight', 'patch_embed.norm.weight', 'layers.0.residual_group.blocks.0.attn.qkv.weight',
+         'layers.0.residual_group.blocks.1.attn.relative_position_bias_table',
+         'layers.2.residual_group.blocks.3.attn.proj.weight', 'layers.2.residual_group.blocks.3.norm1.bias',
+         'layers.3.residual_group.blocks.5.mlp.fc1.weight', 'layers.5.residual_group.blocks.5.mlp.fc2.bias',
+         'layers.5.conv.weight', 'norm.weight', 'conv_after_body.weight', 'conv_before_upsample.0.weight',
+         'upsample.2.weight', 'conv_last.weight'])
+
+
+# ------------------------------------------------------------------ (vi) reproducibility
+def test_run_to_run_reproducibility(cuda):
+    """What repeats bit for bit and what does not.  EDSR / SwinIR forwards have a fixed reduction order: bit-identical.
+    Weight / bias gradients are merged across split-K CTAs with fp32 atomics (wgrad.cu, the epilogue column sums) and
+    RCAN's pooled means likewise, so they repeat only to fp32 round-off: documented here with a 1e-5 relative bar."""
+    from basicsr4rs_b200.archs import build_network
+    for kw, shape in ((dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=64, num_block=3, upscale=4), (2, 3, 24, 24)),
+                      (dict(type='SwinIR', **dict(SWIN_S, drop_path_rate=0.0)), (2, 3, 16, 16))):
+        torch.manual_seed(0)
+        net = build_network(kw).to(cuda).train()
+        x = torch.rand(shape, device=cuda)
+        runs = []
+        for _ in range(2):
+            net.zero_grad(set_to_none=True)
+            out = net(x)
+            (out**2).mean().backward()
+            runs.append((out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()}))
+        assert torch.equal(runs[0][0], runs[1][0]), kw['type']
+        for k in runs[0][1]:
+            a, b = runs[0][1][k], runs[1][1][k]
+            assert (a - b).abs().max().item() <= 1e-5 * a.abs().max().item() + 1e-12, (kw['type'], k)
+
+
+# ------------------------------------------------------------------ EMA -> packed-weight cache (ADVICE, high)
+@pytest.mark.parametrize('how', ['data_loop', 'fused'])
+def test_ema_update_reaches_the_next_eval_forward(cuda, how):
+    """BaseModel.model_ema (base_model.py:75-82) writes ``p.data`` (no ``_version`` bump) and FusedEMA writes raw
+    pointers: the evaluation forward of net_g_ema (SRModel.test, sr_model.py:120-129) must see the new weights."""
+    from basicsr4rs_b200.archs import build_network
+    from basicsr4rs_b200.utils.ema import FusedEMA
+    torch.manual_seed(0)
+    kw = dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=64, num_block=2, upscale=2, res_scale=1.0)
+    net = build_network(kw).to(cuda)
+    ema = copy.deepcopy(net).eval()
+    x = torch.rand((1, 3, 16, 16), device=cuda)
+    with torch.no_grad():
+        y0 = ema(x)
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.05)
+        want = net(x)  # (in-place op under no_grad bumps _version: the training net repacks by itself)
+    fused = FusedEMA(net, ema) if how == 'fused' else None
+    for _ in range(2):
+        if how == 'fused':
+            fused.step(0.0)  # decay 0: ema <- net
+        else:
+            src = dict(net.named_parameters())
+            for k, p in ema.named_parameters():
+                p.data.mul_(0.0).add_(src[k].data, alpha=1.0)
+        with torch.no_grad():
+            y1 = ema(x)
+        assert not torch.equal(y0, y1), 'evaluation used stale packed weights'
+        assert torch.equal(y1, want)
+
+
+# ------------------------------------------------------------------ fall-through configurations
+@pytest.mark.parametrize('extra,train', [
+    (dict(window_size=16, img_size=32), False),   # window > 8: attention through the reference expression
+    (dict(ape=True), False),                      # absolute position embedding
+    (dict(num_heads=[3, 3]), False),              # odd head count
+    (dict(drop_rate=0.2, attn_drop_rate=0.2), True),  # dropout: runs (stochastic: finite + differs from eval)
+])
+def test_swinir_unfused_configurations_run_and_match(cuda, extra, train):
+    from basicsr4rs_b200.archs import build_network
+    kw = dict(SWIN_S, drop_path_rate=0.0)
+    kw.update(extra)
+    torch.manual_seed(0)
+    net = build_network(dict(type='SwinIR', **kw))
+    sd0 = net.state_dict()
+    sr_oracle.fill_state_dict_(sd0)
+    net.load_state_dict(sd0)
+    sd = _oracle_sd(net)
+    net = net.to(cuda).eval()
+    hw = kw['img_size']
+    x = torch.rand((2, 3, hw, hw), generator=torch.Generator().manual_seed(2))
+    out = net(x.to(cuda))
+    ref = _swin_oracle({k: v.detach() for k, v in sd.items()}, x, kw, ape=kw.get('ape', False))
+    err = (out.detach().cpu() - ref).abs().max().item()
+    assert err <= MAX_ABS, f'max-abs {err:.3e}'
+    (out**2).mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    if train:
+        net.train()
+        o2 = net(x.to(cuda))
+        assert torch.isfinite(o2).all() and not torch.equal(o2, out)
+
+
+def test_submodule_forward_contracts(cuda):
+    """The reference's own calling conventions of the sub-modules (swinir_arch.py:54-60, 144-175, 283-323, 458-466,
+    557-558, 600-604, 638-640; rcan_arch.py:22-24) -- each against its oracle expression."""
+    from basicsr4rs_b200.archs import rcan_arch, swinir_arch
+    torch.manual_seed(0)
+    c, heads, ws, h, w, b = 60, 6, 8, 16, 24, 2
+    blk = swinir_arch.SwinTransformerBlock(c, (h, w), heads, window_size=ws, shift_size=4, mlp_ratio=2.).to(cuda)
+    sd = {'b.' + k: v.detach().cpu() for k, v in blk.state_dict().items()}
+    x = torch.randn((b, h * w, c))
+    y = blk(x.to(cuda), (h, w))
+    want = sr_oracle.swin_block(sd, 'b', x, h, w, heads, ws, 4)
+    assert y.shape == want.shape and (y.cpu() - want).abs().max().item() <= 3e-2 * want.abs().max().item()
+    # Mlp
+    m = blk.mlp(x.to(cuda))
+    want = F.linear(F.gelu(F.linear(x, sd['b.mlp.fc1.weight'], sd['b.mlp.fc1.bias'])), sd['b.mlp.fc2.weight'],
+                    sd['b.mlp.fc2.bias'])
+    assert (m.cpu() - want).abs().max().item() <= 3e-2 * want.abs().max().item()
+    # WindowAttention: windows in, optional explicit mask
+    xw = torch.randn((6, ws * ws, c))
+    a = blk.attn(xw.to(cuda))
+    want = sr_oracle.window_attention(sd, 'b.attn', xw, None, heads, ws)
+    assert (a.cpu() - want).abs().max().item() <= 3e-2 * want.abs().max().item()
+    mask = sr_oracle.calculate_mask(h, w, ws, 4)
+    a = blk.attn(xw.to(cuda), mask=mask.to(cuda))
+    want = sr_oracle.window_attention(sd, 'b.attn', xw, mask, heads, ws)
+    assert (a.cpu() - want).abs().max().item() <= 1e-4 * want.abs().max().item() + 1e-5
+    # gradients flow through the stand-alone forwards
+    xg = x.to(cuda).requires_grad_(True)
+    blk(xg, (h, w)).sum().backward()
+    assert xg.grad is not None and all(p.grad is not None for p in blk.parameters())
+    # PatchEmbed / PatchUnEmbed / RSTB / DropPath
+    pe = swinir_arch.PatchEmbed(img_size=16, patch_size=1, in_chans=c, embed_dim=c, norm_layer=torch.nn.LayerNorm).to(cuda)
+    img = torch.randn((b, c, h, w), device=cuda)
+    t = pe(img)
+    want = F.layer_norm(img.flatten(2).transpose(1, 2), (c,), pe.norm.weight, pe.norm.bias, 1e-5)
+    assert t.shape == (b, h * w, c) and (t - want).abs().max().item() <= 3e-2
+    pu = swinir_arch.PatchUnEmbed(img_size=16, patch_size=1, in_chans=c, embed_dim=c)
+    assert torch.equal(pu(t, (h, w)), t.transpose(1, 2).reshape(b, c, h, w))
+    rstb = swinir_arch.RSTB(c, (h, w), 2, heads, ws, mlp_ratio=2., img_size=16, patch_size=1).to(cuda)
+    assert rstb(t, (h, w)).shape == (b, h * w, c)
+    assert rstb.flops() > 0 and blk.flops() > 0
+    dp = swinir_arch.DropPath(0.5).train()
+    z = dp(torch.ones((64, 3, 5), device=cuda))
+    assert set(z.unique().tolist()) <= {0.0, 2.0}
+    # ChannelAttention
+    ca = rcan_arch.ChannelAttention(64, 16).to(cuda)
+    xi = torch.randn((2, 64, 12, 10), device=cuda, requires_grad=True)
+    yo = ca(xi)
+    p = xi.detach().mean((2, 3), keepdim=True)
+    w1, b1, w2, b2 = ca.fc_params()
+    s = torch.sigmoid(F.conv2d(F.relu(F.conv2d(p, w1, b1)), w2, b2))
+    assert (yo - xi.detach() * s).abs().max().item() <= 3e-2
+    yo.sum().backward()
+    assert xi.grad is not None and w1.grad is not None
+
+
+# ------------------------------------------------------------------ the live reference on the GPU (oracle/_ref)
+@pytest.mark.skipif(not ref_shim.available(), reason='no reference tree (oracle/_ref is vendored by oracle/make_ref.py)')
+@pytest.mark.parametrize('arch,kw,shape,scale', [
+    ('EDSR', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=4, upscale=4, res_scale=1., img_range=255.),
+     (2, 3, 24, 20), 4),
+    ('RCAN', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_group=2, num_block=3, squeeze_factor=16, upscale=2,
+                  res_scale=1, img_range=255.), (2, 3, 16, 16), 2),
+    ('SwinIR', dict(SWIN_S, depths=[2, 2], drop_path_rate=0.0), (2, 3, 24, 16), 2),
+])
+def test_against_the_unmodified_reference_on_gpu(cuda, arch, kw, shape, scale):
+    """The reference's own nn.Module (verbatim files, stock aten kernels, fp32, TF32 off) and ours, same seeded
+    default init, same input, same device: output bar of north_star and gradient bars of test_gpu_nets."""
+    from basicsr4rs_b200.archs import build_network
+    ref_ns = ref_shim.load_reference_archs()
+    torch.manual_seed(21)
+    theirs = getattr(ref_ns, arch)(**kw).to(cuda).eval()
+    torch.manual_seed(21)
+    ours = build_network(dict(type=arch, **kw)).to(cuda).eval()
+    for (ka, a), (kb, bb) in zip(theirs.state_dict().items(), ours.state_dict().items()):
+        assert ka == kb and torch.equal(a, bb), ka
+    g = torch.Generator().manual_seed(4)
+    b, c, h, w = shape
+    x = torch.rand(shape, generator=g).to(cuda)
+    gt = torch.rand((b, c, h * scale, w * scale), generator=g).to(cuda)
+    outs = []
+    for net in (theirs, ours):
+        out = net(x)
+        ((out - gt)**2).mean().backward()
+        outs.append(out.detach())
+    err = (outs[0] - outs[1]).abs().max().item()
+    assert err <= MAX_ABS, f'max-abs {err:.3e}'
+    pt = dict(theirs.named_parameters())
+    for k, p in ours.named_parameters():
+        if pt[k].grad is None or pt[k].grad.norm() == 0:
+            continue
+        _check_grad(p.grad, pt[k].grad.cpu())

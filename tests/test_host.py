@@ -81,6 +81,11 @@ def test_edsr_param_count_known_answer():
 @pytest.mark.parametrize('arch,kwargs', [
     ('EDSR', EDSR_M),
     ('EDSR', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=2, upscale=3, res_scale=0.1)),
+    ('RCAN', dict(num_in_ch=3, num_out_ch=3, num_feat=64, num_group=2, num_block=3, squeeze_factor=16, upscale=4)),
+    ('SwinIR', dict(upscale=4, in_chans=3, img_size=64, window_size=8, img_range=1., depths=[6] * 6, embed_dim=180,
+                    num_heads=[6] * 6, mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv')),
+    ('SwinIR', dict(upscale=2, in_chans=4, img_size=48, window_size=6, img_range=1., depths=[2, 2], embed_dim=60,
+                    num_heads=[6, 6], mlp_ratio=2, upsampler='pixelshuffledirect', resi_connection='3conv', ape=True)),
 ])
 def test_seeded_init_identical_to_reference(arch, kwargs):
     """Same seed -> bit-identical state dict (names, order, shapes, values): 'identical random-init weights'."""

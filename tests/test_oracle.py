@@ -96,3 +96,32 @@ def test_oracle_matches_live_reference(arch, kwargs, shape):
         want = net(x)
         got = oracle_forward({'arch': arch, 'kwargs': kwargs}, sd, x)
     assert (got - want).abs().max().item() <= 1e-5
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='reference tree not available')
+def test_oracle_droppath_and_ape_match_live_reference_training_mode():
+    """TRAINING mode with stochastic depth (the configuration bench.py times for SwinIR) and ``ape=True``: the oracle,
+    fed the per-block keep masks drawn in the reference's own RNG order (``drop_path_masks``), reproduces the live
+    reference's output and gradients.  This pins the oracle leg the GPU DropPath parity test relies on."""
+    ref = ref_shim.load_reference_archs()
+    kw = dict(upscale=2, in_chans=3, img_size=16, window_size=8, img_range=1., depths=[2, 2], embed_dim=60,
+              num_heads=[6, 6], mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv', drop_path_rate=0.5,
+              ape=True)
+    torch.manual_seed(11)
+    net = ref.SwinIR(**kw).train()
+    with torch.no_grad():
+        net.absolute_pos_embed.normal_(std=0.1)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in net.state_dict().items()}
+    x = torch.rand((4, 3, 16, 16))
+    torch.manual_seed(123)
+    want = net(x)
+    torch.manual_seed(123)
+    masks = sr_oracle.drop_path_masks(4, kw['depths'], kw['drop_path_rate'])
+    assert any((m[0] == 0).any() or (m[1] == 0).any() for m in masks.values())  # some branch really was dropped
+    got = sr_oracle.swinir_forward(sd, x, embed_dim=60, depths=[2, 2], num_heads=[6, 6], window_size=8, upscale=2,
+                                   img_range=1., drop_masks=masks, ape=True)
+    assert (got - want).abs().max().item() <= 1e-5
+    (want**2).mean().backward()
+    (got**2).mean().backward()
+    for k, p in net.named_parameters():
+        assert torch.allclose(sd[k].grad, p.grad, rtol=1e-4, atol=1e-6 * p.grad.abs().max().item() + 1e-9), k
