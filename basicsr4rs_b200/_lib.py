@@ -83,8 +83,8 @@ SIGNATURES = {
     'srb200_layernorm_fwd': (c_int, [c_void_p] * 6 + [c_int64, c_int, c_int, c_float, c_void_p]),
     'srb200_layernorm_bwd': (c_int, [c_void_p] * 9 + [c_int64, c_int, c_int, c_void_p]),
     'srb200_scale_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
-    'srb200_window_attention_fwd': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_float, c_void_p]),
-    'srb200_window_attention_bwd': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_float, c_void_p]),
+    'srb200_window_attention_fwd': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_float, c_void_p]),
+    'srb200_window_attention_bwd': (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_void_p]),
     'srb200_channel_pool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'srb200_channel_dot': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     'srb200_ca_fc': (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_void_p]),
@@ -95,6 +95,7 @@ SIGNATURES = {
     'srb200_set_pdl': (c_int, [c_int]),
     'srb200_debug_set_trace': (c_int, [c_void_p]),
     'srb200_debug_set_wgrad_trace': (c_int, [c_void_p]),
+    'srb200_debug_set_attn_trace': (c_int, [c_void_p]),
     'srb200_ca_apply_bwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 

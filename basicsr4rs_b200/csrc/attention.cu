@@ -417,13 +417,26 @@ static int check_geom(int B, int H, int W, int nH, int Cp, int ws, int shift) {
 
 using namespace srb;
 
+// attention_tc.cu: the tcgen05 / TMEM / TMA kernels (window 8); SRB200_EINVAL = shape outside their domain
+int srb_window_attention_fwd_tc(const void* qkv_bf16, const float* rpb_table, void* out_bf16, float* stats, int B,
+                                int H, int W, int num_heads, int Ca, int shift, float scale, cudaStream_t stream);
+int srb_window_attention_bwd_tc(const void* qkv_bf16, const void* gout_bf16, const float* rpb_table,
+                                const float* stats, void* gqkv_bf16, float* g_rpb_table, float* workspace, int B,
+                                int H, int W, int num_heads, int Ca, int shift, float scale, cudaStream_t stream);
+
 extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table,
-                                           void* out_bf16, int B, int H, int W, int num_heads,
+                                           void* out_bf16, float* stats, int B, int H, int W, int num_heads,
                                            int Cp, int window_size, int shift, float scale,
                                            srb200_stream_t stream) {
   if (!qkv_bf16 || !rpb_table || !out_bf16) return SRB200_EINVAL;
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
+  if (window_size == 8 && SRB_ENV("SRB_ATTN_MMA_SYNC") == nullptr) {
+    // window 8 (every classical-SR recipe): the tcgen05 kernel; other windows / odd head counts: mma.sync below
+    const int rc_tc = srb_window_attention_fwd_tc(qkv_bf16, rpb_table, out_bf16, stats, B, H, W, num_heads, Cp, shift, scale,
+                                                  static_cast<cudaStream_t>(stream));
+    if (rc_tc != SRB200_EINVAL) return rc_tc;
+  }
   AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
   const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
   if (wins * num_heads > 0x7fffffffLL || B > 65535) return SRB200_EINVAL;
@@ -438,13 +451,19 @@ extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rp
 }
 
 extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gout_bf16,
-                                           const float* rpb_table, void* gqkv_bf16,
-                                           float* g_rpb_table, int B, int H, int W, int num_heads,
+                                           const float* rpb_table, const float* stats, void* gqkv_bf16,
+                                           float* g_rpb_table, float* workspace, int B, int H, int W, int num_heads,
                                            int Cp, int window_size, int shift, float scale,
                                            srb200_stream_t stream) {
   if (!qkv_bf16 || !gout_bf16 || !rpb_table || !gqkv_bf16 || !g_rpb_table) return SRB200_EINVAL;
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
+  if (window_size == 8 && stats != nullptr && workspace != nullptr && SRB_ENV("SRB_ATTN_MMA_SYNC") == nullptr &&
+      SRB_ENV("SRB_ATTN_BWD_MMA_SYNC") == nullptr) {
+    const int rc_tc = srb_window_attention_bwd_tc(qkv_bf16, gout_bf16, rpb_table, stats, gqkv_bf16, g_rpb_table, workspace, B, H, W,
+                                                  num_heads, Cp, shift, scale, static_cast<cudaStream_t>(stream));
+    if (rc_tc != SRB200_EINVAL) return rc_tc;
+  }
   AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
   const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
   if (wins * num_heads > 0x7fffffffLL || B > 65535) return SRB200_EINVAL;

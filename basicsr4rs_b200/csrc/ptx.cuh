@@ -52,6 +52,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// one non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -220,6 +233,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- integer division by a launch constant
+// n / d for 0 <= n < 2^24 with magic = ceil(2^48 / d) (host: srb::div_magic): one 64-bit multiply-high instead of the
+// ~30-instruction, ~150-cycle dependent sequence of a runtime 32-bit division
+__device__ __forceinline__ int fast_div(int n, unsigned long long magic) {
+  return static_cast<int>(__umul64hi(static_cast<unsigned long long>(static_cast<unsigned>(n)) << 16, magic));
+}
+__host__ __device__ inline unsigned long long div_magic(long long d) {
+  return static_cast<unsigned long long>(((1ULL << 48) + d - 1) / d);
 }
 
 // ---------------------------------------------------------------- bf16 helpers

@@ -123,9 +123,6 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& d) {
   d = fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
-__device__ __forceinline__ int fast_div(int n, unsigned long long magic) {
-  return static_cast<int>(__umul64hi(static_cast<unsigned long long>(static_cast<unsigned>(n)) << 16, magic));
-}
 
 // Column sums over the 32 rows a warp owns: butterfly reduce-scatter (31 shuffles); lane l returns the sum of
 // column l.  w is destroyed.

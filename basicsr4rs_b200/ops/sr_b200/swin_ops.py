@@ -10,6 +10,7 @@ The padding lives only in the packed bf16 weight copies (index maps below); para
 reference's shapes, so state dicts are interchangeable.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -58,27 +59,40 @@ def scale_rows(g, alpha):
     return out
 
 
-def window_attention_fwd(qkv, table, num_heads, ws, shift, scale):
+def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=False):
+    """Fused window attention.  ``want_stats``: also return the softmax statistics buffer (fp32
+    [windows, heads, ws*ws], opaque) that lets :func:`window_attention_bwd` skip the row maxima / sums."""
     _chk(qkv, 'qkv', torch.bfloat16)
     _chk(table, 'rpb_table', torch.float32)
     b, h, w, c3 = qkv.shape
     ca = c3 // 3
     out = torch.empty((b, h, w, ca), dtype=torch.bfloat16, device=qkv.device)
+    stats = torch.empty((b * (h // ws) * (w // ws), num_heads, ws * ws), dtype=torch.float32, device=qkv.device) \
+        if want_stats else None
     raw.probed('window_attn_fwd', (b, h, w, num_heads, ws), lambda: L.check(L.load().srb200_window_attention_fwd(
-        _ptr(qkv), _ptr(table), _ptr(out), b, h, w, num_heads, ca, ws, shift, float(scale), _stream()),
+        _ptr(qkv), _ptr(table), _ptr(out), _ptr(stats), b, h, w, num_heads, ca, ws, shift, float(scale), _stream()),
         'window_attention_fwd'))
-    return out
+    return (out, stats) if want_stats else out
 
 
-def window_attention_bwd(qkv, gout, table, num_heads, ws, shift, scale):
+# The tcgen05 backward (attention_tc_bwd.cu) is parity-green but, at 95-110 us for B16 x 64x64, not yet ahead of the
+# mma.sync kernel (118 us): its stage pipeline still serialises phase B behind the thread phase (DESIGN.md section 3.2).
+# It runs when asked for (tests, SRB_ATTN_BWD_TC=1); the default backward stays on the faster-to-date kernel.
+ATTN_BWD_TC = os.environ.get('SRB_ATTN_BWD_TC', '0') == '1'
+
+
+def window_attention_bwd(qkv, gout, table, num_heads, ws, shift, scale, stats=None, use_tc=None):
     _chk(gout, 'gout', torch.bfloat16)
     b, h, w, c3 = qkv.shape
     ca = c3 // 3
     gqkv = torch.empty_like(qkv)
     gtable = raw.zeros_f32(tuple(table.shape), table.device)
+    # zeroed workspace of the tcgen05 backward (window 8 with the forward's statistics): dS sums [heads, 64, 64] + counter
+    use_tc = ATTN_BWD_TC if use_tc is None else use_tc
+    work = raw.zeros_f32((num_heads * 4096 + 32,), table.device) if (use_tc and stats is not None and ws == 8) else None
     raw.probed('window_attn_bwd', (b, h, w, num_heads, ws), lambda: L.check(L.load().srb200_window_attention_bwd(
-        _ptr(qkv), _ptr(gout), _ptr(table), _ptr(gqkv), _ptr(gtable), b, h, w, num_heads, ca, ws, shift, float(scale),
-        _stream()), 'window_attention_bwd'))
+        _ptr(qkv), _ptr(gout), _ptr(table), _ptr(stats), _ptr(gqkv), _ptr(gtable), _ptr(work), b, h, w, num_heads, ca,
+        ws, shift, float(scale), _stream()), 'window_attention_bwd'))
     return gqkv, gtable
 
 
@@ -146,7 +160,11 @@ class _SwinBlock(Function):
         xn, mean1, rstd1 = layernorm_fwd(x, n1w.detach(), n1b.detach(), c, eps)
         qkv = raw.tapgemm(xn, _packed(qkv_w, 'fprop', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=3 * ca,
                           bias=_padded_bias(qkv_b, 3 * ca, p_qkv))
-        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale)
+        want_stats = any(ctx.needs_input_grad)
+        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale, want_stats=want_stats)
+        stats = None
+        if want_stats:
+            o, stats = o
         x1 = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
                          bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1)
         xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c, eps)
@@ -155,14 +173,15 @@ class _SwinBlock(Function):
         x2 = raw.tapgemm(h, _packed(fc2_w, 'fprop', cs, ch), ksize=1, cout=cs, bias=_padded_bias(fc2_b, cs),
                          residual=x1, alpha_per_sample=alpha2)
         ctx.save_for_backward(x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table,
-                              proj_w, proj_b, n2w, fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2)
+                              proj_w, proj_b, n2w, fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2, stats)
         ctx.cfg = (c, cs, ca, ch, hd, num_heads, ws, shift, scale)
         raw.stash_backward_scratch(ctx, _SwinBlock._scratch_floats(c, cs, ca, ch, table.numel()), dev)
         return x2
 
     @staticmethod
     def _scratch_floats(c, cs, ca, ch, table_numel):
-        return 2 * cs * ch + cs * ca + 3 * ca * cs + 2 * cs + ch + 3 * ca + 4 * c + table_numel + 64
+        return 2 * cs * ch + cs * ca + 3 * ca * cs + 2 * cs + ch + 3 * ca + 4 * c + table_numel + 64 + \
+            (ca // HD_PAD) * 4096 + 96  # (+ the attention backward's dS-sum workspace)
 
     @staticmethod
     def backward(ctx, g2):
@@ -170,7 +189,7 @@ class _SwinBlock(Function):
         # ctx.saved_tensors raises "already unpacked once")
         saved = ctx.saved_tensors
         (x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table, proj_w, proj_b, n2w,
-         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = saved
+         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2, stats) = saved
         c, cs, ca, ch, hd, num_heads, ws, shift, scale = ctx.cfg
         dev = x.device
         p_qkv = head_perm(num_heads, hd, 3, dev)
@@ -183,7 +202,7 @@ class _SwinBlock(Function):
     @staticmethod
     def _backward(ctx, g2, arena, saved):
         (x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table, proj_w, proj_b, n2w,
-         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2) = saved
+         fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2, stats) = saved
         c, cs, ca, ch, hd, num_heads, ws, shift, scale = ctx.cfg
         dev = x.device
         p_qkv = head_perm(num_heads, hd, 3, dev)
@@ -202,7 +221,7 @@ class _SwinBlock(Function):
         acc_proj = raw.wgrad(g1s, o, ksize=1)
         cs_proj = raw.colsum(g1s)
         go = raw.tapgemm(g1s, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
-        gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale)
+        gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale, stats=stats)
         acc_qkv = raw.wgrad(gqkv, xn, ksize=1)
         gxn = raw.tapgemm(gqkv, _packed(qkv_w, 'dgrad', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=cs, flip=True)
         gx, g_n1w, g_n1b = layernorm_bwd(gxn, x, mean1, rstd1, n1w.detach(), c, gres=gx1)
@@ -292,17 +311,17 @@ class _WindowAttn(Function):
         scale = hd**-0.5
         qkv = raw.tapgemm(x, _packed(qkv_w, 'fprop', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=3 * ca,
                           bias=_padded_bias(qkv_b, 3 * ca, p_qkv))
-        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale)
+        o, stats = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale, want_stats=True)
         y = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
                         bias=_padded_bias(proj_b, cs))
-        ctx.save_for_backward(x, qkv, o, qkv_w, qkv_b, table, proj_w, proj_b)
+        ctx.save_for_backward(x, qkv, o, qkv_w, qkv_b, table, proj_w, proj_b, stats)
         ctx.cfg = (c, cs, ca, hd, num_heads, ws, shift, scale)
         raw.stash_backward_scratch(ctx, cs * ca + 3 * ca * cs + 2 * cs + 3 * ca + table.numel() + 64, x.device)
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, qkv, o, qkv_w, qkv_b, table, proj_w, proj_b = ctx.saved_tensors
+        x, qkv, o, qkv_w, qkv_b, table, proj_w, proj_b, stats = ctx.saved_tensors
         c, cs, ca, hd, num_heads, ws, shift, scale = ctx.cfg
         p_qkv = head_perm(num_heads, hd, 3, x.device)
         p_o = head_perm(num_heads, hd, 1, x.device)
@@ -311,7 +330,7 @@ class _WindowAttn(Function):
             acc_proj = raw.wgrad(g, o, ksize=1)
             cs_proj = raw.colsum(g)
             go = raw.tapgemm(g, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
-            gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale)
+            gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale, stats=stats)
             acc_qkv = raw.wgrad(gqkv, x, ksize=1)
             gx = raw.tapgemm(gqkv, _packed(qkv_w, 'dgrad', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=cs, flip=True) \
                 if ctx.needs_input_grad[0] else None

@@ -283,15 +283,22 @@ int srb200_scale_rows(const void* g_bf16, const float* alpha, void* out_bf16, in
  *   qkv [B,H,W,3*Cp] bf16, channel = which*Cp + head*32 + d  (head_dim <= 32, zero padded)
  *   out [B,H,W,Cp]   bf16, channel = head*32 + d
  *   rpb_table fp32 [(2*ws-1)^2, num_heads] exactly as stored in the state dict
- * window_size must be 8; H, W multiples of 8; shift in [0, 8).
- * bwd also accumulates the bias-table gradient into g_rpb_table (zero it first).                         */
-int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table, void* out_bf16, int B,
-                                int H, int W, int num_heads, int Cp, int window_size, int shift,
+ * window_size 2..8; H, W multiples of it; shift in [0, window_size).  Window 8 with shift 0 / 4 and an even head
+ * count runs on the tcgen05 / TMEM / TMA kernels (attention_tc.cu), everything else on the mma.sync kernels.
+ * stats (optional, may be NULL): fp32 [B*(H/ws)*(W/ws)][num_heads][ws*ws] softmax statistics, the log2-domain
+ * log-sum-exp of every (window, head, query) row in the kernel's own token order -- an opaque buffer that the
+ * forward fills and the backward of the SAME geometry reads so that it need not redo the row maxima and sums
+ * (without it the backward recomputes them on the mma.sync path).
+ * bwd also accumulates the bias-table gradient into g_rpb_table (zero it first).
+ * workspace (optional, may be NULL): num_heads*4096 + 32 ZEROED floats the tcgen05 backward uses to merge the
+ * bias-table gradient across CTAs; without stats or workspace the backward runs on the mma.sync path.     */
+int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table, void* out_bf16, float* stats,
+                                int B, int H, int W, int num_heads, int Cp, int window_size, int shift,
                                 float scale, srb200_stream_t stream);
 int srb200_window_attention_bwd(const void* qkv_bf16, const void* gout_bf16, const float* rpb_table,
-                                void* gqkv_bf16, float* g_rpb_table, int B, int H, int W,
-                                int num_heads, int Cp, int window_size, int shift, float scale,
-                                srb200_stream_t stream);
+                                const float* stats, void* gqkv_bf16, float* g_rpb_table, float* workspace,
+                                int B, int H, int W, int num_heads, int Cp, int window_size, int shift,
+                                float scale, srb200_stream_t stream);
 
 /* out = g * act'(y) for ReLU (slope 0) / LeakyReLU, y = forward output (bf16, n % 8 == 0). */
 int srb200_act_bwd(const void* g_bf16, const void* y_bf16, void* out_bf16, int64_t n, float slope,
@@ -310,6 +317,8 @@ int srb200_set_pdl(int on);
  * following srb200_tapgemm launches (NULL switches it off). */
 int srb200_debug_set_trace(void* dev_buf);
 int srb200_debug_set_wgrad_trace(void* dev_buf); /* same for srb200_wgrad: 64 uint64 */
+/* same for the tcgen05 window-attention kernels (window 8): [4 roles][64 stages][8 slots] uint64 */
+int srb200_debug_set_attn_trace(void* dev_buf);
 
 #ifdef __cplusplus
 }

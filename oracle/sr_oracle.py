@@ -67,7 +67,7 @@ def upsample(sd, prefix, x, scale):
 
 
 def _mean(x, rgb_mean):
-    return torch.tensor(rgb_mean, dtype=x.dtype).view(1, -1, 1, 1)
+    return torch.tensor(rgb_mean, dtype=x.dtype, device=x.device).view(1, -1, 1, 1)
 
 
 # ------------------------------------------------------------------ EDSR (edsr_arch.py:50-61)
@@ -161,7 +161,7 @@ def window_attention(sd, prefix, xw, mask, num_heads, ws):
     qkv = qkv.reshape(b_, n, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0] * hd**-0.5, qkv[1], qkv[2]
     attn = q @ k.transpose(-2, -1)
-    idx = relative_position_index(ws).reshape(-1)
+    idx = relative_position_index(ws).reshape(-1).to(xw.device)
     bias = sd[prefix + '.relative_position_bias_table'][idx].reshape(n, n, -1).permute(2, 0, 1)
     attn = attn + bias.unsqueeze(0)
     if mask is not None:
@@ -183,7 +183,7 @@ def swin_block(sd, prefix, x, h, w, num_heads, ws, shift, drop_keep=None):
     if shift > 0:
         t = torch.roll(t, shifts=(-shift, -shift), dims=(1, 2))
     xw = window_partition(t, ws).reshape(-1, ws * ws, c)
-    mask = calculate_mask(h, w, ws, shift) if shift > 0 else None
+    mask = calculate_mask(h, w, ws, shift).to(x.device) if shift > 0 else None
     aw = window_attention(sd, prefix + '.attn', xw, mask, num_heads, ws).reshape(-1, ws, ws, c)
     t = window_reverse(aw, ws, h, w)
     if shift > 0:
@@ -235,7 +235,7 @@ def swinir_forward(sd, x, embed_dim=180, depths=(6, 6, 6, 6, 6, 6), num_heads=(6
         v = F.leaky_relu(conv(sd, prefix + '.2', v, padding=0), 0.2)
         return conv(sd, prefix + '.4', v)
 
-    mean = _mean(x, RGB_MEAN) if in_chans == 3 else torch.zeros(1, 1, 1, 1)
+    mean = _mean(x, RGB_MEAN) if in_chans == 3 else torch.zeros(1, 1, 1, 1, device=x.device)
     x_in = x
     x = (x - mean) * img_range
     x = conv(sd, 'conv_first', x)

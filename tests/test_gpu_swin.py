@@ -75,6 +75,7 @@ def _ref_window_attention(qkv_pad, table, nh, hd, ws, shift, h, w):
 
 
 @pytest.mark.parametrize('b,h,w,nh,hd,shift,ws', [(2, 16, 24, 6, 30, 0, 8), (2, 16, 24, 6, 30, 4, 8), (1, 8, 8, 6, 10, 0, 8),
+                                                  (3, 24, 40, 4, 32, 4, 8), (16, 64, 64, 6, 30, 4, 8),
                                                   (1, 64, 64, 6, 30, 4, 8), (1, 24, 16, 2, 32, 3, 8),
                                                   # the fork's remote-sensing recipes: 6-wide windows; and 7 (Swin default)
                                                   (2, 12, 18, 6, 30, 0, 6), (2, 12, 18, 6, 30, 3, 6), (1, 48, 48, 6, 30, 3, 6),
@@ -87,7 +88,8 @@ def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift, ws):
     qkv[..., :hd] = torch.randn((b, h, w, 3, nh, hd), generator=g)
     qkv = qkv.reshape(b, h, w, 3 * ca).to(cuda).to(torch.bfloat16)
     table = (torch.randn(((2 * ws - 1)**2, nh), generator=g) * 0.5).to(cuda)
-    out = so.window_attention_fwd(qkv, table, nh, ws, shift, hd**-0.5)
+    out, stats = so.window_attention_fwd(qkv, table, nh, ws, shift, hd**-0.5, want_stats=True)
+    assert torch.equal(out, so.window_attention_fwd(qkv, table, nh, ws, shift, hd**-0.5))
     qr = qkv.float().requires_grad_(True)
     tr = table.clone().requires_grad_(True)
     ref = _ref_window_attention(qr, tr, nh, hd, ws, shift, h, w)
@@ -99,12 +101,15 @@ def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift, ws):
     go[..., :hd] = torch.randn((b, h, w, nh, hd), generator=g)
     go = go.reshape(b, h, w, ca).to(cuda).to(torch.bfloat16)
     ref.backward(go.reshape(b, h, w, nh, 32)[..., :hd].float())
-    gqkv, gtable = so.window_attention_bwd(qkv, go, table, nh, ws, shift, hd**-0.5)
-    want = qr.grad
-    rel = ((gqkv.float() - want).norm() / want.norm()).item()
-    assert rel <= 2e-2, f'gqkv rel-L2 {rel:.3e}'
-    relt = ((gtable - tr.grad).norm() / tr.grad.norm()).item()
-    assert relt <= 2e-2, f'gtable rel-L2 {relt:.3e}'
+    # with the forward's statistics buffer (window 8: the tcgen05 backward) and without it (mma.sync, recomputes them)
+    for st in (stats, None):
+        gqkv, gtable = so.window_attention_bwd(qkv, go, table, nh, ws, shift, hd**-0.5, stats=st, use_tc=True)
+        want = qr.grad
+        assert torch.count_nonzero(gqkv.reshape(b, h, w, 3, nh, 32)[..., hd:]) == 0
+        rel = ((gqkv.float() - want).norm() / want.norm()).item()
+        assert rel <= 2e-2, f'gqkv rel-L2 {rel:.3e} (stats: {st is not None})'
+        relt = ((gtable - tr.grad).norm() / tr.grad.norm()).item()
+        assert relt <= 2e-2, f'gtable rel-L2 {relt:.3e} (stats: {st is not None})'
 
 
 def test_swin_block_vs_oracle(cuda):

@@ -79,7 +79,7 @@ def test_shipped_yaml_options_build_through_the_reference_registry(grafted):
 
 
 def _sr_opt(network_g, dist=False, ema=0.999):
-    return {'num_gpu': 1, 'is_train': True, 'dist': dist, 'scale': network_g.get('upscale', 4), 'network_g': network_g,
+    return {'num_gpu': 1, 'is_train': True, 'dist': dist, 'rank': 0, 'world_size': 1, 'scale': network_g.get('upscale', 4), 'network_g': network_g,
             'path': {'pretrain_network_g': None, 'strict_load_g': True},
             'train': {'ema_decay': ema, 'optim_g': {'type': 'Adam', 'lr': 2e-4, 'weight_decay': 0, 'betas': [0.9, 0.99]},
                       'scheduler': {'type': 'MultiStepLR', 'milestones': [1000], 'gamma': 0.5},

@@ -47,8 +47,10 @@ y, mean, rstd = so.layernorm_fwd(x192, g, b_, 180)
 us = timeit(lambda: so.layernorm_bwd(x192, x192, mean, rstd, g, 180, gres=x192)); rec('layernorm_bwd(+gres)', us, mbytes=4 * T * 192 * 2 / 1e6)
 table = torch.randn(225, 6, device=dev) * 0.1
 for shift in (0, 4):
-    us = timeit(lambda: so.window_attention_fwd(x576, table, 6, 8, shift, 30**-0.5)); rec(f'attn_fwd shift{shift}', us, mbytes=4 * T * 192 * 2 / 1e6)
-    us = timeit(lambda: so.window_attention_bwd(x576, x192, table, 6, 8, shift, 30**-0.5)); rec(f'attn_bwd shift{shift}', us, mbytes=8 * T * 192 * 2 / 1e6)
+    us = timeit(lambda: so.window_attention_fwd(x576, table, 6, 8, shift, 30**-0.5)); rec(f'attn_fwd shift{shift}', us, mbytes=4 * T * 180 * 2 / 1e6)
+    _, stats = so.window_attention_fwd(x576, table, 6, 8, shift, 30**-0.5, want_stats=True)
+    us = timeit(lambda: so.window_attention_bwd(x576, x192, table, 6, 8, shift, 30**-0.5, stats=stats, use_tc=True)); rec(f'attn_bwd shift{shift}', us, mbytes=7 * T * 180 * 2 / 1e6)
+    us = timeit(lambda: so.window_attention_bwd(x576, x192, table, 6, 8, shift, 30**-0.5)); rec(f'attn_bwd(mma.sync) shift{shift}', us, mbytes=7 * T * 180 * 2 / 1e6)
 w = lin(576, 192)
 us = timeit(lambda: raw.pack_weight(w, 576, 192)); rec('pack 576x192', us)
 acc = torch.zeros(1, 576, 192, device=dev)
