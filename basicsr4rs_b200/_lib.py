@@ -40,6 +40,10 @@ class TapGemmExt(ctypes.Structure):
                 ('colsum_scale', c_float), ('reserved', ctypes.c_int32)]
 
 
+# numpy mirror of ``srb200_patch_item`` (one crop of a batched patch extraction)
+PATCH_ITEM_FIELDS = [('src', '<i8'), ('pitch', '<i8'), ('top', '<i4'), ('left', '<i4'), ('flags', '<i4'),
+                     ('reserved', '<i4')]
+
 # numpy mirror of ``srb200_pack_item`` (one row per weight of a batched pack / unpack launch)
 PACK_ITEM_FIELDS = [('src', '<i8'), ('dst', '<i8'), ('perm_out', '<i8'), ('perm_in', '<i8'), ('Co', '<i8'),
                     ('Ci', '<i8'), ('taps', '<i8'), ('Np', '<i8'), ('Kp', '<i8'), ('transpose', '<i8'),
@@ -96,6 +100,9 @@ SIGNATURES = {
     'srb200_debug_set_trace': (c_int, [c_void_p]),
     'srb200_debug_set_wgrad_trace': (c_int, [c_void_p]),
     'srb200_debug_set_attn_trace': (c_int, [c_void_p]),
+    'srb200_patch_from_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'srb200_tile_blend_add': (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
+    'srb200_tensor2img_u8': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     'srb200_ca_apply_bwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 

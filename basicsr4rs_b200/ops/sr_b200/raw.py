@@ -596,3 +596,58 @@ def ca_apply_bwd(g, s, gp, res_scale, want_colsum=False):
     L.check(L.load().srb200_ca_apply_bwd(_ptr(g), _ptr(s), _ptr(gp), _ptr(gt), b, h * w, c, float(res_scale),
                                          _ptr(cs), _stream()), 'ca_apply_bwd')
     return (gt, cs) if want_colsum else gt
+
+
+# ------------------------------------------------------------------ image entry / exit (callers' side)
+def patch_items(rows, device):
+    """Device table of ``srb200_patch_item``: ``rows`` = (image uint8 [H,W,C] CUDA tensor, top, left, flags)."""
+    import numpy as np
+    tab = np.zeros(len(rows), dtype=np.dtype(L.PATCH_ITEM_FIELDS))
+    for i, (img, top, left, flags) in enumerate(rows):
+        tab[i] = (img.data_ptr(), img.stride(0) * img.element_size(), top, left, flags, 0)
+    return torch.from_numpy(tab.view(np.uint8).reshape(len(rows), -1).copy()).to(device, non_blocking=True)
+
+
+def patch_from_u8(images, tops, lefts, flags, ph, pw, bgr2rgb=True, scale=1.0 / 255.0):
+    """Batched crop + augment + img2tensor (transforms.py:28-96,166-225; img_util.py:9-37) on the GPU.
+
+    ``images``: list of uint8 [H, W, C] CUDA tensors (rows contiguous); item i is the ``ph x pw`` crop of images[i] at
+    (tops[i], lefts[i]) with flags[i] (bit 0 hflip, bit 1 vflip, bit 2 rot90).  Returns fp32 [n, C, oh, ow]."""
+    n = len(images)
+    c = images[0].shape[2]
+    rot = [bool(f & 4) for f in flags]
+    if any(rot) and not all(rot) and ph != pw:
+        raise RuntimeError('mixed rot90 flags need square patches')
+    oh, ow = (pw, ph) if rot[0] else (ph, pw)
+    for img, t, l in zip(images, tops, lefts):
+        if img.dtype != torch.uint8 or not img.is_cuda or img.dim() != 3 or img.stride(2) != 1 or img.stride(1) != c:
+            raise RuntimeError('patch_from_u8 wants uint8 [H, W, C] CUDA images with contiguous rows')
+        if t < 0 or l < 0 or t + ph > img.shape[0] or l + pw > img.shape[1]:
+            raise RuntimeError('crop outside the image')
+    dev = images[0].device
+    tab = patch_items(list(zip(images, tops, lefts, flags)), dev)
+    out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=dev)
+    L.check(L.load().srb200_patch_from_u8(_ptr(tab), n, c, ph, pw, int(bgr2rgb), float(scale), _ptr(out), _stream()),
+            'patch_from_u8')
+    return out
+
+
+def tile_blend_add(sr_tile, acc, y0, x0, ov, guard):
+    """acc [C, H, W] += ramp-weighted sr_tile [C, th, tw]; ``ov`` = (top, bottom, left, right) overlaps in pixels."""
+    _chk(sr_tile, 'sr_tile', torch.float32)
+    _chk(acc, 'acc', torch.float32)
+    c, th, tw = sr_tile.shape[-3:]
+    L.check(L.load().srb200_tile_blend_add(_ptr(sr_tile), _ptr(acc), c, th, tw, acc.shape[-2], acc.shape[-1], int(y0),
+                                           int(x0), int(ov[0]), int(ov[1]), int(ov[2]), int(ov[3]), int(guard),
+                                           _stream()), 'tile_blend_add')
+
+
+def tensor2img_u8(src, lo=0.0, hi=1.0, rgb2bgr=True, out=None):
+    """tensor2img (img_util.py:40-96) on the GPU: fp32 [C, H, W] -> uint8 [H, W, C]."""
+    _chk(src, 'src', torch.float32)
+    c, h, w = src.shape[-3:]
+    if out is None:
+        out = torch.empty((h, w, c), dtype=torch.uint8, device=src.device)
+    L.check(L.load().srb200_tensor2img_u8(_ptr(src), _ptr(out), c, h, w, float(lo), float(hi), int(rgb2bgr), _stream()),
+            'tensor2img_u8')
+    return out

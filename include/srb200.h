@@ -320,6 +320,34 @@ int srb200_debug_set_wgrad_trace(void* dev_buf); /* same for srb200_wgrad: 64 ui
 /* same for the tcgen05 window-attention kernels (window 8): [4 roles][64 stages][8 slots] uint64 */
 int srb200_debug_set_attn_trace(void* dev_buf);
 
+/* ------------------------------------------------------------------ image entry / exit (the callers' side)
+ * One crop of a batched patch extraction: basicsr/data/transforms.py:28-96 (paired_random_crop), :166-225 (augment:
+ * hflip, vflip, rot90 = transpose, in that order) and utils/img_util.py:9-37 (img2tensor: BGR->RGB, HWC->CHW, float)
+ * in one pass over uint8 HWC images that are already in device memory.                                          */
+typedef struct srb200_patch_item {
+  const void* src;   /* uint8 HWC image, device memory                          */
+  int64_t pitch;     /* bytes per image row                                     */
+  int32_t top, left; /* crop origin (pixels)                                    */
+  int32_t flags;     /* bit 0 hflip, bit 1 vflip, bit 2 rot90 (transpose)       */
+  int32_t reserved;
+} srb200_patch_item;
+/* out fp32 [n, C, oh, ow] = scale * augmented crop, (oh, ow) = rot90 ? (pw, ph) : (ph, pw); all n items share ph x pw.
+ * bgr2rgb swaps channels 0 and 2 of 3-channel images.  items_dev: device array of n srb200_patch_item.            */
+int srb200_patch_from_u8(const void* items_dev, int n, int C, int ph, int pw, int bgr2rgb, float scale, float* out,
+                         srb200_stream_t stream);
+/* acc[c, y0+y, x0+x] += w(y, x) * sr_tile[c, y, x]: one super-resolved tile into the fp32 scene accumulator
+ * [C, acc_h, acc_w] with separable linear-ramp weights over its overlaps with the neighbouring tiles (ov_* pixels,
+ * 0 = image border; the two tiles' ramps sum to 1; the outer `guard` pixels of a tile carry no weight).  Pixels
+ * outside the accumulator are clipped (a rank's band of a larger scene).  Tiles that overlap each other must be
+ * ordered on the stream (the adds are plain read-modify-writes).                                                 */
+int srb200_tile_blend_add(const float* sr_tile, float* acc, int C, int th, int tw, int acc_h, int acc_w, int y0,
+                          int x0, int ov_top, int ov_bottom, int ov_left, int ov_right, int guard,
+                          srb200_stream_t stream);
+/* tensor2img (basicsr/utils/img_util.py:40-96): fp32 CHW -> uint8 HWC, clamp to [lo, hi], normalise, x255, round half
+ * to even (numpy .round()), optional RGB->BGR.                                                                    */
+int srb200_tensor2img_u8(const float* src_chw, void* dst_hwc_u8, int C, int H, int W, float lo, float hi, int rgb2bgr,
+                         srb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
