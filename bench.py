@@ -384,6 +384,8 @@ def main():
     ap.add_argument('--impl', default='srb200', choices=['srb200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
+    ap.add_argument('--grad-comm', default='fp32', choices=['fp32', 'bf16'],
+                    help="DDP gradient all-reduce payload: fp32 (the reference's) or torch's bf16_compress_hook")
     ap.add_argument('--configs', default='all', help="'all', 'none' or a comma list of the other BASELINE configs "
                     f"({', '.join(list(TRAIN_CONFIGS) + list(INFER_CONFIGS))}); measured at N=1 only")
     args = ap.parse_args()
@@ -420,6 +422,9 @@ def main():
                              graph_input_shape=[BATCH, 3, LR, LR])).to(dev)  # graphs captured here, before DDP
     model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True) \
         if world > 1 else net
+    if world > 1 and args.grad_comm == 'bf16':
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
     crit = nn.L1Loss()
 
@@ -502,7 +507,8 @@ def main():
         line = {
             'metric': 'SR train patches/s (fwd+bwd)', 'value': value, 'unit': 'patches/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': CONFIG,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': dict(CONFIG, grad_comm=args.grad_comm if world > 1 else 'none (1 GPU)'),
             'e2e': {'value': patches / (ms_e2e / 1e3), 'unit': 'patches/s',
                     'h2d_bytes_per_step': (lq_h.numel() + gt_h.numel()) * 4, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches, 'clocks': clocks,

@@ -77,3 +77,40 @@ def test_reference_arm_only_rank0_prints():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2'], env=env,
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def _lazy_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from collections import OrderedDict
+    from basicsr4rs_b200.utils.train_hooks import install_lazy_loss_log
+
+    class M:  # the two attributes BaseModel.reduce_loss_dict reads (base_model.py:385,393-394)
+        opt = {'dist': True, 'rank': rank, 'world_size': world}
+
+    m = install_lazy_loss_log(M())
+    logs = [m.reduce_loss_dict(OrderedDict(l_pix=torch.tensor(float(rank + 1 + it)), l_percep=torch.ones(3) * it))
+            for it in range(5)]  # five iterations, nothing read: no collective was issued
+    last = logs[-1]
+    q.put((rank, f"{last['l_pix']:.4e}", float(last['l_percep']), list(last.keys())))
+    dist.destroy_process_group()
+
+
+def test_lazy_loss_log_matches_reduce_loss_dict_world2():
+    """install_lazy_loss_log: same keys, the value read at print time is the cross-rank mean of base_model.py:376-401."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_lazy_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    for rank, s, percep, keys in got:
+        assert keys == ['l_pix', 'l_percep']
+        assert s == f'{(5 + 6) / 2:.4e}' and percep == 4.0  # iteration 4: ranks hold 5 and 6 -> mean 5.5
