@@ -48,6 +48,7 @@ struct AttnGeom {
   int B, H, W, nH, Cp, shift;
   float scale;
   int ws;  // window size (<= WS_MAX)
+  int ones;  // forward: head 0 writes 1.0 into its pad channel 31 (SRB200_ATTN_ONES)
 };
 
 // global element offset of token n of window (b, wy, wx) in an NHWC tensor with `ld` channels
@@ -286,6 +287,8 @@ __global__ void __launch_bounds__(128) window_attn_fwd_kernel(const __nv_bfloat1
         pack_bf16x2(o[nt][2] * inv[1], o[nt][3] * inv[1]);
   }
   __syncthreads();
+  if (g.ones && head == 0 && threadIdx.x < NTOK) sQ[threadIdx.x * QROW + 31] = __float2bfloat16(1.0f);
+  __syncthreads();
   store_tile(sQ, out, slots, g.Cp, head * HD);
 }
 
@@ -419,14 +422,15 @@ using namespace srb;
 
 // attention_tc.cu: the tcgen05 / TMEM / TMA kernels (window 8); SRB200_EINVAL = shape outside their domain
 int srb_window_attention_fwd_tc(const void* qkv_bf16, const float* rpb_table, void* out_bf16, float* stats, int B,
-                                int H, int W, int num_heads, int Ca, int shift, float scale, cudaStream_t stream);
+                                int H, int W, int num_heads, int Ca, int shift, float scale, int flags,
+                                cudaStream_t stream);
 int srb_window_attention_bwd_tc(const void* qkv_bf16, const void* gout_bf16, const float* rpb_table,
                                 const float* stats, void* gqkv_bf16, float* g_rpb_table, float* workspace, int B,
                                 int H, int W, int num_heads, int Ca, int shift, float scale, cudaStream_t stream);
 
 extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table,
                                            void* out_bf16, float* stats, int B, int H, int W, int num_heads,
-                                           int Cp, int window_size, int shift, float scale,
+                                           int Cp, int window_size, int shift, float scale, int flags,
                                            srb200_stream_t stream) {
   if (!qkv_bf16 || !rpb_table || !out_bf16) return SRB200_EINVAL;
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
@@ -434,10 +438,10 @@ extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rp
   if (window_size == 8 && SRB_ENV("SRB_ATTN_MMA_SYNC") == nullptr) {
     // window 8 (every classical-SR recipe): the tcgen05 kernel; other windows / odd head counts: mma.sync below
     const int rc_tc = srb_window_attention_fwd_tc(qkv_bf16, rpb_table, out_bf16, stats, B, H, W, num_heads, Cp, shift, scale,
-                                                  static_cast<cudaStream_t>(stream));
+                                                  flags, static_cast<cudaStream_t>(stream));
     if (rc_tc != SRB200_EINVAL) return rc_tc;
   }
-  AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
+  AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size, (flags & SRB200_ATTN_ONES) ? 1 : 0};
   const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
   if (wins * num_heads > 0x7fffffffLL || B > 65535) return SRB200_EINVAL;
   const dim3 grid(static_cast<unsigned>(wins * num_heads), 1, B);
@@ -464,7 +468,7 @@ extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gou
                                                   num_heads, Cp, shift, scale, static_cast<cudaStream_t>(stream));
     if (rc_tc != SRB200_EINVAL) return rc_tc;
   }
-  AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size};
+  AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size, 0};
   const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
   if (wins * num_heads > 0x7fffffffLL || B > 65535) return SRB200_EINVAL;
   const dim3 grid(static_cast<unsigned>(wins * num_heads), 1, B);

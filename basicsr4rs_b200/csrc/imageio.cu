@@ -20,10 +20,10 @@ struct PatchItem {          // mirror of srb200_patch_item
   int reserved;
 };
 
-// out[b][c][y][x] (fp32, CHW) = scale * crop_b[r'][s'][c'],  (r, s) = rot90 ? (x, y) : (y, x),
+// out[b][c][y][x] (fp32, CHW) = crop_b[r'][s'][c'] / div,  (r, s) = rot90 ? (x, y) : (y, x),
 // r' = vflip ? ph-1-r : r,  s' = hflip ? pw-1-s : s,  c' = bgr2rgb ? C-1-c : c (3-channel images only)
 __global__ void patch_from_u8_kernel(const PatchItem* __restrict__ items, int C, int ph, int pw, int bgr2rgb,
-                                     float scale, float* __restrict__ out) {
+                                     float div, float* __restrict__ out) {
   const PatchItem it = items[blockIdx.z];
   const bool rot = (it.flags & 4) != 0;
   const int oh = rot ? pw : ph, ow = rot ? ph : pw;
@@ -38,7 +38,7 @@ __global__ void patch_from_u8_kernel(const PatchItem* __restrict__ items, int C,
   const size_t plane = static_cast<size_t>(oh) * ow;
   for (int c = 0; c < C; ++c) {
     const int cs = (bgr2rgb && C == 3) ? 2 - c : c;
-    o[c * plane] = static_cast<float>(px[cs]) * scale;
+    o[c * plane] = __fdiv_rn(static_cast<float>(px[cs]), div);  // a true division: bit-equal to numpy's img / 255.
   }
 }
 
@@ -96,13 +96,14 @@ __global__ void tensor2img_u8_kernel(const float* __restrict__ src, uint8_t* __r
 
 using namespace srb;
 
-extern "C" int srb200_patch_from_u8(const void* items_dev, int n, int C, int ph, int pw, int bgr2rgb, float scale,
+extern "C" int srb200_patch_from_u8(const void* items_dev, int n, int C, int ph, int pw, int bgr2rgb, float div,
                                     float* out, srb200_stream_t stream) {
-  if (!items_dev || !out || n <= 0 || n > 65535 || C <= 0 || C > 16 || ph <= 0 || pw <= 0) return SRB200_EINVAL;
+  if (!items_dev || !out || n <= 0 || n > 65535 || C <= 0 || C > 16 || ph <= 0 || pw <= 0 || !(div > 0.0f))
+    return SRB200_EINVAL;
   const int m = ph > pw ? ph : pw;
   const dim3 block(32, 8), grid((m + 31) / 32, (m + 7) / 8, n);
   patch_from_u8_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const PatchItem*>(items_dev), C,
-                                                                             ph, pw, bgr2rgb, scale, out);
+                                                                             ph, pw, bgr2rgb, div, out);
   return launch_status();
 }
 

@@ -39,7 +39,7 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                                      float* __restrict__ rstd_out, long long T, int C, int Cp,
-                                     float eps) {
+                                     float eps, int ones_ch) {
   pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
   constexpr int TOK = (NVEC == 1) ? 2 : 1;  // tokens per warp iteration (independent loads in flight)
   const int lane = threadIdx.x & 31;
@@ -93,12 +93,104 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = (v[k][i][e] - mean) * rstd * gm[i][e] + bt[i][e];
+          // optional constant-one PAD channel: the weight-gradient GEMM of the Linear that consumes this tensor then
+          // delivers sum_tokens dY * 1 = that layer's bias gradient in column ones_ch for free
+          if (ones_ch >= 0 && (ones_ch >> 3) == vec) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (e == (ones_ch & 7)) o[e] = 1.0f;
+          }
           *(reinterpret_cast<uint4*>(y + (t0 + k) * Cp) + vec) = ln_pack(o);
         }
       }
       if (lane == 0) {
         if (mean_out) mean_out[t0 + k] = mean;
         if (rstd_out) rstd_out[t0 + k] = rstd;
+      }
+    }
+  }
+}
+
+
+// Forward, 8 lanes per token: a warp handles 4 tokens per iteration, every lane NV 16-byte vectors of its token
+// (vector index (lane & 7) + 8 i), so all 32 lanes move data whatever Cp is (the warp-per-token kernel above keeps
+// only Cp/8 of them busy: 24 of 32 at Cp = 192) and a reduction is 3 shuffles shared by four tokens instead of 5 per
+// token.  gamma / beta live in shared memory (read as float4 when a row is written).
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd8_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta,
+                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                                             float* __restrict__ rstd_out, long long T, int C, int Cp,
+                                                             float eps, int ones_ch) {
+  pdl_trigger();
+  extern __shared__ float s_gb[];  // gamma[Cp] | beta[Cp], zero beyond C
+  for (int i = threadIdx.x; i < Cp; i += blockDim.x) {
+    s_gb[i] = i < C ? __ldg(gamma + i) : 0.0f;
+    s_gb[Cp + i] = i < C ? __ldg(beta + i) : 0.0f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = Cp / 8;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  for (long long t = warp_global * 4 + slot; t < T + slot; t += nwarps * 4) {  // (whole warps stay in the shuffles)
+    const bool tv = t < T;
+    uint4 raw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vec = sub + 8 * i;
+      raw[i] = (tv && vec < nv) ? __ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float v[NV][8];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      ln_unpack(raw[i], v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];  // pad channels are zero by the layout invariant
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float mean = sum * inv_c;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        sq += ((sub + 8 * i) * 8 + e < C) ? d * d : 0.0f;
+      }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+    if (tv) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vec = sub + 8 * i;
+        if (vec < nv) {
+          const float4 g0 = *reinterpret_cast<const float4*>(s_gb + vec * 8), g1 = *reinterpret_cast<const float4*>(s_gb + vec * 8 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(s_gb + Cp + vec * 8),
+                       b1 = *reinterpret_cast<const float4*>(s_gb + Cp + vec * 8 + 4);
+          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gm[e] + bt[e];
+          if (ones_ch >= 0 && (ones_ch >> 3) == vec) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (e == (ones_ch & 7)) o[e] = 1.0f;
+          }
+          *(reinterpret_cast<uint4*>(y + t * Cp) + vec) = ln_pack(o);
+        }
+      }
+      if (sub == 0) {
+        if (mean_out) mean_out[t] = mean;
+        if (rstd_out) rstd_out[t] = rstd;
       }
     }
   }
@@ -236,9 +328,11 @@ using namespace srb;
 
 extern "C" int srb200_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta,
                                     void* y_bf16, float* mean, float* rstd, int64_t T, int C, int Cp,
-                                    float eps, srb200_stream_t stream) {
+                                    float eps, int ones_channel, srb200_stream_t stream) {
   if (!x_bf16 || !gamma || !beta || !y_bf16 || T <= 0 || C <= 0 || Cp < C || Cp % 8 != 0)
     return SRB200_EINVAL;
+  if (ones_channel >= 0 && (ones_channel < C || ones_channel >= Cp)) return SRB200_EINVAL;  // a PAD channel only
+  const int oc = ones_channel;
   if (Cp > 256 * LN_MAX_VEC) return SRB200_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int block = 256;
@@ -247,10 +341,24 @@ extern "C" int srb200_layernorm_fwd(const void* x_bf16, const float* gamma, cons
   if (blocks > cap) blocks = cap;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
   __nv_bfloat16* y = static_cast<__nv_bfloat16*>(y_bf16);
+  if (Cp <= 256 && SRB_ENV("SRB_LN_WARP_PER_TOKEN") == nullptr) {
+    // 8 lanes per token: 32 tokens per 256-thread block iteration, a few blocks per SM, grid-stride
+    long long b8 = (T + 31) / 32;
+    const long long cap8 = static_cast<long long>(num_sms()) * 6;
+    if (b8 > cap8) b8 = cap8;
+    const size_t smem = 2 * static_cast<size_t>(Cp) * sizeof(float);
+    const int g8 = static_cast<int>(b8);
+    const int nvl = (Cp / 8 + 7) / 8;
+    if (nvl == 1) layernorm_fwd8_kernel<1><<<g8, block, smem, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);
+    else if (nvl == 2) layernorm_fwd8_kernel<2><<<g8, block, smem, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);
+    else if (nvl == 3) layernorm_fwd8_kernel<3><<<g8, block, smem, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);
+    else layernorm_fwd8_kernel<4><<<g8, block, smem, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);
+    return launch_status();
+  }
   const int g = static_cast<int>(blocks);
-  if (Cp <= 256) layernorm_fwd_kernel<1><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps);
-  else if (Cp <= 512) layernorm_fwd_kernel<2><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps);
-  else layernorm_fwd_kernel<4><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps);
+  if (Cp <= 256) layernorm_fwd_kernel<1><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);
+  else if (Cp <= 512) layernorm_fwd_kernel<2><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);
+  else layernorm_fwd_kernel<4><<<g, block, 0, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);
   return launch_status();
 }
 

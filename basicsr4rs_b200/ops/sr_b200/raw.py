@@ -344,6 +344,14 @@ def finalize_grads(items):
             g = torch.empty(tuple(w_shape), dtype=torch.float32, device=acc.device)
             rows.append(dict(src=acc, dst=g, Co=w_shape[0], Ci=w_shape[1], taps=taps, Np=n_pad, Kp=k_pad,
                              perm_out=perm_out, perm_in=perm_in, alpha=alpha))
+        elif it[0] == 'bcol':
+            # a bias gradient that sits in COLUMN `col` of a weight-gradient accumulator [1, Np, Kp] (the layer's input
+            # carried a constant-one pad channel there, see srb200_layernorm_fwd): a strided [Np x 1] item
+            _, acc, col, n_bias, perm_out, alpha = it
+            _, n_pad, k_pad = acc.shape
+            g = torch.empty((n_bias,), dtype=torch.float32, device=acc.device)
+            rows.append(dict(src=acc[0, :, col:], dst=g, Co=n_bias, Ci=1, taps=1, Np=n_pad, Kp=k_pad, perm_out=perm_out,
+                             alpha=alpha))
         else:
             _, cs, n_bias, perm_out, alpha = it
             g = torch.empty((n_bias,), dtype=torch.float32, device=cs.device)
@@ -608,7 +616,7 @@ def patch_items(rows, device):
     return torch.from_numpy(tab.view(np.uint8).reshape(len(rows), -1).copy()).to(device, non_blocking=True)
 
 
-def patch_from_u8(images, tops, lefts, flags, ph, pw, bgr2rgb=True, scale=1.0 / 255.0):
+def patch_from_u8(images, tops, lefts, flags, ph, pw, bgr2rgb=True, div=255.0):
     """Batched crop + augment + img2tensor (transforms.py:28-96,166-225; img_util.py:9-37) on the GPU.
 
     ``images``: list of uint8 [H, W, C] CUDA tensors (rows contiguous); item i is the ``ph x pw`` crop of images[i] at
@@ -627,7 +635,7 @@ def patch_from_u8(images, tops, lefts, flags, ph, pw, bgr2rgb=True, scale=1.0 / 
     dev = images[0].device
     tab = patch_items(list(zip(images, tops, lefts, flags)), dev)
     out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=dev)
-    L.check(L.load().srb200_patch_from_u8(_ptr(tab), n, c, ph, pw, int(bgr2rgb), float(scale), _ptr(out), _stream()),
+    L.check(L.load().srb200_patch_from_u8(_ptr(tab), n, c, ph, pw, int(bgr2rgb), float(div), _ptr(out), _stream()),
             'patch_from_u8')
     return out
 

@@ -25,7 +25,9 @@ LN_EPS = 1e-5
 
 
 # ------------------------------------------------------------------ raw wrappers
-def layernorm_fwd(x, gamma, beta, c, eps=LN_EPS):
+def layernorm_fwd(x, gamma, beta, c, eps=LN_EPS, ones_channel=-1):
+    """``ones_channel``: a pad channel of the output set to 1.0 (the consuming Linear's bias gradient then falls out of
+    its weight-gradient GEMM, see include/srb200.h)."""
     _chk(x, 'x', torch.bfloat16)
     cp = x.shape[-1]
     t = x.numel() // cp
@@ -33,7 +35,8 @@ def layernorm_fwd(x, gamma, beta, c, eps=LN_EPS):
     mean = torch.empty((t,), dtype=torch.float32, device=x.device)
     rstd = torch.empty((t,), dtype=torch.float32, device=x.device)
     raw.probed('layernorm_fwd', (t, c, cp), lambda: L.check(L.load().srb200_layernorm_fwd(
-        _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), t, c, cp, float(eps), _stream()),
+        _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), t, c, cp, float(eps), int(ones_channel),
+        _stream()),
         'layernorm_fwd'))
     return y, mean, rstd
 
@@ -59,9 +62,10 @@ def scale_rows(g, alpha):
     return out
 
 
-def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=False):
+def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=False, ones=False):
     """Fused window attention.  ``want_stats``: also return the softmax statistics buffer (fp32
-    [windows, heads, ws*ws], opaque) that lets :func:`window_attention_bwd` skip the row maxima / sums."""
+    [windows, heads, ws*ws], opaque) that lets :func:`window_attention_bwd` skip the row maxima / sums.
+    ``ones``: output channel 31 (a pad lane of head 0, head_dim < 32) carries 1.0 (SRB200_ATTN_ONES)."""
     _chk(qkv, 'qkv', torch.bfloat16)
     _chk(table, 'rpb_table', torch.float32)
     b, h, w, c3 = qkv.shape
@@ -70,8 +74,8 @@ def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=Fal
     stats = torch.empty((b * (h // ws) * (w // ws), num_heads, ws * ws), dtype=torch.float32, device=qkv.device) \
         if want_stats else None
     raw.probed('window_attn_fwd', (b, h, w, num_heads, ws), lambda: L.check(L.load().srb200_window_attention_fwd(
-        _ptr(qkv), _ptr(table), _ptr(out), _ptr(stats), b, h, w, num_heads, ca, ws, shift, float(scale), _stream()),
-        'window_attention_fwd'))
+        _ptr(qkv), _ptr(table), _ptr(out), _ptr(stats), b, h, w, num_heads, ca, ws, shift, float(scale), int(bool(ones)),
+        _stream()), 'window_attention_fwd'))
     return (out, stats) if want_stats else out
 
 
@@ -157,17 +161,21 @@ class _SwinBlock(Function):
         p_o = head_perm(num_heads, hd, 1, dev)
         scale = hd**-0.5
 
-        xn, mean1, rstd1 = layernorm_fwd(x, n1w.detach(), n1b.detach(), c, eps)
+        # a constant-one pad channel in both LayerNorm outputs: the qkv / fc1 bias gradients then come out of the weight-
+        # gradient GEMMs (column `ones`), no column-sum passes in the backward
+        ones = cs - 1 if (c < cs and any(ctx.needs_input_grad)) else -1
+        xn, mean1, rstd1 = layernorm_fwd(x, n1w.detach(), n1b.detach(), c, eps, ones)
         qkv = raw.tapgemm(xn, _packed(qkv_w, 'fprop', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=3 * ca,
                           bias=_padded_bias(qkv_b, 3 * ca, p_qkv))
         want_stats = any(ctx.needs_input_grad)
-        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale, want_stats=want_stats)
+        o_ones = ones >= 0 and hd < HD_PAD  # same trick for proj: its bias gradient = column 31 of its weight gradient
+        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale, want_stats=want_stats, ones=o_ones)
         stats = None
         if want_stats:
             o, stats = o
         x1 = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
                          bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1)
-        xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c, eps)
+        xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c, eps, ones)
         h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=_padded_bias(fc1_b, ch),
                            act=L.ACT_GELU, want_aux=True, aux_grad=True)  # a = gelu'(fc1 out): all the backward needs
         x2 = raw.tapgemm(h, _packed(fc2_w, 'fprop', cs, ch), ksize=1, cout=cs, bias=_padded_bias(fc2_b, cs),
@@ -175,6 +183,8 @@ class _SwinBlock(Function):
         ctx.save_for_backward(x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table,
                               proj_w, proj_b, n2w, fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2, stats)
         ctx.cfg = (c, cs, ca, ch, hd, num_heads, ws, shift, scale)
+        ctx.ones = ones
+        ctx.o_ones = o_ones
         raw.stash_backward_scratch(ctx, _SwinBlock._scratch_floats(c, cs, ca, ch, table.numel()), dev)
         return x2
 
@@ -211,27 +221,37 @@ class _SwinBlock(Function):
         g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
         acc_fc2 = raw.wgrad(g2s, h, ksize=1)
         cs_fc2 = raw.colsum(g2s)
-        ga, cs_fc1 = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
-                                 mask_mode=L.MASK_MUL, want_colsum=True)  # column sums = fc1's bias gradient
+        ones = ctx.ones
+        if ones >= 0:  # fc1's bias gradient = column `ones` of acc_fc1 (xn2 carries a constant-one channel there)
+            ga = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
+                             mask_mode=L.MASK_MUL)
+            cs_fc1 = None
+        else:
+            ga, cs_fc1 = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
+                                     mask_mode=L.MASK_MUL, want_colsum=True)  # column sums = fc1's bias gradient
         acc_fc1 = raw.wgrad(ga, xn2, ksize=1)
         gxn2 = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True)
         gx1, g_n2w, g_n2b = layernorm_bwd(gxn2, x1, mean2, rstd2, n2w.detach(), c, gres=g2)
         # ---- attention branch
         g1s = scale_rows(gx1, alpha1) if alpha1 is not None else gx1
         acc_proj = raw.wgrad(g1s, o, ksize=1)
-        cs_proj = raw.colsum(g1s)
+        proj_b_item = ('bcol', acc_proj, HD_PAD - 1, proj_b.numel(), None, 1.0) if ctx.o_ones else \
+            ('b', raw.colsum(g1s), proj_b.numel(), None, 1.0)
         go = raw.tapgemm(g1s, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
         gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale, stats=stats)
         acc_qkv = raw.wgrad(gqkv, xn, ksize=1)
         gxn = raw.tapgemm(gqkv, _packed(qkv_w, 'dgrad', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=cs, flip=True)
         gx, g_n1w, g_n1b = layernorm_bwd(gxn, x, mean1, rstd1, n1w.detach(), c, gres=gx1)
         # ---- all eight parameter gradients of the four Linear layers leave through ONE launch
+        fc1_b_item = ('bcol', acc_fc1, ones, fc1_b.numel(), None, 1.0) if ones >= 0 else \
+            ('b', cs_fc1, fc1_b.numel(), None, 1.0)
         items = [('w', acc_fc2, fc2_w.shape, None, None, 1.0), ('b', cs_fc2, fc2_b.numel(), None, 1.0),
-                 ('w', acc_fc1, fc1_w.shape, None, None, 1.0), ('b', cs_fc1, fc1_b.numel(), None, 1.0),
-                 ('w', acc_proj, proj_w.shape, None, p_o, 1.0), ('b', cs_proj, proj_b.numel(), None, 1.0),
+                 ('w', acc_fc1, fc1_w.shape, None, None, 1.0), fc1_b_item,
+                 ('w', acc_proj, proj_w.shape, None, p_o, 1.0), proj_b_item,
                  ('w', acc_qkv, qkv_w.shape, p_qkv, None, 1.0)]
         if qkv_b is not None:
-            items.append(('b', raw.colsum(gqkv), qkv_b.numel(), p_qkv, 1.0))
+            items.append(('bcol', acc_qkv, ones, qkv_b.numel(), p_qkv, 1.0) if ones >= 0 else
+                         ('b', raw.colsum(gqkv), qkv_b.numel(), p_qkv, 1.0))
         grads = raw.finalize_grads(items)
         g_fc2_w, g_fc2_b, g_fc1_w, g_fc1_b, g_proj_w, g_proj_b, g_qkv_w = grads[:7]
         g_qkv_b = grads[7] if qkv_b is not None else None

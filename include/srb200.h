@@ -269,8 +269,11 @@ int srb200_ca_backward(const void* g_bf16, const void* t_bf16, const float* s, c
  * bwd: gx = LN'(gy) + gres (gres optional: fused add of the skip-path gradient);
  *      ggamma[c] += sum_t gy*xhat, gbeta[c] += sum_t gy (zero them first).                               */
 int srb200_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16,
-                         float* mean, float* rstd, int64_t T, int C, int Cp, float eps,
+                         float* mean, float* rstd, int64_t T, int C, int Cp, float eps, int ones_channel,
                          srb200_stream_t stream);
+/* ones_channel (-1 = none): a PAD channel (C <= ones_channel < Cp) of y that is set to 1.0 instead of 0.  The Linear
+ * that consumes y has zero weights there, and its weight-gradient GEMM acc[n][ones_channel] = sum_tokens dY[n] * 1 is
+ * that layer's bias gradient -- no separate column-sum pass.                                                        */
 int srb200_layernorm_bwd(const void* gy_bf16, const void* x_bf16, const float* mean, const float* rstd,
                          const float* gamma, const void* gres_bf16, void* gx_bf16, float* ggamma,
                          float* gbeta, int64_t T, int C, int Cp, srb200_stream_t stream);
@@ -292,9 +295,13 @@ int srb200_scale_rows(const void* g_bf16, const float* alpha, void* out_bf16, in
  * bwd also accumulates the bias-table gradient into g_rpb_table (zero it first).
  * workspace (optional, may be NULL): num_heads*4096 + 32 ZEROED floats the tcgen05 backward uses to merge the
  * bias-table gradient across CTAs; without stats or workspace the backward runs on the mma.sync path.     */
+/* flags: SRB200_ATTN_ONES -- write 1.0 instead of 0 into out channel 31 (a pad lane of head 0; needs head_dim < 32): the
+ * proj Linear that consumes `out` has zero weights there and its weight-gradient GEMM then yields its bias gradient in
+ * column 31 (same trick as srb200_layernorm_fwd's ones_channel).                                                   */
+#define SRB200_ATTN_ONES 1
 int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table, void* out_bf16, float* stats,
                                 int B, int H, int W, int num_heads, int Cp, int window_size, int shift,
-                                float scale, srb200_stream_t stream);
+                                float scale, int flags, srb200_stream_t stream);
 int srb200_window_attention_bwd(const void* qkv_bf16, const void* gout_bf16, const float* rpb_table,
                                 const float* stats, void* gqkv_bf16, float* g_rpb_table, float* workspace,
                                 int B, int H, int W, int num_heads, int Cp, int window_size, int shift,
@@ -331,9 +338,10 @@ typedef struct srb200_patch_item {
   int32_t flags;     /* bit 0 hflip, bit 1 vflip, bit 2 rot90 (transpose)       */
   int32_t reserved;
 } srb200_patch_item;
-/* out fp32 [n, C, oh, ow] = scale * augmented crop, (oh, ow) = rot90 ? (pw, ph) : (ph, pw); all n items share ph x pw.
+/* out fp32 [n, C, oh, ow] = augmented crop / div (255 for uint8 images: bit-equal to the reference's float32 img / 255.),
+ * (oh, ow) = rot90 ? (pw, ph) : (ph, pw); all n items share ph x pw.
  * bgr2rgb swaps channels 0 and 2 of 3-channel images.  items_dev: device array of n srb200_patch_item.            */
-int srb200_patch_from_u8(const void* items_dev, int n, int C, int ph, int pw, int bgr2rgb, float scale, float* out,
+int srb200_patch_from_u8(const void* items_dev, int n, int C, int ph, int pw, int bgr2rgb, float div, float* out,
                          srb200_stream_t stream);
 /* acc[c, y0+y, x0+x] += w(y, x) * sr_tile[c, y, x]: one super-resolved tile into the fp32 scene accumulator
  * [C, acc_h, acc_w] with separable linear-ramp weights over its overlaps with the neighbouring tiles (ov_* pixels,

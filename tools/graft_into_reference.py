@@ -46,7 +46,7 @@ REWIRE = [
     (r'^from \.\.\. import _lib as L$', 'from . import _lib as L'),
     # archs/graphed.py -> ops/sr_b200/graphed.py
     (r'^from \.\. import _lib as L$', 'from . import _lib as L'),
-    (r'^from \.\.ops\.sr_b200 import raw$', 'from . import raw'),
+    (r'^(\s*)from \.\.ops\.sr_b200 import raw$', r'\1from . import raw'),
     (r'^from \.\.ops\.sr_b200\.sr_b200 import (.*)$', r'from .sr_b200 import \1'),
     # arch files
     (r'^from \.\.ops import sr_b200 as ops$', 'from basicsr.ops import sr_b200 as ops'),
@@ -118,6 +118,8 @@ def graft(ref_root=None, out_dir=None):
     _copy_rewired(os.path.join(PKG, 'archs', 'graphed.py'), os.path.join(op, 'graphed.py'))
     _copy_rewired(os.path.join(PKG, 'utils', 'ema.py'), os.path.join(op, 'ema.py'))
     _copy_rewired(os.path.join(PKG, 'utils', 'tiling.py'), os.path.join(op, 'tiling.py'))
+    _copy_rewired(os.path.join(PKG, 'utils', 'data_gpu.py'), os.path.join(op, 'data_gpu.py'))
+    _copy_rewired(os.path.join(PKG, 'utils', 'train_hooks.py'), os.path.join(op, 'train_hooks.py'))
     _copy_rewired(os.path.join(PKG, 'archs', 'arch_util.py'), os.path.join(op, 'arch_blocks.py'))
     os.makedirs(os.path.join(op, 'src'), exist_ok=True)
     for name in os.listdir(os.path.join(PKG, 'csrc')):
