@@ -135,14 +135,25 @@ __global__ void __launch_bounds__(256) layernorm_fwd8_kernel(const __nv_bfloat16
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int nv = Cp / 8;
   const float inv_c = 1.0f / static_cast<float>(C);
-  for (long long t = warp_global * 4 + slot; t < T + slot; t += nwarps * 4) {  // (whole warps stay in the shuffles)
-    const bool tv = t < T;
-    uint4 raw[NV];
+  const float npad = static_cast<float>(NV * 64 - C);  // zero channels this token's 8 lanes sum over (incl. vec >= nv)
+  auto load = [&](long long t, uint4 (&raw)[NV]) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vec = sub + 8 * i;
-      raw[i] = (tv && vec < nv) ? __ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec) : make_uint4(0u, 0u, 0u, 0u);
+      raw[i] = (t < T && vec < nv) ? __ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec) : make_uint4(0u, 0u, 0u, 0u);
     }
+  };
+  // software pipeline: the loads of the next token group are in flight while this one is reduced and written (the
+  // plain loop was latency-bound: ncu showed 33 % warp occupancy and neither DRAM nor the issue slots saturated)
+  uint4 nxt[NV];
+  long long t = warp_global * 4 + slot;
+  load(t, nxt);
+  for (; t < T + slot; t += nwarps * 4) {  // (whole warps stay in the shuffles)
+    const bool tv = t < T;
+    uint4 raw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) raw[i] = nxt[i];
+    load(t + nwarps * 4, nxt);
     float v[NV][8];
     float sum = 0.0f;
 #pragma unroll
@@ -161,12 +172,13 @@ __global__ void __launch_bounds__(256) layernorm_fwd8_kernel(const __nv_bfloat16
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float d = v[i][e] - mean;
-        sq += ((sub + 8 * i) * 8 + e < C) ? d * d : 0.0f;
+        sq = fmaf(d, d, sq);
       }
     sq += __shfl_xor_sync(0xffffffffu, sq, 1);
     sq += __shfl_xor_sync(0xffffffffu, sq, 2);
     sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-    const float rstd = rsqrtf(sq * inv_c + eps);
+    // every zero pad channel added mean^2 to the sum: take them out instead of testing each element
+    const float rstd = rsqrtf(fmaxf(sq - npad * mean * mean, 0.0f) * inv_c + eps);
     if (tv) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd8_kernel(const __nv_bfloat16
           const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gm[e] + bt[e];
+          for (int e = 0; e < 8; ++e) o[e] = fmaf((v[i][e] - mean) * rstd, gm[e], bt[e]);  // (gamma = beta = 0 on pads)
           if (ones_ch >= 0 && (ones_ch >> 3) == vec) {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -214,7 +226,11 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int nv = Cp / 8;
+  // lm = 1 on real channels, 0 on pads.  gy is zero on pad channels (it is the data gradient of a Linear whose packed
+  // weights are zero there) and so is gamma, so the sums need no per-element test; only the stored gx is masked (ncu:
+  // this kernel is issue-bound, 63-66 % issue-slot use, and the three selects per element were a fifth of it)
   float ag[NVEC][8], ab[NVEC][8], gm[NVEC][8];
+  uint4 lm[NVEC];  // bit mask of the packed bf16 output vector: all ones on real channels, zero on pads
 #pragma unroll
   for (int i = 0; i < NVEC; ++i)
 #pragma unroll
@@ -224,6 +240,12 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
       const int c = (lane + 32 * i) * 8 + e;
       gm[i][e] = (c < C) ? __ldg(gamma + c) : 0.0f;
     }
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int c0 = (lane + 32 * i) * 8;
+    auto half_mask = [&](int c) { return (c < C ? 0x0000FFFFu : 0u) | (c + 1 < C ? 0xFFFF0000u : 0u); };
+    lm[i] = make_uint4(half_mask(c0), half_mask(c0 + 2), half_mask(c0 + 4), half_mask(c0 + 6));
+  }
   // TOK tokens per warp iteration: all their 16-byte loads (gy, x, gres) are issued before the first reduction, so
   // a warp keeps 3 * TOK * NVEC requests in flight instead of 2 (the one-token loop ran at 1.9 TB/s)
   for (long long t0 = warp_global * TOK; t0 < T; t0 += nwarps * TOK) {
@@ -261,14 +283,12 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
           ln_unpack(rx[k][i], xv);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const bool live = vec * 8 + e < C;
-            xh[i][e] = live ? (xv[e] - mean[k]) * rstd[k] : 0.0f;
-            const float gv = live ? g[i][e] : 0.0f;
-            ag[i][e] += gv * xh[i][e];
-            ab[i][e] += gv;
-            g[i][e] = gv * gm[i][e];  // d xhat
+            xh[i][e] = (xv[e] - mean[k]) * rstd[k];
+            ag[i][e] = fmaf(g[i][e], xh[i][e], ag[i][e]);
+            ab[i][e] += g[i][e];
+            g[i][e] *= gm[i][e];  // d xhat (zero on pads)
             s1 += g[i][e];
-            s2 += g[i][e] * xh[i][e];
+            s2 = fmaf(g[i][e], xh[i][e], s2);
           }
         }
       }
@@ -281,11 +301,13 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
           float o[8], r[8];
           ln_unpack(rr[k][i], r);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const bool live = vec * 8 + e < C;
-            o[e] = (live ? rstd[k] * (g[i][e] - s1 - xh[i][e] * s2) : 0.0f) + r[e];
-          }
-          *(reinterpret_cast<uint4*>(gx + t * Cp) + vec) = ln_pack(o);
+          for (int e = 0; e < 8; ++e) o[e] = fmaf(rstd[k], g[i][e] - s1 - xh[i][e] * s2, r[e]);
+          uint4 pk = ln_pack(o);
+          pk.x &= lm[i].x;
+          pk.y &= lm[i].y;
+          pk.z &= lm[i].z;
+          pk.w &= lm[i].w;
+          *(reinterpret_cast<uint4*>(gx + t * Cp) + vec) = pk;
         }
       }
     }
