@@ -34,8 +34,14 @@ class EDSR(ArchMixin, nn.Module):
                  rgb_mean=(0.4488, 0.4371, 0.4040),
                  cuda_graph=False,
                  graph_segments=4,
-                 graph_input_shape=None):
+                 graph_input_shape=None,
+                 compute_dtype='bf16'):
         super(EDSR, self).__init__()
+        if compute_dtype not in ('bf16', 'fp32'):
+            raise ValueError(f"compute_dtype must be 'bf16' or 'fp32', got {compute_dtype!r}")
+        # 'fp32': evaluation in fp32-class arithmetic (error-compensated bf16 operands, ops/sr_b200/fp32_mode.py) --
+        # north_star's "TF32/fp32 mode", max-abs <= 1e-4 against the reference; training always runs the bf16 path
+        self.compute_dtype = compute_dtype
         self.cuda_graph = cuda_graph
         self.graph_segments = max(1, int(graph_segments))
         self.graph_input_shape = graph_input_shape  # e.g. [16, 3, 48, 48]: capture on .to(device), before DDP
@@ -86,8 +92,28 @@ class EDSR(ArchMixin, nn.Module):
         segs.append(Segment(self._tail, [self.conv_after_body, self.upsample, self.conv_last]))
         return segs
 
+    def _forward_fp32(self, x):
+        """edsr_arch.py:50-61 in fp32 mode (no autograd): fp32 NHWC activations, split-bf16 tap-GEMMs."""
+        from ..ops.sr_b200 import fp32_mode as f32
+        from .. import _lib as L
+        mean = self._device_mean(x)
+        t = f32.image_to_nhwc32(x, mean, self.img_range, ops.pad64(x.shape[1]))
+        first = f32.conv(t, self.conv_first.weight, self.conv_first.bias)
+        res = first
+        for blk in self.body:
+            h = f32.conv(res, blk.conv1.weight, blk.conv1.bias, act=L.ACT_RELU)
+            res = f32.conv(h, blk.conv2.weight, blk.conv2.bias, alpha=blk.res_scale, residual32=res)
+        res = f32.conv(res, self.conv_after_body.weight, self.conv_after_body.bias, residual32=first)
+        mods = list(self.upsample)
+        for conv, shuffle in zip(mods[0::2], mods[1::2]):
+            res = f32.conv(res, conv.weight, conv.bias, shuffle_r=shuffle.upscale_factor)
+        return f32.conv_to_image(res, self.conv_last.weight, self.conv_last.bias, 1.0 / self.img_range, mean)
+
     def _forward(self, x):
         require_cuda(x, 'EDSR')
+        if self.compute_dtype == 'fp32' and not torch.is_grad_enabled():
+            out = self._forward_fp32(x)
+            return out if out.dtype == x.dtype else out.to(x.dtype)
         if self.cuda_graph and self.training and torch.is_grad_enabled():
             graphs = GRAPHS.get(self)
             if graphs is None:

@@ -97,8 +97,12 @@ class RCAN(ArchMixin, nn.Module):
                  rgb_mean=(0.4488, 0.4371, 0.4040),
                  cuda_graph=False,
                  graph_segments=5,
-                 graph_input_shape=None):
+                 graph_input_shape=None,
+                 compute_dtype='bf16'):
         super(RCAN, self).__init__()
+        if compute_dtype not in ('bf16', 'fp32'):
+            raise ValueError(f"compute_dtype must be 'bf16' or 'fp32', got {compute_dtype!r}")
+        self.compute_dtype = compute_dtype  # 'fp32': evaluation in fp32-class arithmetic (ops/sr_b200/fp32_mode.py)
         self.cuda_graph = cuda_graph          # optional: replay training fwd/bwd from CUDA graphs (archs/graphed.py)
         self.graph_segments = graph_segments
         self.graph_input_shape = graph_input_shape
@@ -160,8 +164,36 @@ class RCAN(ArchMixin, nn.Module):
         n_rcab = sum(len(grp.residual_group) for grp in groups)
         return n_rcab * (batch * self.conv_first.weight.shape[0] + 8)
 
+    def _forward_fp32(self, x):
+        """rcan_arch.py:124-135 in fp32 mode (no autograd): split-bf16 tap-GEMMs with fp32 accumulation for the 411 convs;
+        the channel attention (a [B, C] pool, two tiny FCs, one multiply-add pass) in plain fp32."""
+        from ..ops.sr_b200 import fp32_mode as f32
+        from .. import _lib as L
+        mean = self._device_mean(x)
+        t = f32.image_to_nhwc32(x, mean, self.img_range, ops.pad64(x.shape[1]))
+        first = f32.conv(t, self.conv_first.weight, self.conv_first.bias)
+        res = first
+        for group in self.body:
+            r = res
+            for blk in group.residual_group:
+                c1, c2, ca = blk.rcab[0], blk.rcab[2], blk.rcab[3]
+                u = f32.conv(f32.conv(r, c1.weight, c1.bias, act=L.ACT_RELU), c2.weight, c2.bias)
+                wa1, ba1, wa2, ba2 = ca.fc_params()
+                _, s = ops.raw.ca_fc(u.mean(dim=(1, 2)).contiguous(), wa1.detach().contiguous(), ba1.detach(),
+                                     wa2.detach().contiguous(), ba2.detach())
+                r = r + blk.res_scale * u * s.view(s.shape[0], 1, 1, -1)
+            res = f32.conv(r, group.conv.weight, group.conv.bias, residual32=res)
+        res = f32.conv(res, self.conv_after_body.weight, self.conv_after_body.bias, residual32=first)
+        mods = list(self.upsample)
+        for conv, shuffle in zip(mods[0::2], mods[1::2]):
+            res = f32.conv(res, conv.weight, conv.bias, shuffle_r=shuffle.upscale_factor)
+        return f32.conv_to_image(res, self.conv_last.weight, self.conv_last.bias, 1.0 / self.img_range, mean)
+
     def _forward(self, x):
         require_cuda(x, 'RCAN')
+        if self.compute_dtype == 'fp32' and not torch.is_grad_enabled():
+            out = self._forward_fp32(x)
+            return out if out.dtype == x.dtype else out.to(x.dtype)
         if self.cuda_graph and self.training and torch.is_grad_enabled():
             self._device_mean(x)
             nseg = len(split_even(list(self.body), self.graph_segments)) + 1

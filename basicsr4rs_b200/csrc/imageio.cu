@@ -5,6 +5,7 @@
 //                     that already live in device memory -- also the uint8 tile entry of the tiled-inference driver
 //   tile_blend_add    linear-ramp overlap blending of super-resolved tiles into an fp32 scene accumulator
 //   tensor2img_u8     tensor2img of utils/img_util.py:40-96: clamp, normalise, x255, round-half-even, uint8, RGB->BGR, HWC
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -131,4 +132,47 @@ extern "C" int srb200_tensor2img_u8(const float* src_chw, void* dst_hwc_u8, int 
   tensor2img_u8_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src_chw, static_cast<uint8_t*>(dst_hwc_u8), C, H, W, lo, 1.0f / (hi - lo), rgb2bgr);
   return launch_status();
+}
+
+// ------------------------------------------------------------------ fp32 mode: error-compensated bf16 operands
+// x (fp32) = hi + lo + O(2^-17 |x|) with hi = bf16(x), lo = bf16(x - hi).  The tap-GEMM then sees the activation
+// [hi | lo | hi] (3 * C channels) against the weight [w_hi ; w_hi ; w_lo]: sum_k (x_hi w_hi + x_lo w_hi + x_hi w_lo),
+// every product exact in the fp32 TMEM accumulator -- fp32-class results (relative 2^-16 per product, 32x tighter than
+// TF32's 2^-11) from the bf16 tensor-core kernels (north_star's "TF32/fp32 mode", BASELINE.md section 4: <= 1e-4).
+namespace srb {
+__global__ void split3_kernel(const float4* __restrict__ x, uint4* __restrict__ out, size_t nvec8, int c8) {
+  // one thread: 8 consecutive channels of one pixel; out row = [hi (C) | lo (C) | hi (C)]
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nvec8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * e] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1));
+      hi[e] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      lo[e] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+    const size_t pix = i / c8, v8 = i - pix * c8;
+    uint4* row = out + pix * (3 * static_cast<size_t>(c8));
+    const uint4 h = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    row[v8] = h;
+    row[c8 + v8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    row[2 * c8 + v8] = h;
+  }
+}
+}  // namespace srb
+
+extern "C" int srb200_split3_bf16(const float* x_f32, void* out_bf16, int64_t rows, int C, srb200_stream_t stream) {
+  if (!x_f32 || !out_bf16 || rows <= 0 || C <= 0 || C % 8 != 0) return SRB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(x_f32) | reinterpret_cast<uintptr_t>(out_bf16)) & 15u) return SRB200_EINVAL;
+  const size_t nvec8 = static_cast<size_t>(rows) * (C / 8);
+  size_t blocks = (nvec8 + 255) / 256;
+  const size_t cap = static_cast<size_t>(srb::num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  srb::split3_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x_f32), static_cast<uint4*>(out_bf16), nvec8, C / 8);
+  return srb::launch_status();
 }

@@ -1,0 +1,100 @@
+"""fp32 mode of the conv trunk (north_star: "max-abs 1e-4 in the TF32/fp32 mode").
+
+The reference computes in fp32 (cuDNN, TF32 off by default).  The B200 path keeps ONE set of kernels -- the bf16
+tcgen05 tap-GEMM with fp32 TMEM accumulators -- and reaches fp32-class results by error compensation instead of a
+second ``kind::tf32`` kernel family: every fp32 operand is split into two bf16 numbers, ``x = hi + lo``
+(``srb200_split3_bf16``), and the GEMM runs over the concatenated reduction ``[x_hi | x_lo | x_hi] . [w_hi ; w_hi ; w_lo]``:
+three exact bf16 products per term, accumulated in fp32.  Relative error 2^-16 per product against TF32's 2^-11, at
+three times the tensor-core work -- an inference / validation mode (``compute_dtype='fp32'`` on the arch), not the
+training path.  Activations travel between layers as fp32 NHWC (the tap-GEMM's ``out_f32`` twin); bias, ReLU,
+``res_scale`` and skip adds are the same fp32 epilogue as in the bf16 path.
+"""
+import torch
+
+from ... import _lib as L
+from . import raw
+from .raw import _ptr, _stream
+from .sr_b200 import pad64, shuffle_perm
+
+
+def split3(x32):
+    """fp32 NHWC [B,H,W,C] -> bf16 [B,H,W,3C] = [hi | lo | hi]."""
+    raw._chk(x32, 'x32', torch.float32)
+    b, h, w, c = x32.shape
+    out = torch.empty((b, h, w, 3 * c), dtype=torch.bfloat16, device=x32.device)
+    L.check(L.load().srb200_split3_bf16(_ptr(x32), _ptr(out), b * h * w, c, _stream()), 'split3_bf16')
+    return out
+
+
+_wcache = {}
+
+
+def split_weight(weight, n_pad, k_pad, perm_out=None):
+    """bf16 [taps, n_pad, 3*k_pad] = [w_hi | w_hi | w_lo] along K of an fp32 conv / linear weight (cached per version)."""
+    key = (id(weight), weight.data_ptr(), weight._version, n_pad, k_pad, id(perm_out))
+    hit = _wcache.get(id(weight))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    w = weight.detach().float().contiguous()
+    hi = w.to(torch.bfloat16).float()
+    lo = (w - hi).contiguous()
+    p_hi = raw.pack_weight(hi.contiguous(), n_pad, k_pad, perm_out=perm_out)
+    p_lo = raw.pack_weight(lo, n_pad, k_pad, perm_out=perm_out)
+    packed = torch.cat([p_hi, p_hi, p_lo], dim=2).contiguous()
+    _wcache[id(weight)] = (key, packed)
+    return packed
+
+
+def _bias(bias, n_pad, perm_out=None):
+    if bias is None:
+        return None
+    b = torch.zeros((n_pad,), dtype=torch.float32, device=bias.device)
+    if perm_out is None:
+        b[:bias.numel()] = bias.detach().float()
+    else:
+        valid = perm_out >= 0
+        b[valid] = bias.detach().float()[perm_out[valid].long()]
+    return b
+
+
+def conv(x32, weight, bias=None, act=L.ACT_NONE, alpha=1.0, residual32=None, shuffle_r=1):
+    """fp32-mode conv3x3 / conv1x1 on fp32 NHWC (channels padded to 64): returns the fp32 NHWC result."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    k_pad = x32.shape[-1]
+    assert k_pad == pad64(cin)
+    ksize = weight.shape[-1] if weight.dim() == 4 else 1
+    if shuffle_r > 1:
+        perm = shuffle_perm(cout // (shuffle_r * shuffle_r), shuffle_r, x32.device)
+        n_pad = cout
+    else:
+        perm, n_pad = None, pad64(cout)
+    wp = split_weight(weight, n_pad, k_pad, perm)
+    _, y32 = raw.tapgemm(split3(x32), wp, ksize=ksize, cout=n_pad, bias=_bias(bias, n_pad, perm), act=act, alpha=alpha,
+                         residual_f32=residual32, want_f32=True, out_mode=L.OUT_SHUFFLE if shuffle_r > 1 else L.OUT_NHWC,
+                         out_r=shuffle_r)
+    return y32
+
+
+def image_to_nhwc32(x, shift, scale, c_pad=64):
+    """NCHW float image -> fp32 NHWC padded to ``c_pad`` channels, ``(x - shift) * scale`` (edsr_arch.py:53)."""
+    x = x.float()
+    if shift is not None:
+        x = x - shift.view(1, -1, 1, 1)
+    t = (x * scale).permute(0, 2, 3, 1)
+    return torch.nn.functional.pad(t, (0, c_pad - t.shape[-1])).contiguous()
+
+
+def conv_to_image(x32, weight, bias, out_scale, out_shift):
+    """conv_last (3x3, <= 7 output bands) + ``x * out_scale + out_shift`` + NCHW exit, fp32 mode: the same
+    fold-the-taps-into-channels trick as the bf16 path (one 1x1 GEMM + ``srb200_tap_stencil``)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    k_pad = x32.shape[-1]
+    tp = pad64(9 * cout)
+    wf = torch.zeros((tp, k_pad, 1, 1), dtype=torch.float32, device=weight.device)
+    wf[:9 * cout, :cin, 0, 0] = weight.detach().float().permute(2, 3, 0, 1).reshape(9 * cout, cin)
+    hi = wf.to(torch.bfloat16).float()
+    wp = torch.cat([raw.pack_weight(hi.contiguous(), tp, k_pad), raw.pack_weight(hi.contiguous(), tp, k_pad),
+                    raw.pack_weight((wf - hi).contiguous(), tp, k_pad)], dim=2).contiguous()
+    _, t32 = raw.tapgemm(split3(x32), wp, ksize=1, cout=tp, want_f32=True)
+    return raw.tap_stencil(t32, cout, bias=bias.detach().float() if bias is not None else None, shift=out_shift,
+                           scale=out_scale)

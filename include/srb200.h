@@ -356,6 +356,12 @@ int srb200_tile_blend_add(const float* sr_tile, float* acc, int C, int th, int t
 int srb200_tensor2img_u8(const float* src_chw, void* dst_hwc_u8, int C, int H, int W, float lo, float hi, int rgb2bgr,
                          srb200_stream_t stream);
 
+/* fp32 mode (north_star: "1e-4 in the TF32/fp32 mode"): x fp32 [rows, C] -> bf16 [rows, 3*C] = [hi | lo | hi] with
+ * hi = bf16(x), lo = bf16(x - hi).  Fed to srb200_tapgemm with Cin = 3*C against weights packed as
+ * [w_hi ; w_hi ; w_lo] along K, the fp32 accumulator receives x_hi w_hi + x_lo w_hi + x_hi w_lo: fp32-class results
+ * (2^-16 relative per product) on the bf16 tensor-core kernel.  C % 8 == 0.                                        */
+int srb200_split3_bf16(const float* x_f32, void* out_bf16, int64_t rows, int C, srb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
