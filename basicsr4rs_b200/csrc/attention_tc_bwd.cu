@@ -13,8 +13,8 @@
 //             rows of head h keep columns [32h, 32h+32) of the 64-wide results (N = 64, K = 64).
 //   epilogue: dQ | dK | dV -> bf16 -> staging -> TMA stores (window_reverse + roll).
 //   bias-table gradient: every thread owns fixed (query, 16 keys) cells, so it accumulates its dS in REGISTERS over all
-//             windows of the CTA; the CTA walks its work pair-of-heads-outermost, and at each change of pair the
-//             accumulators are binned through shared memory into <= 450 global atomics.
+//             windows of the CTA (a CTA works on ONE pair of heads); at the end they go to a global [head][query][key]
+//             sheet with vector reductions and the last CTA to finish bins the sheet into the [225][heads] table.
 // TMEM: S | dP of ONE head (256 columns) + dQ | dK | dV of ONE window (192 columns): phase A of the next head / stage
 // overlaps phase B and the thread work.  Warp roles (704 threads): warps 0-15 = P / dS (lane quarter = warp & 3, column
 // chunk = warp >> 2), 16-19 = epilogue, 20 = TMA producer, 21 = MMA issuer.
@@ -114,10 +114,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
+  // A CTA works on ONE pair of heads for a strided subset of the window units: its bias-table gradient accumulators
+  // then live in registers for the whole kernel and leave once, at the end (an earlier version walked all pairs per CTA
+  // and paid ~14k cycles of reductions + table reload at every change of pair).
   const int n_pairs = p.nH >> 1;
-  const int my_units = (p.n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                       static_cast<int>(gridDim.x);
-  const int n_iter = my_units * n_pairs;  // stage it = (pair it / my_units, unit blockIdx.x + (it % my_units) * gridDim.x)
+  const int my_pair = static_cast<int>(blockIdx.x) % n_pairs;
+  const int cta_in_pair = static_cast<int>(blockIdx.x) / n_pairs;
+  const int ctas_of_pair = (static_cast<int>(gridDim.x) - my_pair + n_pairs - 1) / n_pairs;
+  const int my_units = cta_in_pair < p.n_units ? (p.n_units - cta_in_pair + ctas_of_pair - 1) / ctas_of_pair : 0;
+  const int n_iter = my_units;  // stage it = unit cta_in_pair + it * ctas_of_pair, pair my_pair
   auto window_of = [&](int unit, int w, int& b, int& wy, int& wx) -> bool {
     int idx = 2 * unit + w;
     const bool real = idx < p.n_windows;
@@ -145,10 +150,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
   if (warp == 20) {
     // ===================================================== TMA producer: lane = (window, tensor q|k|v|dO, box)
     const int w = lane >> 4, t = (lane >> 2) & 3, quad = lane & 3;
-    int u = 0, pair = 0;
+    const int pair = my_pair;
     for (int it = 0; it < n_iter; ++it) {
       const int st = it & 1;
-      const int unit = static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x);
+      const int unit = cta_in_pair + it * ctas_of_pair;
       stamp(0, it, 0);
       mbar_wait(empty_bar(st), ((it >> 1) & 1u) ^ 1u);
       stamp(0, it, 1);
@@ -169,10 +174,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
       }
       __syncwarp();
       stamp(0, it, 2);
-      if (++u == my_units) {
-        u = 0;
-        ++pair;
-      }
     }
   } else if (warp == 21) {
     // ===================================================== MMA issuer
@@ -297,11 +298,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
       }
     };
 
-    load_table(0);
+    const int pair = my_pair;
+    load_table(pair);
     asm volatile("bar.sync 6, 512;" ::: "memory");
-    int u = 0, pair = 0;
     for (int it = 0; it < n_iter; ++it) {
-      const int unit = static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x);
+      const int unit = cta_in_pair + it * ctas_of_pair;
       int b, wy, wx;
       const bool real = window_of(unit, half, b, wy, wx);
       const int win = real ? 2 * unit + half : 2 * unit;
@@ -393,15 +394,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(tfull_bar);
-      if (++u == my_units) {  // last unit of this pair: its bias-table gradient leaves, the next pair's table comes in
-        u = 0;
-        flush(pair);
-        ++pair;
-        asm volatile("bar.sync 6, 512;" ::: "memory");  // every P/dS warp is done with the old table
-        if (pair < n_pairs) load_table(pair);
-        asm volatile("bar.sync 6, 512;" ::: "memory");
-      }
     }
+    if (n_iter > 0) flush(pair);
   } else if (warp < 20) {
     // ===================================================== epilogue: warps 16..19 (lane quarter = warp & 3)
     const int L = (warp & 3) * 32 + lane;
@@ -409,9 +403,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const bool store_warp = warp == 16;
     const int st_t = lane >> 2, st_quad = lane & 3;  // store lane -> (tensor dq|dk|dv, box)
-    int u = 0, pair = 0;
+    const int pair = my_pair;
     for (int j = 0; j < n_iter; ++j) {
-      const int unit = static_cast<int>(blockIdx.x) + u * static_cast<int>(gridDim.x);
+      const int unit = cta_in_pair + j * ctas_of_pair;
 #pragma unroll 1
       for (int w = 0; w < 2; ++w) {
         const int cw = 2 * j + w;
@@ -458,10 +452,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
           tma_store_commit();
         }
         if (warp == 16) stamp(3, j, 3 * w + 2);
-      }
-      if (++u == my_units) {
-        u = 0;
-        ++pair;
       }
     }
     if (store_warp && lane < 12) tma_store_wait_all<0>();
@@ -559,6 +549,7 @@ int srb_window_attention_bwd_tc(const void* qkv_bf16, const void* gout_bf16, con
   p.trace = g_attn_bwd_trace.load(std::memory_order_relaxed);
   static PerDeviceOnce configured;
   if (configured.ensure(window_attn_bwd_tc_kernel, kBwdSmem) != SRB200_OK) return SRB200_ELAUNCH;
-  const int grid = p.n_units < num_sms() ? p.n_units : num_sms();
+  const long long work = static_cast<long long>(p.n_units) * (num_heads / 2);
+  const int grid = work < num_sms() ? static_cast<int>(work) : num_sms();
   return launch_ex(window_attn_bwd_tc_kernel, grid, kBwdThreads, kBwdSmem, stream, 1, p);
 }

@@ -79,10 +79,9 @@ def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=Fal
     return (out, stats) if want_stats else out
 
 
-# The tcgen05 backward (attention_tc_bwd.cu) is parity-green but, at 95-110 us for B16 x 64x64, not yet ahead of the
-# mma.sync kernel (118 us): its stage pipeline still serialises phase B behind the thread phase.
-# It runs when asked for (tests, SRB_ATTN_BWD_TC=1); the default backward stays on the faster-to-date kernel.
-ATTN_BWD_TC = os.environ.get('SRB_ATTN_BWD_TC', '0') == '1'
+# Window 8 with the forward's statistics buffer: the tcgen05 backward (attention_tc_bwd.cu, 95 us at B16 x 64x64 against
+# 118 us for the mma.sync kernel); SRB_ATTN_BWD_TC=0 forces the mma.sync kernel (tests run both).
+ATTN_BWD_TC = os.environ.get('SRB_ATTN_BWD_TC', '1') == '1'
 
 
 def window_attention_bwd(qkv, gout, table, num_heads, ws, shift, scale, stats=None, use_tc=None):

@@ -102,8 +102,8 @@ def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift, ws):
     go = go.reshape(b, h, w, ca).to(cuda).to(torch.bfloat16)
     ref.backward(go.reshape(b, h, w, nh, 32)[..., :hd].float())
     # with the forward's statistics buffer (window 8: the tcgen05 backward) and without it (mma.sync, recomputes them)
-    for st in (stats, None):
-        gqkv, gtable = so.window_attention_bwd(qkv, go, table, nh, ws, shift, hd**-0.5, stats=st, use_tc=True)
+    for st, tc in ((stats, True), (stats, False), (None, True)):
+        gqkv, gtable = so.window_attention_bwd(qkv, go, table, nh, ws, shift, hd**-0.5, stats=st, use_tc=tc)
         want = qr.grad
         assert torch.count_nonzero(gqkv.reshape(b, h, w, 3, nh, 32)[..., hd:]) == 0
         rel = ((gqkv.float() - want).norm() / want.norm()).item()

@@ -51,6 +51,8 @@ REWIRE = [
     # arch files
     (r'^from \.\.ops import sr_b200 as ops$', 'from basicsr.ops import sr_b200 as ops'),
     (r'^from \.\.ops\.sr_b200 import swin_ops$', 'from basicsr.ops.sr_b200 import swin_ops'),
+    (r'^(\s+)from \.\.ops\.sr_b200 import (\w+ as \w+)$', r'\1from basicsr.ops.sr_b200 import \2'),
+    (r'^(\s+)from \.\. import _lib as L$', r'\1from basicsr.ops.sr_b200 import _lib as L'),
     (r'^from \.\.utils\.registry import ARCH_REGISTRY$', 'from basicsr.utils.registry import ARCH_REGISTRY'),
     (r'^from \.graphed import (.*)$', r'from basicsr.ops.sr_b200.graphed import \1'),
     (r'^from \.arch_util import (.*)$', r'from basicsr.archs.arch_util import \1'),
@@ -64,7 +66,7 @@ ARCH_UTIL_TAIL = '''
 # srb200 graft (tools/graft_into_reference.py): the hot-path blocks now compute on the B200 kernels.  Same names,
 # constructor arguments, parameter names and init order; everything above that is not rebound stays the reference's.
 from basicsr.ops.sr_b200.arch_blocks import (ResidualBlockNoBN, Upsample, default_init_weights, make_layer,  # noqa: E402,F401,F811
-                                             nchw_roundtrip, require_cuda)
+                                             _NHWCToImage, nchw_roundtrip, require_cuda)
 '''
 
 
@@ -112,7 +114,7 @@ def graft(ref_root=None, out_dir=None):
     with open(os.path.join(dst, 'version.py'), 'w') as f:
         f.write("__version__ = '1.4.2+srb200'\n__gitsha__ = 'graft'\nversion_info = (1, 4, 2)\n")
     op = os.path.join(dst, 'ops', 'sr_b200')
-    for name in ('__init__.py', 'raw.py', 'sr_b200.py', 'swin_ops.py'):
+    for name in ('__init__.py', 'raw.py', 'sr_b200.py', 'swin_ops.py', 'fp32_mode.py'):
         _copy_rewired(os.path.join(PKG, 'ops', 'sr_b200', name), os.path.join(op, name))
     _copy_rewired(os.path.join(PKG, '_lib.py'), os.path.join(op, '_lib.py'))
     _copy_rewired(os.path.join(PKG, 'archs', 'graphed.py'), os.path.join(op, 'graphed.py'))
@@ -130,7 +132,7 @@ def graft(ref_root=None, out_dir=None):
     lib = os.path.join(PKG, 'csrc', 'libsrb200.so')
     if os.path.exists(lib):  # prebuilt (BASICSR_EXT=True path); BASICSR_JIT=True builds it on first import otherwise
         shutil.copyfile(lib, os.path.join(op, 'libsrb200.so'))
-    for name in ('edsr_arch.py', 'rcan_arch.py', 'swinir_arch.py'):
+    for name in ('edsr_arch.py', 'rcan_arch.py', 'swinir_arch.py', 'resshift_swin.py'):
         _copy_rewired(os.path.join(PKG, 'archs', name), os.path.join(dst, 'archs', name))
     with open(os.path.join(dst, 'archs', 'arch_util.py'), 'a') as f:
         f.write(ARCH_UTIL_TAIL)
