@@ -16,8 +16,8 @@
 //             windows of the CTA (a CTA works on ONE pair of heads); at the end they go to a global [head][query][key]
 //             sheet with vector reductions and the last CTA to finish bins the sheet into the [225][heads] table.
 // TMEM: S | dP of ONE head (256 columns) + dQ | dK | dV of ONE window (192 columns): phase A of the next head / stage
-// overlaps phase B and the thread work.  Warp roles (704 threads): warps 0-15 = P / dS (lane quarter = warp & 3, column
-// chunk = warp >> 2), 16-19 = epilogue, 20 = TMA producer, 21 = MMA issuer.
+// overlaps phase B and the thread work.  Warp roles (800 threads): warps 0-15 = P / dS (lane quarter = warp & 3, column
+// chunk = warp >> 2), 16-19 = epilogue, 21 = MMA issuer, 20 / 22 / 23 / 24 = TMA producers (one tensor each).
 // Algorithmic traffic: read q, k, v, dO + write dq, dk, dv = 7 * T * C * 2 bytes.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -45,7 +45,7 @@ struct AttnBwdParams {
   unsigned long long* trace;
 };
 
-constexpr int kBwdThreads = 704;
+constexpr int kBwdThreads = 800;  // 16 P/dS warps, 4 epilogue warps, warp 21 = MMA issuer, warps 20, 22, 23, 24 = TMA producers
 constexpr int kBwdStage = 4 * kSlab;                     // q, k, v, dO
 constexpr int kBOffLoad = 0;                             // 2 stages
 constexpr int kBOffTile = kBOffLoad + 2 * kBwdStage;     // P tiles (2 windows) | dS tiles (2 windows)
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
   }
   if (warp == 21 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 4);  // four producer warps, one tensor (q | k | v | dO) each
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(afull_bar, 1);
@@ -147,19 +147,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
     }
   };
 
-  if (warp == 20) {
-    // ===================================================== TMA producer: lane = (window, tensor q|k|v|dO, box)
-    const int w = lane >> 4, t = (lane >> 2) & 3, quad = lane & 3;
+  if (warp == 20 || warp >= 22) {
+    // ===================================================== TMA producers: one warp per tensor (q | k | v | dO), lane =
+    // (window, box).  A TMA instruction costs its issuing warp ~150 cycles and a warp's lanes issue one after another
+    // (16 loads from one warp took 2.4k cycles on the critical path slot-free -> data-landed); four warps issue in parallel.
+    const int t = warp == 20 ? 0 : warp - 21;
+    const int w = lane >> 2, quad = lane & 3;
     const int pair = my_pair;
     for (int it = 0; it < n_iter; ++it) {
       const int st = it & 1;
       const int unit = cta_in_pair + it * ctas_of_pair;
-      stamp(0, it, 0);
+      if (t == 0) stamp(0, it, 0);
       mbar_wait(empty_bar(st), ((it >> 1) & 1u) ^ 1u);
-      stamp(0, it, 1);
-      if (lane == 0) mbar_expect_tx(full_bar(st), kBwdStage);
+      if (t == 0) stamp(0, it, 1);
+      if (lane == 0) mbar_expect_tx(full_bar(st), kSlab);
       __syncwarp();
-      {
+      if (lane < 8) {
         int b, wy, wx, x, y;
         window_of(unit, w, b, wy, wx);
         const bool quadrants = is_quad(wy, wx);
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
         }
       }
       __syncwarp();
-      stamp(0, it, 2);
+      if (t == 0) stamp(0, it, 2);
     }
   } else if (warp == 21) {
     // ===================================================== MMA issuer
