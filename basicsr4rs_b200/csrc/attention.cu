@@ -462,7 +462,7 @@ extern "C" int srb200_window_attention_bwd(const void* qkv_bf16, const void* gou
   if (!qkv_bf16 || !gout_bf16 || !rpb_table || !gqkv_bf16 || !g_rpb_table) return SRB200_EINVAL;
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
-  if (window_size == 8 && stats != nullptr && workspace != nullptr && SRB_ENV("SRB_ATTN_MMA_SYNC") == nullptr &&
+  if (window_size == 8 && stats != nullptr && SRB_ENV("SRB_ATTN_MMA_SYNC") == nullptr &&
       SRB_ENV("SRB_ATTN_BWD_MMA_SYNC") == nullptr) {
     const int rc_tc = srb_window_attention_bwd_tc(qkv_bf16, gout_bf16, rpb_table, stats, gqkv_bf16, g_rpb_table, workspace, B, H, W,
                                                   num_heads, Cp, shift, scale, static_cast<cudaStream_t>(stream));

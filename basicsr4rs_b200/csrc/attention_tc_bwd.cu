@@ -13,8 +13,8 @@
 //             rows of head h keep columns [32h, 32h+32) of the 64-wide results (N = 64, K = 64).
 //   epilogue: dQ | dK | dV -> bf16 -> staging -> TMA stores (window_reverse + roll).
 //   bias-table gradient: every thread owns fixed (query, 16 keys) cells, so it accumulates its dS in REGISTERS over all
-//             windows of the CTA (a CTA works on ONE pair of heads); at the end they go to a global [head][query][key]
-//             sheet with vector reductions and the last CTA to finish bins the sheet into the [225][heads] table.
+//             windows of the CTA (a CTA works on ONE pair of heads); at the end the CTA bins them by relative position
+//             in shared memory and adds its 2 x 225 sums to the global [225][heads] table.
 // TMEM: S | dP of ONE head (256 columns) + dQ | dK | dV of ONE window (192 columns): phase A of the next head / stage
 // overlaps phase B and the thread work.  Warp roles (800 threads): warps 0-15 = P / dS (lane quarter = warp & 3, column
 // chunk = warp >> 2), 16-19 = epilogue, 21 = MMA issuer, 20 / 22 / 23 / 24 = TMA producers (one tensor each).
@@ -36,7 +36,6 @@ struct AttnBwdParams {
   const float* table;                // [225][nH]
   const float* stats;                // [n_windows][nH][64] log2-domain log-sum-exp from the forward
   float* gtable;                     // [225][nH] (zeroed by the caller)
-  float* sheet;                      // workspace [nH][64 queries][64 keys] fp32 sums of dS + 1 counter word, zeroed by the caller
   int B, H, W, nH, Ca, shift;
   int nWx, nWy, n_windows, n_units;
   unsigned long long magic_per, magic_x, magic_units;
@@ -113,6 +112,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
   else pdl_trigger();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  auto wall = [&](int slot) {  // debug: per-CTA wall-clock stamps behind the role timeline of CTA 0
+    if (p.trace != nullptr && threadIdx.x == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.trace[4 * 64 * 8 + 4 * blockIdx.x + slot] = gt;
+    }
+  };
+  wall(0);
 
   // A CTA works on ONE pair of heads for a strided subset of the window units: its bias-table gradient accumulators
   // then live in registers for the whole kernel and leave once, at the end (an earlier version walked all pairs per CTA
@@ -286,18 +293,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
         s_tab[h * kTabHead + r * kTabPitch + cc] = __ldg(p.table + bin * p.nH + 2 * pair + h) * kLog2e;
       }
     };
-    // bias-table gradient of `pair`: this thread's (query, 16 keys) sums of dS over all its windows go to the global
-    // [head][query][key] sheet with vector reductions (fire and forget; both windows' rows and all CTAs merge there);
-    // the last CTA to finish bins the sheet into the table
+    // bias-table gradient of `pair`: this thread's (query, 16 keys) sums of dS over all its windows are binned by
+    // relative position into the CTA's (dead) shared bias table -- same (dy + 7, dx + 7) addressing as the lookup --
+    // and the CTA adds its 2 x 225 bins to the global table.  (An earlier version merged all CTAs in a global
+    // [head][query][key] sheet that the last CTA binned: a 3 us flush on every CTA plus an 11 us single-CTA tail.)
     auto flush = [&](int pair) {
+      asm volatile("bar.sync 6, 512;" ::: "memory");  // every P / dS warp is done with the bias table
+      for (int i = threadIdx.x; i < 2 * kTabHead; i += 512) s_tab[i] = 0.0f;
+      asm volatile("bar.sync 6, 512;" ::: "memory");
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float4* dst = reinterpret_cast<float4*>(p.sheet + (static_cast<size_t>(2 * pair + h) * 64 + tok) * 64 + 16 * c);
+        float* tab = s_tab + h * kTabHead + tab_ofs;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          atomicAdd(dst + v, make_float4(acc[h][4 * v], acc[h][4 * v + 1], acc[h][4 * v + 2], acc[h][4 * v + 3]));
-          acc[h][4 * v] = acc[h][4 * v + 1] = acc[h][4 * v + 2] = acc[h][4 * v + 3] = 0.0f;
-        }
+        for (int j = 0; j < 16; ++j) atomicAdd(tab - ((j >> 2) * kTabPitch + (j & 3)), acc[h][j]);
+      }
+      asm volatile("bar.sync 6, 512;" ::: "memory");
+      for (int i = threadIdx.x; i < 2 * kNumBias; i += 512) {
+        const int h = i / kNumBias, bin = i - h * kNumBias;
+        const int r = bin / 15, cc = bin - r * 15;
+        atomicAdd(p.gtable + bin * p.nH + 2 * pair + h, s_tab[h * kTabHead + r * kTabPitch + cc]);
       }
     };
 
@@ -398,7 +412,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
       __syncwarp();
       if (lane == 0) mbar_arrive(tfull_bar);
     }
-    if (n_iter > 0) flush(pair);
+    flush(pair);  // (every CTA: the named barriers inside count all 512 threads)
   } else if (warp < 20) {
     // ===================================================== epilogue: warps 16..19 (lane quarter = warp & 3)
     const int L = (warp & 3) * 32 + lane;
@@ -462,33 +476,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_tc_kernel(cons
 
   tc_fence_before();
   __syncthreads();
+  wall(1);
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 
-  // ---- bias-table gradient: the last CTA to arrive bins the [head][query][key] sheet into [225][heads]
-  __shared__ unsigned s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned* counter = reinterpret_cast<unsigned*>(p.sheet + static_cast<size_t>(p.nH) * 4096);
-    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int t = threadIdx.x; t < p.nH * kNumBias; t += kBwdThreads) {
-      const int h = t / kNumBias, bin = t - h * kNumBias;
-      const int dy = bin / 15 - 7, dx = bin % 15 - 7;
-      const float* sh = p.sheet + static_cast<size_t>(h) * 4096;
-      float sum = 0.0f;
-      for (int y = (dy > 0 ? dy : 0); y < (dy < 0 ? 8 + dy : 8); ++y)
-        for (int x = (dx > 0 ? dx : 0); x < (dx < 0 ? 8 + dx : 8); ++x) {
-          const int i = (x >> 2) * 32 + y * 4 + (x & 3);
-          const int yy = y - dy, xx = x - dx;
-          sum += __ldcg(sh + i * 64 + (xx >> 2) * 32 + yy * 4 + (xx & 3));
-        }
-      p.gtable[bin * p.nH + h] += sum;
-    }
-  }
+  wall(2);
 }
 
 }  // namespace srb
@@ -502,7 +493,7 @@ int srb_window_attention_bwd_tc(const void* qkv_bf16, const void* gout_bf16, con
                                 const float* stats, void* gqkv_bf16, float* g_rpb_table, float* workspace, int B,
                                 int H, int W, int num_heads, int Ca, int shift, float scale, cudaStream_t stream) {
   if ((shift != 0 && shift != 4) || H % 8 != 0 || W % 8 != 0 || (num_heads & 1) || num_heads > kMaxHeads ||
-      Ca != num_heads * 32 || stats == nullptr || workspace == nullptr)
+      Ca != num_heads * 32 || stats == nullptr)
     return SRB200_EINVAL;
   if ((reinterpret_cast<uintptr_t>(qkv_bf16) | reinterpret_cast<uintptr_t>(gout_bf16) |
        reinterpret_cast<uintptr_t>(gqkv_bf16)) & 15u)
@@ -530,7 +521,6 @@ int srb_window_attention_bwd_tc(const void* qkv_bf16, const void* gout_bf16, con
   p.table = rpb_table;
   p.stats = stats;
   p.gtable = g_rpb_table;
-  p.sheet = workspace;
   p.B = B;
   p.H = H;
   p.W = W;

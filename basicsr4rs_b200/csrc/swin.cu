@@ -330,6 +330,147 @@ __global__ void __launch_bounds__(256, NVEC == 1 ? 3 : 1) layernorm_bwd_kernel(c
   }
 }
 
+// Backward, 8 lanes per token (the forward's layout): a warp handles 4 tokens per iteration, lane (slot, sub) owns the
+// 16-byte vectors sub + 8 i of token slot, so every lane moves data at Cp = 192 (the warp-per-token kernel keeps 24 of
+// 32 busy), a row reduction is 3 shuffles shared by four tokens, and a lane's gamma / beta partial sums stay on the
+// same channels for the whole kernel.  The gy / x loads of the next token group are in flight while this one is
+// reduced (the residual gradient is only needed for the final store and is fetched at the top of its own iteration).
+template <int NV>
+__global__ void __launch_bounds__(NV <= 2 ? 256 : 384, NV <= 2 ? 2 : 1) layernorm_bwd8_kernel(const __nv_bfloat16* __restrict__ gy,
+                                                                const __nv_bfloat16* __restrict__ x,
+                                                                const float* __restrict__ mean_in,
+                                                                const float* __restrict__ rstd_in,
+                                                                const float* __restrict__ gamma,
+                                                                const __nv_bfloat16* __restrict__ gres,
+                                                                __nv_bfloat16* __restrict__ gx, float* __restrict__ ggamma,
+                                                                float* __restrict__ gbeta, long long T, int C, int Cp) {
+  pdl_trigger();
+  extern __shared__ float s_red[];  // gamma[Cp] | sum gy*xhat [Cp] | sum gy [Cp]
+  for (int i = threadIdx.x; i < Cp; i += blockDim.x) {
+    s_red[i] = i < C ? __ldg(gamma + i) : 0.0f;
+    s_red[Cp + i] = 0.0f;
+    s_red[2 * Cp + i] = 0.0f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nv = Cp / 8;
+  const float inv_c = 1.0f / static_cast<float>(C);
+  float ag[NV][8], ab[NV][8];
+  uint4 lm[NV];  // bit mask of the packed output vector: ones on real channels, zero on pads (gy, gamma are zero there)
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ag[i][e] = ab[i][e] = 0.0f;
+    const int c0 = (sub + 8 * i) * 8;
+    auto half_mask = [&](int c) { return (c < C ? 0x0000FFFFu : 0u) | (c + 1 < C ? 0xFFFF0000u : 0u); };
+    lm[i] = make_uint4(half_mask(c0), half_mask(c0 + 2), half_mask(c0 + 4), half_mask(c0 + 6));
+  }
+  auto load = [&](long long t, uint4 (&rg)[NV], uint4 (&rx)[NV], float& mean, float& rstd) {
+    const bool tv = t < T;
+    mean = tv ? __ldg(mean_in + t) : 0.0f;
+    rstd = tv ? __ldg(rstd_in + t) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vec = sub + 8 * i;
+      const bool ok = tv && vec < nv;
+      rg[i] = ok ? __ldg(reinterpret_cast<const uint4*>(gy + t * Cp) + vec) : make_uint4(0u, 0u, 0u, 0u);
+      rx[i] = ok ? __ldg(reinterpret_cast<const uint4*>(x + t * Cp) + vec) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  uint4 ng[NV], nx[NV];
+  float nmean, nrstd;
+  long long t = warp_global * 4 + slot;
+  load(t, ng, nx, nmean, nrstd);
+  for (; t < T + slot; t += nwarps * 4) {  // (whole warps stay in the shuffles)
+    const bool tv = t < T;
+    uint4 rr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vec = sub + 8 * i;
+      rr[i] = (gres != nullptr && tv && vec < nv) ? __ldg(reinterpret_cast<const uint4*>(gres + t * Cp) + vec)
+                                                  : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float g[NV][8], xh[NV][8];
+    const float mean = nmean, rstd = nrstd;
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float xv[8];
+      ln_unpack(ng[i], g[i]);
+      ln_unpack(nx[i], xv);
+      const float4 g0 = *reinterpret_cast<const float4*>(s_red + (sub + 8 * i) * 8),
+                   g1 = *reinterpret_cast<const float4*>(s_red + (sub + 8 * i) * 8 + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        xh[i][e] = (xv[e] - mean) * rstd;  // (rstd = 0 on tokens beyond T: nothing accumulates)
+        ag[i][e] = fmaf(g[i][e], xh[i][e], ag[i][e]);
+        ab[i][e] += g[i][e];
+        g[i][e] *= gm[e];  // d xhat (zero on pads)
+        s1 += g[i][e];
+        s2 = fmaf(g[i][e], xh[i][e], s2);
+      }
+    }
+    load(t + nwarps * 4, ng, nx, nmean, nrstd);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+    s1 *= inv_c;
+    s2 *= inv_c;
+    if (tv) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vec = sub + 8 * i;
+        if (vec < nv) {
+          float o[8], r[8];
+          ln_unpack(rr[i], r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaf(rstd, g[i][e] - s1 - xh[i][e] * s2, r[e]);
+          uint4 pk = ln_pack(o);
+          pk.x &= lm[i].x;
+          pk.y &= lm[i].y;
+          pk.z &= lm[i].z;
+          pk.w &= lm[i].w;
+          *(reinterpret_cast<uint4*>(gx + t * Cp) + vec) = pk;
+        }
+      }
+    }
+  }
+  // column sums: the four token slots of a warp fold with two shuffles, warps meet in shared memory, CTAs in L2
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ag[i][e] += __shfl_xor_sync(0xffffffffu, ag[i][e], 8);
+      ab[i][e] += __shfl_xor_sync(0xffffffffu, ab[i][e], 8);
+      ag[i][e] += __shfl_xor_sync(0xffffffffu, ag[i][e], 16);
+      ab[i][e] += __shfl_xor_sync(0xffffffffu, ab[i][e], 16);
+    }
+  if (slot == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vec = sub + 8 * i;
+      if (vec < nv) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          atomicAdd(&s_red[Cp + vec * 8 + e], ag[i][e]);
+          atomicAdd(&s_red[2 * Cp + vec * 8 + e], ab[i][e]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(ggamma + c, s_red[Cp + c]);
+    atomicAdd(gbeta + c, s_red[2 * Cp + c]);
+  }
+}
+
 __global__ void scale_rows_kernel(const uint4* __restrict__ g, const float* __restrict__ alpha,
                                   uint4* __restrict__ out, size_t nvec, size_t vec_per_sample) {
   pdl_trigger();  // a following programmatically serialized GEMM may start its prologue
@@ -403,6 +544,22 @@ extern "C" int srb200_layernorm_bwd(const void* gy_bf16, const void* x_bf16, con
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_bf16);
   const __nv_bfloat16* gr = static_cast<const __nv_bfloat16*>(gres_bf16);
   __nv_bfloat16* gx = static_cast<__nv_bfloat16*>(gx_bf16);
+  if (Cp <= 256 && SRB_ENV("SRB_LN_WARP_PER_TOKEN") == nullptr) {
+    // 8 lanes per token; Cp <= 128: two resident 256-thread blocks per SM, above (48 accumulator registers per lane)
+    // one 384-thread block with up to 170 registers per thread
+    const int nvl = (Cp / 8 + 7) / 8;
+    const int block8 = nvl <= 2 ? 256 : 384;
+    long long b8 = (T * 8 + block8 - 1) / block8;
+    const long long cap8 = static_cast<long long>(num_sms()) * (nvl <= 2 ? 2 : 1);
+    if (b8 > cap8) b8 = cap8;
+    const size_t smem8 = 3 * static_cast<size_t>(Cp) * sizeof(float);
+    const int g8 = static_cast<int>(b8);
+    if (nvl == 1) layernorm_bwd8_kernel<1><<<g8, block8, smem8, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+    else if (nvl == 2) layernorm_bwd8_kernel<2><<<g8, block8, smem8, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+    else if (nvl == 3) layernorm_bwd8_kernel<3><<<g8, block8, smem8, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+    else layernorm_bwd8_kernel<4><<<g8, block8, smem8, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);
+    return launch_status();
+  }
   const int g = static_cast<int>(blocks);
   if (Cp <= 256)
     layernorm_bwd_kernel<1, 2><<<g, block, smem, st>>>(gy, x, mean, rstd, gamma, gr, gx, ggamma, gbeta, T, C, Cp);

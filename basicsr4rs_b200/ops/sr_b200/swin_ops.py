@@ -90,11 +90,11 @@ def window_attention_bwd(qkv, gout, table, num_heads, ws, shift, scale, stats=No
     ca = c3 // 3
     gqkv = torch.empty_like(qkv)
     gtable = raw.zeros_f32(tuple(table.shape), table.device)
-    # zeroed workspace of the tcgen05 backward (window 8 with the forward's statistics): dS sums [heads, 64, 64] + counter
     use_tc = ATTN_BWD_TC if use_tc is None else use_tc
-    work = raw.zeros_f32((num_heads * 4096 + 32,), table.device) if (use_tc and stats is not None and ws == 8) else None
+    if not use_tc:
+        stats = None  # without the statistics buffer the library takes the mma.sync kernel
     raw.probed('window_attn_bwd', (b, h, w, num_heads, ws), lambda: L.check(L.load().srb200_window_attention_bwd(
-        _ptr(qkv), _ptr(gout), _ptr(table), _ptr(stats), _ptr(gqkv), _ptr(gtable), _ptr(work), b, h, w, num_heads, ca,
+        _ptr(qkv), _ptr(gout), _ptr(table), _ptr(stats), _ptr(gqkv), _ptr(gtable), None, b, h, w, num_heads, ca,
         ws, shift, float(scale), _stream()), 'window_attention_bwd'))
     return gqkv, gtable
 

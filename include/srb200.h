@@ -293,8 +293,8 @@ int srb200_scale_rows(const void* g_bf16, const float* alpha, void* out_bf16, in
  * forward fills and the backward of the SAME geometry reads so that it need not redo the row maxima and sums
  * (without it the backward recomputes them on the mma.sync path).
  * bwd also accumulates the bias-table gradient into g_rpb_table (zero it first).
- * workspace (optional, may be NULL): num_heads*4096 + 32 ZEROED floats the tcgen05 backward uses to merge the
- * bias-table gradient across CTAs; without stats or workspace the backward runs on the mma.sync path.     */
+ * workspace: reserved, may be NULL (earlier builds merged the bias-table gradient across CTAs through it; every CTA
+ * now bins its own sums in shared memory); without stats the backward runs on the mma.sync path.                  */
 /* flags: SRB200_ATTN_ONES -- write 1.0 instead of 0 into out channel 31 (a pad lane of head 0; needs head_dim < 32): the
  * proj Linear that consumes `out` has zero weights there and its weight-gradient GEMM then yields its bias gradient in
  * column 31 (same trick as srb200_layernorm_fwd's ones_channel).                                                   */

@@ -14,6 +14,7 @@ def timeit(fn, iters=30):
     for _ in range(5): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(0.02 * 1.9e9))  # queue the launches behind a device-side delay: device time, not host pace
     e0.record()
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
