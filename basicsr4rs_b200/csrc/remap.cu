@@ -488,7 +488,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const srb200_pack_ite
     const float* src = reinterpret_cast<const float*>(it.src) + (static_cast<size_t>(live ? o : 0) * Ci + (live ? i : 0)) * taps;
     if (it.transpose == 2) {  // fp32 copy (padded / permuted bias vectors ride in the same launch)
       float* outf = reinterpret_cast<float*>(it.dst);
-      for (int t = 0; t < taps; ++t) outf[static_cast<size_t>(t) * pairs + idx] = live ? __ldg(src + t) : 0.0f;
+      // (reserved = 1 + index of ONE pad element that gets the constant `alpha` instead of zero: e.g. the bias that
+      // makes a pad channel of a GELU output a constant one, see srb200_pack_item)
+      const float pad = (it.reserved > 0 && idx == static_cast<size_t>(it.reserved - 1)) ? it.alpha : 0.0f;
+      for (int t = 0; t < taps; ++t) outf[static_cast<size_t>(t) * pairs + idx] = live ? __ldg(src + t) : pad;
       continue;
     }
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(it.dst);

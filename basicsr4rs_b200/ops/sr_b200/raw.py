@@ -321,6 +321,7 @@ def _item_table(rows):
             tab[i][k] = int(r[k])
         tab[i]['transpose'] = int(r.get('transpose', 0))  # 0 / 1: bf16 operand layouts, 2: fp32 copy (bias)
         tab[i]['alpha'] = float(r.get('alpha', 1.0))
+        tab[i]['reserved'] = int(r.get('fill_index', -1)) + 1  # fp32-copy items: one pad element := alpha
         tab[i]['chunk_begin'] = chunk
         chunk += (int(r['Np']) * int(r['Kp']) + 255) // 256
     return tab, chunk

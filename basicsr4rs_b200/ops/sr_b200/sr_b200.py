@@ -95,9 +95,10 @@ class PackBook:
             self.refresh()
         return e[1]
 
-    def get_bias(self, bias, n_pad, perm_out):
-        """fp32 [n_pad] bias in the packed channel order (zero padded): an fp32 item of the same batched launch."""
-        key = (id(bias), 'bias', n_pad, 1, id(perm_out) if perm_out is not None else 0, 0)
+    def get_bias(self, bias, n_pad, perm_out, fill=None):
+        """fp32 [n_pad] bias in the packed channel order (zero padded): an fp32 item of the same batched launch.
+        ``fill = (index, value)``: that one pad element holds ``value`` instead of zero."""
+        key = (id(bias), 'bias', n_pad, 1, id(perm_out) if perm_out is not None else 0, fill or 0)
         e = self.entries.get(key)
         capturing = torch.cuda.is_current_stream_capturing()
         if e is None or e[0]() is not bias:
@@ -105,6 +106,8 @@ class PackBook:
                 return None
             buf = torch.empty((n_pad,), dtype=torch.float32, device=bias.device)
             spec = dict(Co=bias.numel(), Ci=1, taps=1, Np=n_pad, Kp=1, perm_out=perm_out, perm_in=None, transpose=2)
+            if fill is not None:
+                spec.update(fill_index=int(fill[0]), alpha=float(fill[1]))
             self.entries[key] = [weakref.ref(bias), buf, spec, None]  # tag None: filled by the refresh below
             self.table = None
             self.refresh(force=True)
@@ -209,7 +212,8 @@ def _packed(weight, kind, n_pad, k_pad, perm_out=None, perm_in=None):
     return cache[kind]
 
 
-def _padded_bias(bias, n_pad, perm_out=None):
+def _padded_bias(bias, n_pad, perm_out=None, fill=None):
+    """fp32 [n_pad] bias in the packed channel order.  ``fill = (index, value)``: one PAD element holds ``value``."""
     if bias is None:
         return None
     if perm_out is None and bias.numel() == n_pad and bias.dtype == torch.float32:
@@ -221,7 +225,7 @@ def _padded_bias(bias, n_pad, perm_out=None):
     else:
         bias.__dict__['_srb200_book'] = weakref.ref(book)
     if book is not None:
-        buf = book.get_bias(bias, n_pad, perm_out)
+        buf = book.get_bias(bias, n_pad, perm_out, fill)
         if buf is not None:
             return buf
     capturing = torch.cuda.is_current_stream_capturing()  # see _packed: no host-side cache inside a capture
@@ -230,7 +234,8 @@ def _padded_bias(bias, n_pad, perm_out=None):
     if cache.get('tag') != tag or not torch.is_grad_enabled():
         cache.clear()
         cache['tag'] = tag
-    if capturing or 'b' not in cache:
+    ck = ('b', fill)
+    if capturing or ck not in cache:
         b = bias.detach().float()
         if perm_out is not None:
             key = ('safe', id(perm_out))
@@ -244,10 +249,13 @@ def _padded_bias(bias, n_pad, perm_out=None):
             bp = torch.zeros(n_pad, device=b.device)
             bp[:b.numel()] = b
         bp = bp.contiguous()
+        if fill is not None:
+            bp = bp.clone() if bp is b else bp
+            bp[fill[0]] = fill[1]
         if capturing:
             return bp
-        cache['b'] = bp
-    return cache['b']
+        cache[ck] = bp
+    return cache[ck]
 
 
 # The bias gradient of a layer is the column sum of its dY, and dY is almost always the OUTPUT of the previous

@@ -21,6 +21,17 @@ from .raw import _chk, _ptr, _stream
 from .sr_b200 import _packed, _padded_bias, _perm_cache, _unpad_bias_grad, pad64
 
 HD_PAD = 32
+# v with GELU(v) = v Phi(v) = 1 (any v whose GELU rounds to 1.0 in bf16 would do)
+def _gelu_one():
+    import math
+    lo, hi = 1.0, 1.3
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if 0.5 * mid * (1.0 + math.erf(mid / math.sqrt(2.0))) < 1.0 else (lo, mid)
+    return 0.5 * (lo + hi)
+
+
+GELU_ONE = _gelu_one()
 LN_EPS = 1e-5
 
 
@@ -175,8 +186,15 @@ class _SwinBlock(Function):
         x1 = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
                          bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1)
         xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c, eps, ones)
-        h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=_padded_bias(fc1_b, ch),
-                           act=L.ACT_GELU, want_aux=True, aux_grad=True)  # a = gelu'(fc1 out): all the backward needs
+        # fc1's last PAD output channel gets the bias v with GELU(v) = 1: h carries a constant one there (fc2's packed
+        # weights are zero on pad inputs), so fc2's weight-gradient GEMM also yields fc2's bias gradient -- no column-sum pass
+        h_ones = hidden < ch and fc1_b is not None
+        b1p = _padded_bias(fc1_b, ch, fill=(ch - 1, GELU_ONE) if h_ones else None)
+        if want_stats:
+            h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=b1p, act=L.ACT_GELU,
+                               want_aux=True, aux_grad=True)  # a = gelu'(fc1 out): all the backward needs
+        else:  # evaluation: no derivative tensor (50 MB of stores and half of the epilogue math at B16 x 64 x 64)
+            h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=b1p, act=L.ACT_GELU), None
         x2 = raw.tapgemm(h, _packed(fc2_w, 'fprop', cs, ch), ksize=1, cout=cs, bias=_padded_bias(fc2_b, cs),
                          residual=x1, alpha_per_sample=alpha2)
         ctx.save_for_backward(x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table,
@@ -184,6 +202,7 @@ class _SwinBlock(Function):
         ctx.cfg = (c, cs, ca, ch, hd, num_heads, ws, shift, scale)
         ctx.ones = ones
         ctx.o_ones = o_ones
+        ctx.h_ones = h_ones
         raw.stash_backward_scratch(ctx, _SwinBlock._scratch_floats(c, cs, ca, ch, table.numel()), dev)
         return x2
 
@@ -219,7 +238,8 @@ class _SwinBlock(Function):
         # ---- MLP branch
         g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
         acc_fc2 = raw.wgrad(g2s, h, ksize=1)
-        cs_fc2 = raw.colsum(g2s)
+        fc2_b_item = ('bcol', acc_fc2, ch - 1, fc2_b.numel(), None, 1.0) if ctx.h_ones else \
+            ('b', raw.colsum(g2s), fc2_b.numel(), None, 1.0)
         ones = ctx.ones
         if ones >= 0:  # fc1's bias gradient = column `ones` of acc_fc1 (xn2 carries a constant-one channel there)
             ga = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
@@ -244,7 +264,7 @@ class _SwinBlock(Function):
         # ---- all eight parameter gradients of the four Linear layers leave through ONE launch
         fc1_b_item = ('bcol', acc_fc1, ones, fc1_b.numel(), None, 1.0) if ones >= 0 else \
             ('b', cs_fc1, fc1_b.numel(), None, 1.0)
-        items = [('w', acc_fc2, fc2_w.shape, None, None, 1.0), ('b', cs_fc2, fc2_b.numel(), None, 1.0),
+        items = [('w', acc_fc2, fc2_w.shape, None, None, 1.0), fc2_b_item,
                  ('w', acc_fc1, fc1_w.shape, None, None, 1.0), fc1_b_item,
                  ('w', acc_proj, proj_w.shape, None, p_o, 1.0), proj_b_item,
                  ('w', acc_qkv, qkv_w.shape, p_qkv, None, 1.0)]

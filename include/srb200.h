@@ -128,8 +128,10 @@ typedef struct {
   int64_t transpose;       /* pack only: 0 / 1 = bf16 operand layouts of srb200_pack_weight, 2 = fp32 copy
                               out[n] = w[perm_out[n]] (zero padded): bias vectors (taps = Kp = Ci = 1) */
   int64_t chunk_begin;
-  float alpha;             /* unpack only */
-  int32_t reserved;
+  float alpha;             /* unpack: gradient scale.  pack, transpose = 2: the pad constant (see reserved) */
+  int32_t reserved;        /* pack, transpose = 2: 1 + index of ONE pad element that receives `alpha` instead of zero
+                              (0 = none) -- e.g. the bias v with GELU(v) = 1 that turns a pad channel of fc1's output
+                              into a constant one, so that fc2's weight-gradient GEMM also yields its bias gradient */
 } srb200_pack_item;
 int srb200_pack_weights(const srb200_pack_item* items_dev, int n_items, int64_t total_chunks,
                         srb200_stream_t stream);
