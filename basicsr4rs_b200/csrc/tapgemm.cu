@@ -28,6 +28,8 @@ struct TapGemmParams {
   CUtensorMap tmap_w;
   CUtensorMap tmap_out[9];  // output views for the TMA-store epilogue (out_r^2 views for the fused PixelShuffle)
   CUtensorMap tmap_aux;
+  CUtensorMap tmap_res;     // RES kernels: the staged epilogue operand (mask_src or residual), geometry of tmap_out[0]
+  int res_kind;             // RES kernels: 1 = mask_src, 2 = residual arrives through shared memory (TMA), 0 = neither
   int tma_store;            // 1: bf16 results leave through smem staging + cp.async.bulk.tensor stores
   unsigned long long* trace;  // debug: per-role clock64 timeline of CTA 0 (NULL = off)
   int B, H, W;
@@ -66,7 +68,13 @@ struct TapGemmParams {
 // TWO = CTA pair (cluster of 2, tcgen05 cta_group::2): one M=256 tile per pair, every CTA stages its own 128
 // rows of A but only HALF of B -- 32 KB instead of 48 KB of TMA traffic per 512-cycle k-block (N=256), which is
 // what a single SM's TMA path cannot sustain (measured ~80 B/cycle/SM: 616 cycles per k-block with one CTA).
-template <int BLOCK_N, bool TWO = false>
+// RES: the bf16 epilogue operand of a Linear (the residual, or the mask / derivative tensor of a data-gradient GEMM)
+// is staged through shared memory by TMA, one 64-column chunk ahead of the epilogue team that consumes it (2 slots per
+// team), at the price of two operand stages.  Read straight from global memory -- every thread four 16-byte pieces of
+// its own row per 32 columns, issued only when the accumulator is already in registers -- that operand made the
+// HBM-bound linears latency-bound (ncu: 5.6-7.2 warps stalled on long_scoreboard per issue; fc2's data gradient took
+// 53 us for 125 MB).
+template <int BLOCK_N, bool TWO = false, bool RES = false>
 struct TapCfg {
   static constexpr int BLOCK_M = 128;
   static constexpr int A_BYTES = BLOCK_M * 128;
@@ -77,7 +85,8 @@ struct TapCfg {
   // store holds its buffer for ~1.4k cycles, so 4 buffers (where the operand ring leaves room) keep 3 in flight.
   static constexpr int NBUF = (BLOCK_N >= 64 && BLOCK_N <= 192) ? 4 : 2;
   static constexpr int STORE_BYTES = BLOCK_N >= 64 ? NBUF * 128 * 128 : 0;
-  static constexpr int STAGES_RAW = (232448 - 1024 - 256 - 1024 - STORE_BYTES) / STAGE_BYTES;
+  static constexpr int RES_BYTES = RES ? 4 * 128 * 128 : 0;
+  static constexpr int STAGES_RAW = (232448 - 1024 - 256 - 1024 - STORE_BYTES - RES_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
@@ -85,7 +94,8 @@ struct TapCfg {
                                    : (2 * BLOCK_N <= 256) ? 256
                                                           : 512;
   static constexpr int CHUNK = BLOCK_N >= 32 ? 32 : 16;  // epilogue columns per tcgen05.ld
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + STORE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): one ex2 + one rcp + 5 FMA
@@ -144,23 +154,26 @@ __device__ __forceinline__ float warp_colsum32(float (&w)[32], int lane) {
 // accumulator buffer a.  For small-K layers (SwinIR's linears, 64-channel convs) a tile's MMAs take ~1.2k cycles but
 // its epilogue 4k, so both accumulators are usually full and two tiles' epilogues can run side by side -- each team
 // has its own named barrier, staging slots and TMA-store issuer.
-template <int BLOCK_N, bool TWO = false, bool TEAMS = false>
+template <int BLOCK_N, bool TWO = false, bool TEAMS = false, bool RES = false>
 __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
-  using Cfg = TapCfg<BLOCK_N, TWO>;
+  using Cfg = TapCfg<BLOCK_N, TWO, RES>;
   static_assert(!TEAMS || (!TWO && BLOCK_N >= 64 && BLOCK_N <= 192), "teams: single-CTA, TMA-store tile widths");
+  static_assert(!RES || TEAMS, "staged epilogue operand: two-team kernels only");
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CHUNK = Cfg::CHUNK;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t store_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = store_base + Cfg::STORE_BYTES;
-  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  const uint32_t res_base = store_base + Cfg::STORE_BYTES;  // RES: [2 teams][2 slots][128 rows x 64 ch] swizzled
+  const uint32_t bar_base = res_base + Cfg::RES_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr, res_full[2 teams][2 slots]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+  auto rfull_bar = [&](int team, int slot) { return bar_base + 8u * (2 * STAGES + 5 + 2 * team + slot); };
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));  // [BLOCK_N]
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
@@ -178,6 +191,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
     tma_prefetch_desc(&p.tmap_w);
+    if constexpr (RES) tma_prefetch_desc(&p.tmap_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -187,6 +201,9 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), TWO ? 16 : (TEAMS ? 4 : 8));  // (pair: both CTAs' epilogue warps; teams: one team)
+    }
+    if constexpr (RES) {
+      for (int a = 0; a < 4; ++a) mbar_init(rfull_bar(a >> 1, a & 1), 1);
     }
     fence_barrier_init();
   }
@@ -382,6 +399,26 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       }
       csum_n0 = -1;
     };
+    // RES: this team's staged-operand chunks, numbered g = 0, 1, ... over (tile, 64-column chunk); chunk g lives in slot
+    // g & 1 and is requested one chunk ahead by the team's issuer thread
+    const uint32_t my_res_base = res_base + team * 2 * 16384;
+    uint32_t res_g = 0;
+    auto res_issue = [&](int t, int cc, uint32_t g) {  // (issuer thread only)
+      const int t_div = fast_div(t, p.magic_n);
+      const int n_t = t - t_div * p.n_tiles;
+      const int b = fast_div(t_div, p.magic_xy);
+      const int m_in = t_div - b * (p.tiles_x * p.tiles_y);
+      const int ty = fast_div(m_in, p.magic_x);
+      const int tx = m_in - ty * p.tiles_x;
+      const uint32_t bar = rfull_bar(team, g & 1u);
+      mbar_expect_tx(bar, 16384);
+      tma_load_4d(my_res_base + (g & 1u) * 16384, &p.tmap_res, bar, n_t * BLOCK_N + cc * 64, tx * p.tile_w,
+                  ty * p.tile_h, b);
+    };
+    if constexpr (RES) {
+      const int t_first = unit0 + team * unit_stride;
+      if (issuer && t_first < total_tiles) res_issue(t_first, 0, 0u);
+    }
     if constexpr (TEAMS) {
       // the launch grid is a multiple of n_tiles (host-checked): one N tile, one bias vector per CTA, loaded once
       // by all eight warps -- the teams never meet again
@@ -442,7 +479,15 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
         return pix * p.Cout + nc;
       };
       // v: accumulators of CHUNK channels starting at nc -> final values (everything between MMA and store)
-      auto finish = [&](float (&v)[CHUNK], size_t off) {
+      // (staged: shared-memory address of this thread's 64-byte piece of the staged operand, 0 = read global memory)
+      auto finish = [&](float (&v)[CHUNK], size_t off, uint32_t staged = 0u, int piece0 = 0) {
+        auto ld_staged = [&](int j) {
+          uint4 m;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
+                       : "r"(staged + (((piece0 + j) ^ (row & 7)) << 4)));
+          return m;
+        };
         const uint32_t act = ef & F_ACT;
         if (act != SRB200_ACT_NONE && !(ef & F_AUX_GRAD)) {  // (with F_AUX_GRAD the activation is already applied)
           if (act == SRB200_ACT_RELU) {
@@ -460,23 +505,40 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
         for (int j = 0; j < CHUNK; ++j) v[j] *= al;
         if (!valid || (ef & F_TAIL) == 0) return;  // out-of-image rows of a partial tile: never stored / loaded
         if (ef & F_MASK) {
+          // (the mode test sits OUTSIDE the element loops: tested per element pair, the three-way branch -- one arm of it
+          // the long GELU-derivative code -- made this stage 2.2k cycles per 64-column chunk instead of ~0.6k)
           const uint4* mp = reinterpret_cast<const uint4*>(p.mask_src + off);
+          uint4 mm[CHUNK / 8];
 #pragma unroll
-          for (int j = 0; j < CHUNK / 8; ++j) {
-            const uint4 m = __ldg(mp + j);
-            const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          for (int j = 0; j < CHUNK / 8; ++j) mm[j] = (RES && p.res_kind == 1) ? ld_staged(j) : __ldg(mp + j);
+          if (ef & F_MASK_MUL) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float m0 = bf16_lo(mw[q]), m1 = bf16_hi(mw[q]);
-              if (ef & F_MASK_SIGN) {
-                v[8 * j + 2 * q + 0] *= (m0 > 0.0f) ? 1.0f : p.mask_slope;
-                v[8 * j + 2 * q + 1] *= (m1 > 0.0f) ? 1.0f : p.mask_slope;
-              } else if (ef & F_MASK_MUL) {
-                v[8 * j + 2 * q + 0] *= m0;
-                v[8 * j + 2 * q + 1] *= m1;
-              } else {
-                v[8 * j + 2 * q + 0] *= dgelu_erf(m0);
-                v[8 * j + 2 * q + 1] *= dgelu_erf(m1);
+            for (int j = 0; j < CHUNK / 8; ++j) {
+              const uint32_t mw[4] = {mm[j].x, mm[j].y, mm[j].z, mm[j].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[8 * j + 2 * q + 0] *= bf16_lo(mw[q]);
+                v[8 * j + 2 * q + 1] *= bf16_hi(mw[q]);
+              }
+            }
+          } else if (ef & F_MASK_SIGN) {
+#pragma unroll
+            for (int j = 0; j < CHUNK / 8; ++j) {
+              const uint32_t mw[4] = {mm[j].x, mm[j].y, mm[j].z, mm[j].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[8 * j + 2 * q + 0] *= (bf16_lo(mw[q]) > 0.0f) ? 1.0f : p.mask_slope;
+                v[8 * j + 2 * q + 1] *= (bf16_hi(mw[q]) > 0.0f) ? 1.0f : p.mask_slope;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK / 8; ++j) {
+              const uint32_t mw[4] = {mm[j].x, mm[j].y, mm[j].z, mm[j].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[8 * j + 2 * q + 0] *= dgelu_erf(bf16_lo(mw[q]));
+                v[8 * j + 2 * q + 1] *= dgelu_erf(bf16_hi(mw[q]));
               }
             }
           }
@@ -485,7 +547,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
           for (int j = 0; j < CHUNK / 8; ++j) {
-            const uint4 m = __ldg(rp + j);
+            const uint4 m = (RES && p.res_kind == 2) ? ld_staged(j) : __ldg(rp + j);
             const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -549,7 +611,23 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               buf_out = my_store_base + (store_iter % NSLOT) * 16384;
               if (issuer) tma_store_wait_read<NSLOT - 1>();
             }
+            const bool tr = issuer && it == 2 && cc < 4;  // debug timeline of team 0's second tile: 7 stamps per chunk
+            if (tr) stamp(3, 32 + 7 * cc);
             epi_sync();
+            if (tr) stamp(3, 33 + 7 * cc);
+            uint32_t staged_row = 0u;
+            if constexpr (RES) {
+              // request the NEXT chunk of the staged operand (its slot was last read two chunks ago, before the closing
+              // barrier of that chunk), then wait for this one
+              if (issuer) {
+                if (cc + 1 < BLOCK_N / 64) res_issue(t, cc + 1, res_g + 1);
+                else if (t + 2 * unit_stride < total_tiles) res_issue(t + 2 * unit_stride, 0, res_g + 1);
+              }
+              mbar_wait(rfull_bar(team, res_g & 1u), (res_g >> 1) & 1u);
+              staged_row = my_res_base + (res_g & 1u) * 16384 + row * 128;
+              ++res_g;
+            }
+            if (tr) stamp(3, 34 + 7 * cc);
 #pragma unroll 1
             for (int hh = 0; hh < NHALF; ++hh) {
               const int hf = half0 + hh;
@@ -576,7 +654,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                                : "memory");
                 }
               }
-              finish(v, out_offset(n0 + col));
+              finish(v, out_offset(n0 + col), staged_row, hf * 4);
               if constexpr (CHUNK == 32) {
                 if (ef & F_COLSUM) {
                   float w[32];
@@ -599,8 +677,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                              : "memory");
               }
             }
+            if (tr) stamp(3, 35 + 7 * cc);
             fence_proxy_async_smem();
             epi_sync();
+            if (tr) stamp(3, 36 + 7 * cc);
             if (issuer) {
               const int nc = n0 + cc * 64;
               int view = 0, c0 = nc;
@@ -693,16 +773,16 @@ static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
   return launch_ex(tapgemm_kernel<BLOCK_N, true>, 2 * pairs, 320, Cfg::SMEM_BYTES, stream, 2, p);
 }
 
-template <int BLOCK_N, bool TEAMS = false>
+template <int BLOCK_N, bool TEAMS = false, bool RES = false>
 static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
-  using Cfg = TapCfg<BLOCK_N>;
+  using Cfg = TapCfg<BLOCK_N, false, RES>;
   static PerDeviceOnce configured;
-  if (configured.ensure(tapgemm_kernel<BLOCK_N, false, TEAMS>, Cfg::SMEM_BYTES) != SRB200_OK) return SRB200_ELAUNCH;
+  if (configured.ensure(tapgemm_kernel<BLOCK_N, false, TEAMS, RES>, Cfg::SMEM_BYTES) != SRB200_OK) return SRB200_ELAUNCH;
   const int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
   if (grid >= p.n_tiles) grid -= grid % p.n_tiles;  // a CTA keeps its N tile (bias, weight columns) for all its tiles
   if (TEAMS && grid % p.n_tiles != 0) return SRB200_EINVAL;
-  return launch_ex(tapgemm_kernel<BLOCK_N, false, TEAMS>, grid, 320, Cfg::SMEM_BYTES, stream, 1, p);
+  return launch_ex(tapgemm_kernel<BLOCK_N, false, TEAMS, RES>, grid, 320, Cfg::SMEM_BYTES, stream, 1, p);
 }
 
 static std::atomic<unsigned long long*> g_trace{nullptr};
@@ -802,6 +882,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.out_scale = d->out_scale;
   p.trace = g_trace.load(std::memory_order_relaxed);
   p.pdl = pdl_enabled() ? 1 : 0;
+  p.res_kind = 0;
 
   // A views: in[B, H*r, W*r, Cin], view (i,j): element (b,y,x,c) at ((b*H*r + y*r+i)*W*r + x*r+j)*Cin + c
   const int r = d->src_r;
@@ -860,6 +941,19 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
     int grid = total < num_sms() ? total : num_sms();
     if (grid >= p.n_tiles) grid -= grid % p.n_tiles;
     const bool teams = p.tma_store != 0 && grid % p.n_tiles == 0 && SRB_ENV("SRB_TAPGEMM_NO_TEAMS") == nullptr;
+    // Linears whose epilogue reads a bf16 tensor shaped like the output (residual, or the mask / derivative of a data
+    // gradient): that operand goes through shared memory (TapCfg RES)
+    if (teams && bn == 192 && d->ksize == 1 && d->out_mode == SRB200_OUT_NHWC && (mask_src || residual) &&
+        SRB_ENV("SRB_TAPGEMM_NO_RES") == nullptr) {
+      p.res_kind = mask_src ? 1 : 2;
+      const uint64_t Co = static_cast<uint64_t>(d->Cout);
+      const uint64_t dims[4] = {Co, static_cast<uint64_t>(d->W), static_cast<uint64_t>(d->H), static_cast<uint64_t>(d->B)};
+      const uint64_t strides[3] = {Co * 2, static_cast<uint64_t>(d->W) * Co * 2, static_cast<uint64_t>(d->H) * d->W * Co * 2};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
+      const int rc = make_tmap_bf16(&p.tmap_res, mask_src ? mask_src : residual, 4, dims, strides, box);
+      if (rc != SRB200_OK) return rc;
+      return launch_tapgemm<192, true, true>(p, stream);
+    }
     if (teams && bn == 192) return launch_tapgemm<192, true>(p, stream);
     if (teams && bn == 128) return launch_tapgemm<128, true>(p, stream);
   }

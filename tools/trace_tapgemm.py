@@ -26,13 +26,21 @@ def run(name, b, h, w, cin, cout, ks, **kw):
     print(' producer tile starts :', [rel(v) for v in t[0, :12]])
     print(' mma tile start/end   :', [(rel(t[1, 2*i]), rel(t[1, 2*i+1])) for i in range(12) if int(t[1, 2*i])])
     print(' producer k-block (before wait, after A issue) tile 0:', [(rel(t[3, 2*i]), rel(t[3, 2*i+1])) for i in range(16) if int(t[3, 2*i])])
-    print(' epi tile 2 chunk phases (start, slot free, acc loaded, math done, staged, fenced, arrived):', [[rel(v) for v in t[3, 32+7*c:39+7*c]] for c in range(4) if int(t[3, 32+7*c])])
+    print(' epi tile 2 chunk phases (store slot free, team in, staged operand landed, math + staging done, team out):', [[rel(v) for v in t[3, 32+7*c:37+7*c]] for c in range(4) if int(t[3, 32+7*c])])
     print(' epi  acc ready/drained:', [(rel(t[2, 2*i]), rel(t[2, 2*i+1])) for i in range(12) if int(t[2, 2*i])])
 if len(sys.argv) > 1 and sys.argv[1] == 'rcan':
     run('rcan 64->64 48x48 relu', 16, 48, 48, 64, 64, 3, act=L.ACT_RELU)
     run('rcan 64->64 48x48', 16, 48, 48, 64, 64, 3)
     run('rcan 64->64 48x48 B8', 8, 48, 48, 64, 64, 3)
     run('edsr body 256->256 48x48 relu', 16, 48, 48, 256, 256, 3, act=L.ACT_RELU)
+    sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == 'mlp':
+    x384 = torch.randn((16, 64, 64, 384), device=dev).to(torch.bfloat16)
+    x192 = torch.randn((16, 64, 64, 192), device=dev).to(torch.bfloat16)
+    run('fc2 dgrad 192->384 x mask', 16, 64, 64, 192, 384, 1, mask_src=x384, mask_mode=L.MASK_MUL)
+    run('proj 192->192 + residual', 16, 64, 64, 192, 192, 1, residual=x192)
+    run('fc2 384->192 + residual', 16, 64, 64, 384, 192, 1, residual=x192)
+    run('plain 192->384', 16, 64, 64, 192, 384, 1)
     sys.exit(0)
 run('qkv 65536x192 -> 576', 16, 64, 64, 192, 576, 1)
 run('fc1 192->384 gelu+aux', 16, 64, 64, 192, 384, 1, act=L.ACT_GELU, want_aux=True)
