@@ -107,6 +107,13 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// dst[i] += src[i] over `bytes` / 4 contiguous floats: shared -> global bulk REDUCTION executed by the TMA unit (whole
+// L2 lines per request; per-thread red.global.add.v4.f32 with a row pitch between lanes are 16-byte requests)
+__device__ __forceinline__ void bulk_reduce_add_f32(float* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src_smem),
+               "r"(bytes)
+               : "memory");
+}
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");

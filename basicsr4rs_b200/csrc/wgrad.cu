@@ -197,21 +197,34 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ W
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const int n = m0 + row;
       float* dst = p.acc + (static_cast<size_t>(FOLD ? 3 * tap : tap) * p.N + n) * p.K + n0;
+      // Split merge: every thread parks its accumulator row in the (dead) operand ring and hands it to the TMA unit as
+      // ONE bulk reduction per contiguous run -- whole lines at L2 instead of 48 sixteen-byte vector atomics per thread
+      // (measured on 192-wide units: ~8-10k of a CTA's ~20k cycles went into that atomic tail).  The row pitch keeps
+      // the 16-byte shared stores of a quarter-warp on distinct banks.
+      constexpr uint32_t PITCH = BLOCK_N * 4 + 16;
+      static_assert(128 * PITCH <= STAGES * Cfg::STAGE_BYTES, "accumulator staging must fit the operand ring");
+      const uint32_t my_row = smem_base + row * PITCH;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        // folded: columns [64 nb, 64 nb + 64) are tap 3*row + nb; otherwise 32 more input channels of the same tap
-        float* d = FOLD ? dst + static_cast<size_t>(c >> 1) * p.N * p.K + (c & 1) * 32 : dst + c * 32;
-        if (n < p.N) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            atomicAdd(reinterpret_cast<float4*>(d + 4 * j), v);
-          }
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + c * 128 + j * 16), "r"(r[4 * j]),
+                       "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+      }
+      fence_proxy_async_smem();
+      if (n < p.N) {
+        if constexpr (FOLD) {  // columns [64 nb, 64 nb + 64) are tap 3 * row + nb
+#pragma unroll
+          for (int nb = 0; nb < 3; ++nb) bulk_reduce_add_f32(dst + static_cast<size_t>(nb) * p.N * p.K, my_row + nb * 256, 256);
+        } else {
+          bulk_reduce_add_f32(dst, my_row, BLOCK_N * 4);
         }
+        tma_store_commit();
+        tma_store_wait_all<0>();
       }
     }
   }
@@ -372,18 +385,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       float* dst = p.acc + (static_cast<size_t>(tap) * p.N + (m0 + row)) * p.K + n0;
+      // split merge through the TMA unit (see wgrad_kernel): this CTA's operand ring is dead once the pair's last MMA
+      // has retired -- the peer's MMAs read the peer's own shared memory... and ours: tfull is committed by the leader
+      // after ALL MMAs of the pair, which read both CTAs' rings
+      constexpr uint32_t PITCH = 256 * 4 + 16;
+      static_assert(128 * PITCH <= STAGES * Cfg::STAGE_BYTES, "accumulator staging must fit the operand ring");
+      const uint32_t my_row = smem_base + row * PITCH;
 #pragma unroll 1
       for (int c = 0; c < 256 / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + 4 * j), v);
-        }
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + c * 128 + j * 16), "r"(r[4 * j]),
+                       "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
       }
+      fence_proxy_async_smem();
+      bulk_reduce_add_f32(dst, my_row, 256 * 4);
+      tma_store_commit();
+      tma_store_wait_all<0>();
     }
   }
   tc_fence_before();

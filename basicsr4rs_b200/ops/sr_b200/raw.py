@@ -57,6 +57,55 @@ def probed(kind, info, launch):
 
 PROBE = None
 
+# ------------------------------------------------------------------ side branch for weight gradients
+# A layer's weight-gradient GEMM and its data-gradient GEMM both consume dY and neither needs the other; only the
+# data gradient is on the critical path of the backward chain.  ``with side_branch(device): acc = wgrad(...)`` puts the
+# launch on a per-device side stream that waits for what the current stream has been given so far; ``side_join``
+# makes the current stream wait for the side stream again (before the gradients are finalised, and always before the
+# Function returns: the operands are main-stream tensors that must outlive the side kernels).  Inside a CUDA-graph
+# capture the event pair becomes a fork / join of the graph.  SRB_SIDE_WGRAD=0 keeps everything on one stream.
+import os as _os
+
+SIDE_WGRAD = _os.environ.get('SRB_SIDE_WGRAD', '1') == '1'
+_side_streams = {}
+_side_main = threading.local()  # the stream a side branch forked from, while inside the branch
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    s = _side_streams.get(key)
+    if s is None:
+        s = _side_streams[key] = torch.cuda.Stream(device=key)
+    return s
+
+
+class side_branch:
+    def __init__(self, device):
+        self.device = device
+        self.on = SIDE_WGRAD and PROBE is None  # (the event probe times launches on ONE stream)
+
+    def __enter__(self):
+        if self.on:
+            side = _side_stream(self.device)
+            main = torch.cuda.current_stream(self.device)
+            side.wait_stream(main)
+            self.ctx = torch.cuda.stream(side)
+            self.ctx.__enter__()
+            _side_main.cur = main
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _side_main.cur = None
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def side_join(device):
+    if SIDE_WGRAD and PROBE is None:
+        torch.cuda.current_stream(device).wait_stream(_side_stream(device))
+
+
 _arena = threading.local()
 
 
@@ -150,7 +199,11 @@ def zeros_f32(shape, device):
         if start + n <= cur[0].numel():
             cur[1] = start + n
             return cur[0][start:start + n].view(shape)
-    return torch.zeros(shape, dtype=torch.float32, device=device)
+    out = torch.zeros(shape, dtype=torch.float32, device=device)
+    main = getattr(_side_main, 'cur', None)
+    if main is not None:  # allocated on the side stream, consumed (and dropped) on the main one
+        out.record_stream(main)
+    return out
 
 
 def _ptr(t):

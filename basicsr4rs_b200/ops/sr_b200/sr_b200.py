@@ -445,8 +445,10 @@ class _ResBlockNoBN(Function):
         if b2 is not None and ctx.needs_input_grad[4]:
             items.append(('b', _colsum_of(g), b2.numel(), None, s))  # from the epilogue that produced g, if any
         _colsum_tls.slot = None
+        dev = x.device
         if ctx.needs_input_grad[3]:
-            items.append(('w', raw.wgrad(g, h, ksize=3), w2.shape, None, None, s))
+            with raw.side_branch(dev):  # weight gradients next to the data-gradient chain
+                items.append(('w', raw.wgrad(g, h, ksize=3), w2.shape, None, None, s))
         # d(pre-activation of conv1) = dgrad_conv2(s*g) masked by relu'(h); its column sums = conv1's bias gradient
         want_gb1 = b1 is not None and ctx.needs_input_grad[2]
         gh = raw.tapgemm(g, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, alpha=s, flip=True, mask_src=h,
@@ -455,11 +457,13 @@ class _ResBlockNoBN(Function):
             gh, cs = gh
             items.append(('b', cs, b1.numel(), None, 1.0))
         if ctx.needs_input_grad[1]:
-            items.append(('w', raw.wgrad(gh, x, ksize=3), w1.shape, None, None, 1.0))
+            with raw.side_branch(dev):
+                items.append(('w', raw.wgrad(gh, x, ksize=3), w1.shape, None, None, 1.0))
         if ctx.needs_input_grad[0]:
             gx, cs = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g,
                                  want_colsum=True)
             _stash_colsum(gx, cs)
+        raw.side_join(dev)
         grads = iter(raw.finalize_grads(items)) if items else iter(())  # one launch for all four gradients
         if b2 is not None and ctx.needs_input_grad[4]:
             gb2 = next(grads)
@@ -653,15 +657,20 @@ class _RCAB(Function):
         # d s = res_scale * sum_hw g*t  ->  FC backward  ->  d t (+ its column sums = conv2's bias grad): one launch
         gwa1, gba1, gwa2, gba2, gt, cs2 = raw.ca_backward(g, t, s, z, p, wa1.detach().contiguous(),
                                                          wa2.detach().contiguous(), rs)
-        acc2 = raw.wgrad(gt, h, ksize=3)
+        dev = x.device
+        # the weight gradients ride a side stream next to the data-gradient chain (raw.side_branch)
+        with raw.side_branch(dev):
+            acc2 = raw.wgrad(gt, h, ksize=3)
         gh, cs1 = raw.tapgemm(gt, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, mask_src=h,
                               mask_mode=L.MASK_SIGN, mask_slope=0.0, want_colsum=True)
-        acc1 = raw.wgrad(gh, x, ksize=3)
-        gw2, gb2, gw1, gb1 = raw.finalize_grads([('w', acc2, w2.shape, None, None, 1.0), ('b', cs2, b2.numel(), None, 1.0),
-                                                 ('w', acc1, w1.shape, None, None, 1.0), ('b', cs1, b1.numel(), None, 1.0)])
+        with raw.side_branch(dev):
+            acc1 = raw.wgrad(gh, x, ksize=3)
         gx = None
         if ctx.needs_input_grad[0]:
             gx = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g)
+        raw.side_join(dev)
+        gw2, gb2, gw1, gb1 = raw.finalize_grads([('w', acc2, w2.shape, None, None, 1.0), ('b', cs2, b2.numel(), None, 1.0),
+                                                 ('w', acc1, w1.shape, None, None, 1.0), ('b', cs1, b1.numel(), None, 1.0)])
         return gx, None, gw1, gb1, gw2, gb2, gwa1, gba1, gwa2, gba2, None
 
 

@@ -237,7 +237,8 @@ class _SwinBlock(Function):
         p_o = head_perm(num_heads, hd, 1, dev)
         # ---- MLP branch
         g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
-        acc_fc2 = raw.wgrad(g2s, h, ksize=1)
+        with raw.side_branch(dev):  # the four weight gradients ride a side stream next to the data-gradient chain
+            acc_fc2 = raw.wgrad(g2s, h, ksize=1)
         fc2_b_item = ('bcol', acc_fc2, ch - 1, fc2_b.numel(), None, 1.0) if ctx.h_ones else \
             ('b', raw.colsum(g2s), fc2_b.numel(), None, 1.0)
         ones = ctx.ones
@@ -248,19 +249,23 @@ class _SwinBlock(Function):
         else:
             ga, cs_fc1 = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
                                      mask_mode=L.MASK_MUL, want_colsum=True)  # column sums = fc1's bias gradient
-        acc_fc1 = raw.wgrad(ga, xn2, ksize=1)
+        with raw.side_branch(dev):
+            acc_fc1 = raw.wgrad(ga, xn2, ksize=1)
         gxn2 = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True)
         gx1, g_n2w, g_n2b = layernorm_bwd(gxn2, x1, mean2, rstd2, n2w.detach(), c, gres=g2)
         # ---- attention branch
         g1s = scale_rows(gx1, alpha1) if alpha1 is not None else gx1
-        acc_proj = raw.wgrad(g1s, o, ksize=1)
+        with raw.side_branch(dev):
+            acc_proj = raw.wgrad(g1s, o, ksize=1)
         proj_b_item = ('bcol', acc_proj, HD_PAD - 1, proj_b.numel(), None, 1.0) if ctx.o_ones else \
             ('b', raw.colsum(g1s), proj_b.numel(), None, 1.0)
         go = raw.tapgemm(g1s, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
         gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale, stats=stats)
-        acc_qkv = raw.wgrad(gqkv, xn, ksize=1)
+        with raw.side_branch(dev):
+            acc_qkv = raw.wgrad(gqkv, xn, ksize=1)
         gxn = raw.tapgemm(gqkv, _packed(qkv_w, 'dgrad', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=cs, flip=True)
         gx, g_n1w, g_n1b = layernorm_bwd(gxn, x, mean1, rstd1, n1w.detach(), c, gres=gx1)
+        raw.side_join(dev)
         # ---- all eight parameter gradients of the four Linear layers leave through ONE launch
         fc1_b_item = ('bcol', acc_fc1, ones, fc1_b.numel(), None, 1.0) if ones >= 0 else \
             ('b', cs_fc1, fc1_b.numel(), None, 1.0)

@@ -28,6 +28,25 @@ def run(name, b, h, w, cin, cout, ks, **kw):
     print(' producer k-block (before wait, after A issue) tile 0:', [(rel(t[3, 2*i]), rel(t[3, 2*i+1])) for i in range(16) if int(t[3, 2*i])])
     print(' epi tile 2 chunk phases (store slot free, team in, staged operand landed, math + staging done, team out):', [[rel(v) for v in t[3, 32+7*c:37+7*c]] for c in range(4) if int(t[3, 32+7*c])])
     print(' epi  acc ready/drained:', [(rel(t[2, 2*i]), rel(t[2, 2*i+1])) for i in range(12) if int(t[2, 2*i])])
+def run_wgrad(name, b, h, w, cin, cout, ks):
+    x = torch.randn((b, h, w, cin), device=dev).to(torch.bfloat16)
+    dy = torch.randn((b, h, w, cout), device=dev).to(torch.bfloat16)
+    for _ in range(3): raw.wgrad(dy, x, ksize=ks)
+    buf = torch.zeros(128, dtype=torch.int64, device=dev)
+    L.load().srb200_debug_set_wgrad_trace(ctypes.c_void_p(buf.data_ptr()))
+    raw.wgrad(dy, x, ksize=ks)
+    torch.cuda.synchronize(); L.load().srb200_debug_set_wgrad_trace(None)
+    t = buf.cpu(); t0 = int(t[0]); rel = lambda v: int(v) - t0 if int(v) else None
+    print(f'== wgrad {name}: mma issued-all {rel(t[1])}, acc ready {rel(t[2])}, cta end {rel(t[3])}')
+    print('   k-block ready times:', [rel(v) for v in t[8:48]])
+    print('   producer (before wait, after wait, after issue):', [(rel(t[64+3*i]), rel(t[65+3*i]), rel(t[66+3*i])) for i in range(20)])
+if len(sys.argv) > 1 and sys.argv[1] == 'wgrad':
+    run_wgrad('proj 192x192', 16, 64, 64, 192, 192, 1)
+    run_wgrad('qkv 192->576', 16, 64, 64, 192, 576, 1)
+    run_wgrad('fc1 192->384', 16, 64, 64, 192, 384, 1)
+    run_wgrad('fc2 384->192', 16, 64, 64, 384, 192, 1)
+    run_wgrad('rcan 64x64 3x3', 16, 48, 48, 64, 64, 3)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == 'rcan':
     run('rcan 64->64 48x48 relu', 16, 48, 48, 64, 64, 3, act=L.ACT_RELU)
     run('rcan 64->64 48x48', 16, 48, 48, 64, 64, 3)
@@ -49,16 +68,4 @@ run('fc1 192->384 gelu no aux', 16, 64, 64, 192, 384, 1, act=L.ACT_GELU)
 run('edsr body 256->256 48x48 relu', 16, 48, 48, 256, 256, 3, act=L.ACT_RELU)
 run('rcan 64->64 48x48', 16, 48, 48, 64, 64, 3)
 
-def run_wgrad(name, b, h, w, cin, cout, ks):
-    x = torch.randn((b, h, w, cin), device=dev).to(torch.bfloat16)
-    dy = torch.randn((b, h, w, cout), device=dev).to(torch.bfloat16)
-    for _ in range(3): raw.wgrad(dy, x, ksize=ks)
-    buf = torch.zeros(128, dtype=torch.int64, device=dev)
-    L.load().srb200_debug_set_wgrad_trace(ctypes.c_void_p(buf.data_ptr()))
-    raw.wgrad(dy, x, ksize=ks)
-    torch.cuda.synchronize(); L.load().srb200_debug_set_wgrad_trace(None)
-    t = buf.cpu(); t0 = int(t[0]); rel = lambda v: int(v) - t0 if int(v) else None
-    print(f'== wgrad {name}: mma issued-all {rel(t[1])}, acc ready {rel(t[2])}, cta end {rel(t[3])}')
-    print('   k-block ready times:', [rel(v) for v in t[8:48]])
-    print('   producer (before wait, after wait, after issue):', [(rel(t[64+3*i]), rel(t[65+3*i]), rel(t[66+3*i])) for i in range(20)])
 run_wgrad('edsr body 256x256 48x48', 16, 48, 48, 256, 256, 3)
