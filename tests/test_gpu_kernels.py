@@ -414,6 +414,26 @@ def test_tapgemm_gelu_derivative_aux_and_mask_mul(cuda):
     _assert_close(ga, ref)
 
 
+def test_gelu_epilogue_against_the_exact_erf_form_over_its_whole_range(cuda):
+    """The GELU epilogue evaluates erf with a rational approximation and MUFU.EX2 / MUFU.RCP (tapgemm.cu); nn.GELU() of
+    the reference is the exact erf form (swinir_arch.py:46,57).  Sweep the pre-activation over [-9, 9] through an
+    identity Linear: the deviation must stay below the bf16 rounding of the stored value (2^-8 relative) plus 1e-3
+    absolute, and the stored derivative within 4e-3 + rounding of the exact one."""
+    raw, L = _raw(), _L()
+    n = 128 * 64
+    a = torch.linspace(-9.0, 9.0, n * 64, device=cuda).to(torch.bfloat16).view(1, 64, 128, 64)
+    wp = raw.pack_weight(torch.eye(64, device=cuda), 64, 64)
+    out, d = raw.tapgemm(a, wp, ksize=1, cout=64, act=L.ACT_GELU, want_aux=True, aux_grad=True)
+    af = a.float().clone().requires_grad_(True)
+    g = F.gelu(af)
+    g.sum().backward()
+    err = (out.float() - g).abs()
+    assert (err <= g.abs() * 2.0**-8 + 1e-3).all(), err.max().item()
+    assert (d.float() - af.grad).abs().max().item() <= 4e-3 + 2.0**-8 * 1.2
+    plain = raw.tapgemm(a, wp, ksize=1, cout=64, act=L.ACT_GELU)
+    assert torch.equal(plain, out)
+
+
 @pytest.mark.parametrize('b,c,h,w,cin', [(2, 3, 24, 20, 64), (1, 4, 17, 9, 128), (1, 6, 8, 8, 64)])
 def test_conv_to_image_tap_folded(cuda, b, c, h, w, cin):
     """conv_last as 1x1 tap-GEMM + stencil sum / im2col backward == nn.Conv2d(cin, c, 3, 1, 1) * scale + shift,

@@ -158,6 +158,7 @@ def test_swinir_matches_reference_golden(cuda, case):
     net = _build(fx, cuda)
     out = net(fx['x'].to(cuda))
     err = (out.detach().cpu() - fx['out']).abs().max().item()
+    print(f'{case}: max-abs {err:.3e}')
     assert err <= MAX_ABS, f'max-abs {err:.3e}'
     assert abs(sr_oracle.psnr(out.detach().cpu(), fx['gt']) - sr_oracle.psnr(fx['out'], fx['gt'])) <= PSNR_TOL
     ((out - fx['gt'].to(cuda))**2).mean().backward()
