@@ -235,62 +235,27 @@ __global__ void ca_apply_bwd_kernel(const uint4* __restrict__ g, const float* __
 // ------------------------------------------------------------------ fused channel attention (one launch each way)
 // forward:  s = sigmoid(W2 relu(W1 p + b1) + b2) for ALL images in every CTA's shared memory (B*C*Cr MACs: nothing),
 //           then y = x + res_scale * t * s[b,c].  CTA 0 also writes z, s for the backward.
-struct CaFwdArgs {
-  const uint4* t;
-  const uint4* x;
-  const float* x32;
-  const float *p, *w1, *b1, *w2, *b2;
-  float *z_out, *s_out;
-  uint4* y;
-  float* y32;
-  size_t nvec;
-  int B, HW, C, Cr;
-  float res_scale;
-};
-__global__ void __launch_bounds__(256) ca_forward_fused_kernel(const __grid_constant__ CaFwdArgs a) {
-  const uint4* __restrict__ t = a.t;
-  const uint4* __restrict__ x = a.x;
-  const float* __restrict__ x32 = a.x32;
-  const float* __restrict__ p = a.p;
-  const float *__restrict__ w1 = a.w1, *__restrict__ b1 = a.b1, *__restrict__ w2 = a.w2, *__restrict__ b2 = a.b2;
-  float *__restrict__ z_out = a.z_out, *__restrict__ s_out = a.s_out;
-  uint4* __restrict__ y = a.y;
-  float* __restrict__ y32 = a.y32;
-  const size_t nvec = a.nvec;
-  const int B = a.B, HW = a.HW, C = a.C, Cr = a.Cr;
-  const float res_scale = a.res_scale;
-  extern __shared__ float sm[];  // s[B*C], z[B*Cr], p[B*C], w1[Cr*C], w2[C*Cr], b1[Cr], b2[C]
+__global__ void __launch_bounds__(256) ca_forward_fused_kernel(
+    const uint4* __restrict__ t, const uint4* __restrict__ x, const float* __restrict__ x32,
+    const float* __restrict__ p, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ z_out,
+    float* __restrict__ s_out, uint4* __restrict__ y, float* __restrict__ y32, size_t nvec, int B, int HW, int C,
+    int Cr, float res_scale) {
+  extern __shared__ float sm[];  // s[B*C], z[B*Cr]
+  pdl_trigger();  // the next (programmatically serialized) GEMM may start its prologue now
   float* ss = sm;
-  float* sz = ss + static_cast<size_t>(B) * C;
-  float* sp = sz + static_cast<size_t>(B) * Cr;
-  float* sw1 = sp + static_cast<size_t>(B) * C;
-  float* sw2 = sw1 + static_cast<size_t>(Cr) * C;
-  float* sb1 = sw2 + static_cast<size_t>(Cr) * C;
-  float* sb2 = sb1 + Cr;
-  // The FC operands go to shared memory with ONE round of independent loads (read in the dot-product loops straight
-  // from global memory they were ~200 dependent-latency loads per thread: 3-4 us at the head of an 11 us kernel).
-  // The weights do not depend on the preceding kernel: under programmatic dependent launch they are fetched while
-  // conv2 is still draining; the pooled means p (conv2's epilogue) only after griddepcontrol.wait.
-  for (int i = threadIdx.x; i < Cr * C; i += blockDim.x) {
-    sw1[i] = __ldg(w1 + i);
-    sw2[i] = __ldg(w2 + i);
-  }
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sb2[i] = __ldg(b2 + i);
-  for (int i = threadIdx.x; i < Cr; i += blockDim.x) sb1[i] = __ldg(b1 + i);
-  pdl_handoff();  // dependents may start their prologue; OUR prerequisite (conv2) has completed and flushed
-  for (int i = threadIdx.x; i < B * C; i += blockDim.x) sp[i] = __ldcg(p + i);
-  __syncthreads();
+  float* sz = sm + static_cast<size_t>(B) * C;
   for (int i = threadIdx.x; i < B * Cr; i += blockDim.x) {
     const int b = i / Cr, j = i - b * Cr;
-    float acc = sb1[j];
-    for (int c = 0; c < C; ++c) acc += sw1[j * C + c] * sp[b * C + c];
+    float acc = __ldg(b1 + j);
+    for (int c = 0; c < C; ++c) acc += __ldg(w1 + static_cast<size_t>(j) * C + c) * __ldg(p + static_cast<size_t>(b) * C + c);
     sz[i] = fmaxf(acc, 0.0f);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < B * C; i += blockDim.x) {
     const int b = i / C, c = i - b * C;
-    float acc = sb2[c];
-    for (int j = 0; j < Cr; ++j) acc += sw2[c * Cr + j] * sz[b * Cr + j];
+    float acc = __ldg(b2 + c);
+    for (int j = 0; j < Cr; ++j) acc += __ldg(w2 + static_cast<size_t>(c) * Cr + j) * sz[b * Cr + j];
     ss[i] = 1.0f / (1.0f + __expf(-acc));
   }
   __syncthreads();
@@ -600,17 +565,15 @@ extern "C" int srb200_ca_forward(const void* t_bf16, const void* x_bf16, const f
                                  float res_scale, srb200_stream_t stream) {
   if (!t_bf16 || (!x_bf16 && !x_f32) || !p || !w1 || !b1 || !w2 || !b2 || !z || !s || !y_bf16) return SRB200_EINVAL;
   if (B <= 0 || HW <= 0 || C <= 0 || C % 8 != 0 || Cr <= 0) return SRB200_EINVAL;
-  const size_t smem = (2 * static_cast<size_t>(B) * C + static_cast<size_t>(B) * Cr + 2 * static_cast<size_t>(Cr) * C +
-                       Cr + C) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(B) * C + static_cast<size_t>(B) * Cr) * sizeof(float);
   if (smem > 48 * 1024) return SRB200_EINVAL;
   const size_t nvec = static_cast<size_t>(B) * HW * (C / 8);
   int grid = grid1d(nvec, 256);
   if (grid > 4 * num_sms()) grid = 4 * num_sms();  // every CTA repeats the FC: keep them few and fat
-  CaFwdArgs a{static_cast<const uint4*>(t_bf16), static_cast<const uint4*>(x_bf16), x_f32, p, w1, b1, w2, b2, z, s,
-              static_cast<uint4*>(y_bf16), y_f32, nvec, B, HW, C, Cr, res_scale};
-  // (launch_ex: with programmatic stream serialization when the archs have it on, so that this kernel's launch and
-  // weight staging overlap the tail of conv2)
-  return launch_ex(ca_forward_fused_kernel, grid, 256, smem, static_cast<cudaStream_t>(stream), 1, a);
+  ca_forward_fused_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(t_bf16), static_cast<const uint4*>(x_bf16), x_f32, p, w1, b1, w2, b2, z, s,
+      static_cast<uint4*>(y_bf16), y_f32, nvec, B, HW, C, Cr, res_scale);
+  return launch_status();
 }
 
 extern "C" int srb200_ca_backward(const void* g_bf16, const void* t_bf16, const float* s, const float* z,
