@@ -35,7 +35,8 @@ class EDSR(ArchMixin, nn.Module):
                  cuda_graph=False,
                  graph_segments=4,
                  graph_input_shape=None,
-                 compute_dtype='bf16'):
+                 compute_dtype='bf16',
+                 flat_grads=False):
         super(EDSR, self).__init__()
         if compute_dtype not in ('bf16', 'fp32'):
             raise ValueError(f"compute_dtype must be 'bf16' or 'fp32', got {compute_dtype!r}")
@@ -45,6 +46,7 @@ class EDSR(ArchMixin, nn.Module):
         self.cuda_graph = cuda_graph
         self.graph_segments = max(1, int(graph_segments))
         self.graph_input_shape = graph_input_shape  # e.g. [16, 3, 48, 48]: capture on .to(device), before DDP
+        self.flat_grads = bool(flat_grads)  # gradients land in ONE flat buffer (utils/flat_ddp.py) -- for FlatDDP
 
         self.img_range = img_range
         self.mean = torch.Tensor(rgb_mean).view(1, 3, 1, 1)

@@ -202,6 +202,10 @@ class ArchMixin:
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
+        if getattr(self, 'flat_grads', False) and next(self.parameters()).is_cuda:
+            # the flat gradient buffer must exist BEFORE the graphs are captured: the captures record its addresses
+            from ..utils.flat_ddp import flat_grads_of
+            flat_grads_of(self)
         precapture(self)
         return out
 

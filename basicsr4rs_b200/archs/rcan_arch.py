@@ -98,7 +98,8 @@ class RCAN(ArchMixin, nn.Module):
                  cuda_graph=False,
                  graph_segments=5,
                  graph_input_shape=None,
-                 compute_dtype='bf16'):
+                 compute_dtype='bf16',
+                 flat_grads=False):
         super(RCAN, self).__init__()
         if compute_dtype not in ('bf16', 'fp32'):
             raise ValueError(f"compute_dtype must be 'bf16' or 'fp32', got {compute_dtype!r}")
@@ -106,6 +107,7 @@ class RCAN(ArchMixin, nn.Module):
         self.cuda_graph = cuda_graph          # optional: replay training fwd/bwd from CUDA graphs (archs/graphed.py)
         self.graph_segments = graph_segments
         self.graph_input_shape = graph_input_shape
+        self.flat_grads = bool(flat_grads)  # gradients land in ONE flat buffer (utils/flat_ddp.py) -- for FlatDDP
 
         self.img_range = img_range
         self.mean = torch.Tensor(rgb_mean).view(1, 3, 1, 1)

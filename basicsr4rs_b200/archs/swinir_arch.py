@@ -479,6 +479,7 @@ class SwinIR(ArchMixin, nn.Module):
         self.cuda_graph = bool(kwargs.get('cuda_graph', False))
         self.graph_segments = int(kwargs.get('graph_segments', 6))
         self.graph_input_shape = kwargs.get('graph_input_shape', None)
+        self.flat_grads = bool(kwargs.get('flat_grads', False))  # ONE flat gradient buffer (utils/flat_ddp.py)
         num_in_ch = in_chans
         num_out_ch = in_chans
         num_feat = 64

@@ -383,19 +383,37 @@ def _item_table(rows):
 MAX_INLINE_ITEMS = 8
 
 
-def finalize_grads(items):
+# Gradient sink (basicsr4rs_b200.utils.flat_ddp.FlatGrads): parameter storage address -> a preallocated fp32 view of that
+# parameter's slice of ONE flat gradient buffer.  finalize_grads writes a sunk parameter's gradient straight into its
+# slice (the address is fixed, so CUDA-graph captures record it) and returns a fresh alias of it, which autograd adopts
+# as ``param.grad`` without a copy: the data-parallel all-reduce then runs on the flat buffer itself.
+GRAD_SINK = {}
+
+
+def _grad_target(param, shape, device):
+    if param is not None and GRAD_SINK:
+        view = GRAD_SINK.get(param.data_ptr())
+        if view is not None and view.device == device and tuple(view.shape) == tuple(shape):
+            return view
+    return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+
+
+def finalize_grads(items, params=None):
     """All weight and bias gradients of one layer's backward in ONE launch (srb200_unpack_wgrads_inline).
 
     ``items``: list of ('w', acc [taps,Np,Kp] fp32, w_shape, perm_out, perm_in, alpha) or
-    ('b', colsum [Np] fp32, n_bias, perm_out, alpha).  Returns the gradients in the parameter layouts."""
+    ('b', colsum [Np] fp32, n_bias, perm_out, alpha).  Returns the gradients in the parameter layouts.
+    ``params`` (optional, aligned with ``items``): the parameters the gradients belong to -- those registered in
+    :data:`GRAD_SINK` receive their gradient in place."""
     rows, outs = [], []
-    for it in items:
+    params = params if params is not None else [None] * len(items)
+    for it, prm in zip(items, params):
         if it[0] == 'w':
             _, acc, w_shape, perm_out, perm_in, alpha = it
             taps, n_pad, k_pad = acc.shape
             # every parameter element has exactly one packed slot (the index maps are onto: padding only ADDS
             # packed slots), so the scatter writes the whole gradient -- no zero fill needed
-            g = torch.empty(tuple(w_shape), dtype=torch.float32, device=acc.device)
+            g = _grad_target(prm, w_shape, acc.device)
             rows.append(dict(src=acc, dst=g, Co=w_shape[0], Ci=w_shape[1], taps=taps, Np=n_pad, Kp=k_pad,
                              perm_out=perm_out, perm_in=perm_in, alpha=alpha))
         elif it[0] == 'bcol':
@@ -403,12 +421,12 @@ def finalize_grads(items):
             # carried a constant-one pad channel there, see srb200_layernorm_fwd): a strided [Np x 1] item
             _, acc, col, n_bias, perm_out, alpha = it
             _, n_pad, k_pad = acc.shape
-            g = torch.empty((n_bias,), dtype=torch.float32, device=acc.device)
+            g = _grad_target(prm, (n_bias,), acc.device)
             rows.append(dict(src=acc[0, :, col:], dst=g, Co=n_bias, Ci=1, taps=1, Np=n_pad, Kp=k_pad, perm_out=perm_out,
                              alpha=alpha))
         else:
             _, cs, n_bias, perm_out, alpha = it
-            g = torch.empty((n_bias,), dtype=torch.float32, device=cs.device)
+            g = _grad_target(prm, (n_bias,), cs.device)
             rows.append(dict(src=cs, dst=g, Co=n_bias, Ci=1, taps=1, Np=cs.numel(), Kp=1, perm_out=perm_out,
                              alpha=alpha))
         outs.append(g)
@@ -416,7 +434,9 @@ def finalize_grads(items):
         tab, _ = _item_table(rows[i:i + MAX_INLINE_ITEMS])
         L.check(L.load().srb200_unpack_wgrads_inline(tab.ctypes.data_as(ctypes.c_void_p), len(tab), _stream()),
                 'unpack_wgrads_inline')
-    return outs
+    # (fresh tensor objects: autograd adopts an incoming gradient as ``param.grad`` without a copy only when nobody else
+    # holds that tensor object -- the sink keeps its own view)
+    return [g.detach() for g in outs] if GRAD_SINK else outs
 
 
 def pack_items(rows, device):

@@ -376,13 +376,15 @@ class _ConvNHWC(Function):
                 acc = raw.wgrad(g, x, ksize=ksize, dy_r=shuffle_r)
             if bias is not None and ctx.needs_input_grad[2] and gbp is None:
                 gbp = raw.colsum(g, r=shuffle_r)
-            items = []
+            items, prms = [], []
             if ctx.needs_input_grad[1]:
                 items.append(('w', acc, weight.shape, perm, None, alpha))
+                prms.append(weight)
             if bias is not None and ctx.needs_input_grad[2]:
                 items.append(('b', gbp, bias.numel(), perm, alpha))
+                prms.append(bias)
             if items:
-                grads = raw.finalize_grads(items)
+                grads = raw.finalize_grads(items, prms)
                 if ctx.needs_input_grad[1]:
                     gw = grads[0]
                 if bias is not None and ctx.needs_input_grad[2]:
@@ -441,14 +443,16 @@ class _ResBlockNoBN(Function):
     @staticmethod
     def _backward(ctx, g, x, h, w1, b1, w2, b2, s, cp):
         gw1 = gb1 = gw2 = gb2 = gx = None
-        items = []
+        items, prms = [], []
         if b2 is not None and ctx.needs_input_grad[4]:
             items.append(('b', _colsum_of(g), b2.numel(), None, s))  # from the epilogue that produced g, if any
+            prms.append(b2)
         _colsum_tls.slot = None
         dev = x.device
         if ctx.needs_input_grad[3]:
             with raw.side_branch(dev):  # weight gradients next to the data-gradient chain
                 items.append(('w', raw.wgrad(g, h, ksize=3), w2.shape, None, None, s))
+                prms.append(w2)
         # d(pre-activation of conv1) = dgrad_conv2(s*g) masked by relu'(h); its column sums = conv1's bias gradient
         want_gb1 = b1 is not None and ctx.needs_input_grad[2]
         gh = raw.tapgemm(g, _packed(w2, 'dgrad', cp, cp), ksize=3, cout=cp, alpha=s, flip=True, mask_src=h,
@@ -456,15 +460,17 @@ class _ResBlockNoBN(Function):
         if want_gb1:
             gh, cs = gh
             items.append(('b', cs, b1.numel(), None, 1.0))
+            prms.append(b1)
         if ctx.needs_input_grad[1]:
             with raw.side_branch(dev):
                 items.append(('w', raw.wgrad(gh, x, ksize=3), w1.shape, None, None, 1.0))
+                prms.append(w1)
         if ctx.needs_input_grad[0]:
             gx, cs = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g,
                                  want_colsum=True)
             _stash_colsum(gx, cs)
         raw.side_join(dev)
-        grads = iter(raw.finalize_grads(items)) if items else iter(())  # one launch for all four gradients
+        grads = iter(raw.finalize_grads(items, prms)) if items else iter(())  # one launch for all four gradients
         if b2 is not None and ctx.needs_input_grad[4]:
             gb2 = next(grads)
         if ctx.needs_input_grad[3]:
@@ -670,7 +676,8 @@ class _RCAB(Function):
             gx = raw.tapgemm(gh, _packed(w1, 'dgrad', cp, cp), ksize=3, cout=cp, flip=True, residual=g)
         raw.side_join(dev)
         gw2, gb2, gw1, gb1 = raw.finalize_grads([('w', acc2, w2.shape, None, None, 1.0), ('b', cs2, b2.numel(), None, 1.0),
-                                                 ('w', acc1, w1.shape, None, None, 1.0), ('b', cs1, b1.numel(), None, 1.0)])
+                                                 ('w', acc1, w1.shape, None, None, 1.0), ('b', cs1, b1.numel(), None, 1.0)],
+                                                [w2, b2, w1, b1])
         return gx, None, gw1, gb1, gw2, gb2, gwa1, gba1, gwa2, gba2, None
 
 

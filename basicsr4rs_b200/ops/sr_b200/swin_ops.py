@@ -273,10 +273,12 @@ class _SwinBlock(Function):
                  ('w', acc_fc1, fc1_w.shape, None, None, 1.0), fc1_b_item,
                  ('w', acc_proj, proj_w.shape, None, p_o, 1.0), proj_b_item,
                  ('w', acc_qkv, qkv_w.shape, p_qkv, None, 1.0)]
+        prms = [fc2_w, fc2_b, fc1_w, fc1_b, proj_w, proj_b, qkv_w]
         if qkv_b is not None:
             items.append(('bcol', acc_qkv, ones, qkv_b.numel(), p_qkv, 1.0) if ones >= 0 else
                          ('b', raw.colsum(gqkv), qkv_b.numel(), p_qkv, 1.0))
-        grads = raw.finalize_grads(items)
+            prms.append(qkv_b)
+        grads = raw.finalize_grads(items, prms)
         g_fc2_w, g_fc2_b, g_fc1_w, g_fc1_b, g_proj_w, g_proj_b, g_qkv_w = grads[:7]
         g_qkv_b = grads[7] if qkv_b is not None else None
         return (gx, g_n1w, g_n1b, g_qkv_w, g_qkv_b, g_table, g_proj_w, g_proj_b, g_n2w, g_n2b, g_fc1_w, g_fc1_b,

@@ -386,6 +386,10 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of CUDA-graph replay')
     ap.add_argument('--grad-comm', default='fp32', choices=['fp32', 'bf16'],
                     help="DDP gradient all-reduce payload: fp32 (the reference's) or torch's bf16_compress_hook")
+    ap.add_argument('--ddp', default='flat', choices=['flat', 'torch'],
+                    help="N > 1: 'flat' = basicsr4rs_b200.utils.flat_ddp.FlatDDP (gradients written straight into one flat "
+                         "buffer that NCCL all-reduces, no per-parameter bucket copies), 'torch' = DistributedDataParallel "
+                         "exactly as BaseModel.model_to_device wraps it")
     ap.add_argument('--configs', default='all', help="'all', 'none' or a comma list of the other BASELINE configs "
                     f"({', '.join(list(TRAIN_CONFIGS) + list(INFER_CONFIGS))}); measured at N=1 only")
     args = ap.parse_args()
@@ -418,11 +422,16 @@ def main():
     L.check(L.load().srb200_check_device(local_rank), 'srb200_check_device')
 
     torch.manual_seed(0)
-    net = build_network(dict(EDSR_L, cuda_graph=not args.no_graph, graph_segments=4,
+    flat = world > 1 and args.ddp == 'flat'
+    net = build_network(dict(EDSR_L, cuda_graph=not args.no_graph, graph_segments=4, flat_grads=flat,
                              graph_input_shape=[BATCH, 3, LR, LR])).to(dev)  # graphs captured here, before DDP
-    model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True) \
-        if world > 1 else net
-    if world > 1 and args.grad_comm == 'bf16':
+    if flat:
+        from basicsr4rs_b200.utils.flat_ddp import FlatDDP
+        model = FlatDDP(net)
+    else:
+        model = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True) \
+            if world > 1 else net
+    if world > 1 and not flat and args.grad_comm == 'bf16':
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
         model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
@@ -508,7 +517,9 @@ def main():
             'metric': 'SR train patches/s (fwd+bwd)', 'value': value, 'unit': 'patches/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': dict(CONFIG, grad_comm=args.grad_comm if world > 1 else 'none (1 GPU)'),
+            'config': dict(CONFIG, grad_comm=('fp32 NCCL all-reduce (AVG) of one flat gradient buffer, FlatDDP' if flat
+                                              else args.grad_comm + ' buckets, torch DistributedDataParallel')
+                           if world > 1 else 'none (1 GPU)'),
             'e2e': {'value': patches / (ms_e2e / 1e3), 'unit': 'patches/s',
                     'h2d_bytes_per_step': (lq_h.numel() + gt_h.numel()) * 4, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches, 'clocks': clocks,

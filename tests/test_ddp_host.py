@@ -60,6 +60,21 @@ def _worker(rank, world, port, out):
     g = net.module.lin.weight.grad.clone()
     want = torch.full((4, 8), 3.0 * sum(r + 1 for r in range(world)) / world)
     assert torch.allclose(g, want), (g, want)
+    # FlatDDP (utils/flat_ddp.py): same averaging on ONE flat gradient buffer, .grad aliases its slice, two steps
+    from basicsr4rs_b200.utils.flat_ddp import FlatDDP
+    torch.manual_seed(1 + rank)  # different initial weights per rank: the wrap must broadcast rank 0's
+    fnet = FlatDDP(_Net(), bucket_mb=1)
+    w0 = [torch.zeros_like(fnet.module.lin.weight) for _ in range(world)]
+    dist.all_gather(w0, fnet.module.lin.weight.detach())
+    assert torch.equal(w0[0], w0[1])
+    for step in range(2):
+        for p in fnet.parameters():
+            p.grad = None
+        fnet(x * (step + 1)).sum().backward()
+        gw, gb = fnet.module.lin.weight.grad, fnet.module.lin.bias.grad
+        assert torch.allclose(gw, want * (step + 1)), (gw, want)
+        assert torch.allclose(gb, torch.full((4,), 3.0))
+        assert gw.data_ptr() == fnet.flat.views[0].data_ptr() and gb.data_ptr() == fnet.flat.views[1].data_ptr()
     if rank == 0:
         torch.save({'ok': True}, out)
     dist.destroy_process_group()

@@ -13,6 +13,7 @@
 * the live, unmodified reference (``oracle/_ref``, vendored by oracle/make_ref.py) run on the GPU in fp32 against ours.
 """
 import copy
+import os
 
 import pytest
 import torch
@@ -569,3 +570,40 @@ def test_rcan_fp32_mode_full_depth_within_1e4(cuda):
     err = (out - ref).abs().max().item()
     print(f'RCAN fp32 mode max-abs {err:.2e}')
     assert err <= 1e-4, f'max-abs {err:.3e}'
+
+
+# ------------------------------------------------------------------ flat gradient buffer (utils/flat_ddp.py)
+@pytest.mark.parametrize('graph', [False, True])
+def test_flat_grads_alias_one_buffer_and_match_plain_gradients(cuda, graph):
+    """``flat_grads=True``: the layers' gradient finalize writes into ONE flat buffer (registered before the CUDA graphs
+    are captured), ``param.grad`` aliases its slice without a copy, and the values equal those of a plain network --
+    eager and under CUDA-graph replay, over two steps (the second replay overwrites the same addresses)."""
+    import torch.distributed as dist
+    from basicsr4rs_b200.archs import build_network
+    from basicsr4rs_b200.utils.flat_ddp import FlatDDP
+    kw = dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=64, num_block=3, upscale=2, res_scale=0.5)
+    torch.manual_seed(0)
+    plain = build_network(dict(kw)).to(cuda).train()
+    torch.manual_seed(0)
+    flat = build_network(dict(kw, flat_grads=True, cuda_graph=graph, graph_segments=2,
+                              graph_input_shape=[2, 3, 16, 16])).to(cuda).train()
+    if not dist.is_initialized():
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29641')
+        dist.init_process_group('nccl', rank=0, world_size=1)
+    wrapped = FlatDDP(flat)
+    fg = wrapped.flat
+    for step in range(2):
+        x = torch.rand((2, 3, 16, 16), device=cuda, generator=torch.Generator(device=cuda).manual_seed(step))
+        for net in (plain, wrapped):
+            net.zero_grad(set_to_none=True)
+            (net(x)**2).mean().backward()
+        torch.cuda.synchronize()
+        sunk = 0
+        for (k, p), q, view in zip(plain.named_parameters(), flat.parameters(), fg.views):
+            assert q.grad is not None and q.grad.data_ptr() == view.data_ptr(), k  # aliases its slice of the flat buffer
+            rel = (q.grad - p.grad).abs().max().item() / (p.grad.abs().max().item() + 1e-12)
+            assert rel <= 1e-3, (k, rel)  # (same arithmetic; split-K / column sums merge in arrival order)
+            sunk += 1
+        assert sunk == len(fg.params)
+    fg.release()

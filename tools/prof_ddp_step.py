@@ -20,6 +20,7 @@ from basicsr4rs_b200.archs import build_network  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--grad-comm', default='fp32', choices=['fp32', 'bf16'])
 ap.add_argument('--steps', type=int, default=4)
+ap.add_argument('--ddp', default='torch', choices=['torch', 'flat'])
 ap.add_argument('--bucket-mb', type=int, default=25)
 args = ap.parse_args()
 world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -30,9 +31,13 @@ dev = torch.device('cuda', local)
 if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 torch.manual_seed(0)
-net = build_network(dict(EDSR_L, cuda_graph=True, graph_segments=4, graph_input_shape=[BATCH, 3, LR, LR])).to(dev)
+net = build_network(dict(EDSR_L, cuda_graph=True, graph_segments=4, graph_input_shape=[BATCH, 3, LR, LR],
+                         flat_grads=args.ddp == 'flat')).to(dev)
 model = net
-if world > 1:
+if world > 1 and args.ddp == 'flat':
+    from basicsr4rs_b200.utils.flat_ddp import FlatDDP
+    model = FlatDDP(net)
+elif world > 1:
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                       bucket_cap_mb=args.bucket_mb)
     if args.grad_comm == 'bf16':
@@ -88,7 +93,7 @@ if rank == 0:
     n = args.steps
     t_nccl, t_comp = union(nccl) / n, union(comp) / n
     t_both = overlap(nccl, comp) / n
-    print(f'## EDSR-L B16 DDP world={world} grad-comm={args.grad_comm} bucket={args.bucket_mb} MB: {ms:.3f} ms/step unprofiled')
+    print(f'## EDSR-L B16 DDP world={world} ddp={args.ddp} grad-comm={args.grad_comm} bucket={args.bucket_mb} MB: {ms:.3f} ms/step unprofiled')
     print(f'compute kernels busy {t_comp / 1e3:.3f} ms/step; NCCL kernels busy {t_nccl / 1e3:.3f} ms/step, of which '
           f'{t_both / 1e3:.3f} ms overlap compute and {(t_nccl - t_both) / 1e3:.3f} ms are exposed')
     agg = collections.defaultdict(lambda: [0, 0.0])
