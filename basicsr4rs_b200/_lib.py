@@ -7,7 +7,7 @@ never routes through PyTorch ops or the CPU oracle.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # this repo: basicsr4rs_b200/csrc/libsrb200.so; grafted into the reference (tools/graft_into_reference.py): the op
@@ -75,6 +75,8 @@ SIGNATURES = {
                                    c_void_p]),
     'srb200_tap_im2col': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     'srb200_multi_axpby': (c_int, [c_void_p, c_int, c_int64, c_float, c_float, c_void_p]),
+    'srb200_multi_adam': (c_int, [c_void_p, c_int, c_int64, c_double, c_double, c_double, c_double, c_double, c_int64,
+                                  c_void_p]),
     'srb200_pack_weights': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     'srb200_unpack_wgrads': (c_int, [c_void_p, c_int, c_int64, c_void_p]),
     'srb200_unpack_wgrads_inline': (c_int, [c_void_p, c_int, c_void_p]),

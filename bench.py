@@ -37,7 +37,7 @@ SWINIR = dict(type='SwinIR', upscale=4, in_chans=3, img_size=64, window_size=8, 
               embed_dim=180, num_heads=[6] * 6, mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv')
 BATCH, LR = 16, 48
 WORKLOAD = 'EDSR-L x4 train step (fwd + L1 + bwd + Adam), 16x3x48x48 LR patches per GPU'
-CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; L1 loss + torch.optim.Adam(fused=True) eager',
+CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; L1 loss + one-launch Adam (utils/fused_adam.FusedAdam) eager',
           'workload': WORKLOAD, 'arch': 'EDSR num_feat=256 num_block=32 res_scale=0.1 upscale=4', 'batch_per_gpu': BATCH,
           'lr_patch': LR, 'parallelism': 'ddp', 'l2': 'per-step working set (>2 GB of activations) exceeds the 126 MB L2'}
 FLOP_PER_PATCH_FWD_BWD = 694.66e9
@@ -273,11 +273,18 @@ def dominant(rooflines):
     return dict(rooflines[name], kernel=name), {k: v for k, v in rooflines.items() if k != name}
 
 
-def bench_train_config(name, dev, steps, pk, raw, build_network, L):
+def make_adam(params, kind='srb200'):
+    if kind == 'torch':
+        return torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.99), fused=True)
+    from basicsr4rs_b200.utils.fused_adam import FusedAdam
+    return FusedAdam(params, lr=1e-4, betas=(0.9, 0.99))
+
+
+def bench_train_config(name, dev, steps, pk, raw, build_network, L, optim_kind='srb200'):
     opt, batch, lr, gflop, segs = TRAIN_CONFIGS[name]
     torch.manual_seed(0)
     net = build_network(dict(opt, cuda_graph=True, graph_segments=segs)).to(dev).train()
-    optim = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
+    optim = make_adam(net.parameters(), optim_kind)
     crit = torch.nn.L1Loss()
     lq_h, gt_h = (t.pin_memory() for t in synthetic_batch(0, batch, lr))
     lq, gt = lq_h.to(dev), gt_h.to(dev)
@@ -390,6 +397,9 @@ def main():
                     help="N > 1: 'flat' = basicsr4rs_b200.utils.flat_ddp.FlatDDP (gradients written straight into one flat "
                          "buffer that NCCL all-reduces, no per-parameter bucket copies), 'torch' = DistributedDataParallel "
                          "exactly as BaseModel.model_to_device wraps it")
+    ap.add_argument('--optim', default='srb200', choices=['srb200', 'torch'],
+                    help="Adam step: 'srb200' = one srb200_multi_adam launch (utils/fused_adam.FusedAdam), 'torch' = "
+                         "torch.optim.Adam(fused=True)")
     ap.add_argument('--configs', default='all', help="'all', 'none' or a comma list of the other BASELINE configs "
                     f"({', '.join(list(TRAIN_CONFIGS) + list(INFER_CONFIGS))}); measured at N=1 only")
     args = ap.parse_args()
@@ -434,7 +444,7 @@ def main():
     if world > 1 and not flat and args.grad_comm == 'bf16':
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
         model.register_comm_hook(None, default_hooks.bf16_compress_hook)
-    optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
+    optim = make_adam(model.parameters(), args.optim)
     crit = nn.L1Loss()
 
     lq_h, gt_h = (t.pin_memory() for t in synthetic_batch(rank))
@@ -517,7 +527,8 @@ def main():
             'metric': 'SR train patches/s (fwd+bwd)', 'value': value, 'unit': 'patches/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': dict(CONFIG, grad_comm=('fp32 NCCL all-reduce (AVG) of one flat gradient buffer, FlatDDP' if flat
+            'config': dict(CONFIG if args.optim == 'srb200' else dict(CONFIG, launch=CONFIG['launch'].replace(
+                'one-launch Adam (utils/fused_adam.FusedAdam)', 'torch.optim.Adam(fused=True)')), grad_comm=('fp32 NCCL all-reduce (AVG) of one flat gradient buffer, FlatDDP' if flat
                                               else args.grad_comm + ' buckets, torch DistributedDataParallel')
                            if world > 1 else 'none (1 GPU)'),
             'e2e': {'value': patches / (ms_e2e / 1e3), 'unit': 'patches/s',
@@ -553,7 +564,7 @@ def main():
             for name in want:
                 try:
                     if name in TRAIN_CONFIGS:
-                        cfgs[name] = bench_train_config(name, dev, max(5, args.steps // 2), pk, raw, build_network, L)
+                        cfgs[name] = bench_train_config(name, dev, max(5, args.steps // 2), pk, raw, build_network, L, args.optim)
                     elif name in INFER_CONFIGS:
                         cfgs[name] = bench_infer_config(name, dev, args.steps, pk, raw, build_network)
                 except Exception as e:  # a failing side config must not take the headline line with it

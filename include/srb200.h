@@ -157,6 +157,23 @@ typedef struct {
 int srb200_multi_axpby(const srb200_vec_item* items_dev, int n_items, int64_t total_chunks, float a, float b,
                        srb200_stream_t stream);
 
+/* ------------------------------------------------------------------ multi-tensor Adam
+ * One launch = torch.optim.Adam's update (amsgrad off, L2 weight decay) of every fp32 tensor of a DEVICE table: the
+ * optimizer step of SRModel.optimize_parameters (basicsr/models/sr_model.py:113) without torch's ~36-tensors-per-launch
+ * argument packing.  Item i covers 1024-float chunks [chunk_begin, chunk_begin + ceil(n/1024)).  `step` = 1, 2, ... is the
+ * update count (the hyper-parameters are doubles, as Python holds them: 1 - beta and the bias corrections 1 - beta^step
+ * are formed on the host in double precision, like torch does, then rounded to fp32 once).                      */
+typedef struct {
+  void* p;        /* parameter, updated in place */
+  const void* g;  /* gradient */
+  void* m;        /* exp_avg */
+  void* v;        /* exp_avg_sq */
+  int64_t n;
+  int64_t chunk_begin;
+} srb200_adam_item;
+int srb200_multi_adam(const srb200_adam_item* items_dev, int n_items, int64_t total_chunks, double lr, double beta1,
+                      double beta2, double eps, double weight_decay, int64_t step, srb200_stream_t stream);
+
 /* ------------------------------------------------------------------ tap-GEMM (conv3x3 / conv1x1 / Linear)
  * out[b,y,x,n] = epi( sum_{t,k} A[b, y+dy(t), x+dx(t), k] * Wp[t][n][k] )
  * TMA-fed tcgen05 implicit GEMM, fp32 accumulation in TMEM.  Replaces nn.Conv2d(…,3,1,1)

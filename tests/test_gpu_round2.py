@@ -607,3 +607,39 @@ def test_flat_grads_alias_one_buffer_and_match_plain_gradients(cuda, graph):
             sunk += 1
         assert sunk == len(fg.params)
     fg.release()
+
+
+# ------------------------------------------------------------------ one-launch Adam (utils/fused_adam.py)
+@pytest.mark.parametrize('wd', [0.0, 1e-2])
+def test_fused_adam_matches_torch_adam_and_interchanges_checkpoints(cuda, wd):
+    """srb200_multi_adam against torch.optim.Adam over several steps on an odd mix of tensor sizes (vector and scalar
+    tails, > 1 chunk), then a checkpoint written by one optimizer continues in the other."""
+    from basicsr4rs_b200.utils.fused_adam import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    shapes = [(64, 64, 3, 3), (64,), (7,), (3, 5), (1030,), (1,)]
+    pa = [torch.randn(s, generator=g).to(cuda).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    kw = dict(lr=2e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    oa, ob = torch.optim.Adam(pa, **kw), FusedAdam(pb, **kw)
+
+    def run(opt_a, opt_b, steps, seed):
+        gg = torch.Generator().manual_seed(seed)
+        for _ in range(steps):
+            for x, y in zip(pa, pb):
+                grad = torch.randn(x.shape, generator=gg).to(cuda)
+                x.grad, y.grad = grad.clone(), grad.clone()
+            opt_a.step()
+            opt_b.step()
+        for x, y in zip(pa, pb):
+            assert torch.allclose(x, y, rtol=2e-6, atol=2e-7), (x - y).abs().max().item()
+
+    run(oa, ob, 5, 10)
+    for x, y in zip(pa, pb):
+        assert torch.allclose(oa.state[x]['exp_avg_sq'], ob.state[y]['exp_avg_sq'], rtol=1e-6, atol=1e-12)
+    # swap the optimizers through their checkpoints: torch's state into FusedAdam and back
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert float(sb['state'][0]['step']) == 5.0 and set(sb['state'][0]) == set(sa['state'][0])
+    oa2, ob2 = torch.optim.Adam(pa, **kw), FusedAdam(pb, **kw)
+    oa2.load_state_dict(sb)
+    ob2.load_state_dict(sa)
+    run(oa2, ob2, 3, 11)

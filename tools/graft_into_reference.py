@@ -59,6 +59,9 @@ REWIRE = [
     # utils/ema.py -> ops/sr_b200/ema.py
     (r'^from \.\. import _lib as L$', 'from . import _lib as L'),
     (r'^(\s+)from \.\.archs\.graphed import BOOKS$', r'\1from .graphed import BOOKS'),
+    # archs/graphed.py -> ops/sr_b200/graphed.py, utils/flat_ddp.py / fused_adam.py -> ops/sr_b200/
+    (r'^(\s+)from \.\.utils\.flat_ddp import (.*)$', r'\1from .flat_ddp import \2'),
+    (r'^from \.\.ops\.sr_b200 import raw$', 'from . import raw'),
 ]
 ARCH_UTIL_TAIL = '''
 
@@ -122,6 +125,8 @@ def graft(ref_root=None, out_dir=None):
     _copy_rewired(os.path.join(PKG, 'utils', 'tiling.py'), os.path.join(op, 'tiling.py'))
     _copy_rewired(os.path.join(PKG, 'utils', 'data_gpu.py'), os.path.join(op, 'data_gpu.py'))
     _copy_rewired(os.path.join(PKG, 'utils', 'train_hooks.py'), os.path.join(op, 'train_hooks.py'))
+    _copy_rewired(os.path.join(PKG, 'utils', 'flat_ddp.py'), os.path.join(op, 'flat_ddp.py'))
+    _copy_rewired(os.path.join(PKG, 'utils', 'fused_adam.py'), os.path.join(op, 'fused_adam.py'))
     _copy_rewired(os.path.join(PKG, 'archs', 'arch_util.py'), os.path.join(op, 'arch_blocks.py'))
     os.makedirs(os.path.join(op, 'src'), exist_ok=True)
     for name in os.listdir(os.path.join(PKG, 'csrc')):

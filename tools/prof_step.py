@@ -18,7 +18,11 @@ opt, batch, lr, _ = TRAIN[name]
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 net = build_network(dict(opt, cuda_graph=graph)).to(dev).train()
-optim = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
+if os.environ.get('TORCH_ADAM'):
+    optim = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.99), fused=True)
+else:
+    from basicsr4rs_b200.utils.fused_adam import FusedAdam
+    optim = FusedAdam(net.parameters(), lr=1e-4, betas=(0.9, 0.99))
 lq = torch.rand((batch, 3, lr, lr), device=dev)
 gt = torch.rand((batch, 3, 4 * lr, 4 * lr), device=dev)
 
