@@ -385,17 +385,20 @@ MAX_INLINE_ITEMS = 8
 
 # Gradient sink (basicsr4rs_b200.utils.flat_ddp.FlatGrads): parameter storage address -> a preallocated fp32 view of that
 # parameter's slice of ONE flat gradient buffer.  finalize_grads writes a sunk parameter's gradient straight into its
-# slice (the address is fixed, so CUDA-graph captures record it) and returns a fresh alias of it, which autograd adopts
-# as ``param.grad`` without a copy: the data-parallel all-reduce then runs on the flat buffer itself.
-GRAD_SINK = {}
+# slice (the address is fixed, so CUDA-graph captures record it) -- already multiplied by the sink's scale, 1 / world_size
+# under data parallelism, so that the all-reduce can be a plain SUM (NCCL's in-switch NVLS reduction does not do
+# pre-multiplied averages) -- and returns a fresh alias of it, which autograd adopts as ``param.grad`` without a copy:
+# the data-parallel all-reduce then runs on the flat buffer itself.
+GRAD_SINK = {}  # parameter data_ptr -> (fp32 view of its slice, scale applied to the gradient written there)
 
 
 def _grad_target(param, shape, device):
+    """(destination tensor, extra gradient scale): the parameter's slice of the flat buffer when it has one."""
     if param is not None and GRAD_SINK:
-        view = GRAD_SINK.get(param.data_ptr())
-        if view is not None and view.device == device and tuple(view.shape) == tuple(shape):
-            return view
-    return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+        hit = GRAD_SINK.get(param.data_ptr())
+        if hit is not None and hit[0].device == device and tuple(hit[0].shape) == tuple(shape):
+            return hit
+    return torch.empty(tuple(shape), dtype=torch.float32, device=device), 1.0
 
 
 def finalize_grads(items, params=None):
@@ -413,22 +416,22 @@ def finalize_grads(items, params=None):
             taps, n_pad, k_pad = acc.shape
             # every parameter element has exactly one packed slot (the index maps are onto: padding only ADDS
             # packed slots), so the scatter writes the whole gradient -- no zero fill needed
-            g = _grad_target(prm, w_shape, acc.device)
+            g, sc = _grad_target(prm, w_shape, acc.device)
             rows.append(dict(src=acc, dst=g, Co=w_shape[0], Ci=w_shape[1], taps=taps, Np=n_pad, Kp=k_pad,
-                             perm_out=perm_out, perm_in=perm_in, alpha=alpha))
+                             perm_out=perm_out, perm_in=perm_in, alpha=alpha * sc))
         elif it[0] == 'bcol':
             # a bias gradient that sits in COLUMN `col` of a weight-gradient accumulator [1, Np, Kp] (the layer's input
             # carried a constant-one pad channel there, see srb200_layernorm_fwd): a strided [Np x 1] item
             _, acc, col, n_bias, perm_out, alpha = it
             _, n_pad, k_pad = acc.shape
-            g = _grad_target(prm, (n_bias,), acc.device)
+            g, sc = _grad_target(prm, (n_bias,), acc.device)
             rows.append(dict(src=acc[0, :, col:], dst=g, Co=n_bias, Ci=1, taps=1, Np=n_pad, Kp=k_pad, perm_out=perm_out,
-                             alpha=alpha))
+                             alpha=alpha * sc))
         else:
             _, cs, n_bias, perm_out, alpha = it
-            g = _grad_target(prm, (n_bias,), cs.device)
+            g, sc = _grad_target(prm, (n_bias,), cs.device)
             rows.append(dict(src=cs, dst=g, Co=n_bias, Ci=1, taps=1, Np=cs.numel(), Kp=1, perm_out=perm_out,
-                             alpha=alpha))
+                             alpha=alpha * sc))
         outs.append(g)
     for i in range(0, len(rows), MAX_INLINE_ITEMS):
         tab, _ = _item_table(rows[i:i + MAX_INLINE_ITEMS])

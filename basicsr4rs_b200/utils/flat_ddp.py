@@ -10,8 +10,10 @@ CUPTI timeline of a 2-GPU step (tools/prof_ddp_step.py, profiles/r02_ddp2_fp32.t
 Here the layers' one-launch gradient finalize (``raw.finalize_grads``) writes every weight / bias gradient straight into
 its slice of a flat fp32 buffer (``FlatGrads``, registered in ``raw.GRAD_SINK`` BEFORE the CUDA graphs are captured, so
 the captures record the final addresses); autograd adopts the returned aliases as ``param.grad`` without a copy, and
-``FlatDDP`` all-reduces the buffer itself -- bucket by bucket as soon as all gradients of a bucket have arrived, averaged
-by NCCL (``ReduceOp.AVG``: no division kernel), waited for at the end of ``backward()`` exactly like DDP.  Gradients
+``FlatDDP`` all-reduces the buffer itself -- bucket by bucket as soon as all gradients of a bucket have arrived, waited
+for at the end of ``backward()`` exactly like DDP.  The finalize launches pre-divide by the world size (their ``alpha``),
+so the collective is a plain SUM with no division kernel: ``ReduceOp.AVG`` is a pre-multiplied sum, which keeps NCCL off
+its in-switch NVLS reduction (measured on 8 GPUs: five ``AllReduce_Sum_f32_RING_LL`` kernels of 760 us per step).  Gradients
 that reach autograd by other routes (LayerNorm, bias tables, the image-exit conv) are folded in with one
 ``torch._foreach_copy_`` per bucket.  One exchange step, no custom collective: NCCL over NVLink does the reduction.
 """
@@ -39,9 +41,14 @@ class FlatGrads:
         self.buf = torch.zeros((total,), dtype=torch.float32, device=dev)
         self.views = [self.buf[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, self.params)]
         self.total = total
-        if dev.type == 'cuda':
+        # gradients written through the sink are pre-divided by the world size known NOW (the CUDA graphs captured after
+        # this point bake the factor into their finalize launches): the all-reduce is then a plain SUM
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.prescale = 1.0 / self.world
+        self.sunk = dev.type == 'cuda'
+        if self.sunk:
             for p, v in zip(self.params, self.views):
-                raw.GRAD_SINK[p.data_ptr()] = v
+                raw.GRAD_SINK[p.data_ptr()] = (v, self.prescale)
 
     def release(self):
         for p in self.params:
@@ -90,7 +97,9 @@ class FlatDDP(nn.Module):
             self.bucket_of[i] = len(self.buckets) - 1
         self._pending = None
         self._works = []
-        self._avg = dist.is_initialized() and dist.get_backend(process_group) == 'nccl'
+        if fg.sunk and fg.world != self.world:
+            raise RuntimeError('FlatDDP: the flat gradient buffer was created for another world size -- build the network '
+                               'after init_process_group')
         for i, p in enumerate(fg.params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
@@ -114,7 +123,8 @@ class FlatDDP(nn.Module):
         fg = self.flat
         lo, hi, idx = self.buckets[b]
         self._launched[b] = True
-        # gradients that did not come through the sink: fold them into the flat buffer, re-point .grad at the slice
+        # gradients that did not come through the sink (LayerNorm, bias tables, the image-exit conv; everything on a CPU
+        # module): fold them into the flat buffer pre-divided like the sunk ones, re-point .grad at the slice
         src, dst = [], []
         for i in idx:
             p = fg.params[i]
@@ -123,16 +133,14 @@ class FlatDDP(nn.Module):
                 dst.append(fg.views[i])
         if src:
             torch._foreach_copy_(dst, src)
+            if self.world > 1:
+                torch._foreach_mul_(dst, 1.0 / self.world)
             for i in idx:
                 p = fg.params[i]
                 if p.grad is not None and p.grad.data_ptr() != fg.views[i].data_ptr():
                     p.grad = fg.views[i].detach()
         if self.world > 1:
-            chunk = fg.buf[lo:hi]
-            if self._avg:
-                self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
-            else:  # gloo (CPU tests): sum, then scale
-                self._works.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True), chunk))
+            self._works.append(dist.all_reduce(fg.buf[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _finish(self):
         """End of the backward pass (still inside ``backward()``): reduce what is left, make the current stream wait."""
@@ -140,10 +148,6 @@ class FlatDDP(nn.Module):
             if not self._launched[b]:  # a bucket with parameters that received no gradient this pass
                 self._reduce(b)
         for w in self._works:
-            if isinstance(w, tuple):
-                w[0].wait()
-                w[1].div_(self.world)
-            else:
-                w.wait()
+            w.wait()
         self._works = []
         self._pending = None

@@ -36,7 +36,7 @@ net = build_network(dict(EDSR_L, cuda_graph=True, graph_segments=4, graph_input_
 model = net
 if world > 1 and args.ddp == 'flat':
     from basicsr4rs_b200.utils.flat_ddp import FlatDDP
-    model = FlatDDP(net)
+    model = FlatDDP(net, bucket_mb=args.bucket_mb)
 elif world > 1:
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                       bucket_cap_mb=args.bucket_mb)
