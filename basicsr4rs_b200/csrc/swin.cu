@@ -117,25 +117,32 @@ __global__ void layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
 // only Cp/8 of them busy: 24 of 32 at Cp = 192) and a reduction is 3 shuffles shared by four tokens instead of 5 per
 // token.  gamma / beta live in shared memory (read as float4 when a row is written).
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_fwd8_kernel(const __nv_bfloat16* __restrict__ x,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta,
-                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
-                                                             float* __restrict__ rstd_out, long long T, int C, int Cp,
-                                                             float eps, int ones_ch) {
+__global__ void __launch_bounds__(256, 2) layernorm_fwd8_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta,
+                                                                __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                                                float* __restrict__ rstd_out, long long T, int C, int Cp,
+                                                                float eps, int ones_ch) {
   pdl_trigger();
-  extern __shared__ float s_gb[];  // gamma[Cp] | beta[Cp], zero beyond C
-  for (int i = threadIdx.x; i < Cp; i += blockDim.x) {
-    s_gb[i] = i < C ? __ldg(gamma + i) : 0.0f;
-    s_gb[Cp + i] = i < C ? __ldg(beta + i) : 0.0f;
-  }
-  __syncthreads();
   const int lane = threadIdx.x & 31, sub = lane & 7, slot = lane >> 3;
   const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int nv = Cp / 8;
   const float inv_c = 1.0f / static_cast<float>(C);
   const float npad = static_cast<float>(NV * 64 - C);  // zero channels this token's 8 lanes sum over (incl. vec >= nv)
+  // A lane always works on the same channels (vectors sub + 8 i): its gamma / beta live in registers.  (Read from
+  // shared memory as four 16-byte loads per vector and token they made the kernel wait on the shared-memory
+  // scoreboard -- ncu: 5.0 warps stalled on short_scoreboard per issue, 0.42 of the HBM roofline on 1M tokens.)
+  float gm[NV][8], bt[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = (sub + 8 * i) * 8 + e;
+      gm[i][e] = c < C ? __ldg(gamma + c) : 0.0f;
+      bt[i][e] = c < C ? __ldg(beta + c) : 0.0f;
+      if (c == ones_ch) bt[i][e] = 1.0f;  // constant-one PAD channel (gamma = 0 there): see the warp-per-token kernel
+    }
   auto load = [&](long long t, uint4 (&raw)[NV]) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -184,19 +191,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd8_kernel(const __nv_bfloat16
       for (int i = 0; i < NV; ++i) {
         const int vec = sub + 8 * i;
         if (vec < nv) {
-          const float4 g0 = *reinterpret_cast<const float4*>(s_gb + vec * 8), g1 = *reinterpret_cast<const float4*>(s_gb + vec * 8 + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(s_gb + Cp + vec * 8),
-                       b1 = *reinterpret_cast<const float4*>(s_gb + Cp + vec * 8 + 4);
-          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = fmaf((v[i][e] - mean) * rstd, gm[e], bt[e]);  // (gamma = beta = 0 on pads)
-          if (ones_ch >= 0 && (ones_ch >> 3) == vec) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (e == (ones_ch & 7)) o[e] = 1.0f;
-          }
+          for (int e = 0; e < 8; ++e) o[e] = fmaf((v[i][e] - mean) * rstd, gm[i][e], bt[i][e]);  // (gamma = 0 on pads)
           *(reinterpret_cast<uint4*>(y + t * Cp) + vec) = ln_pack(o);
         }
       }
@@ -507,9 +504,10 @@ extern "C" int srb200_layernorm_fwd(const void* x_bf16, const float* gamma, cons
   if (Cp <= 256 && SRB_ENV("SRB_LN_WARP_PER_TOKEN") == nullptr) {
     // 8 lanes per token: 32 tokens per 256-thread block iteration, a few blocks per SM, grid-stride
     long long b8 = (T + 31) / 32;
-    const long long cap8 = static_cast<long long>(num_sms()) * 6;
+    const int nvl0 = (Cp / 8 + 7) / 8;
+    const long long cap8 = static_cast<long long>(num_sms()) * (nvl0 >= 3 ? 2 : 4);  // resident blocks: one wave
     if (b8 > cap8) b8 = cap8;
-    const size_t smem = 2 * static_cast<size_t>(Cp) * sizeof(float);
+    const size_t smem = 0;
     const int g8 = static_cast<int>(b8);
     const int nvl = (Cp / 8 + 7) / 8;
     if (nvl == 1) layernorm_fwd8_kernel<1><<<g8, block, smem, st>>>(x, gamma, beta, y, mean, rstd, T, C, Cp, eps, oc);

@@ -40,6 +40,9 @@ def swin(name):
         return lambda: so.window_attention_bwd(x576, x192, table, 6, 8, 4, 30**-0.5, stats=stats)
     if name == 'ln_fwd':
         return lambda: so.layernorm_fwd(x192, g, b_, 180)
+    if name == 'ln_fwd_1m':  # one 1024 x 1024 inference tile
+        big = bf(1, 1024, 1024, 192)
+        return lambda: so.layernorm_fwd(big, g, b_, 180)
     if name == 'ln_bwd':
         _, mean, rstd = so.layernorm_fwd(x192, g, b_, 180)
         return lambda: so.layernorm_bwd(x192, x192, mean, rstd, g, 180, gres=x192)
