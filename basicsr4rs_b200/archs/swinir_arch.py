@@ -38,6 +38,26 @@ def drop_path_scale(batch, drop_prob, training, device):
     return ((keep + torch.rand((batch,), dtype=torch.float32, device=device)).floor_() / keep).contiguous()
 
 
+_drop_path_scale_impl = drop_path_scale
+_KEEP_CACHE = {}
+
+
+def drop_path_bank(batch, probs, training, device):
+    """The stochastic-depth factors of a whole group of DropPath uses from ONE draw: a list with one fp32 [B] tensor (or
+    None where ``p == 0``) per entry of ``probs``.  Drawn one by one (rand, add, floor, divide per use) they are four
+    1.4 us launches per use -- 288 per SwinIR step; a bank of rows costs the same four launches per RSTB layer."""
+    if drop_path_scale is not _drop_path_scale_impl:  # replaced (the parity tests inject masks): one call per use, in order
+        return [drop_path_scale(batch, p, training, device) for p in probs]
+    if not training or not any(p > 0. for p in probs):
+        return [None] * len(probs)
+    key = (tuple(probs), str(device))
+    keep = _KEEP_CACHE.get(key)
+    if keep is None:
+        keep = _KEEP_CACHE[key] = torch.tensor([1. - p for p in probs], dtype=torch.float32, device=device).view(-1, 1)
+    bank = (keep + torch.rand((len(probs), batch), dtype=torch.float32, device=device)).floor_() / keep
+    return [bank[i] if p > 0. else None for i, p in enumerate(probs)]
+
+
 class DropPath(nn.Module):
     """Stochastic depth per sample; in the fused block it becomes a per-sample epilogue scale."""
 
@@ -227,14 +247,23 @@ class SwinTransformerBlock(nn.Module):
                 type(self.norm2) is nn.LayerNorm and self.norm1.eps == self.norm2.eps and
                 self.norm1.elementwise_affine and self.norm2.elementwise_affine)
 
-    def forward_nhwc(self, t):
-        """t: [B, H, W, pad64(C)] bf16."""
+    def drop_probs(self):
+        """The two stochastic-depth probabilities of this block (attention branch, MLP branch)."""
+        p = float(self.drop_path.drop_prob or 0.) if isinstance(self.drop_path, DropPath) else 0.
+        return [p, p]
+
+    def forward_nhwc(self, t, alphas=None):
+        """t: [B, H, W, pad64(C)] bf16.  ``alphas``: this block's two per-sample DropPath factors when the caller drew
+        them for a whole layer at once (:func:`drop_path_bank`)."""
         if not self.on_kernels():
             return self._forward_nhwc_general(t)
         b = t.shape[0]
         dp = self.drop_path
-        a1 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None
-        a2 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None
+        if alphas is not None:
+            a1, a2 = alphas
+        else:
+            a1 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None
+            a2 = dp.scale(b, t.device) if isinstance(dp, DropPath) else None
         at, m = self.attn, self.mlp
         return swin_ops.swin_block(t, self.norm1.weight, self.norm1.bias, at.qkv.weight, at.qkv.bias,
                                    at.relative_position_bias_table, at.proj.weight, at.proj.bias, self.norm2.weight,
@@ -319,11 +348,17 @@ class BasicLayer(nn.Module):
         self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample is not None else None
 
     def forward_nhwc(self, t):
-        for blk in self.blocks:
+        # all DropPath factors of the layer from one draw (blocks without a fused kernel draw their own)
+        bank = None
+        if self.training and all(blk.on_kernels() for blk in self.blocks):
+            probs = [p for blk in self.blocks for p in blk.drop_probs()]
+            bank = drop_path_bank(t.shape[0], probs, True, t.device)
+        for i, blk in enumerate(self.blocks):
+            al = (bank[2 * i], bank[2 * i + 1]) if bank is not None else None
             if self.use_checkpoint and torch.is_grad_enabled():
-                t = torch.utils.checkpoint.checkpoint(blk.forward_nhwc, t, use_reentrant=False)
+                t = torch.utils.checkpoint.checkpoint(blk.forward_nhwc, t, al, use_reentrant=False)
             else:
-                t = blk.forward_nhwc(t)
+                t = blk.forward_nhwc(t, al)
         return t
 
     def forward(self, x, x_size):

@@ -26,23 +26,19 @@ def split3(x32):
     return out
 
 
-_wcache = {}
-
-
 def split_weight(weight, n_pad, k_pad, perm_out=None):
-    """bf16 [taps, n_pad, 3*k_pad] = [w_hi | w_hi | w_lo] along K of an fp32 conv / linear weight (cached per version)."""
-    key = (id(weight), weight.data_ptr(), weight._version, n_pad, k_pad, id(perm_out))
-    hit = _wcache.get(id(weight))
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    """bf16 [taps, n_pad, 3*k_pad] = [w_hi | w_hi | w_lo] along K of an fp32 conv / linear weight.
+
+    Derived afresh on every call: this is the evaluation path, and the network it evaluates is usually ``net_g_ema``,
+    whose parameters the reference updates through ``.data`` (base_model.py:81-82) -- neither ``_version`` nor the storage
+    address changes, so no cache key would notice (an ``id()``-keyed cache can even hand out another, freed network's
+    operand when Python reuses the id).  Every weight is used once per forward anyway."""
     w = weight.detach().float().contiguous()
     hi = w.to(torch.bfloat16).float()
     lo = (w - hi).contiguous()
     p_hi = raw.pack_weight(hi.contiguous(), n_pad, k_pad, perm_out=perm_out)
     p_lo = raw.pack_weight(lo, n_pad, k_pad, perm_out=perm_out)
-    packed = torch.cat([p_hi, p_hi, p_lo], dim=2).contiguous()
-    _wcache[id(weight)] = (key, packed)
-    return packed
+    return torch.cat([p_hi, p_hi, p_lo], dim=2).contiguous()
 
 
 def _bias(bias, n_pad, perm_out=None):
