@@ -52,6 +52,7 @@ struct TapGemmParams {
   const float* residual_f32;  // optional fp32 residual (layout of out)
   float* out_f32;             // optional fp32 copy of the result (layout of out)
   const float* alpha_b;       // optional per-sample scale [B] (stochastic depth)
+  int alpha_on_bias;          // 1: alpha_b multiplies the bias only (SRB200_EXT_ALPHA_ON_BIAS)
   float* colsum;              // optional fp32 [Cout]: += column sums of the stored result (bias gradient)
   int aux_mode;               // 1: aux_out = act'(pre-activation) instead of the pre-activation (GELU only)
   int pdl;                    // launched with programmatic stream serialization: do the griddepcontrol handoff
@@ -454,7 +455,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       if (issuer) stamp(2, 2 * it);
       const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
       const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
-      const float al = (p.alpha_b != nullptr && b < p.B) ? p.alpha * __ldg(p.alpha_b + b) : p.alpha;
+      const float ab = (p.alpha_b != nullptr && b < p.B) ? __ldg(p.alpha_b + b) : 1.0f;
+      // (SRB200_EXT_ALPHA_ON_BIAS: the input already carries alpha[b]; only the bias still needs it)
+      const float al = p.alpha_on_bias ? p.alpha : p.alpha * ab;
+      const float al_bias = p.alpha_on_bias ? ab : 1.0f;
       // bias of this N tile -> smem (every epilogue warp has passed the last barrier of the previous tile); the
       // launch grid is a multiple of n_tiles, so a CTA keeps its N tile for all its tiles and this runs once
       if (bias_n0 != n0) {
@@ -590,10 +594,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 #pragma unroll
         for (int j = 0; j < CHUNK / 4; ++j) {
           const float4 bv = bp[j];
-          v[4 * j + 0] += bv.x;
-          v[4 * j + 1] += bv.y;
-          v[4 * j + 2] += bv.z;
-          v[4 * j + 3] += bv.w;
+          v[4 * j + 0] = fmaf(al_bias, bv.x, v[4 * j + 0]);  // (al_bias == 1: exactly v + bias)
+          v[4 * j + 1] = fmaf(al_bias, bv.y, v[4 * j + 1]);
+          v[4 * j + 2] = fmaf(al_bias, bv.z, v[4 * j + 2]);
+          v[4 * j + 3] = fmaf(al_bias, bv.w, v[4 * j + 3]);
         }
       };
 
@@ -862,6 +866,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.residual_f32 = ext ? ext->residual_f32 : nullptr;
   p.out_f32 = ext ? ext->out_f32 : nullptr;
   p.alpha_b = ext ? ext->alpha_per_sample : nullptr;
+  p.alpha_on_bias = (ext && (ext->flags & SRB200_EXT_ALPHA_ON_BIAS) && p.alpha_b != nullptr) ? 1 : 0;
   p.colsum = ext ? ext->colsum : nullptr;
   p.aux_mode = ext ? ext->aux_mode : 0;
   p.colsum_per_image = ext ? ext->colsum_per_image : 0;

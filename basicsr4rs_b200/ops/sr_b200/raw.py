@@ -479,7 +479,7 @@ def unpack_wgrad(acc, w_shape, perm_out=None, perm_in=None, alpha=1.0):
 def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alpha=1.0, mask_src=None,
             mask_mode=L.MASK_NONE, mask_slope=0.0, residual=None, flip=False, src_r=1, out_mode=L.OUT_NHWC,
             out_r=1, out_c=0, out_scale=1.0, out_shift=None, want_aux=False, residual_f32=None, want_f32=False,
-            alpha_per_sample=None, want_colsum=False, aux_grad=False):
+            alpha_per_sample=None, want_colsum=False, aux_grad=False, alpha_on_bias=False):
     """conv3x3 / conv1x1 / Linear on NHWC bf16 (see include/srb200.h: srb200_tapgemm)."""
     _chk(x, 'x', torch.bfloat16)
     _chk(wp, 'wp', torch.bfloat16)
@@ -520,7 +520,8 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
                                         alpha_per_sample.data_ptr() if alpha_per_sample is not None else None,
                                         1 if aux_grad else 0, 1 if per_image else 0,
                                         csum.data_ptr() if csum is not None else None,
-                                        1.0 / (h * w) if per_image else 1.0, 0))
+                                        1.0 / (h * w) if per_image else 1.0,
+                                        L.EXT_ALPHA_ON_BIAS if (alpha_on_bias and alpha_per_sample is not None) else 0))
     ev = PROBE.begin('tapgemm', (b, h, w, cin * src_r * src_r, cout, ksize)) if PROBE is not None else None
     L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),
                                     _ptr(out_shift), _ptr(out), _ptr(aux), ext, _stream()), 'tapgemm')

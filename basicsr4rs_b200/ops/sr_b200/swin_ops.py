@@ -191,12 +191,16 @@ class _SwinBlock(Function):
         h_ones = hidden < ch and fc1_b is not None
         b1p = _padded_bias(fc1_b, ch, fill=(ch - 1, GELU_ONE) if h_ones else None)
         if want_stats:
+            # h carries the MLP branch's per-sample DropPath factor (h' = alpha2[b] * GELU(a); the stored derivative does
+            # not): fc2 then only scales its bias, and in the backward dW2 = g2^T h' (and fc2's bias gradient, its pad
+            # column) need no row-scaled copy of the incoming gradient
             h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=b1p, act=L.ACT_GELU,
-                               want_aux=True, aux_grad=True)  # a = gelu'(fc1 out): all the backward needs
+                               want_aux=True, aux_grad=True, alpha_per_sample=alpha2)  # a = gelu'(fc1 out)
         else:  # evaluation: no derivative tensor (50 MB of stores and half of the epilogue math at B16 x 64 x 64)
-            h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=b1p, act=L.ACT_GELU), None
+            h, a = raw.tapgemm(xn2, _packed(fc1_w, 'fprop', ch, cs), ksize=1, cout=ch, bias=b1p, act=L.ACT_GELU,
+                               alpha_per_sample=alpha2), None
         x2 = raw.tapgemm(h, _packed(fc2_w, 'fprop', cs, ch), ksize=1, cout=cs, bias=_padded_bias(fc2_b, cs),
-                         residual=x1, alpha_per_sample=alpha2)
+                         residual=x1, alpha_per_sample=alpha2, alpha_on_bias=True)
         ctx.save_for_backward(x, mean1, rstd1, xn, qkv, o, x1, mean2, rstd2, xn2, a, h, n1w, qkv_w, qkv_b, table,
                               proj_w, proj_b, n2w, fc1_w, fc1_b, fc2_w, fc2_b, alpha1, alpha2, stats)
         ctx.cfg = (c, cs, ca, ch, hd, num_heads, ws, shift, scale)
@@ -236,19 +240,24 @@ class _SwinBlock(Function):
         p_qkv = head_perm(num_heads, hd, 3, dev)
         p_o = head_perm(num_heads, hd, 1, dev)
         # ---- MLP branch
-        g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
+        # (h already carries alpha2[b], see forward: the weight gradient takes g2 as it is, the data gradient gets the
+        # factor in its epilogue -- no scale_rows pass)
         with raw.side_branch(dev):  # the four weight gradients ride a side stream next to the data-gradient chain
-            acc_fc2 = raw.wgrad(g2s, h, ksize=1)
-        fc2_b_item = ('bcol', acc_fc2, ch - 1, fc2_b.numel(), None, 1.0) if ctx.h_ones else \
-            ('b', raw.colsum(g2s), fc2_b.numel(), None, 1.0)
+            acc_fc2 = raw.wgrad(g2, h, ksize=1)
+        if ctx.h_ones:
+            fc2_b_item = ('bcol', acc_fc2, ch - 1, fc2_b.numel(), None, 1.0)
+        else:
+            g2s = scale_rows(g2, alpha2) if alpha2 is not None else g2
+            fc2_b_item = ('b', raw.colsum(g2s), fc2_b.numel(), None, 1.0)
         ones = ctx.ones
         if ones >= 0:  # fc1's bias gradient = column `ones` of acc_fc1 (xn2 carries a constant-one channel there)
-            ga = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
-                             mask_mode=L.MASK_MUL)
+            ga = raw.tapgemm(g2, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
+                             mask_mode=L.MASK_MUL, alpha_per_sample=alpha2)
             cs_fc1 = None
         else:
-            ga, cs_fc1 = raw.tapgemm(g2s, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
-                                     mask_mode=L.MASK_MUL, want_colsum=True)  # column sums = fc1's bias gradient
+            ga, cs_fc1 = raw.tapgemm(g2, _packed(fc2_w, 'dgrad', cs, ch), ksize=1, cout=ch, flip=True, mask_src=a,
+                                     mask_mode=L.MASK_MUL, want_colsum=True,
+                                     alpha_per_sample=alpha2)  # column sums = fc1's bias gradient
         with raw.side_branch(dev):
             acc_fc1 = raw.wgrad(ga, xn2, ksize=1)
         gxn2 = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True)

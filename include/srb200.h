@@ -214,8 +214,12 @@ typedef struct {
                                     result (the bias gradient of the layer that consumes `out` as dY);
                                     SRB200_OUT_NHWC with Cout % 64 == 0 only                            */
   float colsum_scale;            /* the sums are multiplied by this when flushed (0 = 1.0; 1/HW for a mean)        */
-  int32_t reserved;
+  int32_t flags;                 /* SRB200_EXT_*                                                                    */
 } srb200_tapgemm_ext;
+/* alpha_per_sample multiplies the BIAS only: v = acc + alpha[b] * bias.  For a Linear whose INPUT already carries the
+ * per-sample DropPath factor (h' = alpha[b] * h stored by the producing epilogue, so that the weight-gradient GEMM
+ * dW = dY^T h' needs no scaled copy of dY): alpha (h W^T + bias) = h' W^T + alpha bias.                              */
+#define SRB200_EXT_ALPHA_ON_BIAS 1
 
 int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16, const void* w_packed,
                    const float* bias,          /* [Cout] or NULL                           */
