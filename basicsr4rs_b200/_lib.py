@@ -92,7 +92,7 @@ SIGNATURES = {
     'srb200_layernorm_fwd': (c_int, [c_void_p] * 6 + [c_int64, c_int, c_int, c_float, c_int, c_void_p]),
     'srb200_layernorm_bwd': (c_int, [c_void_p] * 9 + [c_int64, c_int, c_int, c_void_p]),
     'srb200_scale_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
-    'srb200_window_attention_fwd': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_float, c_int, c_void_p]),
+    'srb200_window_attention_fwd': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_float, c_int, c_void_p, c_void_p]),
     'srb200_window_attention_bwd': (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_float, c_void_p]),
     'srb200_channel_pool': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'srb200_channel_dot': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),

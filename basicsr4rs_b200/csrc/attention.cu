@@ -423,7 +423,7 @@ using namespace srb;
 // attention_tc.cu: the tcgen05 / TMEM / TMA kernels (window 8); SRB200_EINVAL = shape outside their domain
 int srb_window_attention_fwd_tc(const void* qkv_bf16, const float* rpb_table, void* out_bf16, float* stats, int B,
                                 int H, int W, int num_heads, int Ca, int shift, float scale, int flags,
-                                cudaStream_t stream);
+                                const float* out_alpha, cudaStream_t stream);
 int srb_window_attention_bwd_tc(const void* qkv_bf16, const void* gout_bf16, const float* rpb_table,
                                 const float* stats, void* gqkv_bf16, float* g_rpb_table, float* workspace, int B,
                                 int H, int W, int num_heads, int Ca, int shift, float scale, cudaStream_t stream);
@@ -431,16 +431,17 @@ int srb_window_attention_bwd_tc(const void* qkv_bf16, const void* gout_bf16, con
 extern "C" int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table,
                                            void* out_bf16, float* stats, int B, int H, int W, int num_heads,
                                            int Cp, int window_size, int shift, float scale, int flags,
-                                           srb200_stream_t stream) {
+                                           const float* out_alpha, srb200_stream_t stream) {
   if (!qkv_bf16 || !rpb_table || !out_bf16) return SRB200_EINVAL;
   const int rc = check_geom(B, H, W, num_heads, Cp, window_size, shift);
   if (rc != SRB200_OK) return rc;
   if (window_size == 8 && SRB_ENV("SRB_ATTN_MMA_SYNC") == nullptr) {
     // window 8 (every classical-SR recipe): the tcgen05 kernel; other windows / odd head counts: mma.sync below
     const int rc_tc = srb_window_attention_fwd_tc(qkv_bf16, rpb_table, out_bf16, stats, B, H, W, num_heads, Cp, shift, scale,
-                                                  flags, static_cast<cudaStream_t>(stream));
+                                                  flags, out_alpha, static_cast<cudaStream_t>(stream));
     if (rc_tc != SRB200_EINVAL) return rc_tc;
   }
+  if (out_alpha != nullptr) return SRB200_EINVAL;  // the per-sample output scale exists in the tcgen05 kernel only
   AttnGeom g{B, H, W, num_heads, Cp, shift, scale, window_size, (flags & SRB200_ATTN_ONES) ? 1 : 0};
   const long long wins = static_cast<long long>(H / window_size) * (W / window_size);
   if (wins * num_heads > 0x7fffffffLL || B > 65535) return SRB200_EINVAL;

@@ -50,6 +50,7 @@ struct AttnTcParams {
   int pdl;
   unsigned skew_ns;       // start-up delay of softmax group 1 (see the kernel)
   int ones;               // SRB200_ATTN_ONES: out channel 31 (pad lane of head 0) = 1.0
+  const float* out_alpha; // optional [B]: every output row of sample b is multiplied by out_alpha[b] (DropPath)
   unsigned long long* trace;  // debug: clock64 timeline of CTA 0, [role 0..3][64 stages][8 slots] (NULL = off)
 };
 
@@ -402,9 +403,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) window_attn_fwd_tc_kernel(con
       const bool ones_here = p.ones && pair == 0 && half == 0;  // this row ends in out channel 31 (pad lane of head 0)
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        const float inv = s_inv[(((j & 3) * 2 + w) * 2 + half) * 64 + tok];
+        float inv = s_inv[(((j & 3) * 2 + w) * 2 + half) * 64 + tok];
         // SRB200_ATTN_ONES: the pad channel carries 1.0 (x inv below) so that proj's weight-gradient GEMM sums dY there
         if (ones_here) r[w][31] = __float_as_uint(__fdividef(1.0f, inv));
+        if (p.out_alpha != nullptr) {  // per-sample DropPath factor folded into the normalisation (the ones lane too)
+          int b, wy, wx;
+          window_of(unit, w, b, wy, wx);
+          inv *= __ldg(p.out_alpha + b);
+        }
         const int row = w * 64 + tok;
         const uint32_t orow = base + kOffOut + row * 128;
 #pragma unroll
@@ -465,7 +471,7 @@ extern "C" int srb200_debug_set_attn_trace(void* dev_buf) {
 // (the caller then uses the generic mma.sync kernel of attention.cu)
 int srb_window_attention_fwd_tc(const void* qkv_bf16, const float* rpb_table, void* out_bf16, float* stats, int B,
                                 int H, int W, int num_heads, int Ca, int shift, float scale, int flags,
-                                cudaStream_t stream) {
+                                const float* out_alpha, cudaStream_t stream) {
   if ((shift != 0 && shift != 4) || H % 8 != 0 || W % 8 != 0 || (num_heads & 1) || num_heads > kMaxHeads ||
       Ca != num_heads * 32)
     return SRB200_EINVAL;
@@ -492,6 +498,7 @@ int srb_window_attention_fwd_tc(const void* qkv_bf16, const float* rpb_table, vo
   p.table = rpb_table;
   p.stats = stats;
   p.ones = (flags & SRB200_ATTN_ONES) ? 1 : 0;
+  p.out_alpha = out_alpha;
   p.B = B;
   p.H = H;
   p.W = W;

@@ -73,10 +73,21 @@ def scale_rows(g, alpha):
     return out
 
 
-def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=False, ones=False):
+ATTN_TC_MAX_HEADS = 16  # kMaxHeads of csrc/attention_tc.cuh
+
+
+def attn_on_tc(qkv, num_heads, ws, shift):
+    """Does this shape run on the tcgen05 window-attention kernels (attention_tc.cu)?"""
+    return ws == 8 and num_heads % 2 == 0 and num_heads <= ATTN_TC_MAX_HEADS and shift in (0, 4) and \
+        qkv.shape[1] % 8 == 0 and qkv.shape[2] % 8 == 0 and qkv.shape[3] == 3 * num_heads * HD_PAD and \
+        os.environ.get('SRB_ATTN_MMA_SYNC') is None
+
+
+def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=False, ones=False, alpha=None):
     """Fused window attention.  ``want_stats``: also return the softmax statistics buffer (fp32
     [windows, heads, ws*ws], opaque) that lets :func:`window_attention_bwd` skip the row maxima / sums.
-    ``ones``: output channel 31 (a pad lane of head 0, head_dim < 32) carries 1.0 (SRB200_ATTN_ONES)."""
+    ``ones``: output channel 31 (a pad lane of head 0, head_dim < 32) carries 1.0 (SRB200_ATTN_ONES).
+    ``alpha`` (fp32 [B], tcgen05 shapes only -- see :func:`attn_on_tc`): per-sample scale of the output rows."""
     _chk(qkv, 'qkv', torch.bfloat16)
     _chk(table, 'rpb_table', torch.float32)
     b, h, w, c3 = qkv.shape
@@ -86,7 +97,7 @@ def window_attention_fwd(qkv, table, num_heads, ws, shift, scale, want_stats=Fal
         if want_stats else None
     raw.probed('window_attn_fwd', (b, h, w, num_heads, ws), lambda: L.check(L.load().srb200_window_attention_fwd(
         _ptr(qkv), _ptr(table), _ptr(out), _ptr(stats), b, h, w, num_heads, ca, ws, shift, float(scale), int(bool(ones)),
-        _stream()), 'window_attention_fwd'))
+        _ptr(alpha), _stream()), 'window_attention_fwd'))
     return (out, stats) if want_stats else out
 
 
@@ -179,12 +190,16 @@ class _SwinBlock(Function):
                           bias=_padded_bias(qkv_b, 3 * ca, p_qkv))
         want_stats = any(ctx.needs_input_grad)
         o_ones = ones >= 0 and hd < HD_PAD  # same trick for proj: its bias gradient = column 31 of its weight gradient
-        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale, want_stats=want_stats, ones=o_ones)
+        # on the tcgen05 kernels the attention output carries the branch's per-sample DropPath factor (o' = alpha1[b] * o),
+        # proj then scales only its bias, and the backward needs no row-scaled copy of the incoming gradient
+        o_alpha = alpha1 is not None and attn_on_tc(qkv, num_heads, ws, shift)
+        o = window_attention_fwd(qkv, table.detach(), num_heads, ws, shift, scale, want_stats=want_stats, ones=o_ones,
+                                 alpha=alpha1 if o_alpha else None)
         stats = None
         if want_stats:
             o, stats = o
         x1 = raw.tapgemm(o, _packed(proj_w, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
-                         bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1)
+                         bias=_padded_bias(proj_b, cs), residual=x, alpha_per_sample=alpha1, alpha_on_bias=o_alpha)
         xn2, mean2, rstd2 = layernorm_fwd(x1, n2w.detach(), n2b.detach(), c, eps, ones)
         # fc1's last PAD output channel gets the bias v with GELU(v) = 1: h carries a constant one there (fc2's packed
         # weights are zero on pad inputs), so fc2's weight-gradient GEMM also yields fc2's bias gradient -- no column-sum pass
@@ -207,6 +222,7 @@ class _SwinBlock(Function):
         ctx.ones = ones
         ctx.o_ones = o_ones
         ctx.h_ones = h_ones
+        ctx.o_alpha = o_alpha
         raw.stash_backward_scratch(ctx, _SwinBlock._scratch_floats(c, cs, ca, ch, table.numel()), dev)
         return x2
 
@@ -263,12 +279,19 @@ class _SwinBlock(Function):
         gxn2 = raw.tapgemm(ga, _packed(fc1_w, 'dgrad', ch, cs), ksize=1, cout=cs, flip=True)
         gx1, g_n2w, g_n2b = layernorm_bwd(gxn2, x1, mean2, rstd2, n2w.detach(), c, gres=g2)
         # ---- attention branch
-        g1s = scale_rows(gx1, alpha1) if alpha1 is not None else gx1
+        if ctx.o_alpha:  # o already carries alpha1[b] (forward): dW = gx1^T o', the data gradient scales in its epilogue
+            g1s, a1_epi = gx1, alpha1
+        else:
+            g1s, a1_epi = (scale_rows(gx1, alpha1) if alpha1 is not None else gx1), None
         with raw.side_branch(dev):
             acc_proj = raw.wgrad(g1s, o, ksize=1)
-        proj_b_item = ('bcol', acc_proj, HD_PAD - 1, proj_b.numel(), None, 1.0) if ctx.o_ones else \
-            ('b', raw.colsum(g1s), proj_b.numel(), None, 1.0)
-        go = raw.tapgemm(g1s, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True)
+        if ctx.o_ones:
+            proj_b_item = ('bcol', acc_proj, HD_PAD - 1, proj_b.numel(), None, 1.0)
+        else:
+            gb = scale_rows(gx1, alpha1) if (ctx.o_alpha and alpha1 is not None) else g1s
+            proj_b_item = ('b', raw.colsum(gb), proj_b.numel(), None, 1.0)
+        go = raw.tapgemm(g1s, _packed(proj_w, 'dgrad', cs, ca, perm_in=p_o), ksize=1, cout=ca, flip=True,
+                         alpha_per_sample=a1_epi)
         gqkv, g_table = window_attention_bwd(qkv, go, table.detach(), num_heads, ws, shift, scale, stats=stats)
         with raw.side_branch(dev):
             acc_qkv = raw.wgrad(gqkv, xn, ksize=1)

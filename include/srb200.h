@@ -322,9 +322,13 @@ int srb200_scale_rows(const void* g_bf16, const float* alpha, void* out_bf16, in
  * proj Linear that consumes `out` has zero weights there and its weight-gradient GEMM then yields its bias gradient in
  * column 31 (same trick as srb200_layernorm_fwd's ones_channel).                                                   */
 #define SRB200_ATTN_ONES 1
+/* out_alpha (optional, may be NULL; window 8 / even head count only, SRB200_EINVAL otherwise): fp32 [B], every output
+ * row of sample b is multiplied by out_alpha[b] -- the per-sample DropPath factor of the attention branch
+ * (swinir_arch.py:14-26,318), carried by `out` so that proj's weight-gradient GEMM needs no row-scaled copy of dY;
+ * the SRB200_ATTN_ONES lane then holds out_alpha[b].                                                                  */
 int srb200_window_attention_fwd(const void* qkv_bf16, const float* rpb_table, void* out_bf16, float* stats,
                                 int B, int H, int W, int num_heads, int Cp, int window_size, int shift,
-                                float scale, int flags, srb200_stream_t stream);
+                                float scale, int flags, const float* out_alpha, srb200_stream_t stream);
 int srb200_window_attention_bwd(const void* qkv_bf16, const void* gout_bf16, const float* rpb_table,
                                 const float* stats, void* gqkv_bf16, float* g_rpb_table, float* workspace,
                                 int B, int H, int W, int num_heads, int Cp, int window_size, int shift,
