@@ -9,7 +9,8 @@ other BASELINE config under ``configs`` in the same JSON line.
 One "step" = zero_grad + forward + L1 loss + backward + Adam step of EDSR-L x4 (32 ResBlocks, 256 ch,
 res_scale 0.1) on 16 synthetic 3x48x48 LR patches per GPU (weak scaling, DDP over NCCL).  Prints ONE
 JSON line (see the task contract): `value` = device-resident throughput, `e2e` = the same through the
-public nn.Module API with pinned-host inputs copied H2D and the loss read back D2H every step,
+public nn.Module API with pinned-host inputs copied H2D and the loss read back D2H every step (prefetched on a copy
+stream / read back asynchronously, like the reference's CUDAPrefetcher -- class PrefetchedSteps),
 `roofline` = the dominant kernel (conv3x3 256->256 tap-GEMM) timed live with CUDA events,
 `cpu_baseline` = the unmodified reference arch (oracle/_ref, vendored by oracle/make_ref.py; the oracle port when
 absent) on a bounded sample of the same workload, `configs` = EDSR-M / RCAN / SwinIR B4+B16 training and EDSR-L /
@@ -273,6 +274,44 @@ def dominant(rooflines):
     return dict(rooflines[name], kernel=name), {k: v for k, v in rooflines.items() if k != name}
 
 
+class PrefetchedSteps:
+    """End-to-end loop the way the reference feeds its models (CUDAPrefetcher, basicsr/data/prefetch_dataloader.py:
+    82-122: the next batch is uploaded on a side stream while the current step computes): every step's LR / GT batch
+    is copied from PINNED HOST memory to one of two device buffers on a copy stream, and every step's loss is read back
+    to pinned host memory -- asynchronously, the host looks at the values after the last step (what
+    utils/train_hooks.install_lazy_loss_log does to BaseModel.reduce_loss_dict).  All copies are inside the timed region."""
+
+    def __init__(self, lq_h, gt_h, dev, step_fn):
+        self.lq_h, self.gt_h, self.dev, self.step_fn = lq_h, gt_h, dev, step_fn
+        self.copy = torch.cuda.Stream(device=dev)
+        self.bufs = [(torch.empty(lq_h.shape, device=dev), torch.empty(gt_h.shape, device=dev)) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def _prefetch(self, k):
+        i = k & 1
+        with torch.cuda.stream(self.copy):
+            if k >= 2:
+                self.copy.wait_event(self.consumed[i])  # step k - 2 has read this buffer
+            self.bufs[i][0].copy_(self.lq_h, non_blocking=True)
+            self.bufs[i][1].copy_(self.gt_h, non_blocking=True)
+            self.ready[i].record(self.copy)
+
+    def run(self, steps):
+        main = torch.cuda.current_stream(self.dev)
+        losses = torch.empty((steps,), dtype=torch.float32).pin_memory()
+        self._prefetch(0)
+        for k in range(steps):
+            i = k & 1
+            main.wait_event(self.ready[i])
+            if k + 1 < steps:
+                self._prefetch(k + 1)
+            loss = self.step_fn(*self.bufs[i])
+            self.consumed[i].record(main)
+            losses[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        return losses
+
+
 def make_adam(params, kind='srb200'):
     if kind == 'torch':
         return torch.optim.Adam(params, lr=1e-4, betas=(0.9, 0.99), fused=True)
@@ -307,15 +346,14 @@ def bench_train_config(name, dev, steps, pk, raw, build_network, L, optim_kind='
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
 
-    def e2e_step():
-        return step(lq_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True)).item()
-
-    e2e_step()
+    pipe = PrefetchedSteps(lq_h, gt_h, dev, step)
+    pipe.run(2)
+    torch.cuda.synchronize()
     e0.record()
-    for _ in range(steps):
-        e2e_step()
+    losses = pipe.run(steps)
     e1.record()
     torch.cuda.synchronize()
+    assert bool(torch.isfinite(losses).all())
     ms_e2e = e0.elapsed_time(e1) / steps
     roof, others = dominant(summarize_rooflines(probe_eager_steps(net, step, 2, raw), pk, n_steps=2))
     row = {'workload': f'{opt["type"]} x4 train step (fwd + L1 + bwd + Adam), {batch}x3x{lr}x{lr} LR patches, '
@@ -488,15 +526,12 @@ def main():
         launches += args.steps * sum(GRAPHS[net].kernels_per_step.values())
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end-to-end leg: pinned host inputs -> H2D, public nn.Module API, loss read back
-    def e2e_step():
-        lq = lq_h.to(dev, non_blocking=True)
-        gt = gt_h.to(dev, non_blocking=True)
-        return train_step(lq, gt).item()
-
-    for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    # ---- end-to-end leg: pinned host inputs -> H2D every step, public nn.Module API, every loss read back to the host
+    pipe = PrefetchedSteps(lq_h, gt_h, dev, train_step)
+    pipe.run(2)
+    e2e_losses = []
+    ms_e2e = timed(lambda: e2e_losses.append(pipe.run(args.steps)), 1)
+    assert bool(torch.isfinite(e2e_losses[0]).all()), 'e2e: a loss read back from the device is not finite'
 
     # ---- roofline leg: the dominant kernel timed with CUDA events on its launching stream, inside real
     # train steps.  Events cannot be recorded inside a graph replay, so these steps launch eagerly.
@@ -532,7 +567,9 @@ def main():
                                               else args.grad_comm + ' buckets, torch DistributedDataParallel')
                            if world > 1 else 'none (1 GPU)'),
             'e2e': {'value': patches / (ms_e2e / 1e3), 'unit': 'patches/s',
-                    'h2d_bytes_per_step': (lq_h.numel() + gt_h.numel()) * 4, 'd2h_bytes_per_step': 4},
+                    'h2d_bytes_per_step': (lq_h.numel() + gt_h.numel()) * 4, 'd2h_bytes_per_step': 4,
+                    'path': 'nn.Module API; every step: LR+GT batch pinned host -> device on a copy stream (double-buffered, '
+                            'as the reference CUDAPrefetcher does), loss -> pinned host; all copies inside the timed region'},
             'gpu_launches': launches, 'clocks': clocks,
             'model_tflops': value * FLOP_PER_PATCH_FWD_BWD / world / 1e12,
             'roofline': {'bound': 'tensor', 'kernel': 'tapgemm_kernel<256,true> (cta_group::2) conv3x3 256->256, fprop + dgrad launches',
