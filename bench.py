@@ -38,9 +38,10 @@ SWINIR = dict(type='SwinIR', upscale=4, in_chans=3, img_size=64, window_size=8, 
               embed_dim=180, num_heads=[6] * 6, mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv')
 BATCH, LR = 16, 48
 WORKLOAD = 'EDSR-L x4 train step (fwd + L1 + bwd + Adam), 16x3x48x48 LR patches per GPU'
-CONFIG = {'launch': 'CUDA-graph replay (4 segments) of fwd+bwd; L1 loss + one-launch Adam (utils/fused_adam.FusedAdam) eager',
-          'workload': WORKLOAD, 'arch': 'EDSR num_feat=256 num_block=32 res_scale=0.1 upscale=4', 'batch_per_gpu': BATCH,
-          'lr_patch': LR, 'parallelism': 'ddp', 'l2': 'per-step working set (>2 GB of activations) exceeds the 126 MB L2'}
+# `config` names the WORKLOAD only and is identical in both arms (the driver compares them); how each arm runs it is
+# under `launch`
+CONFIG = {'workload': WORKLOAD, 'arch': 'EDSR num_feat=256 num_block=32 res_scale=0.1 upscale=4', 'batch_per_gpu': BATCH,
+          'lr_patch': LR, 'l2': 'per-step working set (>2 GB of activations) exceeds the 126 MB L2'}
 FLOP_PER_PATCH_FWD_BWD = 694.66e9
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, mean of the four 256->256 launches in
 # profiles/r01_ncu_full_tapgemm_v2.txt (one `ncu --set full` capture of this script): 39.09 / 20.14 / 40.10 / 20.14 MB.  The
@@ -181,8 +182,9 @@ def run_reference(args, rank):
     line = {'impl': 'reference', 'metric': 'SR train patches/s (fwd+bwd)', 'value': value, 'unit': 'patches/s',
             'n_gpus': args.gpus, 'steps': len(times), 'warmup': args.warmup, 'ms_per_step': t * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(CONFIG, launch=f'eager torch CPU ops, {threads} host threads; fwd + L1 + bwd of a 2-patch sample',
-                           parallelism='host threads'),
+            'config': dict(CONFIG),
+            'launch': {'how': f'eager torch CPU ops, {threads} host threads; fwd + L1 + bwd of a {n}-patch sample per step',
+                       'parallelism': 'host threads (rank 0 only)'},
             'cpu_baseline': {'value': value, 'unit': 'patches/s', 'cores': threads, 'kind': kind,
                              'sample': f'{n} of 16 patches per step, EDSR-L x4 fwd+L1+bwd, {what}'},
             'e2e': {'value': value, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -562,10 +564,15 @@ def main():
             'metric': 'SR train patches/s (fwd+bwd)', 'value': value, 'unit': 'patches/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': dict(CONFIG if args.optim == 'srb200' else dict(CONFIG, launch=CONFIG['launch'].replace(
-                'one-launch Adam (utils/fused_adam.FusedAdam)', 'torch.optim.Adam(fused=True)')), grad_comm=('fp32 NCCL all-reduce (AVG) of one flat gradient buffer, FlatDDP' if flat
-                                              else args.grad_comm + ' buckets, torch DistributedDataParallel')
-                           if world > 1 else 'none (1 GPU)'),
+            'config': dict(CONFIG),
+            'launch': {'how': ('eager launches' if args.no_graph else 'CUDA-graph replay (4 segments)') + ' of fwd+bwd; L1 loss + '
+                              + ('one-launch Adam (utils/fused_adam.FusedAdam)' if args.optim == 'srb200'
+                                 else 'torch.optim.Adam(fused=True)') + ' eager',
+                       'parallelism': 'one process per GPU, weak scaling' if world > 1 else 'single GPU',
+                       'grad_comm': (('fp32 NCCL all-reduce (SUM of pre-divided gradients) of one flat gradient buffer, '
+                                      'utils/flat_ddp.FlatDDP' if flat
+                                      else args.grad_comm + ' buckets, torch DistributedDataParallel')
+                                     if world > 1 else 'none (1 GPU)')},
             'e2e': {'value': patches / (ms_e2e / 1e3), 'unit': 'patches/s',
                     'h2d_bytes_per_step': (lq_h.numel() + gt_h.numel()) * 4, 'd2h_bytes_per_step': 4,
                     'path': 'nn.Module API; every step: LR+GT batch pinned host -> device on a copy stream (double-buffered, '
