@@ -112,6 +112,38 @@ def test_window_attention_fwd_bwd(cuda, b, h, w, nh, hd, shift, ws):
         assert relt <= 2e-2, f'gtable rel-L2 {relt:.3e} (stats: {st is not None})'
 
 
+@pytest.mark.parametrize('shift', [0, 4])
+def test_window_attention_out_alpha_and_alpha_on_bias(cuda, shift):
+    """The attention branch's per-sample DropPath factor carried by the attention output (``out_alpha``: every row of
+    sample b times alpha[b], the SRB200_ATTN_ONES lane holds alpha[b]) and the matching Linear epilogue
+    (SRB200_EXT_ALPHA_ON_BIAS: v = acc + alpha[b] * bias): together alpha (o W^T + bias), exactly as the plain path."""
+    so, raw = _ops(), _ops().raw
+    b, h, w, nh, hd = 3, 16, 16, 6, 30
+    g = torch.Generator().manual_seed(5)
+    ca = nh * 32
+    qkv = torch.zeros((b, h, w, 3, nh, 32))
+    qkv[..., :hd] = torch.randn((b, h, w, 3, nh, hd), generator=g)
+    qkv = qkv.reshape(b, h, w, 3 * ca).to(cuda).to(torch.bfloat16)
+    table = (torch.randn((225, nh), generator=g) * 0.5).to(cuda)
+    alpha = torch.tensor([0.0, 1.0 / 0.9, 0.5], device=cuda)
+    assert so.attn_on_tc(qkv, nh, 8, shift)
+    plain = so.window_attention_fwd(qkv, table, nh, 8, shift, hd**-0.5, ones=True)
+    scaled = so.window_attention_fwd(qkv, table, nh, 8, shift, hd**-0.5, ones=True, alpha=alpha)
+    want = plain.float() * alpha.view(b, 1, 1, 1)
+    assert (scaled.float() - want).abs().max().item() <= 2.0**-7 * want.abs().max().item()
+    assert torch.equal(scaled[0], torch.zeros_like(scaled[0]))            # a dropped sample is exactly zero
+    assert torch.allclose(scaled[..., 31].float(), alpha.view(b, 1, 1).expand(b, h, w), rtol=2.0**-8)  # the ones lane
+    # proj with the factor already in its input == proj with the factor in its epilogue
+    wt = (torch.randn((192, ca), generator=g) * 0.05).to(cuda)
+    bias = torch.randn((192,), generator=g).to(cuda)
+    res = torch.randn((b, h, w, 192), generator=g).to(cuda).to(torch.bfloat16)
+    wp = raw.pack_weight(wt, 192, ca)
+    y_epi = raw.tapgemm(plain, wp, ksize=1, cout=192, bias=bias, residual=res, alpha_per_sample=alpha)
+    y_in = raw.tapgemm(scaled, wp, ksize=1, cout=192, bias=bias, residual=res, alpha_per_sample=alpha, alpha_on_bias=True)
+    assert (y_epi.float() - y_in.float()).abs().max().item() <= 3e-2 * y_epi.float().abs().max().item()
+    assert torch.equal(y_in[0], (res[0].float() + 0.0).to(torch.bfloat16))  # alpha = 0: the skip passes through untouched
+
+
 def test_swin_block_vs_oracle(cuda):
     """One shifted SwinTransformerBlock (C=180, 6 heads, ws 8, shift 4) forward + all gradients."""
     so = _ops()
