@@ -17,6 +17,8 @@ its in-switch NVLS reduction (measured on 8 GPUs: five ``AllReduce_Sum_f32_RING_
 that reach autograd by other routes (LayerNorm, bias tables, the image-exit conv) are folded in with one
 ``torch._foreach_copy_`` per bucket.  One exchange step, no custom collective: NCCL over NVLink does the reduction.
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 from torch import nn
@@ -51,8 +53,10 @@ class FlatGrads:
                 raw.GRAD_SINK[p.data_ptr()] = (v, self.prescale)
 
     def release(self):
-        for p in self.params:
-            raw.GRAD_SINK.pop(p.data_ptr(), None)
+        for p, v in zip(self.params, self.views):
+            hit = raw.GRAD_SINK.get(p.data_ptr())
+            if hit is not None and hit[0] is v:
+                del raw.GRAD_SINK[p.data_ptr()]
 
 
 def flat_grads_of(module):
@@ -63,7 +67,17 @@ def flat_grads_of(module):
         if fg is not None:
             fg.release()
         fg = module.__dict__['_srb200_flat_grads'] = FlatGrads(module)
+        # the sink is keyed by storage address: drop the entries when the module dies, or a later, unrelated parameter
+        # that the allocator places at the same address would have its gradient redirected (and pre-divided)
+        weakref.finalize(module, _unsink, [p.data_ptr() for p in fg.params], fg.buf.data_ptr())
     return fg
+
+
+def _unsink(ptrs, buf_ptr):
+    for ptr in ptrs:
+        hit = raw.GRAD_SINK.get(ptr)
+        if hit is not None and hit[0].untyped_storage().data_ptr() == buf_ptr:
+            del raw.GRAD_SINK[ptr]
 
 
 class FlatDDP(nn.Module):
