@@ -198,3 +198,54 @@ def test_segment_sizes_its_backward_scratch_on_the_first_grad_enabled_run():
     assert got[-1] == (None, None)
     seg(torch.ones(4, 3))
     assert got[-1][0] is not None
+
+
+def test_drop_path_bank_draws_a_layer_at_once_with_the_reference_distribution(monkeypatch):
+    """All DropPath factors of an RSTB layer from one draw (swinir_arch.drop_path_bank): every row is
+    floor(keep + U) / keep per sample as in the reference (swinir_arch.py:14-26), p = 0 entries are None, nothing is
+    drawn in eval mode, and a replaced ``drop_path_scale`` (the parity tests inject masks) is honoured call by call."""
+    from basicsr4rs_b200.archs import swinir_arch as sa
+    torch.manual_seed(0)
+    probs = [0.0, 0.0, 0.05, 0.05, 0.3, 0.3]
+    bank = sa.drop_path_bank(4096, probs, True, torch.device('cpu'))
+    assert bank[0] is None and bank[1] is None
+    for p, row in zip(probs[2:], bank[2:]):
+        keep = 1.0 - p
+        assert row.shape == (4096,) and row.dtype == torch.float32 and row.is_contiguous()
+        vals = set(round(v, 5) for v in row.unique().tolist())
+        assert vals <= {0.0, round(1.0 / keep, 5)}
+        assert abs((row > 0).float().mean().item() - keep) < 0.03     # P(keep) = 1 - p
+        assert abs(row.mean().item() - 1.0) < 0.05                     # unbiased
+    assert not torch.equal(bank[2], bank[3])                            # the two branches of a block draw separately
+    assert sa.drop_path_bank(8, probs, False, torch.device('cpu')) == [None] * 6
+    calls = []
+
+    def injected(batch, p, training, device):
+        calls.append(p)
+        return None if p == 0 else torch.full((batch,), 2.0)
+
+    monkeypatch.setattr(sa, 'drop_path_scale', injected)
+    out = sa.drop_path_bank(3, probs, True, torch.device('cpu'))
+    assert calls == probs and out[0] is None and torch.equal(out[5], torch.full((3,), 2.0))
+
+
+def test_flat_grads_layout_and_buckets():
+    """FlatGrads / FlatDDP host logic on CPU: 16-byte aligned slices in registration order, buckets in reverse
+    registration order that cover the buffer exactly once."""
+    from basicsr4rs_b200.utils.flat_ddp import FlatDDP, FlatGrads
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 300))
+    fg = FlatGrads(net)
+    assert [o % 4 for o in fg.offsets] == [0] * 6 and fg.offsets == sorted(fg.offsets)
+    for p, v in zip(fg.params, fg.views):
+        assert v.shape == p.shape and v.untyped_storage().data_ptr() == fg.buf.untyped_storage().data_ptr()
+    ddp = FlatDDP(net, bucket_mb=300 * 4 / 2**20)   # ~300 floats per bucket
+    fg = ddp.flat                                     # (the wrap owns the network's buffer: flat_grads_of)
+    seen = sorted(i for b in ddp.buckets for i in b[2])
+    assert seen == list(range(6))
+    assert ddp.buckets[0][2][0] == 5                  # the LAST registered parameter arrives first
+    spans = sorted((b[0], b[1]) for b in ddp.buckets)
+    assert spans[0][0] == 0 and spans[-1][1] == fg.total and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    # without a process group a backward still leaves .grad aliasing the flat slices
+    net(torch.ones(2, 7)).sum().backward()
+    for p, v in zip(fg.params, fg.views):
+        assert p.grad.data_ptr() == v.data_ptr()
