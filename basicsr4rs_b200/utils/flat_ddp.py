@@ -83,9 +83,10 @@ def _unsink(ptrs, buf_ptr):
 class FlatDDP(nn.Module):
     """``FlatDDP(net)`` where the reference writes ``DistributedDataParallel(net, device_ids=[...])``.
 
-    ``bucket_mb``: all-reduce granularity (default 40 MB, 4-5 buckets for EDSR-L's 172 MB of gradients)."""
+    ``bucket_mb``: all-reduce granularity (default 40 MB, 5 buckets for EDSR-L's 172 MB of gradients); ``last_mb``: size of
+    the bucket that is reduced last (the first parameters), whose all-reduce nothing overlaps."""
 
-    def __init__(self, module, bucket_mb=40, process_group=None):
+    def __init__(self, module, bucket_mb=40, process_group=None, last_mb=8):
         super().__init__()
         self.module = module
         self.group = process_group
@@ -96,17 +97,20 @@ class FlatDDP(nn.Module):
         if self.world > 1:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, 0, group=process_group)
-        # buckets in REVERSE registration order (gradients arrive roughly back to front)
-        cap = int(bucket_mb * 2**20 / 4)
+        # Buckets = contiguous index ranges, cut from the FRONT of the registration order: gradients arrive roughly back to
+        # front, so the bucket holding the first parameters is reduced last, with nothing left to overlap it -- it is kept
+        # small (``last_mb``); the others hold ``bucket_mb``.
         self.bucket_of, self.buckets = {}, []  # param index -> bucket, bucket = [lo, hi, param indices]
-        cur = None
-        for i in reversed(range(len(fg.params))):
+        cur, cap = None, int(last_mb * 2**20 / 4)
+        for i in range(len(fg.params)):
             lo = fg.offsets[i]
             hi = fg.offsets[i] + (fg.params[i].numel() + 3) // 4 * 4
-            if cur is None or (cur[1] - lo) > cap:
+            if cur is None or (hi - cur[0]) > cap:
+                if cur is not None:
+                    cap = int(bucket_mb * 2**20 / 4)
                 cur = [lo, hi, []]
                 self.buckets.append(cur)
-            cur[0] = lo
+            cur[1] = hi
             cur[2].append(i)
             self.bucket_of[i] = len(self.buckets) - 1
         self._pending = None

@@ -440,6 +440,8 @@ def main():
     ap.add_argument('--optim', default='srb200', choices=['srb200', 'torch'],
                     help="Adam step: 'srb200' = one srb200_multi_adam launch (utils/fused_adam.FusedAdam), 'torch' = "
                          "torch.optim.Adam(fused=True)")
+    ap.add_argument('--segments', type=int, default=4, help='CUDA-graph segments of the headline net (the gradients of the '
+                    'LAST backward segment are all-reduced with nothing left to overlap; 8 measured no better at N=4)')
     ap.add_argument('--configs', default='all', help="'all', 'none' or a comma list of the other BASELINE configs "
                     f"({', '.join(list(TRAIN_CONFIGS) + list(INFER_CONFIGS))}); measured at N=1 only")
     args = ap.parse_args()
@@ -473,7 +475,8 @@ def main():
 
     torch.manual_seed(0)
     flat = world > 1 and args.ddp == 'flat'
-    net = build_network(dict(EDSR_L, cuda_graph=not args.no_graph, graph_segments=4, flat_grads=flat,
+    segments = max(1, args.segments)
+    net = build_network(dict(EDSR_L, cuda_graph=not args.no_graph, graph_segments=segments, flat_grads=flat,
                              graph_input_shape=[BATCH, 3, LR, LR])).to(dev)  # graphs captured here, before DDP
     if flat:
         from basicsr4rs_b200.utils.flat_ddp import FlatDDP
@@ -565,7 +568,7 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': dict(CONFIG),
-            'launch': {'how': ('eager launches' if args.no_graph else 'CUDA-graph replay (4 segments)') + ' of fwd+bwd; L1 loss + '
+            'launch': {'how': ('eager launches' if args.no_graph else f'CUDA-graph replay ({segments} segments)') + ' of fwd+bwd; L1 loss + '
                               + ('one-launch Adam (utils/fused_adam.FusedAdam)' if args.optim == 'srb200'
                                  else 'torch.optim.Adam(fused=True)') + ' eager',
                        'parallelism': 'one process per GPU, weak scaling' if world > 1 else 'single GPU',
