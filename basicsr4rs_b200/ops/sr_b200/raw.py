@@ -397,7 +397,11 @@ def _grad_target(param, shape, device):
     if param is not None and GRAD_SINK:
         hit = GRAD_SINK.get(param.data_ptr())
         if hit is not None and hit[0].device == device and tuple(hit[0].shape) == tuple(shape):
-            return hit
+            if param.grad is None:
+                return hit
+            # gradient accumulation (a second backward before zero_grad): param.grad already aliases the slice, writing
+            # it again would lose the first pass -- hand autograd a fresh, equally scaled tensor to add instead
+            return torch.empty(tuple(shape), dtype=torch.float32, device=device), hit[1]
     return torch.empty(tuple(shape), dtype=torch.float32, device=device), 1.0
 
 

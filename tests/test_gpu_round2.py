@@ -609,6 +609,32 @@ def test_flat_grads_alias_one_buffer_and_match_plain_gradients(cuda, graph):
     fg.release()
 
 
+def test_flat_grads_accumulate_over_two_eager_backwards(cuda):
+    """A second backward before zero_grad must ADD to the flat slice (the finalize sees a live ``param.grad`` and returns a
+    fresh tensor for autograd to accumulate) -- the same sums as a plain network."""
+    from basicsr4rs_b200.archs import build_network
+    from basicsr4rs_b200.utils.flat_ddp import flat_grads_of
+    kw = dict(type='EDSR', num_in_ch=3, num_out_ch=3, num_feat=64, num_block=2, upscale=2)
+    torch.manual_seed(0)
+    plain = build_network(dict(kw)).to(cuda).train()
+    torch.manual_seed(0)
+    flat = build_network(dict(kw, flat_grads=True)).to(cuda).train()
+    fg = flat_grads_of(flat)
+    xs = [torch.rand((2, 3, 16, 16), device=cuda, generator=torch.Generator(device=cuda).manual_seed(s)) for s in (1, 2)]
+    for net in (plain, flat):
+        net.zero_grad(set_to_none=True)
+        for x in xs:
+            (net(x)**2).mean().backward()
+    torch.cuda.synchronize()
+    aliased = 0
+    for (k, p), q, view in zip(plain.named_parameters(), flat.parameters(), fg.views):
+        aliased += q.grad.data_ptr() == view.data_ptr()  # (without the FlatDDP wrap only the sunk gradients alias)
+        rel = (q.grad - p.grad).abs().max().item() / (p.grad.abs().max().item() + 1e-12)
+        assert rel <= 1e-3, (k, rel)
+    assert aliased >= len(fg.views) - 2
+    fg.release()
+
+
 # ------------------------------------------------------------------ one-launch Adam (utils/fused_adam.py)
 @pytest.mark.parametrize('wd', [0.0, 1e-2])
 def test_fused_adam_matches_torch_adam_and_interchanges_checkpoints(cuda, wd):
