@@ -519,13 +519,13 @@ class _ConvToImage(Function):
         _, t32 = raw.tapgemm(x, wf.to(torch.bfloat16).view(1, tp, k_pad), ksize=1, cout=tp, want_f32=True)
         y = raw.tap_stencil(t32, cout, bias=bias.detach() if bias is not None else None, shift=out_shift,
                             scale=out_scale)
-        ctx.save_for_backward(x, weight, bias)
+        ctx.save_for_backward(x, weight, bias, wf)  # (wf: the backward's data-gradient operand is its transpose)
         ctx.out_scale = out_scale
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, weight, bias = ctx.saved_tensors
+        x, weight, bias, wf = ctx.saved_tensors
         cout, cin = weight.shape[0], weight.shape[1]
         k_pad = x.shape[-1]
         tp = pad64(9 * cout)
@@ -539,7 +539,7 @@ class _ConvToImage(Function):
             if bias is not None and ctx.needs_input_grad[2]:
                 gb = raw.colsum(gn)[4 * cout:5 * cout].clone()  # centre tap: every pixel of g exactly once
             if ctx.needs_input_grad[0]:
-                wd = _tap_folded_weight(weight, k_pad, tp).t().contiguous().to(torch.bfloat16).view(1, k_pad, tp)
+                wd = wf.t().contiguous().to(torch.bfloat16).view(1, k_pad, tp)
                 gx, cs = raw.tapgemm(gn, wd, ksize=1, cout=k_pad, want_colsum=True)
                 _stash_colsum(gx, cs)
         return gx, gw, gb, None, None
