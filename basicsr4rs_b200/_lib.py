@@ -108,6 +108,8 @@ SIGNATURES = {
     'srb200_patch_from_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     'srb200_tile_blend_add': (c_int, [c_void_p, c_void_p] + [c_int] * 12 + [c_void_p]),
     'srb200_split3_bf16': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'srb200_layernorm_f32': (c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_float, c_void_p]),
+    'srb200_window_attention_f32': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_float, c_void_p]),
     'srb200_tensor2img_u8': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p]),
     'srb200_ca_apply_bwd': (c_int, [c_void_p] * 4 + [c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }

@@ -515,6 +515,11 @@ class SwinIR(ArchMixin, nn.Module):
         self.graph_segments = int(kwargs.get('graph_segments', 6))
         self.graph_input_shape = kwargs.get('graph_input_shape', None)
         self.flat_grads = bool(kwargs.get('flat_grads', False))  # ONE flat gradient buffer (utils/flat_ddp.py)
+        # 'fp32': evaluation in fp32-class arithmetic (north_star "1e-4 in the TF32/fp32 mode"): split-bf16 tap-GEMMs,
+        # fp32 LayerNorm / window attention kernels (ops/sr_b200/fp32_mode.py, csrc/swin_f32.cu)
+        self.compute_dtype = kwargs.get('compute_dtype', 'bf16')
+        if self.compute_dtype not in ('bf16', 'fp32'):
+            raise ValueError(f"compute_dtype must be 'bf16' or 'fp32', got {self.compute_dtype!r}")
         num_in_ch = in_chans
         num_out_ch = in_chans
         num_feat = 64
@@ -696,8 +701,108 @@ class SwinIR(ArchMixin, nn.Module):
         segs.append(Segment(self._tail, tail_mods))
         return segs
 
+    # ------------------------------------------------------------------ fp32 mode (evaluation)
+    def _fp32_supported(self):
+        return all(blk.on_kernels() for layer in self.layers for blk in layer.residual_group.blocks) and \
+            (self.patch_embed.norm is None or type(self.patch_embed.norm) is nn.LayerNorm) and \
+            type(self.norm) is nn.LayerNorm
+
+    @staticmethod
+    def _block_fp32(blk, t32):
+        """SwinTransformerBlock.forward (reference :283-323) on fp32 NHWC [B,H,W,pad64(C)], evaluation mode (DropPath and
+        dropout are the identity): 4 split-operand tap-GEMMs, 2 fp32 LayerNorms and the fp32 window attention, the two
+        skip adds in the proj / fc2 epilogues."""
+        from ..ops.sr_b200 import fp32_mode as f32
+        from .. import _lib as L
+        at, m = blk.attn, blk.mlp
+        nh = blk.num_heads
+        hd = blk.dim // nh
+        cs = t32.shape[-1]
+        ca = nh * swin_ops.HD_PAD
+        p_qkv = swin_ops.head_perm(nh, hd, 3, t32.device)
+        p_o = swin_ops.head_perm(nh, hd, 1, t32.device)
+        qkv = f32.conv_split(f32.layer_norm(t32, blk.norm1, split=True), at.qkv.weight, at.qkv.bias, n_pad=3 * ca,
+                             perm_out=p_qkv)
+        o = f32.window_attention(qkv, at.relative_position_bias_table, nh, blk.window_size, blk.shift_size, at.scale)
+        x1 = f32.conv_split(o, at.proj.weight, at.proj.bias, n_pad=cs, perm_in=p_o, residual32=t32)
+        h = f32.conv_split(f32.layer_norm(x1, blk.norm2, split=True), m.fc1.weight, m.fc1.bias, act=L.ACT_GELU)
+        return f32.conv(h, m.fc2.weight, m.fc2.bias, residual32=x1)
+
+    @staticmethod
+    def _resi_conv_fp32(conv, rs, skip32):
+        """'1conv' / '3conv' residual connection + skip (reference :532-539, :818-824) in fp32 mode; ``rs`` is the
+        split operand [hi | lo | hi] of the first conv."""
+        from ..ops.sr_b200 import fp32_mode as f32
+        from .. import _lib as L
+        if isinstance(conv, nn.Conv2d):
+            return f32.conv_split(rs, conv.weight, conv.bias, residual32=skip32)
+        c0, c2, c4 = conv[0], conv[2], conv[4]
+        r32 = f32.conv_split(rs, c0.weight, c0.bias, act=L.ACT_LRELU, slope=conv[1].negative_slope)
+        r32 = f32.conv(r32, c2.weight, c2.bias, act=L.ACT_LRELU, slope=conv[3].negative_slope)
+        return f32.conv(r32, c4.weight, c4.bias, residual32=skip32)
+
+    def _forward_fp32(self, x):
+        """swinir_arch.py:876-921 in fp32 mode (no autograd, evaluation): fp32 NHWC activations end to end."""
+        from ..ops.sr_b200 import fp32_mode as f32
+        from .. import _lib as L
+        cin = x.shape[1]
+        mean = self._device_mean(x) if self.mean.numel() == cin else None
+        first = f32.conv(f32.image_to_nhwc32(x, mean, self.img_range, ops.pad64(cin)), self.conv_first.weight,
+                         self.conv_first.bias)
+        t = first
+        if self.patch_embed.norm is not None:
+            t = f32.layer_norm(t, self.patch_embed.norm)
+        if self.ape:
+            b, h, w, cp = t.shape
+            pe = self.absolute_pos_embed
+            if pe.shape[1] != h * w:
+                raise RuntimeError(f'ape=True: absolute_pos_embed holds {pe.shape[1]} positions, the input has {h * w} '
+                                   '(same restriction as the reference, :880)')
+            t = t + nn.functional.pad(pe.detach().float().view(1, h, w, -1), (0, cp - pe.shape[-1]))
+        for layer in self.layers:
+            r = t
+            for blk in layer.residual_group.blocks:
+                r = self._block_fp32(blk, r)
+            t = self._resi_conv_fp32(layer.conv, f32.split3(r), t)
+        feat = self._resi_conv_fp32(self.conv_after_body, f32.layer_norm(t, self.norm, split=True), first)
+        inv = 1.0 / self.img_range
+        if self.upsampler == 'pixelshuffle':
+            c = self.conv_before_upsample[0]
+            u = f32.conv(feat, c.weight, c.bias, act=L.ACT_LRELU, slope=self.conv_before_upsample[1].negative_slope)
+            mods = list(self.upsample)
+            for conv, shuffle in zip(mods[0::2], mods[1::2]):
+                u = f32.conv(u, conv.weight, conv.bias, shuffle_r=shuffle.upscale_factor)
+            return f32.conv_to_image(u, self.conv_last.weight, self.conv_last.bias, inv, mean)
+        if self.upsampler == '':
+            return x.float() + f32.conv_to_image(feat, self.conv_last.weight, self.conv_last.bias, inv, None)
+        if self.upsampler == 'pixelshuffledirect':
+            conv, shuffle = self.upsample[0], self.upsample[1]
+            r = shuffle.upscale_factor
+            u = f32.conv(feat, conv.weight, conv.bias)[..., :conv.weight.shape[0]]  # [B,H,W,c_img*r*r], channel c*r*r+i*r+j
+            b, h, w, _ = u.shape
+            img = u.reshape(b, h, w, -1, r, r).permute(0, 3, 1, 4, 2, 5).reshape(b, -1, h * r, w * r) * inv
+            return img + mean.view(1, -1, 1, 1) if mean is not None else img
+        if self.upsampler == 'nearest+conv':
+            def up2(z):  # F.interpolate(scale_factor=2, mode='nearest') on NHWC: a pure index remap
+                b, h, w, c = z.shape
+                return z[:, :, None, :, None, :].expand(b, h, 2, w, 2, c).reshape(b, 2 * h, 2 * w, c)
+            c = self.conv_before_upsample[0]
+            s02 = self.lrelu.negative_slope
+            u = f32.conv(feat, c.weight, c.bias, act=L.ACT_LRELU, slope=self.conv_before_upsample[1].negative_slope)
+            u = f32.conv(up2(u), self.conv_up1.weight, self.conv_up1.bias, act=L.ACT_LRELU, slope=s02)
+            u = f32.conv(up2(u), self.conv_up2.weight, self.conv_up2.bias, act=L.ACT_LRELU, slope=s02)
+            u = f32.conv(u, self.conv_hr.weight, self.conv_hr.bias, act=L.ACT_LRELU, slope=s02)
+            return f32.conv_to_image(u, self.conv_last.weight, self.conv_last.bias, inv, mean)
+        raise ValueError(f"unknown upsampler '{self.upsampler}'")
+
     def _forward(self, x):
         require_cuda(x, 'SwinIR')
+        if self.compute_dtype == 'fp32' and not torch.is_grad_enabled() and not self.training:
+            if not self._fp32_supported():
+                raise NotImplementedError("compute_dtype='fp32' covers the configurations of the fused Swin block "
+                                          '(window_size <= 8, even head count, head_dim <= 32, nn.LayerNorm, GELU Mlp)')
+            out = self._forward_fp32(x)
+            return out if out.dtype == x.dtype else out.to(x.dtype)
         if self.cuda_graph and self.training and torch.is_grad_enabled() and self.upsampler != '':
             nseg = len(split_even(list(self.layers), self.graph_segments)) + 1
             out = graphed_forward(self, x, self._build_segments, chain_wire(nseg, carry=1))

@@ -26,7 +26,7 @@ def split3(x32):
     return out
 
 
-def split_weight(weight, n_pad, k_pad, perm_out=None):
+def split_weight(weight, n_pad, k_pad, perm_out=None, perm_in=None):
     """bf16 [taps, n_pad, 3*k_pad] = [w_hi | w_hi | w_lo] along K of an fp32 conv / linear weight.
 
     Derived afresh on every call: this is the evaluation path, and the network it evaluates is usually ``net_g_ema``,
@@ -36,8 +36,8 @@ def split_weight(weight, n_pad, k_pad, perm_out=None):
     w = weight.detach().float().contiguous()
     hi = w.to(torch.bfloat16).float()
     lo = (w - hi).contiguous()
-    p_hi = raw.pack_weight(hi.contiguous(), n_pad, k_pad, perm_out=perm_out)
-    p_lo = raw.pack_weight(lo, n_pad, k_pad, perm_out=perm_out)
+    p_hi = raw.pack_weight(hi.contiguous(), n_pad, k_pad, perm_out=perm_out, perm_in=perm_in)
+    p_lo = raw.pack_weight(lo, n_pad, k_pad, perm_out=perm_out, perm_in=perm_in)
     return torch.cat([p_hi, p_hi, p_lo], dim=2).contiguous()
 
 
@@ -53,22 +53,67 @@ def _bias(bias, n_pad, perm_out=None):
     return b
 
 
-def conv(x32, weight, bias=None, act=L.ACT_NONE, alpha=1.0, residual32=None, shuffle_r=1):
-    """fp32-mode conv3x3 / conv1x1 on fp32 NHWC (channels padded to 64): returns the fp32 NHWC result."""
-    cout, cin = weight.shape[0], weight.shape[1]
-    k_pad = x32.shape[-1]
-    assert k_pad == pad64(cin)
+def conv_split(xs, weight, bias=None, act=L.ACT_NONE, slope=0.0, alpha=1.0, residual32=None, shuffle_r=1, n_pad=None,
+               perm_out=None, perm_in=None):
+    """fp32-mode conv3x3 / conv1x1 / Linear over an operand that is already split: ``xs`` bf16 [B,H,W,3*k_pad]
+    (:func:`split3`, or the split output of :func:`layer_norm` / :func:`window_attention`).  Returns fp32 NHWC.
+    ``perm_out`` / ``perm_in``: packed-channel -> original-channel index maps (-1 = zero) of a Linear whose output /
+    input lives in the attention kernels' padded head layout."""
+    cout = weight.shape[0]
+    k_pad = xs.shape[-1] // 3
     ksize = weight.shape[-1] if weight.dim() == 4 else 1
     if shuffle_r > 1:
-        perm = shuffle_perm(cout // (shuffle_r * shuffle_r), shuffle_r, x32.device)
+        perm_out = shuffle_perm(cout // (shuffle_r * shuffle_r), shuffle_r, xs.device)
         n_pad = cout
-    else:
-        perm, n_pad = None, pad64(cout)
-    wp = split_weight(weight, n_pad, k_pad, perm)
-    _, y32 = raw.tapgemm(split3(x32), wp, ksize=ksize, cout=n_pad, bias=_bias(bias, n_pad, perm), act=act, alpha=alpha,
-                         residual_f32=residual32, want_f32=True, out_mode=L.OUT_SHUFFLE if shuffle_r > 1 else L.OUT_NHWC,
-                         out_r=shuffle_r)
+    elif n_pad is None:
+        n_pad = pad64(cout)
+    wp = split_weight(weight, n_pad, k_pad, perm_out, perm_in)
+    _, y32 = raw.tapgemm(xs, wp, ksize=ksize, cout=n_pad, bias=_bias(bias, n_pad, perm_out), act=act, act_slope=slope,
+                         alpha=alpha, residual_f32=residual32, want_f32=True,
+                         out_mode=L.OUT_SHUFFLE if shuffle_r > 1 else L.OUT_NHWC, out_r=shuffle_r)
     return y32
+
+
+def conv(x32, weight, bias=None, act=L.ACT_NONE, alpha=1.0, residual32=None, shuffle_r=1, slope=0.0):
+    """fp32-mode conv3x3 / conv1x1 on fp32 NHWC (channels padded to 64): returns the fp32 NHWC result."""
+    assert x32.shape[-1] == pad64(weight.shape[1])
+    return conv_split(split3(x32), weight, bias, act=act, slope=slope, alpha=alpha, residual32=residual32,
+                      shuffle_r=shuffle_r)
+
+
+def layer_norm(x32, norm, split=False):
+    """nn.LayerNorm over the real channels of fp32 NHWC rows (pads stay 0): fp32 result, or (``split``) the
+    [hi | lo | hi] bf16 operand of the GEMM that consumes it (srb200_layernorm_f32)."""
+    raw._chk(x32, 'x32', torch.float32)
+    cp = x32.shape[-1]
+    c = norm.normalized_shape[0]
+    gamma = norm.weight.detach().float().contiguous()
+    beta = norm.bias.detach().float().contiguous()
+    if split:
+        out = torch.empty(x32.shape[:-1] + (3 * cp,), dtype=torch.bfloat16, device=x32.device)
+        y32, ys = None, out
+    else:
+        out = torch.empty_like(x32)
+        y32, ys = out, None
+    L.check(L.load().srb200_layernorm_f32(_ptr(x32), _ptr(gamma), _ptr(beta), _ptr(y32), _ptr(ys), x32.numel() // cp, c,
+                                          cp, float(norm.eps), _stream()), 'layernorm_f32')
+    return out
+
+
+def window_attention(qkv32, table, num_heads, ws, shift, scale, split=True):
+    """softmax(scale q k^T + relative position bias [+ SW-MSA mask]) v per (shifted) window in fp32
+    (srb200_window_attention_f32): qkv32 fp32 [B,H,W,3*Ca] in the padded head layout -> [B,H,W,Ca] fp32, or its
+    [hi | lo | hi] bf16 split [B,H,W,3*Ca] for the proj GEMM."""
+    raw._chk(qkv32, 'qkv32', torch.float32)
+    b, h, w, c3 = qkv32.shape
+    ca = c3 // 3
+    tab = table.detach().float().contiguous()
+    out = torch.empty((b, h, w, 3 * ca if split else ca), dtype=torch.bfloat16 if split else torch.float32,
+                      device=qkv32.device)
+    L.check(L.load().srb200_window_attention_f32(_ptr(qkv32), _ptr(tab), None if split else _ptr(out),
+                                                 _ptr(out) if split else None, b, h, w, num_heads, ca, ws, shift,
+                                                 float(scale), _stream()), 'window_attention_f32')
+    return out
 
 
 def image_to_nhwc32(x, shift, scale, c_pad=64):

@@ -389,6 +389,23 @@ int srb200_tensor2img_u8(const float* src_chw, void* dst_hwc_u8, int C, int H, i
  * (2^-16 relative per product) on the bf16 tensor-core kernel.  C % 8 == 0.                                        */
 int srb200_split3_bf16(const float* x_f32, void* out_bf16, int64_t rows, int C, srb200_stream_t stream);
 
+/* fp32 mode of the SwinIR token path (evaluation only, no backward): the Linear layers run as srb200_tapgemm over
+ * split operands (above); the two token kernels between them compute in plain fp32 and can emit their result already
+ * split, so no separate srb200_split3_bf16 pass is needed in front of the next GEMM.
+ * srb200_layernorm_f32: nn.LayerNorm(C, eps) (swinir_arch.py:240,251,602,886) over the C real channels of fp32 rows
+ *   padded to Cp (pads are written as 0).  y_f32 [T, Cp] and / or y_split_bf16 [T, 3*Cp] = [hi | lo | hi]; either may
+ *   be NULL, not both.  Cp % 8 == 0, Cp <= 1024.
+ * srb200_window_attention_f32: WindowAttention.forward minus the two Linears (swinir_arch.py:151-172) with roll /
+ *   window_partition / window_reverse (:293-316) and the analytic 0 / -100 mask (:262-281), same tensor layout as
+ *   srb200_window_attention_fwd but fp32: qkv [B,H,W,3*Cp], channel = which*Cp + head*32 + d (head_dim <= 32, zero
+ *   padded); out_f32 [B,H,W,Cp] and / or out_split_bf16 [B,H,W,3*Cp]; rpb_table fp32 [(2*ws-1)^2, num_heads].
+ *   window_size 2..8, any head count with num_heads*32 <= Cp.                                                        */
+int srb200_layernorm_f32(const float* x_f32, const float* gamma, const float* beta, float* y_f32, void* y_split_bf16,
+                         int64_t T, int C, int Cp, float eps, srb200_stream_t stream);
+int srb200_window_attention_f32(const float* qkv_f32, const float* rpb_table, float* out_f32, void* out_split_bf16,
+                                int B, int H, int W, int num_heads, int Cp, int window_size, int shift, float scale,
+                                srb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,3 +237,88 @@ def test_nearest_up2_bit_exact(cuda):
     back = raw.nearest_up2(g, inverse=True)
     want = g.float().view(2, 7, 2, 5, 2, 64).sum((2, 4)).to(torch.bfloat16)
     assert torch.equal(back.view(torch.int16), want.view(torch.int16))
+
+
+# ------------------------------------------------------------------ fp32 mode of the token path (north_star: <= 1e-4)
+@pytest.mark.parametrize('c,cp,tokens', [(180, 192, 1000), (60, 64, 333), (360, 384, 77), (30, 64, 5)])
+def test_layernorm_f32_kernel(cuda, c, cp, tokens):
+    """srb200_layernorm_f32: fp32 result within fp32 rounding of F.layer_norm; the split output is exactly the
+    [hi | lo | hi] bf16 split of that result; pad channels are written as zero whatever the input holds there."""
+    from basicsr4rs_b200.ops.sr_b200 import fp32_mode as f32
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((1, tokens, 1, cp), generator=g) * 3 + 1  # (pads deliberately non-zero)
+    norm = torch.nn.LayerNorm(c, eps=1e-5)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(c, generator=g))
+        norm.bias.copy_(0.1 * torch.randn(c, generator=g))
+    ref = F.layer_norm(x[..., :c].double(), (c,), norm.weight.double(), norm.bias.double(), 1e-5)
+    norm = norm.to(cuda)
+    y = f32.layer_norm(x.to(cuda), norm)
+    assert torch.count_nonzero(y[..., c:]) == 0
+    err = (y[..., :c].double().cpu() - ref).abs().max().item()
+    assert err <= 5e-6, f'layernorm_f32 max-abs {err:.3e}'
+    ys = f32.layer_norm(x.to(cuda), norm, split=True)
+    assert torch.equal(ys, f32.split3(y))
+
+
+@pytest.mark.parametrize('b,h,w,nh,hd,shift,ws', [(2, 16, 24, 6, 30, 0, 8), (2, 16, 24, 6, 30, 4, 8), (1, 8, 8, 6, 10, 0, 8),
+                                                  (3, 24, 40, 4, 32, 4, 8), (1, 24, 16, 2, 32, 3, 8),
+                                                  (2, 12, 18, 6, 30, 3, 6), (1, 14, 21, 3, 20, 3, 7), (1, 8, 12, 2, 16, 2, 4)])
+def test_window_attention_f32_kernel(cuda, b, h, w, nh, hd, shift, ws):
+    """srb200_window_attention_f32 against the fp64 restatement of swinir_arch.py:151-172 + :293-316 (roll, partition,
+    bias, analytic mask, softmax, reverse): fp32-rounding agreement, zero pad lanes, split output == split3(fp32)."""
+    from basicsr4rs_b200.ops.sr_b200 import fp32_mode as f32
+    g = torch.Generator().manual_seed(1)
+    ca = (nh * 32 + 63) // 64 * 64
+    qkv = torch.zeros((b, h, w, 3, ca))
+    packed = torch.zeros((b, h, w, 3, nh, 32))
+    packed[..., :hd] = torch.randn((b, h, w, 3, nh, hd), generator=g) * 1.5
+    qkv[..., :nh * 32] = packed.reshape(b, h, w, 3, nh * 32)
+    table = torch.randn(((2 * ws - 1)**2, nh), generator=g) * 0.5
+    ref = _ref_window_attention(packed.reshape(b, h, w, 3 * nh * 32).double(), table.double(), nh, hd, ws, shift, h, w)
+    qd = qkv.reshape(b, h, w, 3 * ca).to(cuda)
+    out = f32.window_attention(qd, table.to(cuda), nh, ws, shift, hd**-0.5, split=False)
+    got = out[..., :nh * 32].reshape(b, h, w, nh, 32)
+    assert torch.count_nonzero(got[..., hd:]) == 0
+    err = (got[..., :hd].double().cpu() - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()), f'window_attention_f32 max-abs {err:.3e}'
+    outs = f32.window_attention(qd, table.to(cuda), nh, ws, shift, hd**-0.5, split=True)
+    want = f32.split3(out)
+    for part in range(3):  # (channels beyond the heads are not written by the kernel)
+        assert torch.equal(outs[..., part * ca:part * ca + nh * 32], want[..., part * ca:part * ca + nh * 32]), part
+
+
+@pytest.mark.parametrize('case', ['swinir_c180_d2x2_x4', 'swinir_c60_d2_x2', 'swinir_c60_d2_direct_x2',
+                                  'swinir_c60_d2_nearest_x4', 'swinir_c60_ws6_in4_x2', 'swinir_c60_d2_denoise_x1'])
+def test_swinir_fp32_mode_matches_reference_golden_within_1e4(cuda, case):
+    """compute_dtype='fp32' on SwinIR (split-operand tap-GEMMs + fp32 LayerNorm / window attention kernels): every
+    reconstruction branch within 1e-4 max-abs of the unmodified reference's fp32 output."""
+    fx = torch.load(os.path.join(GOLDEN, case + '.pt'), weights_only=False)
+    net = _build(fx, cuda)
+    with torch.no_grad():
+        out16 = net(fx['x'].to(cuda)).cpu()
+        net.compute_dtype = 'fp32'
+        out = net(fx['x'].to(cuda)).cpu()
+    err, err16 = (out - fx['out']).abs().max().item(), (out16 - fx['out']).abs().max().item()
+    print(f'{case}: fp32 mode max-abs {err:.2e} (bf16 path {err16:.2e})')
+    assert out.shape == fx['out'].shape and err <= 1e-4, f'max-abs {err:.3e}'
+    assert err < 0.2 * err16
+
+
+def test_swinir_fp32_mode_full_size_within_1e4(cuda):
+    """BASELINE config 4 (embed 180, 6 x 6 blocks, window 8, x4, 64x64 LR) in fp32 mode against the fp32 oracle."""
+    from basicsr4rs_b200.archs import build_network
+    kw = dict(upscale=4, in_chans=3, img_size=64, window_size=8, img_range=1., depths=[6] * 6, embed_dim=180,
+              num_heads=[6] * 6, mlp_ratio=2, upsampler='pixelshuffle', resi_connection='1conv')
+    torch.manual_seed(0)
+    net = build_network(dict(type='SwinIR', compute_dtype='fp32', **kw))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(cuda).eval()
+    x = torch.rand((1, 3, 64, 64), generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        out = net(x.to(cuda)).cpu()
+        ref = sr_oracle.swinir_forward(sd, x, embed_dim=180, depths=[6] * 6, num_heads=[6] * 6, window_size=8,
+                                       upscale=4, img_range=1.)
+    err = (out - ref).abs().max().item()
+    print(f'SwinIR full size, fp32 mode: max-abs {err:.2e}')
+    assert err <= 1e-4, f'max-abs {err:.3e}'
