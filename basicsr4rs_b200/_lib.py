@@ -40,7 +40,9 @@ class TapGemmExt(ctypes.Structure):
     """Mirror of ``srb200_tapgemm_ext``."""
     _fields_ = [('residual_f32', c_void_p), ('out_f32', c_void_p), ('alpha_per_sample', c_void_p),
                 ('aux_mode', ctypes.c_int32), ('colsum_per_image', ctypes.c_int32), ('colsum', c_void_p),
-                ('colsum_scale', c_float), ('flags', ctypes.c_int32)]
+                ('colsum_scale', c_float), ('flags', ctypes.c_int32),
+                ('ln_stats_in', c_void_p), ('ln_wsum', c_void_p), ('ln_stats_out', c_void_p),
+                ('ln_channels', ctypes.c_int32), ('ln_eps', c_float)]
 
 
 # numpy mirror of ``srb200_patch_item`` (one crop of a batched patch extraction)

@@ -270,6 +270,38 @@ class SwinTransformerBlock(nn.Module):
                                    self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias,
                                    self.num_heads, self.window_size, self.shift_size, a1, a2, eps=self.norm1.eps)
 
+    def forward_nhwc_folded(self, t, stats, fold_qkv, fold_fc1):
+        """Evaluation forward with both LayerNorms folded into the Linears that consume them (no LayerNorm launch, no
+        normalised copy of the tokens): proj / fc2 also emit (mean, rstd) of the rows they store
+        (``srb200_tapgemm_ext.ln_stats_out``), qkv / fc1 run on the raw rows with gamma-scaled weights and undo the
+        mean in their epilogue (``ln_stats_in``).  ``stats`` = the statistics of ``t`` from the previous block's fc2,
+        or None (first block of a layer: LayerNorm kernel + plain qkv).  ``fold_*`` = (packed W diag(gamma), row sums
+        of it, W beta + b) from :meth:`BasicLayer._fold_bank`.  Returns (x2, stats of x2)."""
+        from .. import _lib as L
+        raw = ops.raw
+        at, m = self.attn, self.mlp
+        c, nh = self.dim, self.num_heads
+        hd = c // nh
+        cs = t.shape[-1]
+        ca = nh * swin_ops.HD_PAD
+        ch = ops.pad64(m.fc1.weight.shape[0])
+        eps = self.norm1.eps
+        p_o = swin_ops.head_perm(nh, hd, 1, t.device)
+        if stats is None:
+            p_qkv = swin_ops.head_perm(nh, hd, 3, t.device)
+            xn = swin_ops.layernorm_fwd(t, self.norm1.weight.detach(), self.norm1.bias.detach(), c, eps)[0]
+            qkv = raw.tapgemm(xn, swin_ops._packed(at.qkv.weight, 'fprop', 3 * ca, cs, perm_out=p_qkv), ksize=1, cout=3 * ca,
+                              bias=swin_ops._padded_bias(at.qkv.bias, 3 * ca, p_qkv))
+        else:
+            qkv = raw.tapgemm(t, fold_qkv[0], ksize=1, cout=3 * ca, bias=fold_qkv[2], ln_in=(stats, fold_qkv[1]))
+        o = swin_ops.window_attention_fwd(qkv, at.relative_position_bias_table.detach(), nh, self.window_size,
+                                          self.shift_size, at.scale)
+        x1, st1 = raw.tapgemm(o, swin_ops._packed(at.proj.weight, 'fprop', cs, ca, perm_in=p_o), ksize=1, cout=cs,
+                              bias=swin_ops._padded_bias(at.proj.bias, cs), residual=t, ln_out=(c, eps))
+        h = raw.tapgemm(x1, fold_fc1[0], ksize=1, cout=ch, bias=fold_fc1[2], act=L.ACT_GELU, ln_in=(st1, fold_fc1[1]))
+        return raw.tapgemm(h, swin_ops._packed(m.fc2.weight, 'fprop', cs, ch), ksize=1, cout=cs,
+                           bias=swin_ops._padded_bias(m.fc2.bias, cs), residual=x1, ln_out=(c, eps))
+
     def _forward_nhwc_general(self, t):
         """Fall-through for configurations without a fused kernel (they must keep running, not
         raise): window_size > 8, odd head counts, head_dim > 32, qk_scale, dropout > 0, a custom norm_layer / act_layer.
@@ -347,7 +379,66 @@ class BasicLayer(nn.Module):
         ])
         self.downsample = downsample(input_resolution, dim=dim, norm_layer=norm_layer) if downsample is not None else None
 
+    # evaluation on big tiles (tiled inference): LayerNorm folded into the Linears; below this many tokens the per-forward
+    # folding of the weights (a dozen small launches per layer) is not worth it
+    FOLD_MIN_TOKENS = int(os.environ.get('SRB_SWIN_FOLD_MIN_TOKENS', '200000'))
+
+    def _fold_ok(self, t):
+        if torch.is_grad_enabled() or self.training or t.shape[0] * t.shape[1] * t.shape[2] < self.FOLD_MIN_TOKENS:
+            return False
+        b0 = self.blocks[0]
+
+        def n_tile(cout):  # srb200_tapgemm's N tile: the folding epilogues exist for the 128- / 192-wide two-team kernels
+            return 256 if cout % 256 == 0 else 192 if cout % 192 == 0 else 128 if cout % 128 == 0 else 64
+
+        widths = (3 * b0.num_heads * swin_ops.HD_PAD, ops.pad64(b0.mlp.fc1.weight.shape[0]))
+        return (t.shape[-1] in (128, 192) and all(n_tile(n) in (128, 192) for n in widths) and all(blk.on_kernels() for blk in self.blocks) and
+                all(blk.norm1.eps == b0.norm1.eps and blk.num_heads == b0.num_heads for blk in self.blocks) and
+                all(blk.mlp.fc1.bias is not None and blk.attn.proj.bias is not None and blk.mlp.fc2.bias is not None
+                    for blk in self.blocks))
+
+    def _fold_bank(self, cs, dev):
+        """Per block: (bf16 packed W diag(gamma), fp32 row sums of that packed operand, fp32 W beta + b) for qkv (norm1
+        folded) and fc1 (norm2 folded), derived afresh per forward (evaluation nets are EMA copies updated through
+        ``.data``), batched over the layer's blocks: two stacks, two products, one pack launch per weight."""
+        raw = ops.raw
+        blocks = list(self.blocks)
+        nh = blocks[0].num_heads
+        hd = self.dim // nh
+
+        def bank(lins, norms, n_pad, perm):
+            w = torch.stack([lin.weight.detach().float() for lin in lins])            # [n, Co, C]
+            g = torch.stack([nm.weight.detach().float() for nm in norms])             # [n, C]
+            bt = torch.stack([nm.bias.detach().float() for nm in norms])
+            wg = (w * g[:, None, :]).contiguous()
+            packed = torch.empty((len(lins), 1, n_pad, cs), dtype=torch.bfloat16, device=dev)
+            for i in range(len(lins)):
+                raw.pack_weight(wg[i], n_pad, cs, perm_out=perm, out=packed[i])
+            wsum = packed.float().sum(dim=3).reshape(len(lins), n_pad).contiguous()
+            b = torch.bmm(w, bt[:, :, None])[:, :, 0]                                 # W beta
+            if lins[0].bias is not None:
+                b = b + torch.stack([lin.bias.detach().float() for lin in lins])
+            if perm is None:
+                bp = nn.functional.pad(b, (0, n_pad - b.shape[1]))
+            else:
+                bp = torch.where(perm >= 0, b[:, perm.clamp(min=0).long()], torch.zeros((), device=dev))
+            bp = bp.contiguous()
+            return [(packed[i], wsum[i], bp[i]) for i in range(len(lins))]
+
+        ca = nh * swin_ops.HD_PAD
+        ch = ops.pad64(blocks[0].mlp.fc1.weight.shape[0])
+        qkv = bank([blk.attn.qkv for blk in blocks], [blk.norm1 for blk in blocks], 3 * ca,
+                   swin_ops.head_perm(nh, hd, 3, dev))
+        fc1 = bank([blk.mlp.fc1 for blk in blocks], [blk.norm2 for blk in blocks], ch, None)
+        return qkv, fc1
+
     def forward_nhwc(self, t):
+        if self._fold_ok(t):
+            fq, f1 = self._fold_bank(t.shape[-1], t.device)
+            stats = None
+            for i, blk in enumerate(self.blocks):
+                t, stats = blk.forward_nhwc_folded(t, stats, fq[i], f1[i])
+            return t
         # all DropPath factors of the layer from one draw (blocks without a fused kernel draw their own)
         bank = None
         if self.training and all(blk.on_kernels() for blk in self.blocks):

@@ -58,6 +58,11 @@ struct TapGemmParams {
   int pdl;                    // launched with programmatic stream serialization: do the griddepcontrol handoff
   int colsum_per_image;       // 1: colsum is [B][Cout] (per-sample sums: RCAN's global average pool)
   float colsum_scale;         // factor applied to the sums when they are flushed (1/HW for the pool)
+  // LayerNorm folded into the GEMMs around it (evaluation): see srb200_tapgemm_ext.ln_*
+  const float2* ln_in;        // [pixels] (mean, rstd) of the INPUT rows: v = rstd * (acc - mean * ln_wsum[n]) + bias[n]
+  const float* ln_wsum;       // [Cout] row sums of the (gamma-folded, bf16-rounded) weights
+  float2* ln_out;             // [pixels] (mean, rstd) of the STORED rows (single N tile, two-team kernels)
+  float ln_inv_c, ln_eps;     // 1 / (real channel count), epsilon of the LayerNorm that will consume ln_out
   int act;
   float act_slope, alpha;
   int mask_mode;
@@ -157,8 +162,12 @@ __device__ __forceinline__ float warp_colsum32(float (&w)[32], int lane) {
 // accumulator buffer a.  For small-K layers (SwinIR's linears, 64-channel convs) a tile's MMAs take ~1.2k cycles but
 // its epilogue 4k, so both accumulators are usually full and two tiles' epilogues can run side by side -- each team
 // has its own named barrier, staging slots and TMA-store issuer.
-template <int BLOCK_N, bool TWO = false, bool TEAMS = false, bool RES = false>
+// LN: the LayerNorm-folding epilogue stages (srb200_tapgemm_ext.ln_*) are compiled in -- separate instantiations, so
+// that the training kernels keep their code size and register budget (as run-time branches in the one kernel they cost
+// the SwinIR training step 4 %).
+template <int BLOCK_N, bool TWO = false, bool TEAMS = false, bool RES = false, bool LN = false>
 __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+  static_assert(!LN || TEAMS, "LayerNorm folding: two-team kernels only");
   using Cfg = TapCfg<BLOCK_N, TWO, RES>;
   static_assert(!TEAMS || (!TWO && BLOCK_N >= 64 && BLOCK_N <= 192), "teams: single-CTA, TMA-store tile widths");
   static_assert(!RES || TEAMS, "staged epilogue operand: two-team kernels only");
@@ -371,7 +380,7 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     // the kernel parameters every stage costs a dependent constant-bank load + uniform compare + branch (~60
     // cycles each, ~8 of them per 32-column chunk even when every stage is off).
     enum : uint32_t { F_ACT = 3u, F_MASK_SIGN = 4u, F_MASK_DGELU = 8u, F_RES = 16u, F_RES32 = 32u, F_OUT32 = 64u,
-                      F_COLSUM = 128u, F_SHUFFLE = 256u, F_MASK_MUL = 512u, F_AUX_GRAD = 1024u,
+                      F_COLSUM = 128u, F_SHUFFLE = 256u, F_MASK_MUL = 512u, F_AUX_GRAD = 1024u, F_LN_IN = 2048u, F_LN_OUT = 4096u,
                       F_MASK = F_MASK_SIGN | F_MASK_DGELU | F_MASK_MUL, F_TAIL = F_MASK | F_RES | F_RES32 | F_OUT32 };
     uint32_t ef = static_cast<uint32_t>(p.act) & F_ACT;
     if (p.mask_mode == SRB200_MASK_SIGN) ef |= F_MASK_SIGN;
@@ -383,6 +392,10 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
     if (p.out_f32 != nullptr) ef |= F_OUT32;
     if (p.colsum != nullptr) ef |= F_COLSUM;
     if (p.out_mode == SRB200_OUT_SHUFFLE) ef |= F_SHUFFLE;
+    if constexpr (LN) {
+      if (p.ln_in != nullptr) ef |= F_LN_IN;
+      if (p.ln_out != nullptr) ef |= F_LN_OUT;
+    }
     asm volatile("mov.b32 %0, %0;" : "+r"(ef));
     // bias-gradient column sums of this warp's (32 rows x 32 columns) of every 64-column chunk; kept in
     // registers across the CTA's tiles when there is a single N tile, flushed with one 128-byte red per chunk
@@ -450,6 +463,16 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
       }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
+      // folded LayerNorm of the input rows: this row's rstd and -rstd * mean (requested before the accumulator wait)
+      float ln_r = 1.0f, ln_nrm = 0.0f;
+      if constexpr (LN) {
+        if ((ef & F_LN_IN) && valid) {
+          const float2 st = __ldg(p.ln_in + (static_cast<size_t>(b) * p.H + y) * p.W + x);
+          ln_r = st.y;
+          ln_nrm = -st.y * st.x;
+        }
+      }
+      float ln_s = 0.0f, ln_ss = 0.0f;  // row sum / sum of squares of the stored (bf16-rounded) values
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (issuer) stamp(2, 2 * it);
@@ -591,6 +614,21 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
 #pragma unroll
         for (int j = 0; j < CHUNK; ++j) v[j] = __uint_as_float(r[j]);
         const float4* bp = reinterpret_cast<const float4*>(s_bias + col);
+        if (LN && (ef & F_LN_IN)) {
+          // LayerNorm folded into this GEMM: acc = sum_c W'[n,c] x[c] with W' = W diag(gamma) over the RAW rows, so
+          // W LN(x) + b = rstd * (acc - mean * sum_c W'[n,c]) + (W beta + b): two FMAs per element, no LN pass
+          const float4* wp = reinterpret_cast<const float4*>(p.ln_wsum + n0 + col);
+#pragma unroll
+          for (int j = 0; j < CHUNK / 4; ++j) {
+            const float4 bv = bp[j];
+            const float4 wv = __ldg(wp + j);
+            v[4 * j + 0] = fmaf(v[4 * j + 0], ln_r, fmaf(ln_nrm, wv.x, bv.x));
+            v[4 * j + 1] = fmaf(v[4 * j + 1], ln_r, fmaf(ln_nrm, wv.y, bv.y));
+            v[4 * j + 2] = fmaf(v[4 * j + 2], ln_r, fmaf(ln_nrm, wv.z, bv.z));
+            v[4 * j + 3] = fmaf(v[4 * j + 3], ln_r, fmaf(ln_nrm, wv.w, bv.w));
+          }
+          return;
+        }
 #pragma unroll
         for (int j = 0; j < CHUNK / 4; ++j) {
           const float4 bv = bp[j];
@@ -672,6 +710,16 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
                     if (q == cc * NHALF + hh) csum[q] += cs;
                 }
               }
+              if (LN && (ef & F_LN_OUT)) {
+                // row statistics of what is stored (the bf16-rounded values, as a LayerNorm kernel would read them)
+#pragma unroll
+                for (int j = 0; j < CHUNK / 2; ++j) {
+                  const uint32_t pk = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                  const float lo = bf16_lo(pk), hi = bf16_hi(pk);
+                  ln_s += lo + hi;
+                  ln_ss = fmaf(lo, lo, fmaf(hi, hi, ln_ss));
+                }
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint32_t dst = buf_out + row * 128 + (((hf * 4 + j) ^ (row & 7)) << 4);
@@ -700,6 +748,14 @@ __global__ void __launch_bounds__(320, 1) tapgemm_kernel(const __grid_constant__
               tma_store_commit();
             }
             ++store_iter;
+          }
+          if constexpr (TEAMS && LN) {
+            // (a two-team warp covers both halves of every chunk: the thread has seen its whole row; host-checked: one N tile)
+            if ((ef & F_LN_OUT) && valid) {
+              const float mean = ln_s * p.ln_inv_c;
+              const float var = fmaxf(fmaf(ln_ss, p.ln_inv_c, -mean * mean), 0.0f);
+              p.ln_out[pix] = make_float2(mean, 1.0f / sqrtf(var + p.ln_eps));
+            }
           }
         }
       } else {
@@ -779,16 +835,17 @@ static int launch_tapgemm2(const TapGemmParams& p, cudaStream_t stream) {
   return launch_ex(tapgemm_kernel<BLOCK_N, true>, 2 * pairs, 320, Cfg::SMEM_BYTES, stream, 2, p);
 }
 
-template <int BLOCK_N, bool TEAMS = false, bool RES = false>
+template <int BLOCK_N, bool TEAMS = false, bool RES = false, bool LN = false>
 static int launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   using Cfg = TapCfg<BLOCK_N, false, RES>;
   static PerDeviceOnce configured;
-  if (configured.ensure(tapgemm_kernel<BLOCK_N, false, TEAMS, RES>, Cfg::SMEM_BYTES) != SRB200_OK) return SRB200_ELAUNCH;
+  if (configured.ensure(tapgemm_kernel<BLOCK_N, false, TEAMS, RES, LN>, Cfg::SMEM_BYTES) != SRB200_OK)
+    return SRB200_ELAUNCH;
   const int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
   if (grid >= p.n_tiles) grid -= grid % p.n_tiles;  // a CTA keeps its N tile (bias, weight columns) for all its tiles
   if (TEAMS && grid % p.n_tiles != 0) return SRB200_EINVAL;
-  return launch_ex(tapgemm_kernel<BLOCK_N, false, TEAMS, RES>, grid, 320, Cfg::SMEM_BYTES, stream, 1, p);
+  return launch_ex(tapgemm_kernel<BLOCK_N, false, TEAMS, RES, LN>, grid, 320, Cfg::SMEM_BYTES, stream, 1, p);
 }
 
 static std::atomic<unsigned long long*> g_trace{nullptr};
@@ -871,6 +928,18 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
   p.aux_mode = ext ? ext->aux_mode : 0;
   p.colsum_per_image = ext ? ext->colsum_per_image : 0;
   p.colsum_scale = (ext && ext->colsum_scale != 0.0f) ? ext->colsum_scale : 1.0f;
+  p.ln_in = ext ? reinterpret_cast<const float2*>(ext->ln_stats_in) : nullptr;
+  p.ln_wsum = ext ? ext->ln_wsum : nullptr;
+  p.ln_out = ext ? reinterpret_cast<float2*>(ext->ln_stats_out) : nullptr;
+  p.ln_inv_c = (ext && ext->ln_channels > 0) ? 1.0f / static_cast<float>(ext->ln_channels) : 0.0f;
+  p.ln_eps = ext ? ext->ln_eps : 0.0f;
+  if ((p.ln_in != nullptr) != (p.ln_wsum != nullptr)) return SRB200_EINVAL;
+  if (p.ln_in != nullptr && (p.alpha_b != nullptr || bn < 32 || d->out_mode == SRB200_OUT_NCHW_F32)) return SRB200_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(p.ln_in) | reinterpret_cast<uintptr_t>(p.ln_out)) & 7u) return SRB200_EINVAL;
+  if (reinterpret_cast<uintptr_t>(p.ln_wsum) & 15u) return SRB200_EINVAL;
+  if (p.ln_out != nullptr && (ext->ln_channels <= 0 || ext->ln_channels > d->Cout || d->Cout != bn ||
+                              d->out_mode != SRB200_OUT_NHWC || aux_out != nullptr))
+    return SRB200_EINVAL;
   if (p.aux_mode != 0 && (p.aux_mode != 1 || d->act != SRB200_ACT_GELU || !aux_out || bn < 64 ||
                           d->out_mode != SRB200_OUT_NHWC))
     return SRB200_EINVAL;
@@ -940,7 +1009,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
       }
     if (aux_out && ro != 1) return SRB200_EINVAL;
   }
-  if (two_cta) return launch_tapgemm2<256>(p, stream);
+  if (two_cta) return (p.ln_in != nullptr || p.ln_out != nullptr) ? SRB200_EINVAL : launch_tapgemm2<256>(p, stream);
   // small-K, wide-N layers (SwinIR's linears) are epilogue-bound: two epilogue teams (needs the TMA-store path and
   // N-tile affinity).  Not for 64-wide tiles: their 2-tiles-per-CTA kernels only see a longer last-tile epilogue.
   {
@@ -948,6 +1017,7 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
     int grid = total < num_sms() ? total : num_sms();
     if (grid >= p.n_tiles) grid -= grid % p.n_tiles;
     const bool teams = p.tma_store != 0 && grid % p.n_tiles == 0 && SRB_ENV("SRB_TAPGEMM_NO_TEAMS") == nullptr;
+    const bool ln = p.ln_in != nullptr || p.ln_out != nullptr;
     // Linears whose epilogue reads a bf16 tensor shaped like the output (residual, or the mask / derivative of a data
     // gradient): that operand goes through shared memory (TapCfg RES)
     if (teams && bn == 192 && d->ksize == 1 && d->out_mode == SRB200_OUT_NHWC && (mask_src || residual) &&
@@ -959,11 +1029,14 @@ extern "C" int srb200_tapgemm(const srb200_tapgemm_desc* d, const void* in_bf16,
       const uint32_t box[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
       const int rc = make_tmap_bf16(&p.tmap_res, mask_src ? mask_src : residual, 4, dims, strides, box);
       if (rc != SRB200_OK) return rc;
+      if (ln) return launch_tapgemm<192, true, true, true>(p, stream);
       return launch_tapgemm<192, true, true>(p, stream);
     }
-    if (teams && bn == 192) return launch_tapgemm<192, true>(p, stream);
-    if (teams && bn == 128) return launch_tapgemm<128, true>(p, stream);
+    if (teams && bn == 192) return ln ? launch_tapgemm<192, true, false, true>(p, stream) : launch_tapgemm<192, true>(p, stream);
+    if (teams && bn == 128) return ln ? launch_tapgemm<128, true, false, true>(p, stream) : launch_tapgemm<128, true>(p, stream);
   }
+  if (p.ln_in != nullptr || p.ln_out != nullptr)
+    return SRB200_EINVAL;  // LayerNorm folding: two-team kernels (128- / 192-wide N tiles) only
   switch (bn) {
     case 256: return launch_tapgemm<256>(p, stream);
     case 192: return launch_tapgemm<192>(p, stream);

@@ -483,8 +483,12 @@ def unpack_wgrad(acc, w_shape, perm_out=None, perm_in=None, alpha=1.0):
 def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alpha=1.0, mask_src=None,
             mask_mode=L.MASK_NONE, mask_slope=0.0, residual=None, flip=False, src_r=1, out_mode=L.OUT_NHWC,
             out_r=1, out_c=0, out_scale=1.0, out_shift=None, want_aux=False, residual_f32=None, want_f32=False,
-            alpha_per_sample=None, want_colsum=False, aux_grad=False, alpha_on_bias=False):
-    """conv3x3 / conv1x1 / Linear on NHWC bf16 (see include/srb200.h: srb200_tapgemm)."""
+            alpha_per_sample=None, want_colsum=False, aux_grad=False, alpha_on_bias=False, ln_in=None, ln_out=None):
+    """conv3x3 / conv1x1 / Linear on NHWC bf16 (see include/srb200.h: srb200_tapgemm).
+
+    ``ln_in=(stats, wsum)``: LayerNorm of the input rows folded into this GEMM (``x`` is the RAW tensor, ``wp`` carries
+    gamma, ``bias`` carries W beta + b); ``ln_out=(channels, eps)``: also return fp32 [B,H,W,2] (mean, rstd) of the
+    stored rows for the next folded GEMM (appended last to the result tuple)."""
     _chk(x, 'x', torch.bfloat16)
     _chk(wp, 'wp', torch.bfloat16)
     b, hf, wf, cin = x.shape
@@ -515,7 +519,13 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
         if out_mode != L.OUT_NHWC or cout % 64 != 0:
             raise RuntimeError('want_colsum needs a plain NHWC output with cout % 64 == 0')
         csum = zeros_f32((b, cout) if per_image else (cout,), x.device)
-    if residual_f32 is not None or want_f32 or alpha_per_sample is not None or csum is not None or aux_grad:
+    stats_out = torch.empty((b, h, w, 2), dtype=torch.float32, device=x.device) if ln_out is not None else None
+    if ln_in is not None:
+        _chk(ln_in[0], 'ln_in stats', torch.float32)
+        _chk(ln_in[1], 'ln_in wsum', torch.float32)
+        assert ln_in[0].numel() == 2 * b * h * w and ln_in[1].numel() == cout
+    if (residual_f32 is not None or want_f32 or alpha_per_sample is not None or csum is not None or aux_grad or
+            ln_in is not None or ln_out is not None):
         for t, name in ((residual_f32, 'residual_f32'), (alpha_per_sample, 'alpha_per_sample')):
             if t is not None:
                 _chk(t, name, torch.float32)
@@ -525,13 +535,19 @@ def tapgemm(x, wp, *, ksize, cout, bias=None, act=L.ACT_NONE, act_slope=0.0, alp
                                         1 if aux_grad else 0, 1 if per_image else 0,
                                         csum.data_ptr() if csum is not None else None,
                                         1.0 / (h * w) if per_image else 1.0,
-                                        L.EXT_ALPHA_ON_BIAS if (alpha_on_bias and alpha_per_sample is not None) else 0))
+                                        L.EXT_ALPHA_ON_BIAS if (alpha_on_bias and alpha_per_sample is not None) else 0,
+                                        ln_in[0].data_ptr() if ln_in is not None else None,
+                                        ln_in[1].data_ptr() if ln_in is not None else None,
+                                        stats_out.data_ptr() if stats_out is not None else None,
+                                        int(ln_out[0]) if ln_out is not None else 0,
+                                        float(ln_out[1]) if ln_out is not None else 0.0))
     ev = PROBE.begin('tapgemm', (b, h, w, cin * src_r * src_r, cout, ksize)) if PROBE is not None else None
     L.check(L.load().srb200_tapgemm(ctypes.byref(d), _ptr(x), _ptr(wp), _ptr(bias), _ptr(mask_src), _ptr(residual),
                                     _ptr(out_shift), _ptr(out), _ptr(aux), ext, _stream()), 'tapgemm')
     if ev is not None:
         PROBE.end(ev)
-    res = (out,) + ((aux,) if want_aux else ()) + ((out32,) if want_f32 else ()) + ((csum,) if want_colsum else ())
+    res = (out,) + ((aux,) if want_aux else ()) + ((out32,) if want_f32 else ()) + ((csum,) if want_colsum else ()) + \
+        ((stats_out,) if ln_out is not None else ())
     return res if len(res) > 1 else out
 
 

@@ -215,6 +215,19 @@ typedef struct {
                                     SRB200_OUT_NHWC with Cout % 64 == 0 only                            */
   float colsum_scale;            /* the sums are multiplied by this when flushed (0 = 1.0; 1/HW for a mean)        */
   int32_t flags;                 /* SRB200_EXT_*                                                                    */
+  /* LayerNorm folded into the GEMMs on either side of it (evaluation; swinir_arch.py:288-289,320-321: norm -> Linear):
+   * the PRODUCER of a row tensor x (Cout = one N tile of 128 / 192 channels, plain NHWC output) also writes
+   * ln_stats_out[pixel] = (mean, rstd) over the first ln_channels stored (bf16-rounded) channels, with ln_eps;
+   * the CONSUMER Linear runs on the raw x with weights W' = W diag(gamma) and computes
+   *     v = rstd * (acc - mean * ln_wsum[n]) + bias[n],  ln_wsum[n] = sum_c W'[n,c] (of the bf16-rounded packed
+   * weights), bias = W beta + b  --  exactly W LN(x) + b, without a LayerNorm pass or a normalised copy of x.
+   * Both sides need a layer whose N tile is 128 or 192 wide (Cout % 192 == 0, or % 128 == 0 and % 256 != 0) on the
+   * TMA-store path; anything else returns SRB200_EINVAL.                                                            */
+  const float* ln_stats_in;      /* fp32 [pixels][2] or NULL (with ln_wsum; not together with alpha_per_sample)     */
+  const float* ln_wsum;          /* fp32 [Cout]                                                                     */
+  float* ln_stats_out;           /* fp32 [pixels][2] or NULL                                                        */
+  int32_t ln_channels;           /* real channel count of the rows ln_stats_out describes                           */
+  float ln_eps;
 } srb200_tapgemm_ext;
 /* alpha_per_sample multiplies the BIAS only: v = acc + alpha[b] * bias.  For a Linear whose INPUT already carries the
  * per-sample DropPath factor (h' = alpha[b] * h stored by the producing epilogue, so that the weight-gradient GEMM

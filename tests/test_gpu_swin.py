@@ -322,3 +322,87 @@ def test_swinir_fp32_mode_full_size_within_1e4(cuda):
     err = (out - ref).abs().max().item()
     print(f'SwinIR full size, fp32 mode: max-abs {err:.2e}')
     assert err <= 1e-4, f'max-abs {err:.3e}'
+
+
+# ------------------------------------------------------------------ LayerNorm folded into the surrounding GEMMs (evaluation)
+@pytest.mark.parametrize('c,cs,n_out,act', [(180, 192, 576, 'none'), (180, 192, 384, 'gelu'), (120, 128, 384, 'gelu')])
+def test_tapgemm_layernorm_fold(cuda, c, cs, n_out, act):
+    """srb200_tapgemm_ext.ln_stats_out / ln_stats_in: the producer's (mean, rstd) of the rows it stores match a
+    LayerNorm's statistics of that bf16 tensor and leave the stored tensor bit-identical; the consumer on the RAW rows
+    with gamma-folded weights reproduces Linear(LayerNorm(x)) (fp32 PyTorch) at least as closely as the
+    LayerNorm-kernel + plain-GEMM path does."""
+    so, raw = _ops(), _ops().raw
+    from basicsr4rs_b200 import _lib as L
+    g = torch.Generator().manual_seed(3)
+    b, h, w = 2, 24, 40
+    o = torch.zeros((b, h, w, cs))
+    o[..., :c] = torch.randn((b, h, w, c), generator=g)
+    res = torch.zeros((b, h, w, cs))
+    res[..., :c] = torch.randn((b, h, w, c), generator=g) * 2 + 0.7
+    o, res = o.to(cuda).to(torch.bfloat16), res.to(cuda).to(torch.bfloat16)
+    wp_ = (torch.randn((c, c), generator=g) * 0.05).to(cuda)
+    bp_ = (torch.randn((c,), generator=g) * 0.1).to(cuda)
+    bias_p = torch.zeros(cs, device=cuda)
+    bias_p[:c] = bp_
+    packed_p = raw.pack_weight(wp_, cs, cs)
+    x1 = raw.tapgemm(o, packed_p, ksize=1, cout=cs, bias=bias_p, residual=res)
+    x1s, st = raw.tapgemm(o, packed_p, ksize=1, cout=cs, bias=bias_p, residual=res, ln_out=(c, 1e-5))
+    assert torch.equal(x1, x1s)
+    xf = x1[..., :c].float()
+    mean, var = xf.mean(-1), xf.var(-1, unbiased=False)
+    assert torch.allclose(st[..., 0], mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(st[..., 1], torch.rsqrt(var + 1e-5), rtol=2e-4)
+    # consumer
+    gamma = (1 + 0.2 * torch.randn(c, generator=g)).to(cuda)
+    beta = (0.2 * torch.randn(c, generator=g)).to(cuda)
+    n_real = n_out - 8
+    wl = (torch.randn((n_real, c), generator=g) * 0.05).to(cuda)
+    bl = (torch.randn((n_real,), generator=g) * 0.1).to(cuda)
+    a = L.ACT_GELU if act == 'gelu' else L.ACT_NONE
+    ref = F.linear(F.layer_norm(xf, (c,), gamma, beta, 1e-5), wl, bl)
+    ref = F.gelu(ref) if act == 'gelu' else ref
+    # (1) the unfolded path: LayerNorm kernel -> plain GEMM
+    xn = so.layernorm_fwd(x1, gamma, beta, c)[0]
+    bias_l = torch.zeros(n_out, device=cuda)
+    bias_l[:n_real] = bl
+    y_plain = raw.tapgemm(xn, raw.pack_weight(wl, n_out, cs), ksize=1, cout=n_out, bias=bias_l, act=a)
+    # (2) folded
+    packed_f = raw.pack_weight((wl * gamma[None, :]).contiguous(), n_out, cs)
+    wsum = packed_f.float().sum(dim=2).reshape(-1).contiguous()
+    bias_f = torch.zeros(n_out, device=cuda)
+    bias_f[:n_real] = wl @ beta + bl
+    y_fold = raw.tapgemm(x1, packed_f, ksize=1, cout=n_out, bias=bias_f, act=a, ln_in=(st, wsum))
+    assert torch.count_nonzero(y_fold[..., n_real:]) == 0
+    e_plain = (y_plain[..., :n_real].float() - ref).abs().max().item()
+    e_fold = (y_fold[..., :n_real].float() - ref).abs().max().item()
+    print(f'fold: max-abs vs fp32 {e_fold:.3e} (LayerNorm kernel + GEMM: {e_plain:.3e})')
+    assert e_fold <= 2e-2 * ref.abs().max().item() and e_fold <= 1.5 * e_plain + 1e-3
+
+
+def test_swinir_eval_with_folded_layernorm(cuda, monkeypatch):
+    """BasicLayer's evaluation path on big tiles (LayerNorm folded into qkv / fc1, statistics from proj / fc2), forced on
+    for a small input: same output as the LayerNorm-kernel path within bf16 noise, and within the 1e-2 bar of the
+    reference golden fixture."""
+    from basicsr4rs_b200.archs import swinir_arch
+    fx = torch.load(os.path.join(GOLDEN, 'swinir_c180_d2x2_x4.pt'), weights_only=False)
+    net = _build(fx, cuda)
+    with torch.no_grad():
+        plain = net(fx['x'].to(cuda)).cpu()
+        monkeypatch.setattr(swinir_arch.BasicLayer, 'FOLD_MIN_TOKENS', 0)
+        n0 = _launches()
+        folded = net(fx['x'].to(cuda)).cpu()
+        n_fold = _launches() - n0
+        n0 = _launches()
+        monkeypatch.setattr(swinir_arch.BasicLayer, 'FOLD_MIN_TOKENS', 1 << 60)
+        net(fx['x'].to(cuda))
+        n_plain = _launches() - n0
+    assert n_fold != n_plain, 'the folded path did not run'
+    err_p, err_f = (plain - fx['out']).abs().max().item(), (folded - fx['out']).abs().max().item()
+    print(f'folded LayerNorm: max-abs {err_f:.3e} (LayerNorm kernels {err_p:.3e}); {n_fold} vs {n_plain} launches')
+    assert err_f <= MAX_ABS, err_f
+    assert (folded - plain).abs().max().item() <= 5e-3
+
+
+def _launches():
+    from basicsr4rs_b200 import _lib
+    return _lib.launch_count
