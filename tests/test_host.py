@@ -39,6 +39,36 @@ def test_struct_layout_matches_header(lib):
     assert ctypes.sizeof(lib.TapGemmDesc) == 17 * 4
 
 
+def test_ctypes_mirrors_have_the_c_layout(tmp_path):
+    """sizeof / offsetof of srb200_tapgemm_desc and srb200_tapgemm_ext as gcc lays them out from include/srb200.h
+    against the ctypes mirrors in _lib.py (a field added on one side only would shift every later pointer)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from basicsr4rs_b200 import _lib as L
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ext_fields = [f[0] for f in L.TapGemmExt._fields_]
+    desc_fields = [f[0] for f in L.TapGemmDesc._fields_]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "srb200.h"', 'int main(void) {',
+             '  printf("%zu %zu\\n", sizeof(srb200_tapgemm_desc), sizeof(srb200_tapgemm_ext));']
+    lines += [f'  printf("%zu\\n", offsetof(srb200_tapgemm_desc, {f}));' for f in desc_fields]
+    lines += [f'  printf("%zu\\n", offsetof(srb200_tapgemm_ext, {f}));' for f in ext_fields]
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'abi.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'abi'
+    r = subprocess.run(['gcc', '-std=c99', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr  # (also: every mirrored field name exists in the header's struct)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    nums = [int(v) for v in out]
+    assert nums[0] == ctypes.sizeof(L.TapGemmDesc) and nums[1] == ctypes.sizeof(L.TapGemmExt), nums[:2]
+    want = [getattr(L.TapGemmDesc, f).offset for f in desc_fields] + [getattr(L.TapGemmExt, f).offset for f in ext_fields]
+    assert nums[2:] == want
+
+
 def test_registry_semantics():
     from basicsr4rs_b200.utils.registry import Registry
     reg = Registry('arch')
