@@ -432,10 +432,11 @@ class BasicLayer(nn.Module):
         fc1 = bank([blk.mlp.fc1 for blk in blocks], [blk.norm2 for blk in blocks], ch, None)
         return qkv, fc1
 
-    def forward_nhwc(self, t):
+    def forward_nhwc(self, t, stats=None):
+        """``stats`` (folded evaluation only): (mean, rstd) of the rows of ``t`` when its producer -- the previous RSTB's
+        conv -- emitted them; the first block then needs no LayerNorm launch either."""
         if self._fold_ok(t):
             fq, f1 = self._fold_bank(t.shape[-1], t.device)
-            stats = None
             for i, blk in enumerate(self.blocks):
                 t, stats = blk.forward_nhwc_folded(t, stats, fq[i], f1[i])
             return t
@@ -552,6 +553,20 @@ class RSTB(nn.Module):
 
     def forward_nhwc(self, t):
         return _resi_conv(self.conv, self.residual_group.forward_nhwc(t), t)
+
+    def forward_nhwc_folded(self, t, stats):
+        """Evaluation on big tiles: (RSTB(t), row statistics of it or None).  The '1conv' residual connection emits the
+        (mean, rstd) of the rows it stores, so the NEXT layer's first block folds its LayerNorm as well."""
+        grp = self.residual_group
+        if not grp._fold_ok(t):
+            return self.forward_nhwc(t), None
+        r = grp.forward_nhwc(t, stats)
+        if not isinstance(self.conv, nn.Conv2d) or self.conv.bias is None:
+            return _resi_conv(self.conv, r, t), None
+        cs = t.shape[-1]
+        return ops.raw.tapgemm(r, swin_ops._packed(self.conv.weight, 'fprop', cs, cs), ksize=3, cout=cs,
+                               bias=swin_ops._padded_bias(self.conv.bias, cs), residual=t,
+                               ln_out=(self.dim, grp.blocks[0].norm1.eps))
 
     def forward(self, x, x_size):
         """Reference contract (:557-558): x [B, h*w, C] tokens."""
@@ -900,7 +915,12 @@ class SwinIR(ArchMixin, nn.Module):
             return out if out.dtype == x.dtype else out.to(x.dtype)
         first = self._head(x)
         t = self._embed(first)
-        for layer in self.layers:
-            t = layer.forward_nhwc(t)
+        if not torch.is_grad_enabled() and not self.training:
+            stats = None  # (evaluation: row statistics handed from one RSTB's conv to the next layer's first block)
+            for layer in self.layers:
+                t, stats = layer.forward_nhwc_folded(t, stats)
+        else:
+            for layer in self.layers:
+                t = layer.forward_nhwc(t)
         out = self._tail(t, first, x)
         return out if out.dtype == x.dtype else out.to(x.dtype)
