@@ -14,7 +14,6 @@ seeded random inits are interchangeable.  What differs is how ``forward`` comput
   is kept only for state-dict compatibility -- nothing is rebuilt on the CPU per call (cf. :305-306);
 * 3x3 convs, pixel-shuffle upsampler and image entry / exit as in EDSR.
 """
-import math
 
 import os
 

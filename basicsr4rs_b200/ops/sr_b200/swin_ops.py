@@ -9,7 +9,6 @@ Layouts (all NHWC bf16, tokens == pixels):
 The padding lives only in the packed bf16 weight copies (index maps below); parameters keep the
 reference's shapes, so state dicts are interchangeable.
 """
-import ctypes
 import os
 
 import torch
@@ -18,7 +17,7 @@ from torch.autograd import Function
 from ... import _lib as L
 from . import raw
 from .raw import _chk, _ptr, _stream
-from .sr_b200 import _packed, _padded_bias, _perm_cache, _unpad_bias_grad, pad64
+from .sr_b200 import _packed, _padded_bias, _perm_cache, pad64
 
 HD_PAD = 32
 # v with GELU(v) = v Phi(v) = 1 (any v whose GELU rounds to 1.0 in bf16 would do)
