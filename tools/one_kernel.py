@@ -3,6 +3,7 @@
     python tools/one_kernel.py NAME [--time]
 
 NAME: attn_fwd attn_bwd ln_fwd ln_bwd qkv proj fc1_gelu fc1_gelu_aux fc2 fc2_dgrad wgrad_fc1 (SwinIR, B16 x 64x64 tokens)
+      qkv_fold_1m fc2_stats_1m (SwinIR evaluation with folded LayerNorm, one 1024 x 1024 tile)
       conv64 conv64_dgrad wgrad64 ca_fwd ca_bwd (RCAN, 16 x 48x48 x 64)   conv256 wgrad256 (EDSR-L, 16 x 48x48 x 256)
 --time: print the device time of back-to-back launches queued behind a device-side delay instead of just launching."""
 import json
@@ -66,6 +67,18 @@ def swin(name):
         return lambda: raw.tapgemm(x192, wp, ksize=1, cout=384, flip=True, mask_src=x384, mask_mode=L.MASK_MUL)
     if name == 'wgrad_fc1':
         return lambda: raw.wgrad(x384, x192, ksize=1)
+    if name in ('qkv_fold_1m', 'fc2_stats_1m'):  # evaluation kernels of the folded LayerNorm on one 1024 x 1024 tile
+        big192 = bf(1, 1024, 1024, 192)
+        big192[..., 180:] = 0
+        if name == 'fc2_stats_1m':
+            big384 = bf(1, 1024, 1024, 384)
+            wp, bias = lin(192, 384)
+            return lambda: raw.tapgemm(big384, wp, ksize=1, cout=192, bias=bias, residual=big192, ln_out=(180, 1e-5))
+        wp, bias = lin(576, 192)
+        xf = big192[..., :180].float()
+        stats = torch.stack([xf.mean(-1), torch.rsqrt(xf.var(-1, unbiased=False) + 1e-5)], dim=-1).contiguous()
+        wsum = wp.float().sum(dim=2).reshape(-1).contiguous()
+        return lambda: raw.tapgemm(big192, wp, ksize=1, cout=576, bias=bias, ln_in=(stats, wsum))
     raise SystemExit(f'unknown kernel {name}')
 
 
