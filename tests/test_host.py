@@ -279,3 +279,58 @@ def test_flat_grads_layout_and_buckets():
     net(torch.ones(2, 7)).sum().backward()
     for p, v in zip(fg.params, fg.views):
         assert p.grad.data_ptr() == v.data_ptr()
+
+
+def test_layernorm_fold_bank_host_logic(monkeypatch):
+    """BasicLayer._fold_bank / _fold_ok on the CPU with the pack launch replaced by its definition (bf16 [1, Np, Kp],
+    rows permuted by perm_out, zero padded): the folded operands reproduce Linear(LayerNorm(x)) through
+    rstd * (W'x - mean * wsum) + bias', in the packed channel order, for qkv (head-padded layout) and fc1."""
+    from basicsr4rs_b200.archs import swinir_arch
+    from basicsr4rs_b200.ops.sr_b200 import raw, swin_ops
+
+    def fake_pack(w, n_pad, k_pad, perm_out=None, perm_in=None, transpose=False, out=None):
+        assert perm_in is None and not transpose
+        full = torch.zeros((n_pad, k_pad))
+        rows = torch.arange(n_pad) if perm_out is None else perm_out.long()
+        ok = (rows >= 0) & (rows < w.shape[0])
+        full[ok, :w.shape[1]] = w[rows[ok]]
+        res = full.to(torch.bfloat16).reshape(1, n_pad, k_pad)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    monkeypatch.setattr(raw, 'pack_weight', fake_pack)
+    torch.manual_seed(0)
+    layer = swinir_arch.BasicLayer(dim=180, input_resolution=(16, 16), depth=2, num_heads=6, window_size=8, mlp_ratio=2.)
+    layer.eval()
+    for blk in layer.blocks:
+        for nm in (blk.norm1, blk.norm2):
+            nm.weight.data.normal_(1.0, 0.2)
+            nm.bias.data.normal_(0.0, 0.2)
+        for lin in (blk.attn.qkv, blk.mlp.fc1):
+            lin.bias.data.normal_(0.0, 0.1)
+    with torch.no_grad():
+        assert layer._fold_ok(torch.zeros((1, 512, 512, 192)))          # a big evaluation tile
+        assert not layer._fold_ok(torch.zeros((1, 64, 64, 192)))        # below FOLD_MIN_TOKENS
+        assert not layer._fold_ok(torch.zeros((1, 512, 512, 64)))       # no two-team kernel for 64-wide rows
+        layer.train()
+        assert not layer._fold_ok(torch.zeros((1, 512, 512, 192)))
+        layer.eval()
+        fq, f1 = layer._fold_bank(192, torch.device('cpu'))
+        x = torch.randn(50, 180) * 2 + 0.3
+        xp = torch.nn.functional.pad(x, (0, 12))
+        mean = x.mean(-1, keepdim=True)
+        rstd = torch.rsqrt(x.var(-1, unbiased=False, keepdim=True) + 1e-5)
+        for i, blk in enumerate(layer.blocks):
+            perm = swin_ops.head_perm(6, 30, 3, torch.device('cpu')).long()
+            for (wp, wsum, bp), lin, nm, pm in ((fq[i], blk.attn.qkv, blk.norm1, perm), (f1[i], blk.mlp.fc1, blk.norm2, None)):
+                ref = lin(nm(x))
+                got = rstd * (xp @ wp[0].float().T - mean * wsum[None]) + bp[None]
+                if pm is None:
+                    want = torch.nn.functional.pad(ref, (0, got.shape[1] - ref.shape[1]))
+                else:
+                    want = torch.where(pm >= 0, ref[:, pm.clamp(min=0)], torch.zeros(()))
+                # (bf16 rounding of W' is the only difference: ~2^-9 relative per weight)
+                assert (got - want).abs().max().item() <= 2e-2 * ref.abs().max().item()
+                assert torch.count_nonzero(got[:, (want == 0).all(0)]) == 0   # pad channels stay exactly zero
