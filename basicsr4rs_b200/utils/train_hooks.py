@@ -72,3 +72,44 @@ def install_lazy_loss_log(model):
     """``model``: a reference ``SRModel`` (or any ``BaseModel``).  Returns it for chaining."""
     model.reduce_loss_dict = types.MethodType(lazy_reduce_loss_dict, model)
     return model
+
+
+# ------------------------------------------------------------------ tiled validation / test (SURVEY.md section 8f, rank 2)
+def tiled_test(self, tile=1024, overlap=32, min_pixels=None):
+    """Drop-in for ``SRModel.test`` (sr_model.py:120-129) / ``SwinIRModel.test`` (swinir_model.py:14-36) on scenes too
+    large for one forward: ``self.lq`` [B,C,H,W] is cut into ``tile`` x ``tile`` LR tiles overlapping by ``overlap``
+    pixels (utils/tiling.tiled_forward; every tile padded to a multiple of the network's ``window_size`` the way
+    ``SwinIRModel.test`` pads the whole image, seams cropped at the middle of the overlap), each forwarded under
+    ``no_grad`` by ``net_g_ema`` when the model keeps one, else by ``net_g`` in eval mode (restored to train mode
+    afterwards, as the reference does).  Images of up to ``min_pixels`` LR pixels (default: one tile) take ONE forward,
+    exactly as the reference's ``test`` -- padding and cropping included."""
+    from .tiling import pad_to_multiple, tiled_forward
+    opt = self.opt
+    multiple = int(opt.get('network_g', {}).get('window_size', 1) or 1)
+    scale = int(opt.get('scale', 1))
+    ema = hasattr(self, 'net_g_ema')
+    net = self.net_g_ema if ema else self.net_g
+    was_training = net.training
+    net.eval()
+    lq = self.lq
+    b, c, h, w = lq.shape
+    limit = tile * tile if min_pixels is None else min_pixels
+    try:
+        with torch.no_grad():
+            if h * w <= limit:
+                img, _ = pad_to_multiple(lq, multiple)
+                self.output = net(img)[:, :, :h * scale, :w * scale]
+            else:
+                outs = [tiled_forward(net, lq[i:i + 1], tile, scale, overlap=overlap, multiple=multiple)[0]
+                        for i in range(b)]
+                self.output = outs[0] if b == 1 else torch.cat(outs, 0)
+    finally:
+        if not ema and was_training:
+            net.train()
+
+
+def install_tiled_test(model, tile=1024, overlap=32, min_pixels=None):
+    """``model``: a reference ``SRModel`` / ``SwinIRModel`` (anything with ``lq``, ``opt`` and ``net_g``): its ``test()``
+    becomes :func:`tiled_test`; ``validation`` / ``nondist_validation`` (sr_model.py:131-201) call it unchanged."""
+    model.test = types.MethodType(lambda self: tiled_test(self, tile, overlap, min_pixels), model)
+    return model

@@ -104,3 +104,41 @@ def test_two_ranks_fill_disjoint_tiles():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def test_tiled_test_hook_matches_the_reference_test_contract():
+    """utils/train_hooks.install_tiled_test on a stand-in model object (lq / opt / net_g [/ net_g_ema], the attributes
+    SRModel.test and SwinIRModel.test use): a pointwise stand-in network makes tiled == whole-image exact, so the hook's
+    plumbing is what is tested -- window padding and cropping, EMA preference, train-mode restore, batch handling."""
+    import types
+    import torch
+    from basicsr4rs_b200.utils.train_hooks import install_tiled_test
+
+    class Up(torch.nn.Module):  # x2 nearest upsample of 2*x + 1: pointwise, so tiling cannot change any pixel
+        def __init__(self, multiple):
+            super().__init__()
+            self.multiple, self.calls, self.w = multiple, 0, torch.nn.Parameter(torch.ones(1))
+
+        def forward(self, x):
+            assert x.shape[-2] % self.multiple == 0 and x.shape[-1] % self.multiple == 0, 'caller must pad'
+            self.calls += 1
+            return torch.repeat_interleave(torch.repeat_interleave(2 * x + self.w, 2, dim=2), 2, dim=3)
+
+    lq = torch.rand((2, 3, 37, 50))
+    want = torch.repeat_interleave(torch.repeat_interleave(2 * lq + 1, 2, dim=2), 2, dim=3)
+    # SwinIRModel-like: window_size 8, no EMA copy, net_g in train mode
+    m = types.SimpleNamespace(opt={'scale': 2, 'network_g': {'window_size': 8}}, lq=lq, net_g=Up(8).train())
+    install_tiled_test(m, tile=16, overlap=4)
+    m.test()
+    assert m.output.shape == want.shape and torch.equal(m.output, want)
+    assert m.net_g.training and m.net_g.calls > 2          # tiled (several forwards), train mode restored
+    # one forward when the image fits a tile -- the reference's own behaviour, padding and cropping included
+    m2 = types.SimpleNamespace(opt={'scale': 2, 'network_g': {'window_size': 8}}, lq=lq, net_g=Up(8).train())
+    install_tiled_test(m2, tile=64, overlap=4)
+    m2.test()
+    assert torch.equal(m2.output, want) and m2.net_g.calls == 1
+    # SRModel-like with an EMA copy: net_g_ema is the one evaluated, net_g is left alone
+    m3 = types.SimpleNamespace(opt={'scale': 2, 'network_g': {}}, lq=lq[:1], net_g=Up(1).train(), net_g_ema=Up(1))
+    install_tiled_test(m3, tile=20, overlap=6)
+    m3.test()
+    assert torch.equal(m3.output, want[:1]) and m3.net_g.calls == 0 and m3.net_g_ema.calls > 1 and m3.net_g.training
