@@ -282,19 +282,6 @@ def _colsum_of(g):
     return raw.colsum(g)
 
 
-def _unpad_bias_grad(gb_packed, bias, perm_out=None):
-    if perm_out is None:
-        return gb_packed[:bias.numel()].clone()
-    key = ('scatter', id(perm_out))
-    if key not in _perm_cache:  # static index tensors (boolean masking would sync and cannot be graph-captured)
-        src = torch.nonzero(perm_out >= 0).flatten()
-        _perm_cache[key] = (src, perm_out[src].long())
-    src, dst = _perm_cache[key]
-    gb = torch.zeros_like(bias, dtype=torch.float32)
-    gb[dst] = gb_packed[src]
-    return gb
-
-
 # ------------------------------------------------------------------ NCHW fp32 image -> NHWC64 bf16
 class _ImageToNHWC(Function):
     """(x - mean) * img_range (edsr_arch.py:53) fused with the NCHW fp32 -> NHWC bf16 conversion."""
